@@ -1,0 +1,161 @@
+"""ctypes mirror of include/b200fusion.h and loader for the in-tree CUDA library.
+
+The structures are byte-for-byte the C-ABI PODs (which are themselves byte-for-byte the
+reference's ITMHashEntry / ITMVoxel_s_rgb / Vector* types, Utils/ITMLibDefines.h:69-84,
+:138-169). There is NO fallback: if dynslam_b200/csrc/libb200fusion.so is missing or fails to
+load, importing the engine raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "csrc", "libb200fusion.so")
+
+SDF_BLOCK_SIZE = 8
+SDF_BLOCK_SIZE3 = 512
+MAX_RENDERING_BLOCKS = 65536 * 4
+TRANSFER_BLOCK_NUM = 0x1000
+
+OK, ERR_CUDA, ERR_VBA_FULL, ERR_EXCESS_FULL, ERR_INVALID, ERR_DECAY_RING_FULL, ERR_UNSUPPORTED = range(7)
+
+RENDER_SHADED_GREYSCALE, RENDER_COLOUR_FROM_VOLUME, RENDER_COLOUR_FROM_NORMAL, \
+    RENDER_COLOUR_FROM_DEPTH_WEIGHT, RENDER_DEPTH_MAP = range(5)
+
+# numpy dtypes of the PODs (itemsize asserts below pin the layout)
+HASH_ENTRY_DTYPE = np.dtype([("pos", np.int16, 3), ("_pad", np.int16), ("offset", np.int32),
+                             ("ptr", np.int32), ("allocatedTime", np.int32)])
+VOXEL_DTYPE = np.dtype([("sdf", np.int16), ("w_depth", np.uint8), ("clr", np.uint8, 3),
+                        ("w_color", np.uint8), ("_pad", np.uint8)])
+assert HASH_ENTRY_DTYPE.itemsize == 20 and VOXEL_DTYPE.itemsize == 8
+
+f16 = C.c_float * 16
+f4 = C.c_float * 4
+
+
+class Scene(C.Structure):
+    _fields_ = [("d_voxels", C.c_void_p), ("d_allocationList", C.c_void_p), ("d_hash", C.c_void_p),
+                ("d_excessList", C.c_void_p), ("d_swapStates", C.c_void_p),
+                ("numBlocks", C.c_int32), ("numBuckets", C.c_int32), ("excessSize", C.c_int32),
+                ("lastFreeBlockId", C.c_int32), ("lastFreeExcessListId", C.c_int32),
+                ("voxelSize", C.c_float), ("mu", C.c_float), ("maxW", C.c_int32),
+                ("viewFrustum_min", C.c_float), ("viewFrustum_max", C.c_float),
+                ("stopIntegratingAtMaxW", C.c_int32), ("useSwapping", C.c_int32)]
+
+
+class RenderState(C.Structure):
+    _fields_ = [("d_visibleBlockPositions", C.c_void_p), ("d_entriesVisibleType", C.c_void_p),
+                ("d_minmax", C.c_void_p), ("d_raycastResult", C.c_void_p),
+                ("d_forwardProjection", C.c_void_p), ("d_fwdProjMissingPoints", C.c_void_p),
+                ("d_raycastImage", C.c_void_p), ("img_w", C.c_int32), ("img_h", C.c_int32),
+                ("noVisibleBlocks", C.c_int32), ("noFwdProjMissingPoints", C.c_int32)]
+
+
+class View(C.Structure):
+    _fields_ = [("d_depth", C.c_void_p), ("d_rgb", C.c_void_p),
+                ("depth_w", C.c_int32), ("depth_h", C.c_int32), ("rgb_w", C.c_int32), ("rgb_h", C.c_int32),
+                ("M_d", f16), ("invM_d", f16), ("M_rgb", f16), ("proj_d", f4), ("proj_rgb", f4),
+                ("depthWeighting", C.c_int32), ("requiresFullRendering", C.c_int32)]
+
+
+class Camera(C.Structure):
+    _fields_ = [("M", f16), ("invM", f16), ("proj", f4)]
+
+
+class EngineConfig(C.Structure):
+    _fields_ = [("device", C.c_int32), ("numBlocks", C.c_int32), ("numBuckets", C.c_int32),
+                ("excessSize", C.c_int32), ("img_w", C.c_int32), ("img_h", C.c_int32),
+                ("decayRingItems", C.c_int64), ("stream", C.c_void_p)]
+
+
+class TransferBuffers(C.Structure):
+    _fields_ = [("d_syncedVoxelBlocks", C.c_void_p), ("d_hasSyncedData", C.c_void_p),
+                ("d_neededEntryIDs", C.c_void_p)]
+
+
+class FrameOpts(C.Structure):
+    _fields_ = [("doDecay", C.c_int32), ("decayMaxWeight", C.c_int32), ("decayMinAge", C.c_int32),
+                ("doRaycast", C.c_int32)]
+
+
+class FrameStats(C.Structure):
+    _fields_ = [("ms_allocate", C.c_float), ("ms_integrate", C.c_float), ("ms_expected", C.c_float),
+                ("ms_raycast", C.c_float), ("ms_decay", C.c_float), ("ms_total", C.c_float),
+                ("launches", C.c_int64), ("noVisibleBlocks", C.c_int32), ("noIntegratedBlocks", C.c_int32)]
+
+
+# every symbol include/b200fusion.h declares; tests assert the .so exports all of them
+EXPORTS = [
+    "b200_engine_create", "b200_engine_destroy", "b200_last_error", "b200_engine_stream",
+    "b200_frame_index", "b200_mat4_inv", "b200_mat4_mul", "b200_reset_scene",
+    "b200_allocate_from_depth", "b200_integrate", "b200_decay", "b200_decayed_block_count",
+    "b200_find_visible_blocks", "b200_expected_depths", "b200_find_surface", "b200_render_image",
+    "b200_icp_maps", "b200_forward_render", "b200_point_cloud", "b200_swap_list_in",
+    "b200_swap_integrate_in", "b200_swap_out", "b200_process_frame_async", "b200_sync",
+    "b200_process_frame_host", "b200_set_timing", "b200_get_stats",
+]
+
+_lib = None
+
+
+def load_library():
+    """Load libb200fusion.so (CDLL only: no CUDA call happens until an engine is created)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'`. "
+            "dynslam_b200 has no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    P = C.POINTER
+    vp = C.c_void_p
+    lib.b200_engine_create.argtypes = [P(EngineConfig), P(vp)]
+    lib.b200_engine_destroy.argtypes = [vp]
+    lib.b200_engine_destroy.restype = None
+    lib.b200_last_error.argtypes = [vp]
+    lib.b200_last_error.restype = C.c_char_p
+    lib.b200_engine_stream.argtypes = [vp]
+    lib.b200_engine_stream.restype = vp
+    lib.b200_frame_index.argtypes = [vp]
+    lib.b200_mat4_inv.argtypes = [P(C.c_float), P(C.c_float)]
+    lib.b200_mat4_mul.argtypes = [P(C.c_float), P(C.c_float), P(C.c_float)]
+    lib.b200_mat4_mul.restype = None
+    lib.b200_reset_scene.argtypes = [vp, P(Scene)]
+    lib.b200_allocate_from_depth.argtypes = [vp, P(Scene), P(RenderState), P(View), C.c_int]
+    lib.b200_integrate.argtypes = [vp, P(Scene), P(RenderState), P(View)]
+    lib.b200_decay.argtypes = [vp, P(Scene), P(RenderState), C.c_int, C.c_int, C.c_int]
+    lib.b200_decayed_block_count.argtypes = [vp]
+    lib.b200_decayed_block_count.restype = C.c_size_t
+    lib.b200_find_visible_blocks.argtypes = [vp, P(Scene), P(RenderState), P(Camera)]
+    lib.b200_expected_depths.argtypes = [vp, P(Scene), P(RenderState), P(Camera)]
+    lib.b200_find_surface.argtypes = [vp, P(Scene), P(RenderState), P(Camera)]
+    lib.b200_render_image.argtypes = [vp, P(Scene), P(RenderState), P(Camera), vp, vp, C.c_int, C.c_int, C.c_int]
+    lib.b200_icp_maps.argtypes = [vp, P(Scene), P(RenderState), P(View), vp, vp]
+    lib.b200_forward_render.argtypes = [vp, P(Scene), P(RenderState), P(View)]
+    lib.b200_point_cloud.argtypes = [vp, P(Scene), P(RenderState), P(View), P(C.c_float), C.c_int, vp, vp,
+                                     P(C.c_uint32)]
+    lib.b200_swap_list_in.argtypes = [vp, P(Scene), P(TransferBuffers), P(C.c_int)]
+    lib.b200_swap_integrate_in.argtypes = [vp, P(Scene), P(TransferBuffers), C.c_int]
+    lib.b200_swap_out.argtypes = [vp, P(Scene), P(RenderState), P(TransferBuffers), P(C.c_int)]
+    lib.b200_process_frame_async.argtypes = [vp, P(Scene), P(RenderState), P(View), vp, vp, P(FrameOpts)]
+    lib.b200_sync.argtypes = [vp, P(Scene), P(RenderState)]
+    lib.b200_process_frame_host.argtypes = [vp, P(Scene), P(RenderState), P(View), vp, vp, vp, vp, vp, vp,
+                                            P(FrameOpts), vp]
+    lib.b200_set_timing.argtypes = [vp, C.c_int]
+    lib.b200_set_timing.restype = None
+    lib.b200_get_stats.argtypes = [vp, P(FrameStats)]
+    _lib = lib
+    return lib
+
+
+def mat_to_c(m):
+    """4x4 row-major numpy matrix -> ITM column-major float[16] (m[col*4+row], OR/Matrix.h:23-33)."""
+    a = np.asarray(m, dtype=np.float32)
+    assert a.shape == (4, 4)
+    return f16(*a.T.reshape(-1).tolist())
+
+
+def c_to_mat(c):
+    return np.array(list(c), dtype=np.float32).reshape(4, 4).T.copy()

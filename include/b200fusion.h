@@ -1,0 +1,266 @@
+/*
+ * b200fusion.h — C-ABI of the B200-native voxel-hashed TSDF fusion / raycast engine.
+ *
+ * This is the drop-in boundary behind DynSLAM's ITMLib engine interfaces. Every entry point
+ * below replaces one virtual of the reference (paths relative to
+ * src/InfiniTAM/InfiniTAM/ITMLib/ in AndreiBarsan/DynSLAM):
+ *
+ *   ITMSceneReconstructionEngine<TVoxel,ITMVoxelBlockHash>   Engine/ITMSceneReconstructionEngine.h:33-78
+ *   IITMVisualisationEngine / ITMVisualisationEngine          Engine/ITMVisualisationEngine.h:19-127
+ *   ITMSwappingEngine<TVoxel,ITMVoxelBlockHash>               Engine/ITMSwappingEngine.h:22-31
+ *
+ * Plain pointers and sizes only; all pointers named d_* are CUDA device pointers owned by the
+ * caller (exactly the buffers ITMScene / ITMRenderState_VH / ITMView already own), the engine
+ * handle owns only its scratch. Byte layouts are those of the reference:
+ *   ITMHashEntry   20 B  Utils/ITMLibDefines.h:69-84
+ *   ITMVoxel_s_rgb  8 B  Utils/ITMLibDefines.h:138-169 (one 8x8x8 block = 4096 B)
+ *   Matrix4f       m[col*4+row]  ORUtils/Matrix.h:23-33
+ *
+ * Error convention (reference: ORcudaSafeCall exits, logic errors throw std::runtime_error,
+ * Reco_CUDA.cu:348-357): every function returns a b200_status; b200_last_error() gives text.
+ * The C++ shim (dynslam_b200/itm_shim) maps the codes back onto throw / exit.
+ */
+#ifndef B200FUSION_H
+#define B200FUSION_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200_SDF_BLOCK_SIZE 8
+#define B200_SDF_BLOCK_SIZE3 512
+#define B200_MAX_RENDERING_BLOCKS (65536 * 4) /* DeviceAgnostic/ITMVisualisationEngine.h:25 */
+#define B200_MINMAX_SUBSAMPLE 8               /* DeviceAgnostic/ITMVisualisationEngine.h:27 */
+#define B200_FAR_AWAY 999999.9f
+#define B200_VERY_CLOSE 0.05f
+#define B200_TRANSFER_BLOCK_NUM 0x1000        /* Utils/ITMLibDefines.h:39 */
+
+typedef enum {
+  B200_OK = 0,
+  B200_ERR_CUDA = 1,          /* reference: ORcudaSafeCall -> exit(-1) */
+  B200_ERR_VBA_FULL = 2,      /* reference: throw runtime_error, Reco_CUDA.cu:348-351 */
+  B200_ERR_EXCESS_FULL = 3,   /* reference: throw runtime_error, Reco_CUDA.cu:353-357 */
+  B200_ERR_INVALID = 4,
+  B200_ERR_DECAY_RING_FULL = 5,
+  B200_ERR_UNSUPPORTED = 6
+} b200_status;
+
+/* ---- byte-exact mirrors of the reference PODs ---------------------------------------- */
+
+typedef struct {            /* ITMHashEntry */
+  int16_t pos[3];
+  int16_t _pad;
+  int32_t offset;           /* 1-based index into the excess part, <1 = end of chain */
+  int32_t ptr;              /* >=0 VBA block id, -1 swapped out, <-1 free */
+  int32_t allocatedTime;
+} b200_hash_entry;
+
+typedef struct {            /* ITMVoxel_s_rgb */
+  int16_t sdf;              /* tsdf * 32767 */
+  uint8_t w_depth;
+  uint8_t clr[3];
+  uint8_t w_color;
+  uint8_t _pad;
+} b200_voxel;
+
+typedef struct { int32_t x, y, z; } b200_vec3i;   /* Vector3i, visible-list item */
+typedef struct { float x, y; } b200_vec2f;        /* Vector2f, min/max image pixel */
+typedef struct { float x, y, z, w; } b200_vec4f;  /* Vector4f */
+typedef struct { uint8_t x, y, z, w; } b200_vec4u;/* Vector4u, RGBA8 */
+
+/* ---- scene (ITMScene = ITMVoxelBlockHash + ITMLocalVBA + ITMSceneParams) --------------- */
+
+typedef struct {
+  b200_voxel *d_voxels;          /* localVBA.GetVoxelBlocks(): numBlocks*512 voxels */
+  int32_t *d_allocationList;     /* localVBA.GetAllocationList(): numBlocks ints */
+  b200_hash_entry *d_hash;       /* index.GetEntries(): numBuckets+excessSize entries */
+  int32_t *d_excessList;         /* index.GetExcessAllocationList(): excessSize ints */
+  uint8_t *d_swapStates;         /* globalCache->GetSwapStates(true) or NULL (swapping off) */
+  int32_t numBlocks;             /* sdfLocalBlockNum */
+  int32_t numBuckets;            /* SDF_BUCKET_NUM, power of two */
+  int32_t excessSize;            /* SDF_EXCESS_LIST_SIZE */
+  /* host-visible counters, valid on return of every synchronous call */
+  int32_t lastFreeBlockId;       /* localVBA.lastFreeBlockId */
+  int32_t lastFreeExcessListId;  /* index.lastFreeExcessListId */
+  /* ITMSceneParams (Objects/ITMSceneParams.h:14-71) */
+  float voxelSize, mu;
+  int32_t maxW;
+  float viewFrustum_min, viewFrustum_max;
+  int32_t stopIntegratingAtMaxW;
+  int32_t useSwapping;
+} b200_scene;
+
+/* ---- render state (ITMRenderState_VH + base) ------------------------------------------ */
+
+typedef struct {
+  b200_vec3i *d_visibleBlockPositions; /* GetVisibleBlockPositions(): numBlocks items */
+  uint8_t *d_entriesVisibleType;       /* GetEntriesVisibleType(): one byte per hash entry */
+  b200_vec2f *d_minmax;                /* renderingRangeImage, w*h, 1/8-res corner used */
+  b200_vec4f *d_raycastResult;         /* raycastResult, w*h */
+  b200_vec4f *d_forwardProjection;     /* forwardProjection, w*h (may be NULL) */
+  int32_t *d_fwdProjMissingPoints;     /* fwdProjMissingPoints, w*h (may be NULL) */
+  b200_vec4u *d_raycastImage;          /* raycastImage, w*h */
+  int32_t img_w, img_h;
+  int32_t noVisibleBlocks;             /* host-visible, in/out */
+  int32_t noFwdProjMissingPoints;      /* host-visible, out */
+} b200_render_state;
+
+/* ---- per-frame inputs (ITMView + ITMTrackingState::pose_d + calib) ----------------------- */
+
+typedef struct {
+  const float *d_depth;          /* view->depth, metres, w*h */
+  const b200_vec4u *d_rgb;       /* view->rgb, RGBA8 */
+  int32_t depth_w, depth_h, rgb_w, rgb_h;
+  float M_d[16];                 /* trackingState->pose_d->GetM() */
+  float invM_d[16];              /* its inverse (Matrix4::inv, ORUtils/Matrix.h:162-224) */
+  float M_rgb[16];               /* calib.trafo_rgb_to_depth.calib_inv * M_d */
+  float proj_d[4];               /* intrinsics_d.projectionParamsSimple.all = fx,fy,cx,cy */
+  float proj_rgb[4];
+  int32_t depthWeighting;        /* WeightParams, Engine/ITMSceneReconstructionEngine.h:21-23 */
+  int32_t requiresFullRendering; /* trackingState->requiresFullRendering (approx. integration off) */
+} b200_view;
+
+typedef struct {               /* pose + intrinsics pair used by the visualisation calls */
+  float M[16];
+  float invM[16];
+  float proj[4];
+} b200_camera;
+
+typedef enum {                 /* IITMVisualisationEngine::RenderImageType, Vis.h:22-32 */
+  B200_RENDER_SHADED_GREYSCALE = 0,
+  B200_RENDER_COLOUR_FROM_VOLUME = 1,
+  B200_RENDER_COLOUR_FROM_NORMAL = 2,
+  B200_RENDER_COLOUR_FROM_DEPTH_WEIGHT = 3,
+  B200_RENDER_DEPTH_MAP = 4
+} b200_render_type;
+
+/* ---- engine handle ---------------------------------------------------------------------- */
+
+typedef struct b200_engine b200_engine;
+
+typedef struct {
+  int32_t device;              /* CUDA ordinal */
+  int32_t numBlocks;           /* capacity the scratch is sized for */
+  int32_t numBuckets;
+  int32_t excessSize;
+  int32_t img_w, img_h;
+  int64_t decayRingItems;      /* capacity (visible-list items) of the decay snapshot ring;
+                                  0 = default 24*numBlocks */
+  void *stream;                /* optional caller cudaStream_t; NULL = engine-owned stream */
+} b200_engine_config;
+
+b200_status b200_engine_create(const b200_engine_config *cfg, b200_engine **out);
+void b200_engine_destroy(b200_engine *e);
+const char *b200_last_error(const b200_engine *e);
+void *b200_engine_stream(b200_engine *e);
+int32_t b200_frame_index(const b200_engine *e);      /* frameIdx, Reco_CUDA.h:37-45 */
+
+/* Matrix4f::inv restated for hosts without ORUtils (ORUtils/Matrix.h:162-224) */
+int b200_mat4_inv(const float *m, float *out);
+void b200_mat4_mul(const float *lhs, const float *rhs, float *out);
+
+/* ---- ITMSceneReconstructionEngine ------------------------------------------------------- */
+
+/* ResetScene — Reco_CUDA.cu:145-172 */
+b200_status b200_reset_scene(b200_engine *e, b200_scene *scene);
+/* AllocateSceneFromDepth — Reco_CUDA.cu:175-358 */
+b200_status b200_allocate_from_depth(b200_engine *e, b200_scene *scene, b200_render_state *rs,
+                                     const b200_view *view, int onlyUpdateVisibleList);
+/* IntegrateIntoScene — Reco_CUDA.cu:361-427 */
+b200_status b200_integrate(b200_engine *e, b200_scene *scene, b200_render_state *rs,
+                           const b200_view *view);
+/* Decay — Reco_CUDA.cu:509-560 */
+b200_status b200_decay(b200_engine *e, b200_scene *scene, b200_render_state *rs, int maxWeight,
+                       int minAge, int forceAllVoxels);
+/* GetDecayedBlockCount — Reco_CUDA.cu:563-566 */
+size_t b200_decayed_block_count(const b200_engine *e);
+
+/* ---- ITMVisualisationEngine ---------------------------------------------------------------- */
+
+/* FindVisibleBlocks — Vis_CUDA.cu:151-180 */
+b200_status b200_find_visible_blocks(b200_engine *e, const b200_scene *scene,
+                                     b200_render_state *rs, const b200_camera *cam);
+/* CreateExpectedDepths — Vis_CUDA.cu:194-240 */
+b200_status b200_expected_depths(b200_engine *e, const b200_scene *scene, b200_render_state *rs,
+                                 const b200_camera *cam);
+/* FindSurface / GenericRaycast — Vis_CUDA.cu:242-265, :484-489 */
+b200_status b200_find_surface(b200_engine *e, const b200_scene *scene, b200_render_state *rs,
+                              const b200_camera *cam);
+/* RenderImage — Vis_CUDA.cu:267-343 */
+b200_status b200_render_image(b200_engine *e, const b200_scene *scene, b200_render_state *rs,
+                              const b200_camera *cam, b200_vec4u *d_outChar, float *d_outFloat,
+                              int out_w, int out_h, b200_render_type type);
+/* CreateICPMaps — Vis_CUDA.cu:372-390. d_points/d_normals = pointCloud->locations/colours */
+b200_status b200_icp_maps(b200_engine *e, const b200_scene *scene, b200_render_state *rs,
+                          const b200_view *view, b200_vec4f *d_points, b200_vec4f *d_normals);
+/* ForwardRender — Vis_CUDA.cu:393-453 */
+b200_status b200_forward_render(b200_engine *e, const b200_scene *scene, b200_render_state *rs,
+                                const b200_view *view);
+/* CreatePointCloud — Vis_CUDA.cu:346-369. *noTotalPoints = pointCloud->noTotalPoints */
+b200_status b200_point_cloud(b200_engine *e, const b200_scene *scene, b200_render_state *rs,
+                             const b200_view *view, const float *calib_rgb_to_depth,
+                             int skipPoints, b200_vec4f *d_locations, b200_vec4f *d_colours,
+                             uint32_t *noTotalPoints);
+
+/* ---- ITMSwappingEngine ------------------------------------------------------------------- */
+
+typedef struct {               /* the device half of ITMGlobalCache, Objects/ITMGlobalCache.h */
+  b200_voxel *d_syncedVoxelBlocks;  /* SDF_TRANSFER_BLOCK_NUM blocks */
+  uint8_t *d_hasSyncedData;         /* bool per transfer slot */
+  int32_t *d_neededEntryIDs;        /* SDF_TRANSFER_BLOCK_NUM ints */
+} b200_transfer_buffers;
+
+/* IntegrateGlobalIntoLocal, device half — Swap_CUDA.cu:44-124.
+   step 1: list entries to swap in; returns the count (<= SDF_TRANSFER_BLOCK_NUM) */
+b200_status b200_swap_list_in(b200_engine *e, b200_scene *scene, b200_transfer_buffers *tb,
+                              int *noNeeded);
+/* step 2: merge the blocks the host has copied into tb into the local VBA */
+b200_status b200_swap_integrate_in(b200_engine *e, b200_scene *scene, b200_transfer_buffers *tb,
+                                   int noNeeded);
+/* SaveToGlobalMemory, device half — Swap_CUDA.cu:126-216 */
+b200_status b200_swap_out(b200_engine *e, b200_scene *scene, b200_render_state *rs,
+                          b200_transfer_buffers *tb, int *noNeeded);
+
+/* ---- fused fast path (no reference twin: removes the per-call blocking copies) */
+
+typedef struct {
+  int32_t doDecay, decayMaxWeight, decayMinAge;
+  int32_t doRaycast;           /* CreateExpectedDepths + CreateICPMaps */
+} b200_frame_opts;
+
+/* Enqueue allocate -> integrate -> expected depths -> ICP maps -> decay for one frame on the
+   engine stream without any host synchronisation. Counters live on the device; the host
+   fields of scene / rs are refreshed by b200_sync(). */
+b200_status b200_process_frame_async(b200_engine *e, b200_scene *scene, b200_render_state *rs,
+                                     const b200_view *view, b200_vec4f *d_points,
+                                     b200_vec4f *d_normals, const b200_frame_opts *opts);
+b200_status b200_sync(b200_engine *e, b200_scene *scene, b200_render_state *rs);
+
+/* Same, from host buffers: depth (float metres) and rgb are copied H2D from pinned staging
+   inside the call and the grey raycast image is copied back to h_outImage (may be NULL). */
+b200_status b200_process_frame_host(b200_engine *e, b200_scene *scene, b200_render_state *rs,
+                                    b200_view *view, const float *h_depth,
+                                    const b200_vec4u *h_rgb, float *d_depth_stage,
+                                    b200_vec4u *d_rgb_stage, b200_vec4f *d_points,
+                                    b200_vec4f *d_normals, const b200_frame_opts *opts,
+                                    b200_vec4u *h_outImage);
+
+/* ---- introspection used by bench.py / tests -------------------------------------------------- */
+
+typedef struct {
+  float ms_allocate, ms_integrate, ms_expected, ms_raycast, ms_decay, ms_total;
+  int64_t launches;            /* kernels launched by this engine since creation */
+  int32_t noVisibleBlocks, noIntegratedBlocks;
+} b200_frame_stats;
+
+/* enable per-stage CUDA-event timing (adds events to the stream; off by default) */
+void b200_set_timing(b200_engine *e, int enabled);
+b200_status b200_get_stats(b200_engine *e, b200_frame_stats *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200FUSION_H */
