@@ -1,0 +1,184 @@
+// common.cuh — shared PODs, canonical float arithmetic and device helpers of libb200fusion.
+//
+// Arithmetic contract: every floating-point expression on the path is evaluated in IEEE binary32
+// in exactly the operation order of the reference's DeviceAgnostic code (and therefore of
+// oracle/tsdf_oracle.c); the library is compiled with -fmad=false and the default
+// -prec-div=true -prec-sqrt=true, so results are bit-identical to the CPU oracle, not merely
+// within the 1e-5 tolerance north_star asks for. (The reference's own CUDA build uses
+// --use_fast_math, ITMLib/CMakeLists.txt:230, which is why it cannot serve as a bit-exact oracle.)
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/b200fusion.h"
+
+#define BS 8
+#define BS3 512
+
+#define HD __host__ __device__ __forceinline__
+#define DEV __device__ __forceinline__
+
+// ---- OR/MathUtils.h:5-23 -------------------------------------------------------------------
+HD float minf_(float a, float b) { return (a < b) ? a : b; }
+HD float maxf_(float a, float b) { return (a < b) ? b : a; }
+HD int mini_(int a, int b) { return (a < b) ? a : b; }
+HD float round_(float x) { return (x < 0) ? (x - 0.5f) : (x + 0.5f); }
+HD int clampi_(int x, int a, int b) { int t = (b < x) ? b : x; return (a < t) ? t : a; }
+
+struct Mat4 { float m[16]; };   // m[col*4+row], OR/Matrix.h:23-33
+struct Vec4 { float x, y, z, w; };
+struct Vec3 { float x, y, z; };
+
+// OR/Matrix.h:115-122
+HD Vec4 m4v4(const Mat4 &M, float x, float y, float z, float w) {
+  Vec4 r;
+  r.x = M.m[0] * x + M.m[4] * y + M.m[8] * z + M.m[12] * w;
+  r.y = M.m[1] * x + M.m[5] * y + M.m[9] * z + M.m[13] * w;
+  r.z = M.m[2] * x + M.m[6] * y + M.m[10] * z + M.m[14] * w;
+  r.w = M.m[3] * x + M.m[7] * y + M.m[11] * z + M.m[15] * w;
+  return r;
+}
+
+// DA/ITMRepresentationAccess.h:10-12
+HD int hash_index(int x, int y, int z, int mask) {
+  return (int)((((unsigned)x * 73856093u) ^ ((unsigned)y * 19349669u) ^ ((unsigned)z * 83492791u)) & (unsigned)mask);
+}
+
+HD int floordiv8(int p) { return ((p < 0) ? p - BS + 1 : p) / BS; }
+
+// ---- hash entry access: 20-byte AoS, 4-byte aligned -> 32-bit words -------------------------
+struct Entry { int x, y, z, offset, ptr; };
+
+DEV Entry load_entry(const b200_hash_entry *table, int idx) {
+  const int *p = reinterpret_cast<const int *>(table) + (size_t)idx * 5;
+  int w0 = __ldg(p), w1 = __ldg(p + 1);
+  Entry e;
+  e.x = (short)(w0 & 0xffff); e.y = (short)(w0 >> 16); e.z = (short)(w1 & 0xffff);
+  e.offset = __ldg(p + 2); e.ptr = __ldg(p + 3);
+  return e;
+}
+// volatile-free but non-__ldg variant for kernels that also write the table
+DEV Entry load_entry_rw(const b200_hash_entry *table, int idx) {
+  const int *p = reinterpret_cast<const int *>(table) + (size_t)idx * 5;
+  int w0 = p[0], w1 = p[1];
+  Entry e;
+  e.x = (short)(w0 & 0xffff); e.y = (short)(w0 >> 16); e.z = (short)(w1 & 0xffff);
+  e.offset = p[2]; e.ptr = p[3];
+  return e;
+}
+
+// findBlock — DA/ITMRepresentationAccess.h:62-85; -1 when absent
+template <bool RW>
+DEV int find_block(const b200_hash_entry *table, int numBuckets, int x, int y, int z, int *ptrOut = nullptr) {
+  int idx = hash_index(x, y, z, numBuckets - 1);
+  for (;;) {
+    Entry e = RW ? load_entry_rw(table, idx) : load_entry(table, idx);
+    if (e.x == x && e.y == y && e.z == z && e.ptr >= 0) { if (ptrOut) *ptrOut = e.ptr; return idx; }
+    if (e.offset < 1) break;
+    idx = numBuckets + e.offset - 1;
+  }
+  return -1;
+}
+
+// ---- device-resident counters (mirrored to pinned host memory by the engine) ----------------
+struct DevCounters {
+  int lastFreeBlockId;
+  int lastFreeExcessListId;
+  int noVisibleBlocks;
+  int allocBaseVba;        // lastFreeBlockId before this frame's requests
+  int allocBaseExl;
+  int noRequests;
+  int noRequestsExcess;
+  int noIntegrated;
+  int decayItems;          // number of list items of the decay pass in flight
+  int decayDeleted;        // unique blocks deleted by the pass
+  int freedLastDecay;
+  int errorFlags;          // bit0: decay ring overflow
+  unsigned noRenderingBlocks;
+  int noNeededEntries;     // swapping
+  unsigned noTotalPoints;
+  int noFwdMissing;
+  long long ringHead;      // device-side bump cursor of the decay ring (items)
+  long long totalDecayed;  // GetDecayedBlockCount, Reco_CUDA.cu:563-566
+};
+
+// ---- chained-scan (decoupled look-back) for ordered compaction --------------------------------
+// Persistent grids only (gridDim.x <= co-resident CTAs) so that every predecessor tile is owned by
+// a resident CTA: tile t is processed by CTA (t % gridDim.x) in round t / gridDim.x.
+// Descriptor: [63:34] generation (30 bit) | [33:32] status (1 = aggregate, 2 = inclusive prefix) |
+// [31:0] value. A fresh generation per launch makes resets unnecessary.
+DEV unsigned long long scan_pack(unsigned gen, unsigned status, unsigned value) {
+  return ((unsigned long long)(gen & 0x3fffffffu) << 34) | ((unsigned long long)status << 32) | value;
+}
+
+// Called by all threads of warp 0 of the CTA. Returns the exclusive prefix of tile `tile`
+// (valid in all lanes of warp 0).
+DEV unsigned scan_lookback(unsigned long long *desc, unsigned gen, int tile, unsigned aggregate) {
+  const int lane = threadIdx.x & 31;
+  volatile unsigned long long *vdesc = desc;
+  if (tile == 0) {
+    if (lane == 0) { vdesc[0] = scan_pack(gen, 2, aggregate); }
+    return 0;
+  }
+  if (lane == 0) { vdesc[tile] = scan_pack(gen, 1, aggregate); }
+  unsigned exclusive = 0;
+  int look = tile - 1;
+  for (;;) {
+    int t = look - lane;
+    unsigned long long d = 0;
+    unsigned status = 0;
+    if (t >= 0) {
+      d = vdesc[t];
+      if ((unsigned)(d >> 34) == (gen & 0x3fffffffu)) status = (unsigned)(d >> 32) & 3u;
+    } else status = 3; // out of range: treat as "prefix 0" sentinel
+    // every tile between this one and the nearest published inclusive prefix must be published
+    const unsigned validMask = __ballot_sync(0xffffffffu, status != 0);
+    const unsigned prefixMask = __ballot_sync(0xffffffffu, status >= 2);
+    const int firstPrefix = prefixMask ? (__ffs(prefixMask) - 1) : 32;
+    const unsigned need = (firstPrefix >= 32) ? 0xffffffffu : ((1u << firstPrefix) - 1u);
+    if ((validMask & need) != need) continue;   // spin (volatile re-read)
+    unsigned v = (lane <= firstPrefix && t >= 0) ? (unsigned)(d & 0xffffffffu) : 0u;
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    exclusive += v;
+    if (prefixMask) break;
+    look -= 32;
+  }
+  if (lane == 0) { __threadfence(); vdesc[tile] = scan_pack(gen, 2, exclusive + aggregate); }
+  return exclusive;
+}
+
+// block-wide exclusive scan of one unsigned per thread; returns exclusive prefix, *total = block sum.
+// smem must hold 33 unsigned.
+DEV unsigned block_exclusive_scan(unsigned v, unsigned *smem, unsigned *total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = (blockDim.x + 31) >> 5;
+  unsigned inc = v;
+  for (int o = 1; o < 32; o <<= 1) { unsigned n = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += n; }
+  if (lane == 31) smem[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    unsigned w = (lane < nwarps) ? smem[lane] : 0;
+    unsigned winc = w;
+    for (int o = 1; o < 32; o <<= 1) { unsigned n = __shfl_up_sync(0xffffffffu, winc, o); if (lane >= o) winc += n; }
+    smem[lane] = winc - w;
+    if (lane == 31) smem[32] = winc;
+  }
+  __syncthreads();
+  unsigned res = smem[warp] + inc - v;
+  *total = smem[32];
+  __syncthreads();
+  return res;
+}
+
+// 128-bit streaming accesses for voxel payloads (8 B voxels -> 2 per access)
+DEV uint4 ld_stream(const uint4 *p) {
+  uint4 r;
+  asm volatile("ld.global.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
+DEV void st_stream(uint4 *p, uint4 v) {
+  asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+// positive-float atomic min/max through the order-preserving int view (all values here are > 0)
+DEV void atomic_min_posf(float *a, float v) { atomicMin(reinterpret_cast<int *>(a), __float_as_int(v)); }
+DEV void atomic_max_posf(float *a, float v) { atomicMax(reinterpret_cast<int *>(a), __float_as_int(v)); }

@@ -1,0 +1,264 @@
+// decay.cu — voxel Decay() garbage collection for sm_100a (partial: blocks visible minAge frames
+// ago; full: every allocated block).
+//
+// Replaces decay_device / decayFull_device -> decayVoxel -> deleteBlock (reference
+// ITMSceneReconstructionEngine_CUDA.cu:1201-1262, :1120-1197, :1012-1115), findAllocatedBlocks
+// (ITMMeshingEngine_CUDA.cu:96-114) and the host logic of Decay/PartialDecay/FullDecay (:430-560).
+//
+// The reference takes a per-bucket lock (4 MiB array memset per call), DROPS a deletion when the
+// lock is contended, and pushes freed slots with atomicAdd — nondeterministic. Here the pass is
+// split so that it equals the serial oracle (blocks in list order):
+//   phase 1  per list item, one CTA iteration: resolve the block once, sweep its 4 KiB with 128-bit
+//            loads, reset noisy voxels, decide "block is empty" with a block-wide vote; the first
+//            item (list order) that empties a block claims it with a 64-bit atomicMax tag;
+//   phase 2  ordered compaction of the claiming items => free-list position = rank in list order;
+//   phase 3  chain leaders: for every bucket chain that loses blocks, ONE thread applies that
+//            chain's deletions in list order with the reference's unlink rules (incl. the
+//            visibility-byte moves and the never-reclaimed excess slots, :1075-1111).
+#include "engine.h"
+
+DEV unsigned long long del_tag(unsigned gen, unsigned item) { return ((unsigned long long)gen << 32) | (0xffffffffu - item); }
+
+// phase 1. MODE 0: items = ring snapshot; MODE 1: items = VBA slots with allocatedPos.w != 0
+template <int MODE>
+__global__ void __launch_bounds__(256)
+k_decay_blocks(b200_voxel *voxels, const b200_hash_entry *__restrict__ table, int numBuckets, const b200_vec3i *ring,
+               long long ringCap, const long long *snapStart, const int *snapCount, int slot, const short4 *allocatedPos,
+               int numBlocks, int minAge, int maxWeight, int currentFrame, unsigned gen, unsigned long long *delTag,
+               int *itemPtr, DevCounters *ctr) {
+  __shared__ int sEmpty[8];
+  const int n = (MODE == 0) ? snapCount[slot] : numBlocks;
+  const long long s0 = (MODE == 0) ? snapStart[slot] : 0;
+  if (blockIdx.x == 0 && threadIdx.x == 0) ctr->decayItems = n;
+  for (int item = blockIdx.x; item < n; item += gridDim.x) {
+    int x, y, z;
+    if (MODE == 0) { b200_vec3i p = ring[(s0 + item) % ringCap]; x = p.x; y = p.y; z = p.z; }
+    else {
+      short4 p = allocatedPos[item];
+      if (p.w == 0) { if (threadIdx.x == 0) itemPtr[item] = -1; continue; }
+      x = p.x; y = p.y; z = p.z;
+    }
+    // findBlock / findVoxel (:1214, :1138): uniform across the CTA
+    int idx = hash_index(x, y, z, numBuckets - 1), ptr = -1, allocatedTime = 0;
+    for (;;) {
+      const int *w = reinterpret_cast<const int *>(table) + (size_t)idx * 5;
+      int w0 = __ldg(w), w1 = __ldg(w + 1), off = __ldg(w + 2), p = __ldg(w + 3);
+      if ((short)(w0 & 0xffff) == x && (short)(w0 >> 16) == y && (short)(w1 & 0xffff) == z && p >= 0) {
+        ptr = p; allocatedTime = __ldg(w + 4); break;
+      }
+      if (off < 1) break;
+      idx = numBuckets + off - 1;
+    }
+    bool claim = false;
+    if (ptr >= 0 && (currentFrame - allocatedTime) >= minAge) {   // safeToClear (:1151-1157)
+      uint4 *blk = reinterpret_cast<uint4 *>(voxels + (size_t)ptr * BS3) + threadIdx.x;
+      uint4 raw = ld_stream(blk);
+      bool ch = false; int empty = 0;
+      {
+        int wd = (raw.x >> 16) & 0xff;
+        if (wd <= maxWeight && wd > 0) { raw.x = 0x00007fffu; raw.y &= 0xff000000u; ch = true; wd = 0; }
+        empty += (wd == 0);
+        wd = (raw.z >> 16) & 0xff;
+        if (wd <= maxWeight && wd > 0) { raw.z = 0x00007fffu; raw.w &= 0xff000000u; ch = true; wd = 0; }
+        empty += (wd == 0);
+      }
+      if (ch) st_stream(blk, raw);
+      // block-wide count of empty voxels (replaces the 512-int shared-memory tree, ITMCUDAUtils.h:145-160)
+      for (int o = 16; o > 0; o >>= 1) empty += __shfl_xor_sync(0xffffffffu, empty, o);
+      if ((threadIdx.x & 31) == 0) sEmpty[threadIdx.x >> 5] = empty;
+      __syncthreads();
+      int tot = 0;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) tot += sEmpty[k];
+      claim = (tot == BS3);
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+      itemPtr[item] = claim ? ptr : -1;
+      if (claim) atomicMax(&delTag[ptr], del_tag(gen, (unsigned)item));
+    }
+  }
+}
+
+// phase 2: ordered compaction of the claiming items, free-list push by rank (:1072-1073)
+#define DEC_TILE 1024
+__global__ void __launch_bounds__(256)
+k_decay_rank(const int *itemPtr, const unsigned long long *delTag, unsigned gen, int *allocList, int *delList, DevCounters *ctr,
+             unsigned long long *scanDesc, unsigned scanGen) {
+  __shared__ unsigned sm[33];
+  __shared__ unsigned tileBase;
+  const int n = ctr->decayItems;
+  const int lastFree = ctr->lastFreeBlockId;
+  const int noTiles = (n + DEC_TILE - 1) / DEC_TILE;
+  for (int tile = blockIdx.x; tile < noTiles; tile += gridDim.x) {
+    const int first = tile * DEC_TILE + threadIdx.x * 4;
+    unsigned mask = 0;
+    int ptrs[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      ptrs[k] = -1;
+      const int item = first + k;
+      if (item < n) {
+        const int p = itemPtr[item];
+        if (p >= 0 && delTag[p] == del_tag(gen, (unsigned)item)) { mask |= 1u << k; ptrs[k] = p; }
+      }
+    }
+    unsigned total;
+    unsigned local = block_exclusive_scan(__popc(mask), sm, &total);
+    if (threadIdx.x < 32) {
+      unsigned ex = scan_lookback(scanDesc, scanGen, tile, total);
+      if (threadIdx.x == 0) { tileBase = ex; if (tile == noTiles - 1) ctr->decayDeleted = (int)(ex + total); }
+    }
+    __syncthreads();
+    unsigned r = tileBase + local;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) if (mask & (1u << k)) {
+      allocList[lastFree + 1 + (int)r] = ptrs[k];
+      delList[r] = first + k;
+      r++;
+    }
+    __syncthreads();
+  }
+  if (noTiles == 0 && blockIdx.x == 0 && threadIdx.x == 0) ctr->decayDeleted = 0;
+}
+
+// phase 3a: leader election per bucket chain (read-only on the table)
+template <int MODE>
+__global__ void k_decay_elect(const b200_hash_entry *table, int numBuckets, const b200_vec3i *ring, long long ringCap,
+                              const long long *snapStart, int slot, const short4 *allocatedPos, const int *delList,
+                              const unsigned long long *delTag, unsigned gen, uint8_t *isLeader, const DevCounters *ctr) {
+  const int nDel = ctr->decayDeleted;
+  const long long s0 = (MODE == 0) ? snapStart[slot] : 0;
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < nDel; r += gridDim.x * blockDim.x) {
+    const int item = delList[r];
+    int x, y, z;
+    if (MODE == 0) { b200_vec3i p = ring[(s0 + item) % ringCap]; x = p.x; y = p.y; z = p.z; }
+    else { short4 p = allocatedPos[item]; x = p.x; y = p.y; z = p.z; }
+    int idx = hash_index(x, y, z, numBuckets - 1);
+    unsigned minItem = 0xffffffffu;
+    for (;;) {
+      Entry en = load_entry_rw(table, idx);
+      if (en.ptr >= 0) {
+        unsigned long long t = delTag[en.ptr];
+        if ((unsigned)(t >> 32) == gen) { unsigned it = 0xffffffffu - (unsigned)(t & 0xffffffffu); if (it < minItem) minItem = it; }
+      }
+      if (en.offset < 1) break;
+      idx = numBuckets + en.offset - 1;
+    }
+    isLeader[r] = (minItem == (unsigned)item) ? 1 : 0;
+  }
+}
+
+// phase 3b: leaders unlink their chain's blocks in list order — deleteBlock :1032-1111
+__global__ void k_decay_unlink(b200_hash_entry *table, int numBuckets, uint8_t *visType, const b200_vec3i *ring, long long ringCap,
+                               const long long *snapStart, int slot, const short4 *allocatedPos, int mode, const int *delList,
+                               const unsigned long long *delTag, unsigned gen, const uint8_t *isLeader, DevCounters *ctr) {
+  const int nDel = ctr->decayDeleted;
+  const long long s0 = (mode == 0) ? snapStart[slot] : 0;
+  int *tw = reinterpret_cast<int *>(table);
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < nDel; r += gridDim.x * blockDim.x) {
+    if (!isLeader[r]) continue;
+    const int item0 = delList[r];
+    int x0, y0, z0;
+    if (mode == 0) { b200_vec3i p = ring[(s0 + item0) % ringCap]; x0 = p.x; y0 = p.y; z0 = p.z; }
+    else { short4 p = allocatedPos[item0]; x0 = p.x; y0 = p.y; z0 = p.z; }
+    const int head = hash_index(x0, y0, z0, numBuckets - 1);
+    // Serial order = ascending list position: repeatedly take the chain entry whose block was claimed
+    // by the smallest item and unlink it on the evolving chain (findVoxel's idx / prev, :1032-1037).
+    for (;;) {
+      int found = -1, foundPrev = -1; unsigned best = 0xffffffffu;
+      for (int idx = head, prev = -1;;) {
+        Entry en = load_entry_rw(table, idx);
+        if (en.ptr >= 0) {
+          unsigned long long t = delTag[en.ptr];
+          if ((unsigned)(t >> 32) == gen) {
+            unsigned it = 0xffffffffu - (unsigned)(t & 0xffffffffu);
+            if (it < best) { best = it; found = idx; foundPrev = prev; }
+          }
+        }
+        if (en.offset < 1) break;
+        prev = idx;
+        idx = numBuckets + en.offset - 1;
+      }
+      if (found < 0) break;
+      const int prev = foundPrev;
+      int *e = tw + (size_t)found * 5;
+      if (prev == -1) {
+        if (e[2] >= 1) {                       // ordered entry with a successor: pull the successor in
+          const int nextIdx = numBuckets + e[2] - 1;
+          int *nx = tw + (size_t)nextIdx * 5;
+          e[0] = nx[0]; e[1] = nx[1]; e[2] = nx[2]; e[3] = nx[3]; e[4] = nx[4];
+          visType[found] = visType[nextIdx];
+          visType[nextIdx] = 0;
+          nx[2] = 0; nx[3] = -2;
+        } else {                               // ordered entry, no successor
+          e[3] = -2;
+          visType[found] = 0;
+        }
+      } else {                                 // excess entry: predecessor inherits the link
+        int *pv = tw + (size_t)prev * 5;
+        pv[2] = e[2];
+        e[2] = 0; e[3] = -2;
+        visType[prev] = visType[found];        // (sic) reference quirk, :1109-1110
+        visType[found] = 0;
+      }
+    }
+  }
+}
+
+// finalise: lastFreeBlockId += deleted; freedLastDecay
+__global__ void k_decay_finish(DevCounters *ctr) {
+  ctr->lastFreeBlockId += ctr->decayDeleted;
+  ctr->freedLastDecay = ctr->decayDeleted;
+  ctr->totalDecayed += ctr->decayDeleted;
+  ctr->decayDeleted = 0;
+  ctr->decayItems = 0;
+}
+
+// findAllocatedBlocks — ITMMeshingEngine_CUDA.cu:96-114 (after a zero fill)
+__global__ void k_find_allocated(const b200_hash_entry *__restrict__ table, int noTotal, short4 *allocatedPos) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < noTotal; i += gridDim.x * blockDim.x) {
+    Entry en = load_entry(table, i);
+    if (en.ptr >= 0) allocatedPos[en.ptr] = make_short4((short)en.x, (short)en.y, (short)en.z, 1);
+  }
+}
+
+static void decay_common(b200_engine *e, const SceneRef &s, int mode, int slot, int minAge, int maxWeight, int frameIdx,
+                         long long items) {
+  cudaStream_t st = e->stream;
+  const unsigned gen = ++e->decayGen;
+  const int grid1 = persistent_grid(e, 6, items);
+  if (mode == 0)
+    k_decay_blocks<0><<<grid1, 256, 0, st>>>(s.voxels, s.hash, s.numBuckets, e->d_ring, e->ringCap, e->d_snapStart, e->d_snapCount,
+                                            slot, e->d_allocatedPos, s.numBlocks, minAge, maxWeight, frameIdx, gen, e->d_delTag,
+                                            e->d_itemPtr, e->d_ctr);
+  else
+    k_decay_blocks<1><<<grid1, 256, 0, st>>>(s.voxels, s.hash, s.numBuckets, e->d_ring, e->ringCap, e->d_snapStart, e->d_snapCount,
+                                            slot, e->d_allocatedPos, s.numBlocks, minAge, maxWeight, frameIdx, gen, e->d_delTag,
+                                            e->d_itemPtr, e->d_ctr);
+  const int noTiles = (int)((items + DEC_TILE - 1) / DEC_TILE);
+  k_decay_rank<<<persistent_grid(e, 4, noTiles), 256, 0, st>>>(e->d_itemPtr, e->d_delTag, gen, s.allocationList, e->d_delList,
+                                                               e->d_ctr, e->d_scanDesc, ++e->scanGen);
+  if (mode == 0)
+    k_decay_elect<0><<<e->smCount, 128, 0, st>>>(s.hash, s.numBuckets, e->d_ring, e->ringCap, e->d_snapStart, slot, e->d_allocatedPos,
+                                                e->d_delList, e->d_delTag, gen, e->d_isLeader, e->d_ctr);
+  else
+    k_decay_elect<1><<<e->smCount, 128, 0, st>>>(s.hash, s.numBuckets, e->d_ring, e->ringCap, e->d_snapStart, slot, e->d_allocatedPos,
+                                                e->d_delList, e->d_delTag, gen, e->d_isLeader, e->d_ctr);
+  k_decay_unlink<<<e->smCount, 128, 0, st>>>(s.hash, s.numBuckets, s.visType, e->d_ring, e->ringCap, e->d_snapStart, slot,
+                                            e->d_allocatedPos, mode, e->d_delList, e->d_delTag, gen, e->d_isLeader, e->d_ctr);
+  k_decay_finish<<<1, 1, 0, st>>>(e->d_ctr);
+  e->launches += 5;
+}
+
+void launch_decay_partial(b200_engine *e, const SceneRef &s, int snapSlot, int minAge, int maxWeight, int frameIdx) {
+  // item count lives on the device (snapCount[slot]); size the grid for the capacity
+  decay_common(e, s, 0, snapSlot, minAge, maxWeight, frameIdx, s.numBlocks);
+}
+
+void launch_decay_full(b200_engine *e, const SceneRef &s, int minAge, int maxWeight, int frameIdx) {
+  cudaMemsetAsync(e->d_allocatedPos, 0, sizeof(short4) * (size_t)s.numBlocks, e->stream);
+  k_find_allocated<<<e->smCount * 8, 256, 0, e->stream>>>(s.hash, s.noTotal, e->d_allocatedPos);
+  e->launches++;
+  decay_common(e, s, 1, 0, minAge, maxWeight, frameIdx, s.numBlocks);
+}

@@ -1,0 +1,448 @@
+// engine.cu — the extern "C" boundary of libb200fusion (include/b200fusion.h) and the host-side
+// sequencing of one volume's engine.
+//
+// Mirrors the host bodies of the reference engines (ITMSceneReconstructionEngine_CUDA.cu:115-566,
+// ITMVisualisationEngine_CUDA.cu:109-533, ITMSwappingEngine_CUDA.cu:20-216) with one structural
+// change: the reference blocks on the host four times per frame to move 4-12 byte counters, and
+// allocates/frees device memory every frame for the decay snapshot. Here the counters live in a
+// device struct that kernels update and read; the synchronous entry points (the ones the ITMLib
+// shim calls, which must return with host-visible counters valid) do exactly one asynchronous
+// upload, the launches, one asynchronous download and one stream synchronise; the fused
+// b200_process_frame_async path does none of that until b200_sync().
+#include "engine.h"
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+#define CK(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t _e = (call);                                                                       \
+    if (_e != cudaSuccess) {                                                                       \
+      snprintf(e->err, sizeof(e->err), "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(_e)); \
+      return B200_ERR_CUDA;                                                                        \
+    }                                                                                              \
+  } while (0)
+
+static Mat4 to_mat(const float *m) { Mat4 r; memcpy(r.m, m, sizeof(r.m)); return r; }
+
+static SceneRef scene_ref(const b200_scene *s, const b200_render_state *rs) {
+  SceneRef r;
+  r.voxels = s->d_voxels; r.allocationList = s->d_allocationList; r.hash = s->d_hash; r.excessList = s->d_excessList;
+  r.swapStates = s->d_swapStates;
+  r.numBlocks = s->numBlocks; r.numBuckets = s->numBuckets; r.excessSize = s->excessSize; r.noTotal = s->numBuckets + s->excessSize;
+  r.visiblePos = rs ? rs->d_visibleBlockPositions : nullptr;
+  r.visType = rs ? rs->d_entriesVisibleType : nullptr;
+  return r;
+}
+
+static FrameGeom frame_geom(const b200_scene *s, const b200_view *v) {
+  FrameGeom g;
+  g.M_d = to_mat(v->M_d); g.invM_d = to_mat(v->invM_d); g.M_rgb = to_mat(v->M_rgb);
+  memcpy(g.proj_d, v->proj_d, sizeof(g.proj_d)); memcpy(g.proj_rgb, v->proj_rgb, sizeof(g.proj_rgb));
+  g.w = v->depth_w; g.h = v->depth_h; g.rgb_w = v->rgb_w; g.rgb_h = v->rgb_h;
+  g.voxelSize = s->voxelSize; g.mu = s->mu; g.maxW = s->maxW; g.vfmin = s->viewFrustum_min; g.vfmax = s->viewFrustum_max;
+  g.depthWeighting = v->depthWeighting; g.stopMaxW = s->stopIntegratingAtMaxW; g.approx = !v->requiresFullRendering;
+  return g;
+}
+
+static b200_status check_scene(b200_engine *e, const b200_scene *s) {
+  if (!s || s->numBlocks > e->numBlocks || s->numBuckets != e->numBuckets || s->excessSize != e->excessSize ||
+      (s->numBuckets & (s->numBuckets - 1))) {
+    snprintf(e->err, sizeof(e->err), "scene sizes do not match the engine configuration");
+    return B200_ERR_INVALID;
+  }
+  return B200_OK;
+}
+
+// host -> device counters (only the three the host owns); device -> host (everything)
+static b200_status upload(b200_engine *e, const b200_scene *s, const b200_render_state *rs) {
+  int *in = reinterpret_cast<int *>(e->h_ctr + 1);   // second pinned struct = upload staging
+  in[0] = s->lastFreeBlockId; in[1] = s->lastFreeExcessListId; in[2] = rs ? rs->noVisibleBlocks : 0;
+  CK(cudaMemcpyAsync(e->d_ctr, in, rs ? 3 * sizeof(int) : 2 * sizeof(int), cudaMemcpyHostToDevice, e->stream));
+  return B200_OK;
+}
+
+static b200_status download_sync(b200_engine *e, b200_scene *s, b200_render_state *rs) {
+  CK(cudaMemcpyAsync(e->h_ctr, e->d_ctr, sizeof(DevCounters), cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  CK(cudaGetLastError());
+  if (s) { s->lastFreeBlockId = e->h_ctr->lastFreeBlockId; s->lastFreeExcessListId = e->h_ctr->lastFreeExcessListId; }
+  if (rs) { rs->noVisibleBlocks = e->h_ctr->noVisibleBlocks; }
+  e->totalDecayed = e->h_ctr->totalDecayed;
+  e->lastNoIntegrated = e->h_ctr->noIntegrated;
+  e->hostAuthoritative = true;
+  if (e->h_ctr->errorFlags & 1) {
+    snprintf(e->err, sizeof(e->err), "decay snapshot ring overflow (raise b200_engine_config.decayRingItems)");
+    return B200_ERR_DECAY_RING_FULL;
+  }
+  return B200_OK;
+}
+
+extern "C" {
+
+b200_status b200_engine_create(const b200_engine_config *cfg, b200_engine **out) {
+  if (!cfg || !out) return B200_ERR_INVALID;
+  b200_engine *e = new b200_engine();
+  memset(e, 0, sizeof(*e));
+  *out = e;
+  e->device = cfg->device;
+  e->numBlocks = cfg->numBlocks; e->numBuckets = cfg->numBuckets; e->excessSize = cfg->excessSize;
+  e->noTotal = cfg->numBuckets + cfg->excessSize; e->img_w = cfg->img_w; e->img_h = cfg->img_h;
+  if (cfg->numBlocks <= 0 || cfg->numBuckets <= 0 || (cfg->numBuckets & (cfg->numBuckets - 1)) || cfg->excessSize < 0 ||
+      (long long)cfg->img_w * cfg->img_h >= (1ll << 24) || (e->noTotal % 32) != 0) {
+    snprintf(e->err, sizeof(e->err), "invalid engine configuration");
+    return B200_ERR_INVALID;
+  }
+  CK(cudaSetDevice(e->device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, e->device));
+  e->smCount = prop.multiProcessorCount;
+  if (prop.major < 9) {
+    snprintf(e->err, sizeof(e->err), "libb200fusion is built for sm_100a; device %d is sm_%d%d", e->device, prop.major, prop.minor);
+    return B200_ERR_UNSUPPORTED;
+  }
+  if (cfg->stream) { e->stream = (cudaStream_t)cfg->stream; e->ownStream = false; }
+  else { CK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking)); e->ownStream = true; }
+  CK(cudaMalloc(&e->d_ctr, sizeof(DevCounters)));
+  CK(cudaMemset(e->d_ctr, 0, sizeof(DevCounters)));
+  CK(cudaMallocHost(&e->h_ctr, 2 * sizeof(DevCounters)));
+  memset(e->h_ctr, 0, 2 * sizeof(DevCounters));
+  e->noWords = e->noTotal / 32;
+  CK(cudaMalloc(&e->d_reqKey, sizeof(unsigned long long) * (size_t)e->noTotal));
+  CK(cudaMemset(e->d_reqKey, 0, sizeof(unsigned long long) * (size_t)e->noTotal));
+  CK(cudaMalloc(&e->d_reqBits, sizeof(unsigned) * (size_t)e->noWords * 4));
+  e->d_req2Bits = e->d_reqBits + e->noWords; e->d_reqPrefix = e->d_req2Bits + e->noWords; e->d_req2Prefix = e->d_reqPrefix + e->noWords;
+  CK(cudaMemset(e->d_reqBits, 0, sizeof(unsigned) * (size_t)e->noWords * 4));
+  long long px = (long long)e->img_w * e->img_h;
+  long long maxTiles = (e->noTotal + 255) / 256 + (px + 255) / 256 + e->numBlocks / 256 + 1024;
+  e->scanDescCap = (int)maxTiles;
+  CK(cudaMalloc(&e->d_scanDesc, sizeof(unsigned long long) * (size_t)e->scanDescCap));
+  CK(cudaMemset(e->d_scanDesc, 0, sizeof(unsigned long long) * (size_t)e->scanDescCap));
+  e->ringCap = cfg->decayRingItems > 0 ? cfg->decayRingItems : 24ll * e->numBlocks;
+  CK(cudaMalloc(&e->d_ring, sizeof(b200_vec3i) * (size_t)e->ringCap));
+  CK(cudaMalloc(&e->d_snapCount, sizeof(int) * SNAP_SLOTS));
+  CK(cudaMalloc(&e->d_snapStart, sizeof(long long) * SNAP_SLOTS));
+  CK(cudaMemset(e->d_snapCount, 0, sizeof(int) * SNAP_SLOTS));
+  CK(cudaMemset(e->d_snapStart, 0, sizeof(long long) * SNAP_SLOTS));
+  CK(cudaMalloc(&e->d_delTag, sizeof(unsigned long long) * (size_t)e->numBlocks));
+  CK(cudaMemset(e->d_delTag, 0, sizeof(unsigned long long) * (size_t)e->numBlocks));
+  CK(cudaMalloc(&e->d_itemPtr, sizeof(int) * (size_t)e->numBlocks));
+  CK(cudaMalloc(&e->d_delList, sizeof(int) * (size_t)e->numBlocks));
+  CK(cudaMalloc(&e->d_isLeader, (size_t)e->numBlocks));
+  CK(cudaMalloc(&e->d_allocatedPos, sizeof(short4) * (size_t)e->numBlocks));
+  CK(cudaMalloc(&e->d_tileCounts, sizeof(unsigned) * (size_t)(px > 0 ? px : 1)));
+  for (int i = 0; i < 8; ++i) CK(cudaEventCreate(&e->ev[i]));
+  e->hostAuthoritative = true;
+  { const char *v = getenv("B200_INTEGRATE_IMPL"); e->integrateImpl = (v && v[0] == 't') ? 1 : 0; }
+  return B200_OK;
+}
+
+void b200_engine_destroy(b200_engine *e) {
+  if (!e) return;
+  cudaSetDevice(e->device);
+  if (e->stream) cudaStreamSynchronize(e->stream);
+  cudaFree(e->d_ctr); cudaFreeHost(e->h_ctr); cudaFree(e->d_reqKey); cudaFree(e->d_reqBits); cudaFree(e->d_scanDesc);
+  cudaFree(e->d_ring); cudaFree(e->d_snapCount); cudaFree(e->d_snapStart); cudaFree(e->d_delTag); cudaFree(e->d_itemPtr);
+  cudaFree(e->d_delList); cudaFree(e->d_isLeader); cudaFree(e->d_allocatedPos); cudaFree(e->d_tileCounts);
+  for (int i = 0; i < 8; ++i) if (e->ev[i]) cudaEventDestroy(e->ev[i]);
+  if (e->ownStream && e->stream) cudaStreamDestroy(e->stream);
+  delete e;
+}
+
+const char *b200_last_error(const b200_engine *e) { return e ? e->err : "null engine"; }
+void *b200_engine_stream(b200_engine *e) { return (void *)e->stream; }
+int32_t b200_frame_index(const b200_engine *e) { return e->frameIdx; }
+size_t b200_decayed_block_count(const b200_engine *e) { return (size_t)e->totalDecayed; }
+void b200_set_timing(b200_engine *e, int enabled) { e->timing = enabled != 0; }
+
+// Matrix4::inv — OR/Matrix.h:162-224
+int b200_mat4_inv(const float *m, float *dst) {
+  float tmp[12], src[16], det;
+  for (int i = 0; i < 4; i++) { src[i] = m[i * 4]; src[i + 4] = m[i * 4 + 1]; src[i + 8] = m[i * 4 + 2]; src[i + 12] = m[i * 4 + 3]; }
+  tmp[0] = src[10] * src[15]; tmp[1] = src[11] * src[14]; tmp[2] = src[9] * src[15]; tmp[3] = src[11] * src[13];
+  tmp[4] = src[9] * src[14]; tmp[5] = src[10] * src[13]; tmp[6] = src[8] * src[15]; tmp[7] = src[11] * src[12];
+  tmp[8] = src[8] * src[14]; tmp[9] = src[10] * src[12]; tmp[10] = src[8] * src[13]; tmp[11] = src[9] * src[12];
+  dst[0] = (tmp[0] * src[5] + tmp[3] * src[6] + tmp[4] * src[7]) - (tmp[1] * src[5] + tmp[2] * src[6] + tmp[5] * src[7]);
+  dst[1] = (tmp[1] * src[4] + tmp[6] * src[6] + tmp[9] * src[7]) - (tmp[0] * src[4] + tmp[7] * src[6] + tmp[8] * src[7]);
+  dst[2] = (tmp[2] * src[4] + tmp[7] * src[5] + tmp[10] * src[7]) - (tmp[3] * src[4] + tmp[6] * src[5] + tmp[11] * src[7]);
+  dst[3] = (tmp[5] * src[4] + tmp[8] * src[5] + tmp[11] * src[6]) - (tmp[4] * src[4] + tmp[9] * src[5] + tmp[10] * src[6]);
+  det = src[0] * dst[0] + src[1] * dst[1] + src[2] * dst[2] + src[3] * dst[3];
+  if (det == 0.0f) return 0;
+  dst[4] = (tmp[1] * src[1] + tmp[2] * src[2] + tmp[5] * src[3]) - (tmp[0] * src[1] + tmp[3] * src[2] + tmp[4] * src[3]);
+  dst[5] = (tmp[0] * src[0] + tmp[7] * src[2] + tmp[8] * src[3]) - (tmp[1] * src[0] + tmp[6] * src[2] + tmp[9] * src[3]);
+  dst[6] = (tmp[3] * src[0] + tmp[6] * src[1] + tmp[11] * src[3]) - (tmp[2] * src[0] + tmp[7] * src[1] + tmp[10] * src[3]);
+  dst[7] = (tmp[4] * src[0] + tmp[9] * src[1] + tmp[10] * src[2]) - (tmp[5] * src[0] + tmp[8] * src[1] + tmp[11] * src[2]);
+  tmp[0] = src[2] * src[7]; tmp[1] = src[3] * src[6]; tmp[2] = src[1] * src[7]; tmp[3] = src[3] * src[5];
+  tmp[4] = src[1] * src[6]; tmp[5] = src[2] * src[5]; tmp[6] = src[0] * src[7]; tmp[7] = src[3] * src[4];
+  tmp[8] = src[0] * src[6]; tmp[9] = src[2] * src[4]; tmp[10] = src[0] * src[5]; tmp[11] = src[1] * src[4];
+  dst[8] = (tmp[0] * src[13] + tmp[3] * src[14] + tmp[4] * src[15]) - (tmp[1] * src[13] + tmp[2] * src[14] + tmp[5] * src[15]);
+  dst[9] = (tmp[1] * src[12] + tmp[6] * src[14] + tmp[9] * src[15]) - (tmp[0] * src[12] + tmp[7] * src[14] + tmp[8] * src[15]);
+  dst[10] = (tmp[2] * src[12] + tmp[7] * src[13] + tmp[10] * src[15]) - (tmp[3] * src[12] + tmp[6] * src[13] + tmp[11] * src[15]);
+  dst[11] = (tmp[5] * src[12] + tmp[8] * src[13] + tmp[11] * src[14]) - (tmp[4] * src[12] + tmp[9] * src[13] + tmp[10] * src[14]);
+  dst[12] = (tmp[2] * src[10] + tmp[5] * src[11] + tmp[1] * src[9]) - (tmp[4] * src[11] + tmp[0] * src[9] + tmp[3] * src[10]);
+  dst[13] = (tmp[8] * src[11] + tmp[0] * src[8] + tmp[7] * src[10]) - (tmp[6] * src[10] + tmp[9] * src[11] + tmp[1] * src[8]);
+  dst[14] = (tmp[6] * src[9] + tmp[11] * src[11] + tmp[3] * src[8]) - (tmp[10] * src[11] + tmp[2] * src[8] + tmp[7] * src[9]);
+  dst[15] = (tmp[10] * src[10] + tmp[4] * src[8] + tmp[9] * src[9]) - (tmp[8] * src[9] + tmp[11] * src[10] + tmp[5] * src[8]);
+  const float s = 1 / det;
+  for (int i = 0; i < 16; ++i) dst[i] *= s;
+  return 1;
+}
+
+// Matrix4 operator* — OR/Matrix.h:102-108
+void b200_mat4_mul(const float *lhs, const float *rhs, float *out) {
+  float r[16];
+  for (int i = 0; i < 16; ++i) r[i] = 0.0f;
+  for (int x = 0; x < 4; x++) for (int y = 0; y < 4; y++) for (int k = 0; k < 4; k++) r[x * 4 + y] += lhs[k * 4 + y] * rhs[x * 4 + k];
+  memcpy(out, r, sizeof(r));
+}
+
+// ---- ITMSceneReconstructionEngine ---------------------------------------------------------------
+
+b200_status b200_reset_scene(b200_engine *e, b200_scene *s) {
+  b200_status st = check_scene(e, s); if (st) return st;
+  CK(cudaSetDevice(e->device));
+  e->totalDecayed = 0;
+  e->qHead += e->qSize; e->qSize = 0;          // clear the decay queue; frameIdx is NOT reset (Reco_CUDA.cu:150-155)
+  launch_reset(e, scene_ref(s, nullptr));
+  return download_sync(e, s, nullptr);
+}
+
+static b200_status enqueue_allocate(b200_engine *e, b200_scene *s, b200_render_state *rs, const b200_view *v, int onlyVisible) {
+  if (e->qSize >= SNAP_SLOTS - 1) {
+    snprintf(e->err, sizeof(e->err), "decay queue deeper than %d frames", SNAP_SLOTS);
+    return B200_ERR_DECAY_RING_FULL;
+  }
+  if (v->depth_w != e->img_w || v->depth_h != e->img_h) {
+    snprintf(e->err, sizeof(e->err), "view size %dx%d differs from engine %dx%d", v->depth_w, v->depth_h, e->img_w, e->img_h);
+    return B200_ERR_INVALID;
+  }
+  const int slot = (e->qHead + e->qSize) % SNAP_SLOTS;
+  launch_allocate(e, scene_ref(s, rs), frame_geom(s, v), v->d_depth, onlyVisible != 0, e->frameIdx, slot);
+  e->qSize++;
+  e->frameIdx++;
+  return B200_OK;
+}
+
+b200_status b200_allocate_from_depth(b200_engine *e, b200_scene *s, b200_render_state *rs, const b200_view *v, int onlyVisible) {
+  b200_status st = check_scene(e, s); if (st) return st;
+  CK(cudaSetDevice(e->device));
+  st = upload(e, s, rs); if (st) return st;
+  st = enqueue_allocate(e, s, rs, v, onlyVisible); if (st) return st;
+  st = download_sync(e, s, rs); if (st) return st;
+  if (s->lastFreeBlockId < 0) { snprintf(e->err, sizeof(e->err), "out of space in the voxel block array"); return B200_ERR_VBA_FULL; }
+  if (s->lastFreeExcessListId < 0) { snprintf(e->err, sizeof(e->err), "out of slots in the hash table excess list"); return B200_ERR_EXCESS_FULL; }
+  return B200_OK;
+}
+
+b200_status b200_integrate(b200_engine *e, b200_scene *s, b200_render_state *rs, const b200_view *v) {
+  b200_status st = check_scene(e, s); if (st) return st;
+  CK(cudaSetDevice(e->device));
+  if (rs->noVisibleBlocks == 0) return B200_OK;   // Reco_CUDA.cu:372-378
+  st = upload(e, s, rs); if (st) return st;
+  CK(cudaMemsetAsync(&e->d_ctr->noIntegrated, 0, sizeof(int), e->stream));
+  launch_integrate(e, scene_ref(s, rs), frame_geom(s, v), v->d_depth, v->d_rgb);
+  return download_sync(e, s, rs);
+}
+
+static void enqueue_decay(b200_engine *e, b200_scene *s, b200_render_state *rs, int maxWeight, int minAge, int forceAll) {
+  SceneRef r = scene_ref(s, rs);
+  if (forceAll) launch_decay_full(e, r, minAge, maxWeight, e->frameIdx);
+  else if ((long)e->qSize > minAge) {
+    const int slot = e->qHead % SNAP_SLOTS;
+    e->qHead++; e->qSize--;
+    launch_decay_partial(e, r, slot, minAge, maxWeight, e->frameIdx);
+  }
+}
+
+b200_status b200_decay(b200_engine *e, b200_scene *s, b200_render_state *rs, int maxWeight, int minAge, int forceAll) {
+  b200_status st = check_scene(e, s); if (st) return st;
+  CK(cudaSetDevice(e->device));
+  st = upload(e, s, rs); if (st) return st;
+  enqueue_decay(e, s, rs, maxWeight, minAge, forceAll);
+  return download_sync(e, s, rs);
+}
+
+// ---- ITMVisualisationEngine ---------------------------------------------------------------------
+
+b200_status b200_find_visible_blocks(b200_engine *e, const b200_scene *s, b200_render_state *rs, const b200_camera *cam) {
+  b200_status st = check_scene(e, s); if (st) return st;
+  CK(cudaSetDevice(e->device));
+  st = upload(e, s, rs); if (st) return st;
+  launch_find_visible(e, scene_ref(s, rs), to_mat(cam->M), cam->proj, rs->img_w, rs->img_h, s->voxelSize);
+  return download_sync(e, nullptr, rs);
+}
+
+b200_status b200_expected_depths(b200_engine *e, const b200_scene *s, b200_render_state *rs, const b200_camera *cam) {
+  b200_status st = check_scene(e, s); if (st) return st;
+  CK(cudaSetDevice(e->device));
+  st = upload(e, s, rs); if (st) return st;
+  launch_expected_depths(e, scene_ref(s, rs), to_mat(cam->M), cam->proj, rs->img_w, rs->img_h, s->voxelSize, rs->d_minmax);
+  return download_sync(e, nullptr, nullptr);
+}
+
+b200_status b200_find_surface(b200_engine *e, const b200_scene *s, b200_render_state *rs, const b200_camera *cam) {
+  b200_status st = check_scene(e, s); if (st) return st;
+  CK(cudaSetDevice(e->device));
+  launch_raycast(e, scene_ref(s, rs), to_mat(cam->invM), cam->proj, rs->img_w, rs->img_h, s->voxelSize, s->mu, rs->d_minmax,
+                 rs->d_raycastResult);
+  CK(cudaStreamSynchronize(e->stream));
+  return B200_OK;
+}
+
+b200_status b200_render_image(b200_engine *e, const b200_scene *s, b200_render_state *rs, const b200_camera *cam, b200_vec4u *d_outChar,
+                              float *d_outFloat, int out_w, int out_h, b200_render_type type) {
+  b200_status st = check_scene(e, s); if (st) return st;
+  CK(cudaSetDevice(e->device));
+  SceneRef r = scene_ref(s, rs);
+  launch_raycast(e, r, to_mat(cam->invM), cam->proj, out_w, out_h, s->voxelSize, s->mu, rs->d_minmax, rs->d_raycastResult);
+  launch_shade(e, r, to_mat(cam->M), to_mat(cam->invM), out_w, out_h, s->voxelSize, s->maxW, rs->d_raycastResult, d_outChar, d_outFloat,
+               (int)type);
+  CK(cudaStreamSynchronize(e->stream));
+  CK(cudaGetLastError());
+  return B200_OK;
+}
+
+b200_status b200_icp_maps(b200_engine *e, const b200_scene *s, b200_render_state *rs, const b200_view *v, b200_vec4f *d_points,
+                          b200_vec4f *d_normals) {
+  b200_status st = check_scene(e, s); if (st) return st;
+  CK(cudaSetDevice(e->device));
+  Mat4 invM = to_mat(v->invM_d);
+  launch_raycast(e, scene_ref(s, rs), invM, v->proj_d, rs->img_w, rs->img_h, s->voxelSize, s->mu, rs->d_minmax, rs->d_raycastResult);
+  launch_icp(e, invM, rs->img_w, rs->img_h, s->voxelSize, rs->d_raycastResult, rs->d_raycastImage, d_points, d_normals);
+  CK(cudaStreamSynchronize(e->stream));
+  CK(cudaGetLastError());
+  return B200_OK;
+}
+
+b200_status b200_forward_render(b200_engine *e, const b200_scene *s, b200_render_state *rs, const b200_view *v) {
+  b200_status st = check_scene(e, s); if (st) return st;
+  CK(cudaSetDevice(e->device));
+  if (!rs->d_forwardProjection || !rs->d_fwdProjMissingPoints) { snprintf(e->err, sizeof(e->err), "forward buffers missing"); return B200_ERR_INVALID; }
+  launch_forward_render(e, scene_ref(s, rs), frame_geom(s, v), v->d_depth, rs->d_minmax, rs->d_raycastResult, rs->d_forwardProjection,
+                        rs->d_fwdProjMissingPoints, rs->d_raycastImage);
+  st = download_sync(e, nullptr, nullptr);
+  rs->noFwdProjMissingPoints = e->h_ctr->noFwdMissing;
+  return st;
+}
+
+b200_status b200_point_cloud(b200_engine *e, const b200_scene *s, b200_render_state *rs, const b200_view *v, const float *calib,
+                             int skipPoints, b200_vec4f *d_locations, b200_vec4f *d_colours, uint32_t *noTotalPoints) {
+  b200_status st = check_scene(e, s); if (st) return st;
+  CK(cudaSetDevice(e->device));
+  float invMf[16];
+  b200_mat4_mul(v->invM_d, calib, invMf);
+  Mat4 invM = to_mat(invMf);
+  SceneRef r = scene_ref(s, rs);
+  launch_raycast(e, r, invM, v->proj_rgb, rs->img_w, rs->img_h, s->voxelSize, s->mu, rs->d_minmax, rs->d_raycastResult);
+  launch_point_cloud(e, r, invM, rs->img_w, rs->img_h, s->voxelSize, skipPoints, rs->d_raycastResult, rs->d_raycastImage, d_locations,
+                     d_colours);
+  st = download_sync(e, nullptr, nullptr);
+  if (noTotalPoints) *noTotalPoints = e->h_ctr->noTotalPoints;
+  return st;
+}
+
+// ---- ITMSwappingEngine ---------------------------------------------------------------------------
+
+b200_status b200_swap_list_in(b200_engine *e, b200_scene *s, b200_transfer_buffers *tb, int *noNeeded) {
+  b200_status st = check_scene(e, s); if (st) return st;
+  if (!s->d_swapStates) { snprintf(e->err, sizeof(e->err), "scene has no swap states"); return B200_ERR_INVALID; }
+  CK(cudaSetDevice(e->device));
+  launch_swap_list_in(e, scene_ref(s, nullptr), tb->d_neededEntryIDs);
+  st = download_sync(e, nullptr, nullptr);
+  *noNeeded = e->h_ctr->noNeededEntries;
+  return st;
+}
+
+b200_status b200_swap_integrate_in(b200_engine *e, b200_scene *s, b200_transfer_buffers *tb, int noNeeded) {
+  b200_status st = check_scene(e, s); if (st) return st;
+  CK(cudaSetDevice(e->device));
+  launch_swap_integrate_in(e, scene_ref(s, nullptr), tb->d_syncedVoxelBlocks, tb->d_neededEntryIDs, noNeeded, s->maxW);
+  CK(cudaStreamSynchronize(e->stream));
+  CK(cudaGetLastError());
+  return B200_OK;
+}
+
+b200_status b200_swap_out(b200_engine *e, b200_scene *s, b200_render_state *rs, b200_transfer_buffers *tb, int *noNeeded) {
+  b200_status st = check_scene(e, s); if (st) return st;
+  if (!s->d_swapStates) { snprintf(e->err, sizeof(e->err), "scene has no swap states"); return B200_ERR_INVALID; }
+  CK(cudaSetDevice(e->device));
+  st = upload(e, s, rs); if (st) return st;
+  SceneRef r = scene_ref(s, rs);
+  launch_swap_list_out(e, r, tb->d_neededEntryIDs);
+  st = download_sync(e, nullptr, nullptr); if (st) return st;   // the count sizes the next grid, as in the reference (:161)
+  const int n = e->h_ctr->noNeededEntries;
+  *noNeeded = n;
+  if (n > 0) {
+    launch_swap_move_out(e, r, tb->d_syncedVoxelBlocks, tb->d_hasSyncedData, tb->d_neededEntryIDs, n);
+    st = download_sync(e, s, nullptr);
+  }
+  return st;
+}
+
+// ---- fused fast path -----------------------------------------------------------------------------
+
+b200_status b200_process_frame_async(b200_engine *e, b200_scene *s, b200_render_state *rs, const b200_view *v, b200_vec4f *d_points,
+                                     b200_vec4f *d_normals, const b200_frame_opts *opts) {
+  b200_status st = check_scene(e, s); if (st) return st;
+  CK(cudaSetDevice(e->device));
+  if (e->hostAuthoritative) { st = upload(e, s, rs); if (st) return st; e->hostAuthoritative = false; }
+  if (e->timing) CK(cudaEventRecord(e->ev[0], e->stream));
+  st = enqueue_allocate(e, s, rs, v, 0); if (st) return st;
+  if (e->timing) CK(cudaEventRecord(e->ev[1], e->stream));
+  CK(cudaMemsetAsync(&e->d_ctr->noIntegrated, 0, sizeof(int), e->stream));
+  SceneRef r = scene_ref(s, rs);
+  FrameGeom g = frame_geom(s, v);
+  launch_integrate(e, r, g, v->d_depth, v->d_rgb);
+  if (e->timing) CK(cudaEventRecord(e->ev[2], e->stream));
+  if (!opts || opts->doRaycast) {
+    launch_expected_depths(e, r, g.M_d, g.proj_d, rs->img_w, rs->img_h, s->voxelSize, rs->d_minmax);
+    if (e->timing) CK(cudaEventRecord(e->ev[3], e->stream));
+    launch_raycast(e, r, g.invM_d, g.proj_d, rs->img_w, rs->img_h, s->voxelSize, s->mu, rs->d_minmax, rs->d_raycastResult);
+    launch_icp(e, g.invM_d, rs->img_w, rs->img_h, s->voxelSize, rs->d_raycastResult, rs->d_raycastImage, d_points, d_normals);
+  } else if (e->timing) CK(cudaEventRecord(e->ev[3], e->stream));
+  if (e->timing) CK(cudaEventRecord(e->ev[4], e->stream));
+  if (opts && opts->doDecay) enqueue_decay(e, s, rs, opts->decayMaxWeight, opts->decayMinAge, 0);
+  if (e->timing) CK(cudaEventRecord(e->ev[5], e->stream));
+  return B200_OK;
+}
+
+b200_status b200_sync(b200_engine *e, b200_scene *s, b200_render_state *rs) {
+  CK(cudaSetDevice(e->device));
+  b200_status st = download_sync(e, s, rs); if (st) return st;
+  if (s && s->lastFreeBlockId < 0) { snprintf(e->err, sizeof(e->err), "out of space in the voxel block array"); return B200_ERR_VBA_FULL; }
+  if (s && s->lastFreeExcessListId < 0) { snprintf(e->err, sizeof(e->err), "out of slots in the hash table excess list"); return B200_ERR_EXCESS_FULL; }
+  return B200_OK;
+}
+
+b200_status b200_process_frame_host(b200_engine *e, b200_scene *s, b200_render_state *rs, b200_view *v, const float *h_depth,
+                                    const b200_vec4u *h_rgb, float *d_depth_stage, b200_vec4u *d_rgb_stage, b200_vec4f *d_points,
+                                    b200_vec4f *d_normals, const b200_frame_opts *opts, b200_vec4u *h_outImage) {
+  CK(cudaSetDevice(e->device));
+  const size_t nd = (size_t)v->depth_w * v->depth_h, nc = (size_t)v->rgb_w * v->rgb_h;
+  CK(cudaMemcpyAsync(d_depth_stage, h_depth, nd * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+  CK(cudaMemcpyAsync(d_rgb_stage, h_rgb, nc * sizeof(b200_vec4u), cudaMemcpyHostToDevice, e->stream));
+  v->d_depth = d_depth_stage; v->d_rgb = d_rgb_stage;
+  b200_status st = b200_process_frame_async(e, s, rs, v, d_points, d_normals, opts); if (st) return st;
+  if (h_outImage) CK(cudaMemcpyAsync(h_outImage, rs->d_raycastImage, (size_t)rs->img_w * rs->img_h * sizeof(b200_vec4u), cudaMemcpyDeviceToHost, e->stream));
+  return b200_sync(e, s, rs);
+}
+
+b200_status b200_get_stats(b200_engine *e, b200_frame_stats *out) {
+  memset(out, 0, sizeof(*out));
+  out->launches = e->launches;
+  out->noVisibleBlocks = e->h_ctr->noVisibleBlocks;
+  out->noIntegratedBlocks = e->h_ctr->noIntegrated;
+  if (e->timing) {
+    CK(cudaEventSynchronize(e->ev[5]));
+    cudaEventElapsedTime(&out->ms_allocate, e->ev[0], e->ev[1]);
+    cudaEventElapsedTime(&out->ms_integrate, e->ev[1], e->ev[2]);
+    cudaEventElapsedTime(&out->ms_expected, e->ev[2], e->ev[3]);
+    cudaEventElapsedTime(&out->ms_raycast, e->ev[3], e->ev[4]);
+    cudaEventElapsedTime(&out->ms_decay, e->ev[4], e->ev[5]);
+    cudaEventElapsedTime(&out->ms_total, e->ev[0], e->ev[5]);
+  }
+  return B200_OK;
+}
+
+}  // extern "C"

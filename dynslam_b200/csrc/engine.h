@@ -1,0 +1,102 @@
+// engine.h — internal: engine state and kernel launchers shared by the .cu files of libb200fusion.
+#pragma once
+#include "common.cuh"
+
+struct FrameGeom {          // per-call constants handed to kernels by value
+  Mat4 M_d, invM_d, M_rgb;
+  float proj_d[4], proj_rgb[4];
+  int w, h, rgb_w, rgb_h;
+  float voxelSize, mu;
+  int maxW;
+  float vfmin, vfmax;
+  int depthWeighting, stopMaxW, approx;
+};
+
+struct SceneRef {           // raw device views of the caller-owned scene / render-state buffers
+  b200_voxel *voxels;
+  int *allocationList;
+  b200_hash_entry *hash;
+  int *excessList;
+  uint8_t *swapStates;
+  int numBlocks, numBuckets, excessSize, noTotal;
+  b200_vec3i *visiblePos;
+  uint8_t *visType;
+};
+
+struct DecaySnap { long long start; int frameIdx; int hostCountKnown; };
+
+struct b200_engine {
+  int device;
+  cudaStream_t stream;
+  bool ownStream;
+  int numBlocks, numBuckets, excessSize, noTotal, img_w, img_h;
+  int smCount;
+  // device scratch
+  DevCounters *d_ctr;
+  DevCounters *h_ctr;                 // pinned mirror
+  unsigned long long *d_reqKey;       // per entry: frameTag | pixel | step of the winning request
+  unsigned *d_reqBits, *d_req2Bits;   // request bitmaps (all / excess-type), noTotal/32 words
+  unsigned *d_reqPrefix, *d_req2Prefix;
+  int noWords;
+  unsigned long long *d_scanDesc;     // chained-scan tile descriptors
+  int scanDescCap;
+  unsigned scanGen;
+  // decay
+  b200_vec3i *d_ring;                 // snapshot ring (items)
+  long long ringCap;
+  int *d_snapCount;                   // device-side count per ring slot (slot = frame % SNAP_SLOTS)
+  long long *d_snapStart;
+  int qHead, qSize;                   // host view of the queue (slots qHead .. qHead+qSize-1)
+  unsigned long long *d_delTag;       // per VBA block: gen | ~itemIndex of the deleting item
+  int *d_itemPtr;                     // per decay item: VBA ptr (or -1)
+  unsigned *d_itemFlag;               // per decay item: 1 = deletes its block
+  int *d_delList;                     // compacted deleting items (list order)
+  uint8_t *d_isLeader;
+  short4 *d_allocatedPos;             // full decay: pos per VBA slot (w = valid)
+  unsigned decayGen;
+  int frameIdx;
+  long long totalDecayed;
+  // vis
+  unsigned *d_tileCounts;
+  // timing / stats
+  bool timing;
+  cudaEvent_t ev[8];
+  long long launches;
+  int lastNoIntegrated;
+  int integrateImpl;                  // 0 = LDG variant, 1 = TMA bulk-copy variant (env B200_INTEGRATE_IMPL=ldg|tma)
+  bool hostAuthoritative;             // host copies of the counters are newer than the device ones
+  char err[512];
+};
+
+#define SNAP_SLOTS 4096
+
+// launchers (each enqueues on e->stream and bumps e->launches)
+void launch_reset(b200_engine *e, const SceneRef &s);
+void launch_allocate(b200_engine *e, const SceneRef &s, const FrameGeom &g, const float *depth, bool onlyVisible,
+                     int frameIdx, int snapSlot);
+void launch_integrate(b200_engine *e, const SceneRef &s, const FrameGeom &g, const float *depth, const b200_vec4u *rgb);
+void launch_decay_partial(b200_engine *e, const SceneRef &s, int snapSlot, int minAge, int maxWeight, int frameIdx);
+void launch_decay_full(b200_engine *e, const SceneRef &s, int minAge, int maxWeight, int frameIdx);
+void launch_find_visible(b200_engine *e, const SceneRef &s, const Mat4 &M, const float proj[4], int w, int h, float voxelSize);
+void launch_expected_depths(b200_engine *e, const SceneRef &s, const Mat4 &M, const float proj[4], int w, int h,
+                            float voxelSize, b200_vec2f *minmax);
+void launch_raycast(b200_engine *e, const SceneRef &s, const Mat4 &invM, const float proj[4], int w, int h, float voxelSize,
+                    float mu, const b200_vec2f *minmax, b200_vec4f *out);
+void launch_shade(b200_engine *e, const SceneRef &s, const Mat4 &M, const Mat4 &invM, int w, int h, float voxelSize, int maxW,
+                  const b200_vec4f *rays, b200_vec4u *outChar, float *outFloat, int type);
+void launch_icp(b200_engine *e, const Mat4 &invM, int w, int h, float voxelSize, const b200_vec4f *rays, b200_vec4u *outImg,
+                b200_vec4f *points, b200_vec4f *normals);
+void launch_forward_render(b200_engine *e, const SceneRef &s, const FrameGeom &g, const float *depth, const b200_vec2f *minmax,
+                           const b200_vec4f *rays, b200_vec4f *fwd, int *missing, b200_vec4u *outImg);
+void launch_point_cloud(b200_engine *e, const SceneRef &s, const Mat4 &invM, int w, int h, float voxelSize, int skipPoints,
+                        const b200_vec4f *rays, b200_vec4u *outImg, b200_vec4f *locations, b200_vec4f *colours);
+void launch_swap_list_in(b200_engine *e, const SceneRef &s, int *needed);
+void launch_swap_integrate_in(b200_engine *e, const SceneRef &s, const b200_voxel *synced, const int *needed, int n, int maxW);
+void launch_swap_list_out(b200_engine *e, const SceneRef &s, int *needed);
+void launch_swap_move_out(b200_engine *e, const SceneRef &s, b200_voxel *synced, uint8_t *hasSynced, const int *needed, int n);
+
+static inline int persistent_grid(const b200_engine *e, int ctasPerSm, long long workItems) {
+  long long g = (long long)e->smCount * ctasPerSm;
+  if (workItems < g) g = workItems;
+  return (int)(g < 1 ? 1 : g);
+}

@@ -1,0 +1,606 @@
+// vis.cu — ITMVisualisationEngine for sm_100a: expected depths, hierarchical raycast, shading,
+// ICP maps, forward render, point cloud.
+//
+// Replaces (reference ITMVisualisationEngine_CUDA.cu): memsetKernel + projectAndSplitBlocks_device +
+// fillBlocks_device (:194-240, :572-637), genericRaycast_device (:672-684) with castRay
+// (DeviceAgnostic/ITMVisualisationEngine.h:93-179), the five render*_device kernels (:735-886),
+// renderICP_device (:716-724), forwardProject/findMissingPoints/genericRaycastMissingPoints/
+// renderForward (:639-733) and renderPointCloud_device (:820-871).
+//
+// Differences in shape: no materialised RenderingBlock list and no blocking copy of its length —
+// each visible block rasterises its own bounding box into the 1/8-resolution min/max image with
+// native integer atomics on the (positive) float bit patterns, the MAX_RENDERING_BLOCKS rule is
+// applied from a list-order prefix of the tile counts; rays are traced by 8x4-pixel warps so that
+// a warp's rays walk the same voxel blocks; the voxel reads fetch the 2-byte sdf only.
+#include "engine.h"
+
+// ------------------------------------------------------------------------------------------------
+// expected depths
+// ------------------------------------------------------------------------------------------------
+__global__ void k_minmax_init(float2 *minmax, int n) {
+  const float2 v = make_float2(B200_FAR_AWAY, B200_VERY_CLOSE);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) minmax[i] = v;
+}
+
+// ProjectSingleBlock — DA/ITMVisualisationEngine.h:29-71
+DEV bool project_single_block(int bx, int by, int bz, const Mat4 &pose, const float *intr, int w, int h, float voxelSize,
+                              int &ulx, int &uly, int &lrx, int &lry, float &zmin, float &zmax) {
+  ulx = w / B200_MINMAX_SUBSAMPLE; uly = h / B200_MINMAX_SUBSAMPLE;
+  lrx = -1; lry = -1;
+  zmin = B200_FAR_AWAY; zmax = B200_VERY_CLOSE;
+#pragma unroll
+  for (int corner = 0; corner < 8; ++corner) {
+    const short tx = (short)(bx + ((corner & 1) ? 1 : 0)), ty = (short)(by + ((corner & 2) ? 1 : 0)), tz = (short)(bz + ((corner & 4) ? 1 : 0));
+    Vec4 q = m4v4(pose, (float)tx * (float)BS * voxelSize, (float)ty * (float)BS * voxelSize, (float)tz * (float)BS * voxelSize, 1.0f);
+    if (q.z < 1e-6) continue;
+    const float px = (intr[0] * q.x / q.z + intr[2]) / B200_MINMAX_SUBSAMPLE;
+    const float py = (intr[1] * q.y / q.z + intr[3]) / B200_MINMAX_SUBSAMPLE;
+    if (ulx > floorf(px)) ulx = (int)floorf(px);
+    if (lrx < ceilf(px)) lrx = (int)ceilf(px);
+    if (uly > floorf(py)) uly = (int)floorf(py);
+    if (lry < ceilf(py)) lry = (int)ceilf(py);
+    if (zmin > q.z) zmin = q.z;
+    if (zmax < q.z) zmax = q.z;
+  }
+  if (ulx < 0) ulx = 0;
+  if (uly < 0) uly = 0;
+  if (lrx >= w) lrx = w - 1;
+  if (lry >= h) lry = h - 1;
+  if (ulx > lrx) return false;
+  if (uly > lry) return false;
+  if (zmin < B200_VERY_CLOSE) zmin = B200_VERY_CLOSE;
+  if (zmax < B200_VERY_CLOSE) return false;
+  return true;
+}
+
+__global__ void __launch_bounds__(256)
+k_project_blocks(const b200_hash_entry *__restrict__ table, int numBuckets, const b200_vec3i *__restrict__ visiblePos, int capacity,
+                 DevCounters *ctr, Mat4 M, float p0, float p1, float p2, float p3, int w, int h, float voxelSize, float2 *minmax,
+                 unsigned long long *scanDesc, unsigned gen) {
+  __shared__ unsigned sm[33];
+  __shared__ unsigned tileBase;
+  const float intr[4] = {p0, p1, p2, p3};
+  int n = ctr->noVisibleBlocks;
+  if (n > capacity) n = capacity;
+  const int noTiles = (n + 255) / 256;
+  const int lane = threadIdx.x & 31;
+  for (int tile = blockIdx.x; tile < noTiles; tile += gridDim.x) {
+    const int item = tile * 256 + threadIdx.x;
+    int ulx = 0, uly = 0, lrx = -1, lry = -1; float zmin = 0, zmax = 0;
+    unsigned required = 0;
+    if (item < n) {
+      const b200_vec3i p = visiblePos[item];
+      if (find_block<false>(table, numBuckets, p.x, p.y, p.z) >= 0) {
+        if (project_single_block(p.x, p.y, p.z, M, intr, w, h, voxelSize, ulx, uly, lrx, lry, zmin, zmax)) {
+          const int rx = (int)ceilf((float)(lrx - ulx + 1) / 16), ry = (int)ceilf((float)(lry - uly + 1) / 16);
+          required = (unsigned)(rx * ry);
+        }
+      }
+    }
+    unsigned total;
+    unsigned local = block_exclusive_scan(required, sm, &total);
+    if (threadIdx.x < 32) {
+      unsigned ex = scan_lookback(scanDesc, gen, tile, total);
+      if (threadIdx.x == 0) { tileBase = ex; if (tile == noTiles - 1) ctr->noRenderingBlocks = ex + total; }
+    }
+    __syncthreads();
+    const unsigned out_offset = tileBase + local;
+    bool draw = required > 0 && (out_offset + required <= (unsigned)B200_MAX_RENDERING_BLOCKS);   // :609
+    // warp-cooperative rasterisation of each lane's bounding box
+    unsigned todo = __ballot_sync(0xffffffffu, draw);
+    while (todo) {
+      const int src = __ffs(todo) - 1;
+      todo &= todo - 1;
+      const int ax = __shfl_sync(0xffffffffu, ulx, src), ay = __shfl_sync(0xffffffffu, uly, src);
+      const int bx = __shfl_sync(0xffffffffu, lrx, src), by = __shfl_sync(0xffffffffu, lry, src);
+      const float zn = __shfl_sync(0xffffffffu, zmin, src), zx = __shfl_sync(0xffffffffu, zmax, src);
+      const int bw = bx - ax + 1, cnt = bw * (by - ay + 1);
+      for (int k = lane; k < cnt; k += 32) {
+        const int yy = ay + k / bw, xx = ax + k % bw;
+        float2 *px = &minmax[xx + yy * w];
+        atomic_min_posf(&px->x, zn);
+        atomic_max_posf(&px->y, zx);
+      }
+    }
+    __syncthreads();
+  }
+  if (noTiles == 0 && blockIdx.x == 0 && threadIdx.x == 0) ctr->noRenderingBlocks = 0;
+}
+
+void launch_expected_depths(b200_engine *e, const SceneRef &s, const Mat4 &M, const float proj[4], int w, int h, float voxelSize,
+                            b200_vec2f *minmax) {
+  k_minmax_init<<<e->smCount * 4, 256, 0, e->stream>>>((float2 *)minmax, w * h);
+  const int noTiles = (s.numBlocks + 255) / 256;
+  k_project_blocks<<<persistent_grid(e, 4, noTiles), 256, 0, e->stream>>>(s.hash, s.numBuckets, s.visiblePos, s.numBlocks, e->d_ctr, M,
+                                                                         proj[0], proj[1], proj[2], proj[3], w, h, voxelSize,
+                                                                         (float2 *)minmax, e->d_scanDesc, ++e->scanGen);
+  e->launches += 2;
+}
+
+// ------------------------------------------------------------------------------------------------
+// voxel access with the one-entry IndexCache (DA/ITMRepresentationAccess.h:176-220,
+// Objects/ITMVoxelBlockHash.h:27-31)
+// ------------------------------------------------------------------------------------------------
+struct IdxCache { int bx, by, bz, blockPtr; };
+DEV void cache_init(IdxCache &c) { c.bx = c.by = c.bz = 0x7fffffff; c.blockPtr = -1; }
+
+// returns the voxel index in the VBA or -1
+DEV int voxel_index(const b200_hash_entry *__restrict__ table, int numBuckets, int px, int py, int pz, IdxCache &c) {
+  const int bx = floordiv8(px), by = floordiv8(py), bz = floordiv8(pz);
+  const int linearIdx = px + (py - bx) * BS + (pz - by) * BS * BS - bz * BS3;
+  if (bx == c.bx && by == c.by && bz == c.bz) return c.blockPtr + linearIdx;
+  int hashIdx = hash_index(bx, by, bz, numBuckets - 1);
+  for (;;) {
+    Entry he = load_entry(table, hashIdx);
+    if (he.x == bx && he.y == by && he.z == bz && he.ptr >= 0) {
+      c.bx = bx; c.by = by; c.bz = bz; c.blockPtr = he.ptr * BS3;
+      return c.blockPtr + linearIdx;
+    }
+    if (he.offset < 1) break;
+    hashIdx = numBuckets + he.offset - 1;
+  }
+  return -1;
+}
+
+DEV float sdf_raw(const b200_voxel *__restrict__ voxels, int vi) {   // (float)voxel.sdf, missing -> TVoxel() = 32767
+  return vi >= 0 ? (float)__ldg(reinterpret_cast<const short *>(voxels + vi)) : 32767.0f;
+}
+
+DEV float rv_sdf(const b200_voxel *__restrict__ voxels, const b200_hash_entry *__restrict__ table, int nb, int x, int y, int z, IdxCache &c) {
+  return sdf_raw(voxels, voxel_index(table, nb, x, y, z, c));
+}
+
+// readFromSDF_float_interpolated — DA/ITMRepresentationAccess.h:252-278
+DEV float sdf_interp(const b200_voxel *__restrict__ voxels, const b200_hash_entry *__restrict__ table, int nb, float px, float py, float pz,
+                     IdxCache &c) {
+  const float fx = floorf(px), fy = floorf(py), fz = floorf(pz);
+  const float cx = px - fx, cy = py - fy, cz = pz - fz;
+  const int x = (int)fx, y = (int)fy, z = (int)fz;
+  float res1, res2, v1, v2;
+  v1 = rv_sdf(voxels, table, nb, x, y, z, c); v2 = rv_sdf(voxels, table, nb, x + 1, y, z, c);
+  res1 = (1.0f - cx) * v1 + cx * v2;
+  v1 = rv_sdf(voxels, table, nb, x, y + 1, z, c); v2 = rv_sdf(voxels, table, nb, x + 1, y + 1, z, c);
+  res1 = (1.0f - cy) * res1 + cy * ((1.0f - cx) * v1 + cx * v2);
+  v1 = rv_sdf(voxels, table, nb, x, y, z + 1, c); v2 = rv_sdf(voxels, table, nb, x + 1, y, z + 1, c);
+  res2 = (1.0f - cx) * v1 + cx * v2;
+  v1 = rv_sdf(voxels, table, nb, x, y + 1, z + 1, c); v2 = rv_sdf(voxels, table, nb, x + 1, y + 1, z + 1, c);
+  res2 = (1.0f - cy) * res2 + cy * ((1.0f - cx) * v1 + cx * v2);
+  return ((1.0f - cz) * res1 + cz * res2) / 32767.0f;
+}
+
+// castRay — DA/ITMVisualisationEngine.h:93-179
+__device__ bool cast_ray(float4 &out, int x, int y, const b200_voxel *__restrict__ voxels, const b200_hash_entry *__restrict__ table,
+                         int nb, const Mat4 &invM, float invfx, float invfy, float cxp, float cyp, float oneOverVoxelSize, float mu,
+                         float2 minmax) {
+  const float stepScale = mu * oneOverVoxelSize * 1.0f;
+  float cz = minmax.x;
+  float cx = cz * (((float)x - cxp) * invfx), cy = cz * (((float)y - cyp) * invfy);
+  float totalLength = sqrtf(cx * cx + cy * cy + cz * cz) * oneOverVoxelSize;
+  Vec4 r = m4v4(invM, cx, cy, cz, 1.0f);
+  const float sx = r.x * oneOverVoxelSize, sy = r.y * oneOverVoxelSize, sz = r.z * oneOverVoxelSize;
+  cz = minmax.y;
+  cx = cz * (((float)x - cxp) * invfx); cy = cz * (((float)y - cyp) * invfy);
+  const float totalLengthMax = sqrtf(cx * cx + cy * cy + cz * cz) * oneOverVoxelSize;
+  r = m4v4(invM, cx, cy, cz, 1.0f);
+  float dx = r.x * oneOverVoxelSize - sx, dy = r.y * oneOverVoxelSize - sy, dz = r.z * oneOverVoxelSize - sz;
+  const float direction_norm = 1.0f / sqrtf(dx * dx + dy * dy + dz * dz);
+  dx *= direction_norm; dy *= direction_norm; dz *= direction_norm;
+  float px = sx, py = sy, pz = sz;
+  IdxCache cache; cache_init(cache);
+  float sdfValue = 1.0f, stepLength;
+  while (totalLength < totalLengthMax) {
+    const int vi = voxel_index(table, nb, (int)round_(px), (int)round_(py), (int)round_(pz), cache);
+    sdfValue = sdf_raw(voxels, vi) / 32767.0f;
+    if (vi < 0) {
+      stepLength = BS;
+    } else {
+      if ((sdfValue <= 20.0f) && (sdfValue >= -100.0f)) sdfValue = sdf_interp(voxels, table, nb, px, py, pz, cache);
+      if (sdfValue <= 0.0f) break;
+      stepLength = maxf_(sdfValue * stepScale, 1.0f);
+    }
+    px += stepLength * dx; py += stepLength * dy; pz += stepLength * dz;
+    totalLength += stepLength;
+  }
+  bool found;
+  if (sdfValue <= 0.0f) {
+    stepLength = sdfValue * stepScale;
+    px += stepLength * dx; py += stepLength * dy; pz += stepLength * dz;
+    sdfValue = sdf_interp(voxels, table, nb, px, py, pz, cache);
+    stepLength = sdfValue * stepScale;
+    px += stepLength * dx; py += stepLength * dy; pz += stepLength * dz;
+    found = true;
+  } else found = false;
+  out = make_float4(px, py, pz, found ? 1.0f : 0.0f);
+  return found;
+}
+
+__global__ void __launch_bounds__(256)
+k_raycast(float4 *out, const b200_voxel *__restrict__ voxels, const b200_hash_entry *__restrict__ table, int nb, int w, int h, Mat4 invM,
+          float fx, float fy, float cxp, float cyp, float voxelSize, float mu, const float2 *__restrict__ minmax) {
+  const int tilesX = (w + 7) >> 3, tilesY = (h + 3) >> 2;
+  const int warpGlobal = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (warpGlobal >= tilesX * tilesY) return;
+  const int lane = threadIdx.x & 31;
+  const int x = (warpGlobal % tilesX) * 8 + (lane & 7), y = (warpGlobal / tilesX) * 4 + (lane >> 3);
+  if (x >= w || y >= h) return;
+  const int locId2 = (int)floorf((float)x / B200_MINMAX_SUBSAMPLE) + (int)floorf((float)y / B200_MINMAX_SUBSAMPLE) * w;
+  float4 o;
+  cast_ray(o, x, y, voxels, table, nb, invM, 1.0f / fx, 1.0f / fy, cxp, cyp, 1.0f / voxelSize, mu, __ldg(minmax + locId2));
+  out[x + y * w] = o;
+}
+
+void launch_raycast(b200_engine *e, const SceneRef &s, const Mat4 &invM, const float proj[4], int w, int h, float voxelSize, float mu,
+                    const b200_vec2f *minmax, b200_vec4f *out) {
+  const int tiles = ((w + 7) / 8) * ((h + 3) / 4);
+  k_raycast<<<(tiles + 7) / 8, 256, 0, e->stream>>>((float4 *)out, s.voxels, s.hash, s.numBuckets, w, h, invM, proj[0], proj[1], proj[2],
+                                                   proj[3], voxelSize, mu, (const float2 *)minmax);
+  e->launches++;
+}
+
+// ------------------------------------------------------------------------------------------------
+// shading from the volume
+// ------------------------------------------------------------------------------------------------
+DEV float rvs(const b200_voxel *__restrict__ voxels, const b200_hash_entry *__restrict__ table, int nb, int x, int y, int z) {
+  IdxCache c; cache_init(c);   // the 4-argument readVoxel builds a fresh cache per read (:222-228)
+  return rv_sdf(voxels, table, nb, x, y, z, c);
+}
+
+// computeSingleNormalFromSDF — DA/ITMRepresentationAccess.h:336-449
+__device__ void normal_from_sdf(const b200_voxel *__restrict__ voxels, const b200_hash_entry *__restrict__ table, int nb, float px, float py,
+                                float pz, float &rx, float &ry, float &rz) {
+  const float fx = floorf(px), fy = floorf(py), fz = floorf(pz);
+  const float cx = px - fx, cy = py - fy, cz = pz - fz;
+  const int X = (int)fx, Y = (int)fy, Z = (int)fz;
+  const float nx = 1.0f - cx, ny = 1.0f - cy, nz = 1.0f - cz;
+#define RV(a, b, c) rvs(voxels, table, nb, X + (a), Y + (b), Z + (c))
+  const float f0 = RV(0, 0, 0), f1 = RV(1, 0, 0), f2 = RV(0, 1, 0), f3 = RV(1, 1, 0);
+  const float b0 = RV(0, 0, 1), b1 = RV(1, 0, 1), b2 = RV(0, 1, 1), b3 = RV(1, 1, 1);
+  float t0, t1, t2, t3, p1, p2, v1;
+  p1 = f0 * ny * nz + f2 * cy * nz + b0 * ny * cz + b2 * cy * cz;
+  t0 = RV(-1, 0, 0); t1 = RV(-1, 1, 0); t2 = RV(-1, 0, 1); t3 = RV(-1, 1, 1);
+  p2 = t0 * ny * nz + t1 * cy * nz + t2 * ny * cz + t3 * cy * cz;
+  v1 = p1 * cx + p2 * nx;
+  p1 = f1 * ny * nz + f3 * cy * nz + b1 * ny * cz + b3 * cy * cz;
+  t0 = RV(2, 0, 0); t1 = RV(2, 1, 0); t2 = RV(2, 0, 1); t3 = RV(2, 1, 1);
+  p2 = t0 * ny * nz + t1 * cy * nz + t2 * ny * cz + t3 * cy * cz;
+  rx = (p1 * nx + p2 * cx - v1) / 32767.0f;
+  p1 = f0 * nx * nz + f1 * cx * nz + b0 * nx * cz + b1 * cx * cz;
+  t0 = RV(0, -1, 0); t1 = RV(1, -1, 0); t2 = RV(0, -1, 1); t3 = RV(1, -1, 1);
+  p2 = t0 * nx * nz + t1 * cx * nz + t2 * nx * cz + t3 * cx * cz;
+  v1 = p1 * cy + p2 * ny;
+  p1 = f2 * nx * nz + f3 * cx * nz + b2 * nx * cz + b3 * cx * cz;
+  t0 = RV(0, 2, 0); t1 = RV(1, 2, 0); t2 = RV(0, 2, 1); t3 = RV(1, 2, 1);
+  p2 = t0 * nx * nz + t1 * cx * nz + t2 * nx * cz + t3 * cx * cz;
+  ry = (p1 * ny + p2 * cy - v1) / 32767.0f;
+  p1 = f0 * nx * ny + f1 * cx * ny + f2 * nx * cy + f3 * cx * cy;
+  t0 = RV(0, 0, -1); t1 = RV(1, 0, -1); t2 = RV(0, 1, -1); t3 = RV(1, 1, -1);
+  p2 = t0 * nx * ny + t1 * cx * ny + t2 * nx * cy + t3 * cx * cy;
+  v1 = p1 * cz + p2 * nz;
+  p1 = b0 * nx * ny + b1 * cx * ny + b2 * nx * cy + b3 * cx * cy;
+  t0 = RV(0, 0, 2); t1 = RV(1, 0, 2); t2 = RV(0, 1, 2); t3 = RV(1, 1, 2);
+  p2 = t0 * nx * ny + t1 * cx * ny + t2 * nx * cy + t3 * cx * cy;
+  rz = (p1 * nz + p2 * cz - v1) / 32767.0f;
+#undef RV
+}
+
+// computeNormalAndAngle<TVoxel,TIndex> — DA/ITMVisualisationEngine.h:196-210
+DEV void normal_and_angle_sdf(bool &found, float px, float py, float pz, const b200_voxel *__restrict__ voxels,
+                              const b200_hash_entry *__restrict__ table, int nb, float lx, float ly, float lz, float &nx, float &ny,
+                              float &nz, float &angle) {
+  if (!found) return;
+  normal_from_sdf(voxels, table, nb, px, py, pz, nx, ny, nz);
+  const float normScale = 1.0f / sqrtf(nx * nx + ny * ny + nz * nz);
+  nx *= normScale; ny *= normScale; nz *= normScale;
+  angle = nx * lx + ny * ly + nz * lz;
+  if (!(angle > 0.0)) found = false;
+}
+
+// readFromSDF_color4u_interpolated_noalpha — DA/ITMRepresentationAccess.h:280-318
+__device__ void color_interp(const b200_voxel *__restrict__ voxels, const b200_hash_entry *__restrict__ table, int nb, float px, float py,
+                             float pz, float &r0, float &r1, float &r2) {
+  IdxCache c; cache_init(c);
+  const float fx = floorf(px), fy = floorf(py), fz = floorf(pz);
+  const float cx = px - fx, cy = py - fy, cz = pz - fz;
+  const int X = (int)fx, Y = (int)fy, Z = (int)fz;
+  r0 = r1 = r2 = 0.0f;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int ox = k & 1, oy = (k >> 1) & 1, oz = k >> 2;
+    const int vi = voxel_index(table, nb, X + ox, Y + oy, Z + oz, c);
+    float cr = 0.0f, cg = 0.0f, cb = 0.0f;
+    if (vi >= 0) {
+      const unsigned lo = __ldg(reinterpret_cast<const unsigned *>(voxels + vi)), hi = __ldg(reinterpret_cast<const unsigned *>(voxels + vi) + 1);
+      cr = (float)((lo >> 24) & 0xff); cg = (float)(hi & 0xff); cb = (float)((hi >> 8) & 0xff);
+    }
+    const float wgt = (ox ? cx : (1.0f - cx)) * (oy ? cy : (1.0f - cy)) * (oz ? cz : (1.0f - cz));
+    r0 += wgt * cr; r1 += wgt * cg; r2 += wgt * cb;
+  }
+  r0 = r0 / 255.0f; r1 = r1 / 255.0f; r2 = r2 / 255.0f;
+}
+
+DEV uchar4 grey_px(float angle) {   // drawPixelGrey, DA/ITMVisualisationEngine.h:277-281
+  const float outRes = (0.8f * angle + 0.2f) * 255.0f;
+  const unsigned char g = (unsigned char)outRes;
+  return make_uchar4(g, g, g, g);
+}
+
+DEV uchar4 draw_colour(const b200_voxel *__restrict__ voxels, const b200_hash_entry *__restrict__ table, int nb, float px, float py, float pz) {
+  float c0, c1, c2;
+  color_interp(voxels, table, nb, px, py, pz, c0, c1, c2);
+  return make_uchar4((unsigned char)(c0 * 255.0f), (unsigned char)(c1 * 255.0f), (unsigned char)(c2 * 255.0f), 255);
+}
+
+// RenderImage_common kernels — Vis_CUDA.cu:735-886. WeightRenderingParams(1.0,false,maxW,2) (:303-311).
+__global__ void __launch_bounds__(256)
+k_shade(const float4 *__restrict__ rays, const b200_voxel *__restrict__ voxels, const b200_hash_entry *__restrict__ table, int nb, int w, int h,
+        Mat4 M, float lx, float ly, float lz, float voxelSize, int maxW, uchar4 *outChar, float *outFloat, int type) {
+  const int tilesX = (w + 7) >> 3, tilesY = (h + 3) >> 2;
+  const int warpGlobal = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (warpGlobal >= tilesX * tilesY) return;
+  const int lane = threadIdx.x & 31;
+  const int x = (warpGlobal % tilesX) * 8 + (lane & 7), y = (warpGlobal / tilesX) * 4 + (lane >> 3);
+  if (x >= w || y >= h) return;
+  const int locId = x + y * w;
+  const float4 pr = rays[locId];
+  bool found = pr.w > 0;
+  float nx = 0, ny = 0, nz = 0, angle = 0;
+  if (type == B200_RENDER_DEPTH_MAP) {
+    if (found) {   // drawPixelDepth :304-320
+      Vec4 pc = m4v4(M, pr.x * voxelSize, pr.y * voxelSize, pr.z * voxelSize, 1.0f);
+      outFloat[locId] = pc.z / pc.w;
+    } else outFloat[locId] = 0.0f;
+    return;
+  }
+  normal_and_angle_sdf(found, pr.x, pr.y, pr.z, voxels, table, nb, lx, ly, lz, nx, ny, nz, angle);
+  switch (type) {
+  case B200_RENDER_COLOUR_FROM_VOLUME:
+    outChar[locId] = found ? draw_colour(voxels, table, nb, pr.x, pr.y, pr.z) : make_uchar4(0, 0, 0, 255);
+    break;
+  case B200_RENDER_COLOUR_FROM_NORMAL:
+    if (found) {   // drawPixelNormal :283-288 leaves alpha untouched
+      uchar4 o = outChar[locId];
+      o.x = (unsigned char)((0.3f + (-nx + 1.0f) * 0.35f) * 255.0f);
+      o.y = (unsigned char)((0.3f + (-ny + 1.0f) * 0.35f) * 255.0f);
+      o.z = (unsigned char)((0.3f + (-nz + 1.0f) * 0.35f) * 255.0f);
+      outChar[locId] = o;
+    } else outChar[locId] = make_uchar4(0, 0, 0, 0);
+    break;
+  case B200_RENDER_COLOUR_FROM_DEPTH_WEIGHT:
+    if (found) {   // drawPixelWeight :322-383
+      uchar4 dest = draw_colour(voxels, table, nb, pr.x, pr.y, pr.z);
+      IdxCache c; cache_init(c);
+      const int ix = (int)pr.x, iy = (int)pr.y, iz = (int)pr.z;
+      const int vi = voxel_index(table, nb, ix, iy, iz, c);
+      const int wd = vi >= 0 ? (int)((__ldg(reinterpret_cast<const unsigned *>(voxels + vi)) >> 16) & 0xff) : 0;
+      const unsigned char intensity = (unsigned char)(255.0f * (((float)wd) / maxW));
+      const int blockIdx_ = find_block<false>(table, nb, floordiv8(ix), floordiv8(iy), floordiv8(iz));
+      uchar4 ov;
+      if (blockIdx_ < 0) ov = make_uchar4(255, 255, 255, 255);
+      else if (wd <= 2) ov = make_uchar4(255, 0, 0, 255);
+      else if (wd == maxW) ov = make_uchar4(0, 0, 255, 255);
+      else ov = make_uchar4(intensity, intensity, intensity, 255);
+      const float overlayWeight = 1.0f;
+      const float a = (float)(1.0 - overlayWeight);
+      dest.x = (unsigned char)(((float)dest.x * a) + ((float)ov.x * overlayWeight));
+      dest.y = (unsigned char)(((float)dest.y * a) + ((float)ov.y * overlayWeight));
+      dest.z = (unsigned char)(((float)dest.z * a) + ((float)ov.z * overlayWeight));
+      dest.w = (unsigned char)(((float)dest.w * a) + ((float)ov.w * overlayWeight));
+      outChar[locId] = dest;
+    } else outChar[locId] = make_uchar4(0, 0, 0, 0);
+    break;
+  default:
+    outChar[locId] = found ? grey_px(angle) : make_uchar4(0, 0, 0, 0);
+    break;
+  }
+}
+
+void launch_shade(b200_engine *e, const SceneRef &s, const Mat4 &M, const Mat4 &invM, int w, int h, float voxelSize, int maxW,
+                  const b200_vec4f *rays, b200_vec4u *outChar, float *outFloat, int type) {
+  const int tiles = ((w + 7) / 8) * ((h + 3) / 4);
+  k_shade<<<(tiles + 7) / 8, 256, 0, e->stream>>>((const float4 *)rays, s.voxels, s.hash, s.numBuckets, w, h, M, -invM.m[8], -invM.m[9],
+                                                 -invM.m[10], voxelSize, maxW, (uchar4 *)outChar, outFloat, type);
+  e->launches++;
+}
+
+// ------------------------------------------------------------------------------------------------
+// image-space normals: processPixelICP<true> / processPixelForwardRender<true>
+// ------------------------------------------------------------------------------------------------
+// computeNormalAndAngle<useSmoothing=true> — DA/ITMVisualisationEngine.h:212-275
+DEV void normal_and_angle_img(bool &found, int x, int y, const float4 *__restrict__ pr, float lx, float ly, float lz, float voxelSize,
+                              int w, int h, float &nx, float &ny, float &nz, float &angle) {
+  if (!found) return;
+  if (y <= 2 || y >= h - 3 || x <= 2 || x >= w - 3) { found = false; return; }
+  float4 xp1 = pr[(x + 2) + y * w], yp1 = pr[x + (y + 2) * w], xm1 = pr[(x - 2) + y * w], ym1 = pr[x + (y - 2) * w];
+  float dxx = 0, dxy = 0, dxz = 0, dyx = 0, dyy = 0, dyz = 0;
+  bool doPlus1 = false;
+  if (xp1.w <= 0 || yp1.w <= 0 || xm1.w <= 0 || ym1.w <= 0) doPlus1 = true;
+  else {
+    dxx = xp1.x - xm1.x; dxy = xp1.y - xm1.y; dxz = xp1.z - xm1.z;
+    dyx = yp1.x - ym1.x; dyy = yp1.y - ym1.y; dyz = yp1.z - ym1.z;
+    const float length_diff = maxf_(dxx * dxx + dxy * dxy + dxz * dxz, dyx * dyx + dyy * dyy + dyz * dyz);
+    if (length_diff * voxelSize * voxelSize > (0.15f * 0.15f)) doPlus1 = true;
+  }
+  if (doPlus1) {
+    xp1 = pr[(x + 1) + y * w]; yp1 = pr[x + (y + 1) * w]; xm1 = pr[(x - 1) + y * w]; ym1 = pr[x + (y - 1) * w];
+    dxx = xp1.x - xm1.x; dxy = xp1.y - xm1.y; dxz = xp1.z - xm1.z;
+    dyx = yp1.x - ym1.x; dyy = yp1.y - ym1.y; dyz = yp1.z - ym1.z;
+    if (xp1.w <= 0 || yp1.w <= 0 || xm1.w <= 0 || ym1.w <= 0) { found = false; return; }
+  }
+  nx = -(dxy * dyz - dxz * dyy);
+  ny = -(dxz * dyx - dxx * dyz);
+  nz = -(dxx * dyy - dxy * dyx);
+  const float normScale = 1.0f / sqrtf(nx * nx + ny * ny + nz * nz);
+  nx *= normScale; ny *= normScale; nz *= normScale;
+  angle = nx * lx + ny * ly + nz * lz;
+  if (!(angle > 0.0)) found = false;
+}
+
+__global__ void __launch_bounds__(256)
+k_icp(const float4 *__restrict__ rays, int w, int h, float voxelSize, float lx, float ly, float lz, uchar4 *outImg, float4 *points,
+      float4 *normals) {
+  const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
+  if (x >= w || y >= h) return;
+  const int locId = x + y * w;
+  const float4 p = rays[locId];
+  bool found = p.w > 0.0f;
+  float nx = 0, ny = 0, nz = 0, angle = 0;
+  normal_and_angle_img(found, x, y, rays, lx, ly, lz, voxelSize, w, h, nx, ny, nz, angle);
+  if (found) {
+    outImg[locId] = grey_px(angle);
+    if (points) { points[locId] = make_float4(p.x * voxelSize, p.y * voxelSize, p.z * voxelSize, 1.0f); normals[locId] = make_float4(nx, ny, nz, 0.0f); }
+  } else {
+    outImg[locId] = make_uchar4(0, 0, 0, 0);
+    if (points) { points[locId] = make_float4(0.0f, 0.0f, 0.0f, -1.0f); normals[locId] = make_float4(0.0f, 0.0f, 0.0f, -1.0f); }
+  }
+}
+
+void launch_icp(b200_engine *e, const Mat4 &invM, int w, int h, float voxelSize, const b200_vec4f *rays, b200_vec4u *outImg,
+                b200_vec4f *points, b200_vec4f *normals) {
+  dim3 grid((w + 31) / 32, (h + 7) / 8);
+  k_icp<<<grid, 256, 0, e->stream>>>((const float4 *)rays, w, h, voxelSize, -invM.m[8], -invM.m[9], -invM.m[10], (uchar4 *)outImg,
+                                     (float4 *)points, (float4 *)normals);
+  e->launches++;
+}
+
+// ------------------------------------------------------------------------------------------------
+// forward render (approximate raycast path; dead under DynSLAM settings, kept for the interface)
+// Canonical order (oracle): raster order; the forward splat keeps the LAST source pixel that lands
+// on a target pixel -> atomicMax on the source index, then a gather.
+// ------------------------------------------------------------------------------------------------
+__global__ void k_fwd_splat(const float4 *__restrict__ rays, int w, int h, Mat4 M, float p0, float p1, float p2, float p3, float voxelSize,
+                            int *winner) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= w * h) return;
+  const float4 px = rays[i];
+  // forwardProjectPixel(pixel * voxelSize, ...) — DA/ITMVisualisationEngine.h:181-194
+  Vec4 q = m4v4(M, px.x * voxelSize, px.y * voxelSize, px.z * voxelSize, 1.0f);
+  const float ix = p0 * q.x / q.z + p2, iy = p1 * q.y / q.z + p3;
+  if ((ix < 0) || (ix > w - 1) || (iy < 0) || (iy > h - 1)) return;
+  atomicMax(&winner[(int)(ix + 0.5f) + (int)(iy + 0.5f) * w], i);
+}
+
+#define FWD_TILE 1024
+__global__ void __launch_bounds__(256)
+k_fwd_gather_missing(const float4 *__restrict__ rays, const int *__restrict__ winner, float4 *fwd, const float *__restrict__ depth,
+                     const float2 *__restrict__ minmax, int w, int h, int *missing, DevCounters *ctr, unsigned long long *scanDesc,
+                     unsigned gen) {
+  __shared__ unsigned sm[33];
+  __shared__ unsigned tileBase;
+  const int n = w * h, noTiles = (n + FWD_TILE - 1) / FWD_TILE;
+  for (int tile = blockIdx.x; tile < noTiles; tile += gridDim.x) {
+    unsigned mask = 0;
+    const int first = tile * FWD_TILE + threadIdx.x * 4;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int locId = first + k;
+      if (locId >= n) continue;
+      const int src = winner[locId];
+      const float4 fp = src >= 0 ? rays[src] : make_float4(0, 0, 0, 0);
+      fwd[locId] = fp;
+      const int y = locId / w, x = locId - y * w;
+      const int locId2 = (int)floorf((float)x / B200_MINMAX_SUBSAMPLE) + (int)floorf((float)y / B200_MINMAX_SUBSAMPLE) * w;
+      const float2 mm = minmax[locId2];
+      const float d = depth[locId];
+      if ((fp.w <= 0) && ((fp.x == 0 && fp.y == 0 && fp.z == 0) || (d > 0)) && (mm.x < mm.y)) mask |= 1u << k;
+    }
+    unsigned total;
+    unsigned local = block_exclusive_scan(__popc(mask), sm, &total);
+    if (threadIdx.x < 32) {
+      unsigned ex = scan_lookback(scanDesc, gen, tile, total);
+      if (threadIdx.x == 0) { tileBase = ex; if (tile == noTiles - 1) ctr->noFwdMissing = (int)(ex + total); }
+    }
+    __syncthreads();
+    unsigned o = tileBase + local;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) if (mask & (1u << k)) missing[o++] = first + k;
+    __syncthreads();
+  }
+}
+
+__global__ void k_fwd_raycast_missing(float4 *fwd, const int *__restrict__ missing, const DevCounters *ctr, const b200_voxel *__restrict__ voxels,
+                                      const b200_hash_entry *__restrict__ table, int nb, int w, Mat4 invM, float fx, float fy, float cxp,
+                                      float cyp, float voxelSize, float mu, const float2 *__restrict__ minmax) {
+  const int n = ctr->noFwdMissing;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int locId = missing[i];
+    const int y = locId / w, x = locId - y * w;
+    const int locId2 = (int)floorf((float)x / B200_MINMAX_SUBSAMPLE) + (int)floorf((float)y / B200_MINMAX_SUBSAMPLE) * w;
+    float4 o;
+    cast_ray(o, x, y, voxels, table, nb, invM, 1.0f / fx, 1.0f / fy, cxp, cyp, 1.0f / voxelSize, mu, minmax[locId2]);
+    fwd[locId] = o;
+  }
+}
+
+void launch_forward_render(b200_engine *e, const SceneRef &s, const FrameGeom &g, const float *depth, const b200_vec2f *minmax,
+                           const b200_vec4f *rays, b200_vec4f *fwd, int *missing, b200_vec4u *outImg) {
+  cudaStream_t st = e->stream;
+  const int n = g.w * g.h;
+  int *winner = reinterpret_cast<int *>(e->d_tileCounts);   // per target pixel: last source pixel landing on it
+  cudaMemsetAsync(winner, 0xff, sizeof(int) * (size_t)n, st);   // -1 = none
+  k_fwd_splat<<<(n + 255) / 256, 256, 0, st>>>((const float4 *)rays, g.w, g.h, g.M_d, g.proj_d[0], g.proj_d[1], g.proj_d[2], g.proj_d[3],
+                                              g.voxelSize, winner);
+  const int noTiles = (n + FWD_TILE - 1) / FWD_TILE;
+  k_fwd_gather_missing<<<persistent_grid(e, 4, noTiles), 256, 0, st>>>((const float4 *)rays, winner, (float4 *)fwd, depth,
+                                                                      (const float2 *)minmax, g.w, g.h, missing, e->d_ctr, e->d_scanDesc,
+                                                                      ++e->scanGen);
+  k_fwd_raycast_missing<<<e->smCount * 4, 128, 0, st>>>((float4 *)fwd, missing, e->d_ctr, s.voxels, s.hash, s.numBuckets, g.w, g.invM_d,
+                                                       g.proj_d[0], g.proj_d[1], g.proj_d[2], g.proj_d[3], g.voxelSize, g.mu,
+                                                       (const float2 *)minmax);
+  dim3 grid((g.w + 31) / 32, (g.h + 7) / 8);
+  k_icp<<<grid, 256, 0, st>>>((const float4 *)fwd, g.w, g.h, g.voxelSize, -g.invM_d.m[8], -g.invM_d.m[9], -g.invM_d.m[10], (uchar4 *)outImg,
+                              nullptr, nullptr);
+  e->launches += 4;
+}
+
+// ------------------------------------------------------------------------------------------------
+// point cloud for the colour tracker (dead under DynSLAM settings, kept for the interface);
+// canonical order of the compacted cloud: raster order
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_point_cloud(const float4 *__restrict__ rays, const b200_voxel *__restrict__ voxels, const b200_hash_entry *__restrict__ table, int nb, int w,
+              int h, float lx, float ly, float lz, float voxelSize, int skipPoints, uchar4 *outImg, float4 *locations, float4 *colours,
+              DevCounters *ctr, unsigned long long *scanDesc, unsigned gen) {
+  __shared__ unsigned sm[33];
+  __shared__ unsigned tileBase;
+  const int n = w * h, noTiles = (n + 255) / 256;
+  for (int tile = blockIdx.x; tile < noTiles; tile += gridDim.x) {
+    const int locId = tile * 256 + threadIdx.x;
+    bool found = false; float4 pr = make_float4(0, 0, 0, 0);
+    if (locId < n) {
+      const int y = locId / w, x = locId - y * w;
+      pr = rays[locId];
+      found = pr.w > 0;
+      float nx = 0, ny = 0, nz = 0, angle = 0;
+      normal_and_angle_sdf(found, pr.x, pr.y, pr.z, voxels, table, nb, lx, ly, lz, nx, ny, nz, angle);
+      outImg[locId] = found ? grey_px(angle) : make_uchar4(0, 0, 0, 0);
+      if (skipPoints && ((x % 2 == 0) || (y % 2 == 0))) found = false;
+    }
+    unsigned total;
+    unsigned local = block_exclusive_scan(found ? 1u : 0u, sm, &total);
+    if (threadIdx.x < 32) {
+      unsigned ex = scan_lookback(scanDesc, gen, tile, total);
+      if (threadIdx.x == 0) { tileBase = ex; if (tile == noTiles - 1) ctr->noTotalPoints = ex + total; }
+    }
+    __syncthreads();
+    if (found) {
+      const unsigned o = tileBase + local;
+      float c0, c1, c2;
+      color_interp(voxels, table, nb, pr.x, pr.y, pr.z, c0, c1, c2);
+      float4 tmp = make_float4(c0, c1, c2, 1.0f);
+      tmp.x /= tmp.w; tmp.y /= tmp.w; tmp.z /= tmp.w;
+      colours[o] = tmp;
+      locations[o] = make_float4(pr.x * voxelSize, pr.y * voxelSize, pr.z * voxelSize, 1.0f);
+    }
+    __syncthreads();
+  }
+}
+
+void launch_point_cloud(b200_engine *e, const SceneRef &s, const Mat4 &invM, int w, int h, float voxelSize, int skipPoints,
+                        const b200_vec4f *rays, b200_vec4u *outImg, b200_vec4f *locations, b200_vec4f *colours) {
+  const int noTiles = (w * h + 255) / 256;
+  k_point_cloud<<<persistent_grid(e, 2, noTiles), 256, 0, e->stream>>>((const float4 *)rays, s.voxels, s.hash, s.numBuckets, w, h,
+                                                                      -invM.m[8], -invM.m[9], -invM.m[10], voxelSize, skipPoints,
+                                                                      (uchar4 *)outImg, (float4 *)locations, (float4 *)colours, e->d_ctr,
+                                                                      e->d_scanDesc, ++e->scanGen);
+  e->launches++;
+}

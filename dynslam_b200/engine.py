@@ -1,0 +1,347 @@
+"""Host-side mirror of the reference's engine interfaces for the hot path, over the C-ABI.
+
+Class and method names follow ITMLib (src/InfiniTAM/InfiniTAM/ITMLib/):
+  ITMScene / ITMRenderState_VH / ITMView              Objects/ITMScene.h, ITMRenderState_VH.h, ITMView.h
+  ITMSceneReconstructionEngine                         Engine/ITMSceneReconstructionEngine.h:33-78
+  ITMVisualisationEngine                               Engine/ITMVisualisationEngine.h:19-127
+  ITMSwappingEngine (+ ITMGlobalCache host store)      Engine/ITMSwappingEngine.h:22-31
+Error behaviour mirrors the reference: capacity exhaustion raises RuntimeError (the reference
+throws std::runtime_error, Reco_CUDA.cu:348-357, caught by InstanceReconstructor.cpp:662-671);
+CUDA failures raise CudaError (the reference prints and exits, OR/CUDADefines.cpp:9-47).
+
+torch is used for device memory only. There is no CPU path: constructing an engine without the
+CUDA library or without a GPU raises.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import abi
+
+
+class CudaError(RuntimeError):
+    pass
+
+
+def _ptr(t):
+    return t.data_ptr() if t is not None else None
+
+
+class SceneParams:
+    """ITMSceneParams (Objects/ITMSceneParams.h:14-71); defaults of ITMLibSettings.cpp:23."""
+
+    def __init__(self, voxelSize=0.05, mu=0.75, maxW=50, viewFrustum_min=0.1, viewFrustum_max=300.0,
+                 stopIntegratingAtMaxW=False):
+        self.voxelSize, self.mu, self.maxW = voxelSize, mu, maxW
+        self.viewFrustum_min, self.viewFrustum_max = viewFrustum_min, viewFrustum_max
+        self.stopIntegratingAtMaxW = stopIntegratingAtMaxW
+
+
+class Scene:
+    """ITMScene<ITMVoxel_s_rgb, ITMVoxelBlockHash>: hash table + excess list + VBA + free list."""
+
+    def __init__(self, params, numBlocks=0x60000, numBuckets=0x100000, excessSize=0x80000, device="cuda:0",
+                 useSwapping=False):
+        self.params = params
+        self.device = torch.device(device)
+        self.numBlocks, self.numBuckets, self.excessSize = numBlocks, numBuckets, excessSize
+        self.noTotalEntries = numBuckets + excessSize
+        dev = self.device
+        self.voxels = torch.empty(numBlocks * abi.SDF_BLOCK_SIZE3 * 8, dtype=torch.uint8, device=dev)
+        self.allocationList = torch.empty(numBlocks, dtype=torch.int32, device=dev)
+        self.hash = torch.empty(self.noTotalEntries * 20, dtype=torch.uint8, device=dev)
+        self.excessList = torch.empty(excessSize, dtype=torch.int32, device=dev)
+        self.swapStates = torch.zeros(self.noTotalEntries, dtype=torch.uint8, device=dev) if useSwapping else None
+        s = abi.Scene()
+        s.d_voxels, s.d_allocationList = _ptr(self.voxels), _ptr(self.allocationList)
+        s.d_hash, s.d_excessList, s.d_swapStates = _ptr(self.hash), _ptr(self.excessList), _ptr(self.swapStates)
+        s.numBlocks, s.numBuckets, s.excessSize = numBlocks, numBuckets, excessSize
+        s.lastFreeBlockId, s.lastFreeExcessListId = numBlocks - 1, excessSize - 1
+        s.voxelSize, s.mu, s.maxW = params.voxelSize, params.mu, params.maxW
+        s.viewFrustum_min, s.viewFrustum_max = params.viewFrustum_min, params.viewFrustum_max
+        s.stopIntegratingAtMaxW, s.useSwapping = int(params.stopIntegratingAtMaxW), int(useSwapping)
+        self.c = s
+
+    @property
+    def lastFreeBlockId(self):
+        return self.c.lastFreeBlockId
+
+    @property
+    def lastFreeExcessListId(self):
+        return self.c.lastFreeExcessListId
+
+    def to_host(self):
+        """numpy copies of every persistent buffer (for parity checks)."""
+        return dict(hash=self.hash.cpu().numpy().view(abi.HASH_ENTRY_DTYPE).copy(),
+                    voxels=self.voxels.cpu().numpy().view(abi.VOXEL_DTYPE).copy(),
+                    allocationList=self.allocationList.cpu().numpy().copy(),
+                    excessList=self.excessList.cpu().numpy().copy(),
+                    lastFreeBlockId=self.c.lastFreeBlockId, lastFreeExcessListId=self.c.lastFreeExcessListId)
+
+
+class RenderStateVH:
+    """ITMRenderState_VH (+ base): visible list, visibility bytes, min/max image, raycast images."""
+
+    def __init__(self, scene, imgSize, forward=False):
+        w, h = imgSize
+        dev = scene.device
+        self.w, self.h = w, h
+        self.visibleBlockPositions = torch.zeros(scene.numBlocks * 3, dtype=torch.int32, device=dev)
+        self.entriesVisibleType = torch.zeros(scene.noTotalEntries, dtype=torch.uint8, device=dev)
+        self.renderingRangeImage = torch.zeros(h * w * 2, dtype=torch.float32, device=dev)
+        self.raycastResult = torch.zeros(h * w * 4, dtype=torch.float32, device=dev)
+        self.raycastImage = torch.zeros(h * w * 4, dtype=torch.uint8, device=dev)
+        self.forwardProjection = torch.zeros(h * w * 4, dtype=torch.float32, device=dev) if forward else None
+        self.fwdProjMissingPoints = torch.zeros(h * w, dtype=torch.int32, device=dev) if forward else None
+        r = abi.RenderState()
+        r.d_visibleBlockPositions, r.d_entriesVisibleType = _ptr(self.visibleBlockPositions), _ptr(self.entriesVisibleType)
+        r.d_minmax, r.d_raycastResult, r.d_raycastImage = _ptr(self.renderingRangeImage), _ptr(self.raycastResult), _ptr(self.raycastImage)
+        r.d_forwardProjection, r.d_fwdProjMissingPoints = _ptr(self.forwardProjection), _ptr(self.fwdProjMissingPoints)
+        r.img_w, r.img_h, r.noVisibleBlocks = w, h, 0
+        self.c = r
+
+    @property
+    def noVisibleBlocks(self):
+        return self.c.noVisibleBlocks
+
+    def to_host(self):
+        n = max(self.c.noVisibleBlocks, 0)
+        return dict(visType=self.entriesVisibleType.cpu().numpy().copy(),
+                    visiblePos=self.visibleBlockPositions.cpu().numpy().reshape(-1, 3)[:n].copy(),
+                    noVisibleBlocks=self.c.noVisibleBlocks)
+
+
+class View:
+    """ITMView + pose_d + calibration: device depth (float metres) / rgb (RGBA8) and matrices."""
+
+    def __init__(self, depth, rgb, M_d, proj_d, M_rgb=None, proj_rgb=None, depthWeighting=False,
+                 requiresFullRendering=True):
+        self.depth, self.rgb = depth, rgb
+        v = abi.View()
+        v.d_depth, v.d_rgb = _ptr(depth), _ptr(rgb)
+        v.depth_h, v.depth_w = depth.shape[:2]
+        v.rgb_h, v.rgb_w = rgb.shape[:2]
+        v.proj_d = abi.f4(*[float(x) for x in proj_d])
+        v.proj_rgb = abi.f4(*[float(x) for x in (proj_rgb if proj_rgb is not None else proj_d)])
+        v.depthWeighting, v.requiresFullRendering = int(depthWeighting), int(requiresFullRendering)
+        self.c = v
+        self.set_pose(M_d, M_rgb)
+
+    def set_pose(self, M_d, M_rgb=None):
+        lib = abi.load_library()
+        self.c.M_d = abi.mat_to_c(M_d)
+        inv = abi.f16()
+        if not lib.b200_mat4_inv(self.c.M_d, inv):
+            raise ValueError("singular pose")
+        self.c.invM_d = inv
+        self.c.M_rgb = abi.mat_to_c(M_rgb if M_rgb is not None else M_d)
+
+
+def make_camera(M, proj):
+    lib = abi.load_library()
+    c = abi.Camera()
+    c.M = abi.mat_to_c(M)
+    inv = abi.f16()
+    if not lib.b200_mat4_inv(c.M, inv):
+        raise ValueError("singular pose")
+    c.invM = inv
+    c.proj = abi.f4(*[float(x) for x in proj])
+    return c
+
+
+class Engine:
+    """Opaque per-volume engine handle (owns scratch, decay ring, stream)."""
+
+    def __init__(self, scene, imgSize, decayRingItems=0, stream=None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("dynslam_b200 needs a CUDA device; there is no CPU fallback")
+        self.lib = abi.load_library()
+        cfg = abi.EngineConfig()
+        cfg.device = scene.device.index or 0
+        cfg.numBlocks, cfg.numBuckets, cfg.excessSize = scene.numBlocks, scene.numBuckets, scene.excessSize
+        cfg.img_w, cfg.img_h = imgSize
+        cfg.decayRingItems = decayRingItems
+        cfg.stream = stream
+        h = C.c_void_p()
+        rc = self.lib.b200_engine_create(C.byref(cfg), C.byref(h))
+        self.h = h
+        if rc:
+            msg = self.lib.b200_last_error(h).decode() if h else "engine create failed"
+            raise CudaError(msg)
+        self.scene = scene
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.b200_engine_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def check(self, rc):
+        if rc == abi.OK:
+            return
+        msg = self.lib.b200_last_error(self.h).decode()
+        if rc in (abi.ERR_VBA_FULL, abi.ERR_EXCESS_FULL, abi.ERR_DECAY_RING_FULL):
+            raise RuntimeError(msg)
+        if rc == abi.ERR_CUDA:
+            raise CudaError(msg)
+        raise ValueError(msg)
+
+    @property
+    def frameIdx(self):
+        return self.lib.b200_frame_index(self.h)
+
+    @property
+    def stream(self):
+        return self.lib.b200_engine_stream(self.h)
+
+    def stats(self):
+        st = abi.FrameStats()
+        self.check(self.lib.b200_get_stats(self.h, C.byref(st)))
+        return st
+
+    def set_timing(self, on):
+        self.lib.b200_set_timing(self.h, int(on))
+
+    # ---- fused fast path --------------------------------------------------------------------
+    def process_frame_async(self, renderState, view, points=None, normals=None, decay=None, raycast=True):
+        o = abi.FrameOpts()
+        o.doRaycast = int(raycast)
+        if decay is not None:
+            o.doDecay, o.decayMaxWeight, o.decayMinAge = 1, decay[0], decay[1]
+        self.check(self.lib.b200_process_frame_async(self.h, C.byref(self.scene.c), C.byref(renderState.c), C.byref(view.c),
+                                                      _ptr(points), _ptr(normals), C.byref(o)))
+
+    def sync(self, renderState):
+        self.check(self.lib.b200_sync(self.h, C.byref(self.scene.c), C.byref(renderState.c)))
+
+    def process_frame_host(self, renderState, view, h_depth, h_rgb, d_depth_stage, d_rgb_stage, points=None, normals=None,
+                           decay=None, raycast=True, h_out=None):
+        o = abi.FrameOpts()
+        o.doRaycast = int(raycast)
+        if decay is not None:
+            o.doDecay, o.decayMaxWeight, o.decayMinAge = 1, decay[0], decay[1]
+        self.check(self.lib.b200_process_frame_host(self.h, C.byref(self.scene.c), C.byref(renderState.c), C.byref(view.c),
+                                                     _ptr(h_depth), _ptr(h_rgb), _ptr(d_depth_stage), _ptr(d_rgb_stage),
+                                                     _ptr(points), _ptr(normals), C.byref(o), _ptr(h_out)))
+
+
+class SceneReconstructionEngine:
+    """ITMSceneReconstructionEngine<ITMVoxel, ITMVoxelBlockHash> (B200 back-end)."""
+
+    def __init__(self, engine):
+        self.e = engine
+        self.fusionWeightParams = dict(depthWeighting=False)
+
+    def SetFusionWeightParams(self, depthWeighting):
+        self.fusionWeightParams["depthWeighting"] = bool(depthWeighting)
+
+    def ResetScene(self, scene):
+        self.e.check(self.e.lib.b200_reset_scene(self.e.h, C.byref(scene.c)))
+
+    def AllocateSceneFromDepth(self, scene, view, renderState, onlyUpdateVisibleList=False):
+        self.e.check(self.e.lib.b200_allocate_from_depth(self.e.h, C.byref(scene.c), C.byref(renderState.c), C.byref(view.c),
+                                                          int(onlyUpdateVisibleList)))
+
+    def IntegrateIntoScene(self, scene, view, renderState):
+        view.c.depthWeighting = int(self.fusionWeightParams["depthWeighting"])
+        self.e.check(self.e.lib.b200_integrate(self.e.h, C.byref(scene.c), C.byref(renderState.c), C.byref(view.c)))
+
+    def Decay(self, scene, renderState, maxWeight, minAge, forceAllVoxels=False):
+        self.e.check(self.e.lib.b200_decay(self.e.h, C.byref(scene.c), C.byref(renderState.c), maxWeight, minAge,
+                                           int(forceAllVoxels)))
+
+    def GetDecayedBlockCount(self):
+        return self.e.lib.b200_decayed_block_count(self.e.h)
+
+
+class VisualisationEngine:
+    """ITMVisualisationEngine<ITMVoxel, ITMVoxelBlockHash> (B200 back-end)."""
+
+    def __init__(self, engine, scene):
+        self.e, self.scene = engine, scene
+
+    def CreateRenderState(self, imgSize, forward=False):
+        return RenderStateVH(self.scene, imgSize, forward=forward)
+
+    def FindVisibleBlocks(self, camera, renderState):
+        self.e.check(self.e.lib.b200_find_visible_blocks(self.e.h, C.byref(self.scene.c), C.byref(renderState.c), C.byref(camera)))
+
+    def CreateExpectedDepths(self, camera, renderState):
+        self.e.check(self.e.lib.b200_expected_depths(self.e.h, C.byref(self.scene.c), C.byref(renderState.c), C.byref(camera)))
+
+    def FindSurface(self, camera, renderState):
+        self.e.check(self.e.lib.b200_find_surface(self.e.h, C.byref(self.scene.c), C.byref(renderState.c), C.byref(camera)))
+
+    def RenderImage(self, camera, renderState, outputCharImage, outputFloatImage, type=abi.RENDER_SHADED_GREYSCALE):
+        self.e.check(self.e.lib.b200_render_image(self.e.h, C.byref(self.scene.c), C.byref(renderState.c), C.byref(camera),
+                                                   _ptr(outputCharImage), _ptr(outputFloatImage), renderState.w, renderState.h, type))
+
+    def CreateICPMaps(self, view, renderState, points, normals):
+        self.e.check(self.e.lib.b200_icp_maps(self.e.h, C.byref(self.scene.c), C.byref(renderState.c), C.byref(view.c),
+                                               _ptr(points), _ptr(normals)))
+
+    def ForwardRender(self, view, renderState):
+        self.e.check(self.e.lib.b200_forward_render(self.e.h, C.byref(self.scene.c), C.byref(renderState.c), C.byref(view.c)))
+        return renderState.c.noFwdProjMissingPoints
+
+    def CreatePointCloud(self, view, renderState, locations, colours, skipPoints=False, calib_rgb_to_depth=None):
+        calib = abi.mat_to_c(calib_rgb_to_depth if calib_rgb_to_depth is not None else np.eye(4, dtype=np.float32))
+        n = C.c_uint32()
+        self.e.check(self.e.lib.b200_point_cloud(self.e.h, C.byref(self.scene.c), C.byref(renderState.c), C.byref(view.c), calib,
+                                                  int(skipPoints), _ptr(locations), _ptr(colours), C.byref(n)))
+        return n.value
+
+
+class GlobalCache:
+    """Host half of ITMGlobalCache (Objects/ITMGlobalCache.h:17-129): stored blocks per entry."""
+
+    def __init__(self, scene):
+        dev = scene.device
+        self.stored = {}
+        n = abi.TRANSFER_BLOCK_NUM
+        self.syncedVoxelBlocks = torch.zeros(n * abi.SDF_BLOCK_SIZE3 * 8, dtype=torch.uint8, device=dev)
+        self.hasSyncedData = torch.zeros(n, dtype=torch.uint8, device=dev)
+        self.neededEntryIDs = torch.zeros(n, dtype=torch.int32, device=dev)
+        t = abi.TransferBuffers()
+        t.d_syncedVoxelBlocks, t.d_hasSyncedData, t.d_neededEntryIDs = _ptr(self.syncedVoxelBlocks), _ptr(self.hasSyncedData), _ptr(self.neededEntryIDs)
+        self.c = t
+
+
+class SwappingEngine:
+    """ITMSwappingEngine<ITMVoxel, ITMVoxelBlockHash>: host orchestration of Swap_CUDA.cu:44-216."""
+
+    def __init__(self, engine):
+        self.e = engine
+
+    def IntegrateGlobalIntoLocal(self, scene, cache):
+        n = C.c_int()
+        self.e.check(self.e.lib.b200_swap_list_in(self.e.h, C.byref(scene.c), C.byref(cache.c), C.byref(n)))
+        n = n.value
+        if n > 0:
+            ids = cache.neededEntryIDs[:n].cpu().numpy()
+            blocks = np.zeros((n, abi.SDF_BLOCK_SIZE3 * 8), dtype=np.uint8)
+            for i, entry in enumerate(ids):
+                if int(entry) in cache.stored:
+                    blocks[i] = cache.stored[int(entry)]
+            cache.syncedVoxelBlocks[:n * abi.SDF_BLOCK_SIZE3 * 8].copy_(torch.from_numpy(blocks.reshape(-1)))
+            self.e.check(self.e.lib.b200_swap_integrate_in(self.e.h, C.byref(scene.c), C.byref(cache.c), n))
+        return n
+
+    def SaveToGlobalMemory(self, scene, renderState, cache):
+        n = C.c_int()
+        self.e.check(self.e.lib.b200_swap_out(self.e.h, C.byref(scene.c), C.byref(renderState.c), C.byref(cache.c), C.byref(n)))
+        n = n.value
+        if n > 0:
+            ids = cache.neededEntryIDs[:n].cpu().numpy()
+            has = cache.hasSyncedData[:n].cpu().numpy()
+            blocks = cache.syncedVoxelBlocks[:n * abi.SDF_BLOCK_SIZE3 * 8].cpu().numpy().reshape(n, -1)
+            for i, entry in enumerate(ids):
+                if has[i]:
+                    cache.stored[int(entry)] = blocks[i].copy()
+        return n

@@ -1,0 +1,169 @@
+"""GPU parity tests: the CUDA path (through the C-ABI) against the CPU oracle, bit for bit, on
+seeded synthetic sequences. Tolerance: none — integer/index state must be identical and, because the
+library is built without FMA contraction, so must every float (north_star only asks for 1e-5)."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from dynslam_b200 import abi, engine as E, synth
+from tests import hostlib as H
+from tests import parity as P
+
+pytestmark = pytest.mark.gpu
+
+
+def test_kitti_sequence_all_stages():
+    pair, _ = P.run_sequence(P.Cfg(frames=6))
+    assert pair.rs.noVisibleBlocks > 1000
+    assert pair.scene.lastFreeBlockId < pair.cfg.numBlocks - 1000
+
+
+def test_hash_collisions_excess_list():
+    """1024 buckets for thousands of blocks: most allocations go through the excess list."""
+    cfg = P.Cfg(frames=5, numBuckets=0x400, excessSize=0x4000, numBlocks=16384)
+    pair, _ = P.run_sequence(cfg)
+    used_excess = cfg.excessSize - 1 - pair.scene.lastFreeExcessListId
+    assert used_excess > 1000
+
+
+def test_decay_partial_with_chains():
+    """minAge 2 / maxWeight 3: blocks are reset and deleted every frame, chains get unlinked."""
+    cfg = P.Cfg(frames=10, frame_step=3, numBuckets=0x400, excessSize=0x4000, decay=(3, 2))
+    pair, _ = P.run_sequence(cfg)
+    assert pair.reco.GetDecayedBlockCount() > 200
+
+
+def test_decay_default_parameters():
+    cfg = P.Cfg(frames=8, decay=(1, 3), raycast=False)
+    pair, _ = P.run_sequence(cfg)
+    assert pair.reco.GetDecayedBlockCount() > 0
+
+
+def test_depth_weighting_and_stop_at_max_w():
+    P.run_sequence(P.Cfg(frames=5, depthWeighting=True, stopMaxW=True, maxW=3, frame_step=1))
+
+
+def test_config1_plane_8mm():
+    """BASELINE config 1: 640x480 plane at 1.5 m, 8 mm voxels (mu = 4 voxels), frustum 0.2-3 m."""
+    cfg = P.Cfg(workload="plane", frames=2, voxelSize=0.008, mu=0.032, maxW=100, vf_min=0.2, vf_max=3.0,
+                numBlocks=32768, numBuckets=0x8000, excessSize=0x4000)
+    pair, _ = P.run_sequence(cfg)
+    assert pair.rs.noVisibleBlocks > 1000
+
+
+def test_integrate_tma_variant_matches():
+    os.environ["B200_INTEGRATE_IMPL"] = "tma"
+    try:
+        pair, _ = P.run_sequence(P.Cfg(frames=5, raycast=False, decay=(1, 2)))
+    finally:
+        os.environ.pop("B200_INTEGRATE_IMPL", None)
+    assert pair.rs.noVisibleBlocks > 1000
+
+
+def _oracle_camera(M, proj):
+    return H.make_camera(M, proj)
+
+
+def test_free_view_render_all_types():
+    """FindVisibleBlocks + CreateExpectedDepths + RenderImage (5 types) from a novel pose."""
+    cfg = P.Cfg(frames=5)
+    pair, (gv, hv) = P.run_sequence(cfg)
+    L = pair.L
+    M = synth.kitti_pose(9).copy()
+    M[0, 3] += 0.4
+    M[1, 3] -= 0.2
+    proj = synth.kitti_intrinsics() * np.float32(cfg.scale)
+    cam, ocam = E.make_camera(M, proj), _oracle_camera(M, proj)
+    fv = pair.vis.CreateRenderState((pair.w, pair.h))
+    fv_host_pos = np.zeros((cfg.numBlocks, 3), dtype=np.int32)
+    hrs = abi.RenderState()
+    C.memmove(C.byref(hrs), C.byref(pair.host.rs), C.sizeof(hrs))
+    hrs.d_visibleBlockPositions = fv_host_pos.ctypes.data
+    pair.vis.FindVisibleBlocks(cam, fv)
+    L.oracle_find_visible_blocks(C.byref(pair.host.scene), C.byref(hrs), C.byref(ocam))
+    assert fv.noVisibleBlocks == hrs.noVisibleBlocks > 500
+    P._cmp("freeview list", fv.to_host()["visiblePos"], fv_host_pos[:hrs.noVisibleBlocks])
+    pair.vis.CreateExpectedDepths(cam, fv)
+    L.oracle_expected_depths(C.byref(pair.host.scene), C.byref(hrs), C.byref(ocam))
+    P._cmp("freeview minmax", fv.renderingRangeImage.cpu().numpy(), pair.host.minmax.reshape(-1))
+    dev = pair.scene.device
+    for t in range(5):
+        oc = torch.zeros(pair.h * pair.w * 4, dtype=torch.uint8, device=dev)
+        of = torch.zeros(pair.h * pair.w, dtype=torch.float32, device=dev)
+        hc = np.zeros((pair.h, pair.w, 4), dtype=np.uint8)
+        hf = np.zeros((pair.h, pair.w), dtype=np.float32)
+        pair.vis.RenderImage(cam, fv, oc, of, t)
+        L.oracle_render_image(C.byref(pair.host.scene), C.byref(hrs), C.byref(ocam), H.vptr(hc), H.vptr(hf), t, 0)
+        P._cmp(f"render type {t} rays", fv.raycastResult.cpu().numpy(), pair.host.raycastResult.reshape(-1))
+        P._cmp(f"render type {t} char", oc.cpu().numpy(), hc.reshape(-1))
+        P._cmp(f"render type {t} float", of.cpu().numpy(), hf.reshape(-1))
+    assert hc[..., :3].any()
+
+
+def test_full_decay_reap():
+    """Decay(forceAllVoxels=true): Reap() of a finished track (DS/InfiniTamDriver.h:231-235)."""
+    cfg = P.Cfg(frames=4, numBuckets=0x400, excessSize=0x4000, raycast=False)
+    pair, _ = P.run_sequence(cfg)
+    pair.reco.Decay(pair.scene, pair.rs, 2, 0, True)
+    freed = pair.L.oracle_decay(pair.host.engine, C.byref(pair.host.scene), C.byref(pair.host.rs), 2, 0, 1)
+    assert freed > 100
+    pair.compare_scene("full decay")
+    assert pair.reco.GetDecayedBlockCount() == freed
+
+
+def test_only_update_visible_list_and_empty_frame():
+    cfg = P.Cfg(frames=3, raycast=False)
+    pair, (gv, hv) = P.run_sequence(cfg)
+    L = pair.L
+    pair.reco.AllocateSceneFromDepth(pair.scene, gv, pair.rs, onlyUpdateVisibleList=True)
+    L.oracle_allocate_from_depth(pair.host.engine, C.byref(pair.host.scene), C.byref(pair.host.rs), C.byref(hv), 1, 0)
+    pair.compare_scene("only visible list")
+    # an all-invalid frame: nothing allocated, previous blocks stay type 3 / get demoted
+    depth = np.zeros((pair.h, pair.w), dtype=np.float32)
+    rgb = np.zeros((pair.h, pair.w, 4), dtype=np.uint8)
+    M, proj = synth.kitti_pose(40), synth.kitti_intrinsics() * np.float32(cfg.scale)
+    g2, h2 = pair.views(depth, rgb, M, proj)
+    pair.reco.AllocateSceneFromDepth(pair.scene, g2, pair.rs)
+    L.oracle_allocate_from_depth(pair.host.engine, C.byref(pair.host.scene), C.byref(pair.host.rs), C.byref(h2), 0, 0)
+    pair.compare_scene("empty frame")
+    pair.reco.IntegrateIntoScene(pair.scene, g2, pair.rs)
+    L.oracle_integrate(pair.host.engine, C.byref(pair.host.scene), C.byref(pair.host.rs), C.byref(h2), 0)
+    pair.compare_scene("empty frame integrate")
+    assert pair.eng.frameIdx == L.oracle_frame_index(pair.host.engine)
+
+
+def test_vba_exhaustion_raises_like_reference():
+    """Out of VBA slots: state is mutated, counters go negative, then the call raises (Reco_CUDA.cu:348-351)."""
+    cfg = P.Cfg(frames=1, numBlocks=512, raycast=False)
+    pair = P.Pair(cfg)
+    depth, rgb, M, proj = next(iter(P.frames_of(cfg)))
+    gv, hv = pair.views(depth, rgb, M, proj)
+    with pytest.raises(RuntimeError):
+        pair.reco.AllocateSceneFromDepth(pair.scene, gv, pair.rs)
+    rc = pair.L.oracle_allocate_from_depth(pair.host.engine, C.byref(pair.host.scene), C.byref(pair.host.rs), C.byref(hv), 0, 0)
+    assert rc == abi.ERR_VBA_FULL
+    assert pair.scene.lastFreeBlockId == pair.host.scene.lastFreeBlockId < 0
+    pair.compare_scene("exhausted", voxels=False)
+
+
+def test_fused_async_path_equals_stepwise():
+    """b200_process_frame_async (no host sync inside) leaves the same state as the call-by-call path."""
+    cfg = P.Cfg(frames=6, decay=(1, 2))
+    stepwise, _ = P.run_sequence(cfg)
+    pair = P.Pair(cfg)
+    for depth, rgb, M, proj in P.frames_of(cfg):
+        gv, _ = pair.views(depth, rgb, M, proj)
+        pair.eng.process_frame_async(pair.rs, gv, pair.points, pair.normals, decay=cfg.decay)
+    pair.eng.sync(pair.rs)
+    a, b = pair.scene.to_host(), stepwise.scene.to_host()
+    for k in ("hash", "voxels", "allocationList"):
+        P._cmp("fused " + k, a[k], b[k])
+    assert a["lastFreeBlockId"] == b["lastFreeBlockId"]
+    ra, rb = pair.rs.to_host(), stepwise.rs.to_host()
+    P._cmp("fused visType", ra["visType"], rb["visType"])
+    P._cmp("fused visible", ra["visiblePos"], rb["visiblePos"])
+    P._cmp("fused image", pair.rs.raycastImage.cpu().numpy(), stepwise.rs.raycastImage.cpu().numpy())
+    assert pair.reco.GetDecayedBlockCount() == stepwise.reco.GetDecayedBlockCount()
