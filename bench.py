@@ -1,0 +1,403 @@
+#!/usr/bin/env python
+"""bench.py — frames/s of the per-volume fusion+raycast loop on synthetic KITTI-shaped streams.
+
+    python bench.py --gpus N --steps K --warmup W            (own arm, one rank per GPU)
+    python bench.py --impl reference --gpus N --steps K ...  (reference arm: CPU, rank 0 only)
+
+A step is one frame through {AllocateSceneFromDepth, IntegrateIntoScene, CreateExpectedDepths,
+CreateICPMaps (raycast), Decay(partial)} on one ITMScene volume (BASELINE.json configs[1]).
+value  = frames/s with the frames already resident in HBM (whole job: all ranks' frames / max time)
+e2e    = frames/s through b200_process_frame_host: per frame the depth+RGB are copied from pinned
+         host memory and the grey raycast image is copied back, inside the timed region
+roofline = IntegrateIntoScene: algorithmic bytes (8224 B per integrated block + w*h*8 B of images
+         per launch) / mean launch duration from CUDA events around every launch of the timed region
+cpu_baseline = the CPU oracle (oracle/tsdf_oracle.c, OpenMP at the reference's own pragma sites)
+         timed on this box's host cores on a bounded sample of the same stream.
+N > 1: one independent volume per rank (weak scaling; no data-path collective inside fusion); the
+per-volume raycast image is gathered to rank 0 over NCCL every frame.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from dynslam_b200 import synth  # noqa: E402
+
+METRIC = "frames/sec TSDF fusion+raycast at KITTI 1242x375; Mvoxels/s integrated"
+NUM_BLOCKS, NUM_BUCKETS, EXCESS = 0x60000, 0x100000, 0x80000   # ITMLibSettings.cpp:115, ITMLibDefines.h:42-53
+DECAY = (1, 200)                                                # --max_decay_weight=1 --min_decay_age=200 (DynSLAMGUI.cpp:38-40)
+BYTES_PER_BLOCK = 8192 + 32
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag, self.proc = index, [], False, None
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                if self.stop_flag:
+                    break
+                self.rows.append([x.strip() for x in line.split(",")])
+        except Exception:
+            pass
+
+    def stop(self):
+        self.stop_flag = True
+        if self.proc:
+            self.proc.terminate()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                continue
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def gen_frames(seed, first, count, length_m):
+    scene = synth.StreetScene(seed=seed, length_m=length_m)
+    out = []
+    for f in range(first, first + count):
+        depth, rgb, M, proj = synth.kitti_frame(scene, f)
+        out.append((depth, rgb, M, proj))
+    return out
+
+
+def gen_frames_parallel(seed, first, count, length_m, workers):
+    if count <= 0:
+        return []
+    if workers <= 1 or count < 8:
+        return gen_frames(seed, first, count, length_m)
+    import multiprocessing as mp
+    chunk = (count + workers - 1) // workers
+    jobs = [(seed, first + i * chunk, min(chunk, count - i * chunk), length_m) for i in range(workers) if i * chunk < count]
+    with mp.get_context("fork").Pool(len(jobs)) as pool:
+        parts = pool.starmap(gen_frames, jobs)
+    return [f for p in parts for f in p]
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def ncu_traffic():
+    p = os.path.join(ROOT, "profiles", "integrate_traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)).get("dram_bytes_per_launch")
+        except Exception:
+            return None
+    return None
+
+
+# --------------------------------------------------------------------------------------------------
+# CPU oracle leg (cpu_baseline of the own arm and the whole --impl reference arm)
+# --------------------------------------------------------------------------------------------------
+def cpu_run(seed, preroll, warmup, steps, length_m, omp=True):
+    from tests import hostlib as H
+    L = H.oracle()
+    vol = H.HostVolume(NUM_BLOCKS, NUM_BUCKETS, EXCESS, synth.KITTI_W, synth.KITTI_H)
+    frames = gen_frames_parallel(seed, 0, preroll + warmup + steps, length_m, min(8, os.cpu_count() or 1))
+    times, vox = [], 0
+
+    def one(fr):
+        depth, rgb, M, proj = fr
+        v = H.make_view(depth, rgb, M, proj)
+        L.oracle_allocate_from_depth(vol.engine, C.byref(vol.scene), C.byref(vol.rs), C.byref(v), 0, int(omp))
+        L.oracle_integrate(vol.engine, C.byref(vol.scene), C.byref(vol.rs), C.byref(v), int(omp))
+        n = L.oracle_integrated_blocks(vol.engine)
+        cam = H.make_camera(M, proj)
+        L.oracle_expected_depths(C.byref(vol.scene), C.byref(vol.rs), C.byref(cam))
+        L.oracle_icp_maps(C.byref(vol.scene), C.byref(vol.rs), C.byref(v), H.vptr(vol.points), H.vptr(vol.normals), int(omp))
+        L.oracle_decay(vol.engine, C.byref(vol.scene), C.byref(vol.rs), DECAY[0], DECAY[1], 0)
+        return n
+
+    for i, fr in enumerate(frames):
+        t0 = time.perf_counter()
+        n = one(fr)
+        dt = time.perf_counter() - t0
+        if i >= preroll + warmup:
+            times.append(dt)
+            vox += n * 512
+    total = sum(times)
+    return {"fps": len(times) / total if total > 0 else 0.0, "ms_per_step": 1000.0 * total / max(len(times), 1),
+            "mvoxels_per_s": vox / total / 1e6 if total > 0 else 0.0, "cores": L.oracle_num_threads() if omp else 1,
+            "frames": len(times), "preroll": preroll}
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    steps = min(args.steps, 16)
+    r = cpu_run(6, args.ref_preroll, min(args.warmup, 3), steps, 200.0, omp=True)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": r["fps"], "unit": "frames/s", "n_gpus": args.gpus, "steps": steps,
+        "warmup": min(args.warmup, 3), "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "KITTI-odometry-06-shaped 1242x375 static-map fusion+raycast loop (configs[1])",
+                   "voxel_m": 0.05, "mu_m": 0.75, "maxW": 50, "blocks": NUM_BLOCKS, "buckets": NUM_BUCKETS},
+        "mvoxels_per_s": r["mvoxels_per_s"],
+        "cpu_baseline": {"value": r["fps"], "unit": "frames/s", "cores": r["cores"], "kind": "port",
+                         "sample": f"{r['frames']} consecutive frames after a {r['preroll']}-frame CPU pre-roll of the same stream; "
+                                   "oracle/tsdf_oracle.c with OpenMP at the reference's pragma sites (the reference's own _CPU "
+                                   "hash engines are commented out, SURVEY finding 1)"},
+        "e2e": {"value": r["fps"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------------
+# own arm
+# --------------------------------------------------------------------------------------------------
+def run_own(args, rank, local_rank, world):
+    import torch
+    import torch.distributed as dist
+    from dynslam_b200 import abi, engine as E
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    W, H_ = synth.KITTI_W, synth.KITTI_H
+    K, Wm = args.steps, args.warmup
+    n_e2e = args.e2e_steps
+    total_frames = args.preroll + Wm + K + 3 + n_e2e
+    length_m = total_frames * 0.8 + 60.0
+    seed = 6 + rank
+    t_gen = time.perf_counter()
+    frames = gen_frames_parallel(seed, 0, total_frames, length_m, max(1, min(16, (os.cpu_count() or 2) // max(world, 1))))
+    log(f"[rank {rank}] generated {len(frames)} frames in {time.perf_counter() - t_gen:.1f}s")
+
+    stream = torch.cuda.Stream(device=dev)
+    with torch.cuda.stream(stream):
+        scene = E.Scene(E.SceneParams(), NUM_BLOCKS, NUM_BUCKETS, EXCESS, device=f"cuda:{local_rank}")
+        eng = E.Engine(scene, (W, H_), stream=stream.cuda_stream)
+        reco = E.SceneReconstructionEngine(eng)
+        vis = E.VisualisationEngine(eng, scene)
+        rs = vis.CreateRenderState((W, H_))
+        reco.ResetScene(scene)
+        points = torch.zeros(H_ * W * 4, dtype=torch.float32, device=dev)
+        normals = torch.zeros(H_ * W * 4, dtype=torch.float32, device=dev)
+        gather_buf = [torch.zeros(H_ * W * 4, dtype=torch.uint8, device=dev) for _ in range(world)] if (world > 1 and rank == 0) else None
+        flush_buf = torch.zeros(256 * 1024 * 1024 // 4, dtype=torch.int32, device=dev) if args.flush_l2 else None   # 2x the 126 MB L2
+
+        def dev_view(fr):
+            depth, rgb, M, proj = fr
+            d = torch.from_numpy(depth).to(dev, non_blocking=False)
+            c = torch.from_numpy(rgb).to(dev, non_blocking=False)
+            return E.View(d, c, M, proj)
+
+        def step(view):
+            eng.process_frame_async(rs, view, points, normals, decay=DECAY)
+            if world > 1:
+                dist.gather(rs.raycastImage, gather_buf, dst=0)
+
+        # ---- pre-roll: build the map to steady state (untimed set-up) ----
+        idx = 0
+        for _ in range(args.preroll):
+            step(dev_view(frames[idx])); idx += 1
+        eng.sync(rs)
+        views = [dev_view(frames[idx + i]) for i in range(Wm + K + 3)]
+        idx += Wm + K + 3
+        for i in range(Wm):
+            step(views[i])
+        eng.sync(rs)
+        launches0 = eng.stats().launches
+        blocks0 = eng.stats().totalIntegratedBlocks
+        eng.set_timing(2)
+        sampler = ClockSampler(local_rank)
+        sampler.start()
+        time.sleep(0.3)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        flush_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)] if args.flush_l2 else []
+        t0 = time.perf_counter()
+        ev0.record(stream)
+        for i in range(K):
+            if args.flush_l2:       # evict L2 between timed iterations; the flush itself is timed and subtracted
+                flush_ev[i][0].record(stream)
+                flush_buf.add_(1)
+                flush_ev[i][1].record(stream)
+            step(views[Wm + i])
+        ev1.record(stream)
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        wall_ms = (time.perf_counter() - t0) * 1000.0
+        flush_ms = sum(a.elapsed_time(b) for a, b in flush_ev)
+        gpu_ms = ev0.elapsed_time(ev1) - flush_ms
+        wall_ms -= flush_ms
+        eng.sync(rs)
+        st = eng.stats()
+        sampler.stop()
+        clocks = sampler.summary()
+        launches = st.launches - launches0
+        blocks = st.totalIntegratedBlocks - blocks0
+        int_ms, int_n = st.ring_ms_integrate, st.ring_count
+        n_vis = rs.noVisibleBlocks
+        used_blocks = NUM_BLOCKS - 1 - scene.lastFreeBlockId
+        decayed = reco.GetDecayedBlockCount()
+        # per-stage breakdown of a few extra frames (per-frame sync; not part of the timed region)
+        eng.set_timing(1)
+        stage = np.zeros(6)
+        for i in range(3):
+            step(views[Wm + K + i])
+            eng.sync(rs)
+            s = eng.stats()
+            stage += np.array([s.ms_allocate, s.ms_integrate, s.ms_expected, s.ms_raycast, s.ms_decay, s.ms_total])
+        stage /= 3.0
+        eng.set_timing(0)
+
+        # ---- e2e: host buffers -> H2D -> frame -> D2H image, every step ----
+        h_depth = [torch.from_numpy(frames[idx + i][0]).pin_memory() for i in range(n_e2e)]
+        h_rgb = [torch.from_numpy(frames[idx + i][1]).pin_memory() for i in range(n_e2e)]
+        h_out = torch.zeros(H_ * W * 4, dtype=torch.uint8).pin_memory()
+        d_depth_stage = torch.zeros(H_ * W, dtype=torch.float32, device=dev)
+        d_rgb_stage = torch.zeros(H_ * W * 4, dtype=torch.uint8, device=dev)
+        ev = E.View(d_depth_stage.view(H_, W), d_rgb_stage.view(H_, W, 4), frames[idx][2], frames[idx][3])
+        e2e_warm = min(3, n_e2e // 2)
+        t_e2e = 0.0
+        for i in range(n_e2e):
+            if i == e2e_warm:
+                torch.cuda.synchronize(dev)
+                if world > 1:
+                    dist.barrier()
+                t_e2e = time.perf_counter()
+            ev.set_pose(frames[idx + i][2])
+            eng.process_frame_host(rs, ev, h_depth[i], h_rgb[i], d_depth_stage, d_rgb_stage, points, normals, decay=DECAY,
+                                   h_out=h_out)
+            if world > 1:
+                dist.gather(rs.raycastImage, gather_buf, dst=0)
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        t_e2e = time.perf_counter() - t_e2e
+        e2e_frames = n_e2e - e2e_warm
+
+    # ---- reduce over ranks (max time) ----
+    ms = max(gpu_ms, 0.0)
+    if world > 1:
+        t = torch.tensor([ms, wall_ms, t_e2e, float(blocks), float(launches)], dtype=torch.float64, device=dev)
+        tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        ms, wall_ms, t_e2e = float(tmax[0]), float(tmax[1]), float(tmax[2])
+        blocks_all, launches_all = float(tsum[3]), float(tsum[4])
+    else:
+        blocks_all, launches_all = float(blocks), float(launches)
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    fps = world * K / (ms / 1000.0)
+    mvox = blocks_all * 512 / (ms / 1000.0) / 1e6
+    peak, peak_src = peaks()
+    alg_bytes = blocks * BYTES_PER_BLOCK + int_n * W * H_ * 8
+    achieved = alg_bytes / (int_ms / 1000.0) / 1e9 if int_ms > 0 else 0.0
+    footprint_mb = (n_vis * 4096 * 2 + (NUM_BUCKETS + EXCESS) * 21 + W * H_ * (8 + 8 + 16 + 4 + 32)) / 1e6
+
+    cpu = None
+    if world == 1 or rank == 0:
+        try:
+            c = cpu_run(6, args.cpu_preroll, 1, args.cpu_steps, 120.0, omp=True)
+            cpu = {"value": c["fps"], "unit": "frames/s", "cores": c["cores"], "kind": "port",
+                   "sample": f"{c['frames']} frames after a {c['preroll']}-frame CPU pre-roll of the same stream (smaller map than "
+                             f"the GPU's {args.preroll}-frame pre-roll, which favours the CPU); {c['mvoxels_per_s']:.1f} Mvoxels/s",
+                   "ms_per_step": c["ms_per_step"]}
+        except Exception as ex:  # the baseline is reported, never required for the GPU numbers
+            cpu = {"value": None, "unit": "frames/s", "cores": 0, "kind": "port", "sample": f"failed: {ex}"}
+
+    line = {
+        "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": Wm,
+        "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": "KITTI-odometry-06-shaped 1242x375 static-map fusion+raycast loop (configs[1]); one volume per GPU",
+                   "voxel_m": 0.05, "mu_m": 0.75, "maxW": 50, "blocks": NUM_BLOCKS, "buckets": NUM_BUCKETS, "excess": EXCESS,
+                   "decay": {"maxWeight": DECAY[0], "minAge": DECAY[1]}, "preroll_frames": args.preroll,
+                   "l2": (f"explicit flush between timed steps (256 MB read-modify-write, timed with CUDA events and subtracted, "
+                          f"{flush_ms / max(K, 1) * 1000:.0f} us each); per-step footprint ~{footprint_mb:.0f} MB") if args.flush_l2 else
+                         f"no flush (--no-flush-l2): per-step footprint ~{footprint_mb:.0f} MB, consecutive frames reuse L2",
+                   "integrate_impl": os.environ.get("B200_INTEGRATE_IMPL", "ldg"),
+                   "parallelism": f"{world} independent volume(s), NCCL gather of raycast images to rank 0" if world > 1 else "1 volume"},
+        "mvoxels_per_s": mvox, "visible_blocks": n_vis, "allocated_blocks": used_blocks, "decayed_blocks": int(decayed),
+        "wall_ms_per_step": wall_ms / K,
+        "stage_ms": {"allocate": stage[0], "integrate": stage[1], "expected_depths": stage[2], "raycast_icp": stage[3],
+                     "decay": stage[4], "total": stage[5]},
+        "roofline": {"kernel": "k_integrate_" + os.environ.get("B200_INTEGRATE_IMPL", "ldg"), "bound": "hbm", "achieved": achieved,
+                     "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None, "traffic": ncu_traffic(),
+                     "peak_source": peak_src, "launches_timed": int_n, "mean_launch_us": 1000.0 * int_ms / max(int_n, 1),
+                     "alg_bytes_per_launch": alg_bytes / max(int_n, 1)},
+        "cpu_baseline": cpu,
+        "e2e": {"value": world * e2e_frames / t_e2e, "unit": "frames/s", "h2d_bytes_per_step": W * H_ * 8,
+                "d2h_bytes_per_step": W * H_ * 4, "steps": e2e_frames},
+        "gpu_launches": int(launches_all),
+        "clocks": clocks,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="own", choices=["own", "reference"])
+    ap.add_argument("--preroll", type=int, default=230, help="untimed frames that build the map (> decay minAge)")
+    ap.add_argument("--e2e-steps", type=int, default=23)
+    ap.add_argument("--flush-l2", dest="flush_l2", action="store_true", default=True)
+    ap.add_argument("--no-flush-l2", dest="flush_l2", action="store_false")
+    ap.add_argument("--cpu-steps", type=int, default=6)
+    ap.add_argument("--cpu-preroll", type=int, default=12)
+    ap.add_argument("--ref-preroll", type=int, default=12)
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_own(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

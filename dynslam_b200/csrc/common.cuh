@@ -100,6 +100,7 @@ struct DevCounters {
   int noFwdMissing;
   long long ringHead;      // device-side bump cursor of the decay ring (items)
   long long totalDecayed;  // GetDecayedBlockCount, Reco_CUDA.cu:563-566
+  long long totalIntegrated; // cumulative blocks integrated (never reset; bench reads deltas)
 };
 
 // ---- chained-scan (decoupled look-back) for ordered compaction --------------------------------

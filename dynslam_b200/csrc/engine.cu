@@ -154,7 +154,16 @@ const char *b200_last_error(const b200_engine *e) { return e ? e->err : "null en
 void *b200_engine_stream(b200_engine *e) { return (void *)e->stream; }
 int32_t b200_frame_index(const b200_engine *e) { return e->frameIdx; }
 size_t b200_decayed_block_count(const b200_engine *e) { return (size_t)e->totalDecayed; }
-void b200_set_timing(b200_engine *e, int enabled) { e->timing = enabled != 0; }
+void b200_set_timing(b200_engine *e, int mode) {
+  e->timing = mode != 0;
+  e->evRingCount = 0;
+  if (mode >= 2 && !e->evRing) {
+    e->evRingCap = 8192;
+    e->evRing = (cudaEvent_t *)calloc((size_t)e->evRingCap * 2, sizeof(cudaEvent_t));
+    for (int i = 0; i < e->evRingCap * 2; ++i) cudaEventCreate(&e->evRing[i]);
+  }
+  e->timingMode = mode;
+}
 
 // Matrix4::inv — OR/Matrix.h:162-224
 int b200_mat4_inv(const float *m, float *dst) {
@@ -393,7 +402,10 @@ b200_status b200_process_frame_async(b200_engine *e, b200_scene *s, b200_render_
   CK(cudaMemsetAsync(&e->d_ctr->noIntegrated, 0, sizeof(int), e->stream));
   SceneRef r = scene_ref(s, rs);
   FrameGeom g = frame_geom(s, v);
+  const bool ring = e->timingMode >= 2 && e->evRingCount < e->evRingCap;
+  if (ring) CK(cudaEventRecord(e->evRing[2 * e->evRingCount], e->stream));
   launch_integrate(e, r, g, v->d_depth, v->d_rgb);
+  if (ring) { CK(cudaEventRecord(e->evRing[2 * e->evRingCount + 1], e->stream)); e->evRingCount++; }
   if (e->timing) CK(cudaEventRecord(e->ev[2], e->stream));
   if (!opts || opts->doRaycast) {
     launch_expected_depths(e, r, g.M_d, g.proj_d, rs->img_w, rs->img_h, s->voxelSize, rs->d_minmax);
@@ -433,7 +445,14 @@ b200_status b200_get_stats(b200_engine *e, b200_frame_stats *out) {
   out->launches = e->launches;
   out->noVisibleBlocks = e->h_ctr->noVisibleBlocks;
   out->noIntegratedBlocks = e->h_ctr->noIntegrated;
-  if (e->timing) {
+  out->totalIntegratedBlocks = e->h_ctr->totalIntegrated;
+  if (e->timingMode >= 2 && e->evRingCount > 0) {
+    CK(cudaEventSynchronize(e->evRing[2 * e->evRingCount - 1]));
+    float sum = 0;
+    for (int i = 0; i < e->evRingCount; ++i) { float ms = 0; cudaEventElapsedTime(&ms, e->evRing[2 * i], e->evRing[2 * i + 1]); sum += ms; }
+    out->ring_ms_integrate = sum; out->ring_count = e->evRingCount;
+  }
+  if (e->timing && e->timingMode != 0 && e->frameIdx > 0) {
     CK(cudaEventSynchronize(e->ev[5]));
     cudaEventElapsedTime(&out->ms_allocate, e->ev[0], e->ev[1]);
     cudaEventElapsedTime(&out->ms_integrate, e->ev[1], e->ev[2]);

@@ -61,6 +61,8 @@ struct b200_engine {
   // timing / stats
   bool timing;
   cudaEvent_t ev[8];
+  cudaEvent_t *evRing;                // timing mode 2: event pairs around every integrate launch
+  int evRingCap, evRingCount, timingMode;
   long long launches;
   int lastNoIntegrated;
   int integrateImpl;                  // 0 = LDG variant, 1 = TMA bulk-copy variant (env B200_INTEGRATE_IMPL=ldg|tma)

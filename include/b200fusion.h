@@ -254,9 +254,14 @@ typedef struct {
   float ms_allocate, ms_integrate, ms_expected, ms_raycast, ms_decay, ms_total;
   int64_t launches;            /* kernels launched by this engine since creation */
   int32_t noVisibleBlocks, noIntegratedBlocks;
+  /* timing mode 2: CUDA-event pairs around EVERY IntegrateIntoScene launch since the mode was set */
+  float ring_ms_integrate;     /* sum of the launch durations */
+  int32_t ring_count;          /* number of launches measured */
+  int64_t totalIntegratedBlocks; /* cumulative blocks integrated since engine creation */
 } b200_frame_stats;
 
-/* enable per-stage CUDA-event timing (adds events to the stream; off by default) */
+/* 0 = off; 1 = per-stage CUDA events of the last fused frame; 2 = 1 + an event pair around every
+   integrate launch (ring of 8192 frames), reset whenever the mode is set */
 void b200_set_timing(b200_engine *e, int enabled);
 b200_status b200_get_stats(b200_engine *e, b200_frame_stats *out);
 
