@@ -335,7 +335,7 @@ def run_own(args, rank, local_rank, world):
     footprint_mb = (n_vis * 4096 * 2 + (NUM_BUCKETS + EXCESS) * 21 + W * H_ * (8 + 8 + 16 + 4 + 32)) / 1e6
 
     cpu = None
-    if world == 1 or rank == 0:
+    if args.cpu_steps > 0:
         try:
             c = cpu_run(6, args.cpu_preroll, 1, args.cpu_steps, 120.0, omp=True)
             cpu = {"value": c["fps"], "unit": "frames/s", "cores": c["cores"], "kind": "port",

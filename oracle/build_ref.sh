@@ -5,6 +5,7 @@
 # buildHashAllocAndVisibleTypePP is declared device-only (DA/ITMSceneReconstructionEngine.h:176).
 # No contraction / fast-math so the reference code is evaluated in plain IEEE binary32.
 set -e
+HERE_EARLY=1
 REF=${REF:-/root/reference/src/InfiniTAM/InfiniTAM}
 HERE="$(cd "$(dirname "$0")" && pwd)"
 if [ ! -d "$REF/ITMLib" ]; then echo "reference not present at $REF; keeping prebuilt oracle/_ref" >&2; exit 0; fi
@@ -13,3 +14,33 @@ mkdir -p "$HERE/_ref"
     -DCOMPILE_WITHOUT_CUDA -D__device__= -I"$REF" \
     -o "$HERE/_ref/libitmref.so" "$HERE/ref_driver.cpp"
 echo "built $HERE/_ref/libitmref.so"
+
+# ---- reference CUDA build + ITMLib harness (oracle/_ref/libitmharness.so) -------------------------
+# The reference's own CUDA engines, unmodified, compiled per-TU for sm_100a with the reference's
+# flags (--use_fast_math, ITMLib/CMakeLists.txt:226-230) directly from /root/reference, plus the few
+# host TUs they need, plus oracle/itm_harness.cpp which drives them (and the B200 shim) through the
+# real ITMLib interfaces. libb200fusion.so must already be built (python __graft_entry__.py).
+NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
+LIBB200="$HERE/../dynslam_b200/csrc/libb200fusion.so"
+if [ ! -f "$LIBB200" ]; then echo "libb200fusion.so missing; skipping harness" >&2; exit 0; fi
+OBJ="$HERE/_ref/obj"; mkdir -p "$OBJ"
+CU="ITMLib/Engine/DeviceSpecific/CUDA/ITMSceneReconstructionEngine_CUDA.cu ITMLib/Engine/DeviceSpecific/CUDA/ITMVisualisationEngine_CUDA.cu ITMLib/Engine/DeviceSpecific/CUDA/ITMMeshingEngine_CUDA.cu"
+CPP="ITMLib/Utils/ITMLibSettings.cpp ITMLib/Objects/ITMPose.cpp ITMLib/Engine/ITMVisualisationEngine.cpp ORUtils/CUDADefines.cpp"
+pids=""
+for f in $CU; do
+  o="$OBJ/$(basename $f .cu).o"
+  if [ ! -f "$o" ] || [ "$REF/$f" -nt "$o" ]; then
+    $NVCC -std=c++14 -gencode arch=compute_100a,code=sm_100a --use_fast_math -O3 -w -Xcompiler -fPIC -ccbin /usr/bin/g++ -I"$REF" -c "$REF/$f" -o "$o" &
+    pids="$pids $!"
+  fi
+done
+for f in $CPP; do
+  o="$OBJ/$(basename $f .cpp).o"
+  if [ ! -f "$o" ]; then /usr/bin/g++ -std=c++14 -O2 -w -fPIC -I"$REF" -I/usr/local/cuda/include -c "$REF/$f" -o "$o" & pids="$pids $!"; fi
+done
+for p in $pids; do wait $p; done
+/usr/bin/g++ -std=c++14 -O2 -w -fPIC -I"$REF" -I/usr/local/cuda/include -I"$HERE/../include" -I"$HERE/../dynslam_b200/itm_shim" \
+    -c "$HERE/itm_harness.cpp" -o "$OBJ/itm_harness.o"
+$NVCC -shared -o "$HERE/_ref/libitmharness.so" "$OBJ"/*.o -ccbin /usr/bin/g++ -Xlinker -rpath -Xlinker '$ORIGIN/../../dynslam_b200/csrc' \
+    -L"$HERE/../dynslam_b200/csrc" -lb200fusion -lcudart 2>&1 | grep -v "deprecated" || true
+echo "built $HERE/_ref/libitmharness.so"

@@ -1,0 +1,150 @@
+// itm_harness.cpp — TEST / BASELINE INFRASTRUCTURE. Headless driver of the REAL ITMLib objects
+// (ITMScene, ITMRenderState_VH, ITMView, ITMTrackingState) through the abstract engine interfaces,
+// with either back-end behind them:
+//   impl 0: the UNMODIFIED reference CUDA engines (ITMSceneReconstructionEngine_CUDA /
+//           ITMVisualisationEngine_CUDA), compiled for sm_100a from the sources where they lie under
+//           /root/reference — the "reference CUDA build" that north_star's >=10x is measured against;
+//   impl 1: the B200 shim classes (dynslam_b200/itm_shim/ITMEngines_B200.h) over libb200fusion.
+// The call sequence per frame is the reference's own: ITMDenseMapper::ProcessFrame
+// (Engine/ITMDenseMapper.cpp:53-69), ITMTrackingController::Prepare (Engine/ITMTrackingController.cpp:23-51)
+// and ITMDenseMapper::Decay (:78-86), i.e. what InfiniTamDriver::Integrate / PrepareNextStep / Decay
+// run (DS/InfiniTamDriver.h:137-158, :201-206). View building is outside the path:
+// the float depth and RGBA frames are copied straight into the ITMView images.
+// Built by oracle/build_ref.sh into oracle/_ref/libitmharness.so (git-ignored, ships via gpurun).
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <stdexcept>
+#include <unistd.h>
+#include <fcntl.h>
+
+#include "ITMLib/Engine/DeviceSpecific/CUDA/ITMSceneReconstructionEngine_CUDA.h"
+#include "ITMLib/Engine/DeviceSpecific/CUDA/ITMVisualisationEngine_CUDA.h"
+#include "ITMLib/Objects/ITMRGBDCalib.h"
+#include "ITMLib/Objects/ITMTrackingState.h"
+#include "ITMLib/Objects/ITMView.h"
+#include "ITMLib/Utils/ITMLibSettings.h"
+
+#include "ITMEngines_B200.h"
+
+using namespace ITMLib::Engine;
+using namespace ITMLib::Objects;
+
+struct Harness {
+  int impl;
+  ITMLibSettings *settings;
+  ITMScene<ITMVoxel, ITMVoxelIndex> *scene;
+  ITMSceneReconstructionEngine<ITMVoxel, ITMVoxelIndex> *reco;
+  IITMVisualisationEngine *vis;
+  ITMRenderState *renderState;
+  ITMRGBDCalib calib;
+  ITMView *view;
+  ITMTrackingState *trackingState;
+  Vector2i imgSize;
+  std::shared_ptr<B200EngineHandle> handle;
+  int savedStdout;
+  char err[256];
+};
+
+extern "C" {
+
+// stdout of the reference is chatty (two printf lines per frame, Reco_CUDA.cu:338-346, :546-559);
+// it is part of the reference's cost but must not pollute a caller that prints JSON on stdout.
+void harness_mute_stdout(Harness *H, int mute) {
+  fflush(stdout);
+  if (mute && H->savedStdout < 0) {
+    H->savedStdout = dup(1);
+    int nul = open("/dev/null", O_WRONLY);
+    dup2(nul, 1);
+    close(nul);
+  } else if (!mute && H->savedStdout >= 0) {
+    dup2(H->savedStdout, 1);
+    close(H->savedStdout);
+    H->savedStdout = -1;
+  }
+}
+
+Harness *harness_create(int impl, int w, int h, float fx, float fy, float cx, float cy, float voxelSize, float mu, int maxW,
+                        long numBlocks) {
+  Harness *H = new Harness();
+  H->impl = impl; H->savedStdout = -1; H->err[0] = 0;
+  H->imgSize = Vector2i(w, h);
+  H->settings = new ITMLibSettings();
+  H->settings->sceneParams.voxelSize = voxelSize;
+  H->settings->sceneParams.mu = mu;
+  H->settings->sceneParams.maxW = maxW;
+  H->settings->sdfLocalBlockNum = numBlocks;
+  H->calib.intrinsics_d.SetFrom(fx, fy, cx, cy, (float)w, (float)h);
+  H->calib.intrinsics_rgb.SetFrom(fx, fy, cx, cy, (float)w, (float)h);
+  H->scene = new ITMScene<ITMVoxel, ITMVoxelIndex>(&H->settings->sceneParams, false, MEMORYDEVICE_CUDA, numBlocks);
+  if (impl == 0) {
+    H->reco = new ITMSceneReconstructionEngine_CUDA<ITMVoxel, ITMVoxelIndex>(numBlocks);
+    H->vis = new ITMVisualisationEngine_CUDA<ITMVoxel, ITMVoxelIndex>(H->scene, H->settings);
+  } else {
+    H->handle = std::make_shared<B200EngineHandle>(0, numBlocks, H->imgSize);
+    H->reco = new ITMSceneReconstructionEngine_B200<ITMVoxel, ITMVoxelIndex>(H->handle);
+    H->vis = new ITMVisualisationEngine_B200<ITMVoxel, ITMVoxelIndex>(H->scene, H->settings, H->handle);
+  }
+  H->renderState = H->vis->CreateRenderState(H->imgSize);
+  H->view = new ITMView(&H->calib, H->imgSize, H->imgSize, true);
+  H->trackingState = new ITMTrackingState(H->imgSize, MEMORYDEVICE_CUDA);
+  H->reco->ResetScene(H->scene);
+  return H;
+}
+
+void harness_destroy(Harness *H) {
+  harness_mute_stdout(H, 0);
+  delete H->trackingState; delete H->view; delete H->renderState; delete H->vis; delete H->reco; delete H->scene; delete H->settings;
+  delete H;
+}
+
+const char *harness_error(Harness *H) { return H->err; }
+
+// One frame: H2D of the frame into the ITMView, then the reference's call sequence.
+// Returns 0, or 2 when the engine threw std::runtime_error (VBA / excess exhaustion).
+int harness_process_frame(Harness *H, const float *depth, const unsigned char *rgba, const float *M_d, int decayMaxWeight,
+                          int decayMinAge, int doDecay, int doRaycast) {
+  const size_t n = (size_t)H->imgSize.x * H->imgSize.y;
+  ORcudaSafeCall(cudaMemcpy(H->view->depth->GetData(MEMORYDEVICE_CUDA), depth, n * sizeof(float), cudaMemcpyHostToDevice));
+  ORcudaSafeCall(cudaMemcpy(H->view->rgb->GetData(MEMORYDEVICE_CUDA), rgba, n * 4, cudaMemcpyHostToDevice));
+  Matrix4f M; for (int i = 0; i < 16; ++i) M.m[i] = M_d[i];
+  H->trackingState->pose_d->SetM(M);
+  H->trackingState->requiresFullRendering = true;            // useApproximateRaycast == false (ITMLibSettings.cpp:58)
+  try {
+    H->reco->AllocateSceneFromDepth(H->scene, H->view, H->trackingState, H->renderState);
+    H->reco->IntegrateIntoScene(H->scene, H->view, H->trackingState, H->renderState);
+    if (doRaycast) {
+      H->vis->CreateExpectedDepths(H->trackingState->pose_d, &(H->view->calib->intrinsics_d), H->renderState);
+      H->vis->CreateICPMaps(H->view, H->trackingState, H->renderState);
+      H->trackingState->pose_pointCloud->SetFrom(H->trackingState->pose_d);
+    }
+    if (doDecay) H->reco->Decay(H->scene, H->renderState, decayMaxWeight, decayMinAge, false);
+  } catch (std::runtime_error &e) {
+    snprintf(H->err, sizeof(H->err), "%s", e.what());
+    return 2;
+  }
+  return 0;
+}
+
+void harness_sync(Harness *H) { ORcudaSafeCall(cudaDeviceSynchronize()); }
+
+void harness_counters(Harness *H, int *lastFreeBlockId, int *lastFreeExcess, int *noVisible, long *decayed) {
+  *lastFreeBlockId = H->scene->localVBA.lastFreeBlockId;
+  *lastFreeExcess = H->scene->index.GetLastFreeExcessListId();
+  *noVisible = ((ITMRenderState_VH *)H->renderState)->noVisibleBlocks;
+  *decayed = (long)H->reco->GetDecayedBlockCount();
+}
+
+int harness_table_entries(void) { return ITMVoxelBlockHash::noTotalEntries; }
+
+// device -> host copies for order-free comparisons
+void harness_download(Harness *H, void *hashOut, void *voxelsOut, void *rayOut, void *imgOut) {
+  ORcudaSafeCall(cudaDeviceSynchronize());
+  if (hashOut) ORcudaSafeCall(cudaMemcpy(hashOut, H->scene->index.GetEntries(), sizeof(ITMHashEntry) * (size_t)ITMVoxelBlockHash::noTotalEntries, cudaMemcpyDeviceToHost));
+  if (voxelsOut) ORcudaSafeCall(cudaMemcpy(voxelsOut, H->scene->localVBA.GetVoxelBlocks(), sizeof(ITMVoxel) * (size_t)H->scene->localVBA.allocatedSize, cudaMemcpyDeviceToHost));
+  const size_t n = (size_t)H->imgSize.x * H->imgSize.y;
+  if (rayOut) ORcudaSafeCall(cudaMemcpy(rayOut, H->renderState->raycastResult->GetData(MEMORYDEVICE_CUDA), n * sizeof(Vector4f), cudaMemcpyDeviceToHost));
+  if (imgOut) ORcudaSafeCall(cudaMemcpy(imgOut, H->renderState->raycastImage->GetData(MEMORYDEVICE_CUDA), n * 4, cudaMemcpyDeviceToHost));
+}
+
+}  // extern "C"

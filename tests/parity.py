@@ -5,6 +5,8 @@ oracle and compares EVERY piece of state after every stage, bit for bit:
 hash table, visibility bytes, visible list, counters, free lists, the whole voxel block array,
 min/max image, ray points, ICP maps and the grey raycast image."""
 import ctypes as C
+import json
+import os
 
 import numpy as np
 import torch
@@ -143,3 +145,90 @@ def run_smoke():
     pair, _ = run_sequence(cfg)
     assert pair.rs.noVisibleBlocks > 100
     return pair
+
+
+# ---- golden fixtures (tests/golden/) -----------------------------------------------------------
+import hashlib
+
+
+def _sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()[:32]
+
+
+GOLDEN_CFG = dict(scale=0.25, frames=6, frame_step=2, numBlocks=16384, numBuckets=0x1000, excessSize=0x2000, decay=(3, 2))
+
+
+def state_digests(hash_, visType, visiblePos, voxels, allocationList, minmax, rays, image, points, normals, counters):
+    d = {f"hash.{f}": _sha(hash_[f]) for f in ("pos", "offset", "ptr", "allocatedTime")}
+    d.update(visType=_sha(visType), visiblePos=_sha(visiblePos), voxels=_sha(voxels), allocationList=_sha(allocationList),
+             minmax=_sha(minmax), raycastResult=_sha(rays), raycastImage=_sha(image), points=_sha(points), normals=_sha(normals),
+             counters=[int(c) for c in counters])
+    return d
+
+
+def oracle_sequence_digests(cfg, ref_check=False):
+    """Per-frame digests of the oracle's state on the golden sequence. With ref_check=True every frame's marking,
+    integration of all visible blocks, raycast and ICP output is also recomputed with the reference's own functions
+    (oracle/_ref/libitmref.so) and must be identical — that is what certifies the fixture."""
+    L = H.oracle()
+    w, h = int(round(synth.KITTI_W * cfg.scale)), int(round(synth.KITTI_H * cfg.scale))
+    vol = H.HostVolume(cfg.numBlocks, cfg.numBuckets, cfg.excessSize, w, h,
+                       H.SceneParams(cfg.voxelSize, cfg.mu, cfg.maxW, cfg.vf_min, cfg.vf_max, int(cfg.stopMaxW)))
+    out = []
+    for i, (depth, rgb, M, proj) in enumerate(frames_of(cfg)):
+        hv = H.make_view(depth, rgb, M, proj, depthWeighting=int(cfg.depthWeighting))
+        cam = H.make_camera(M, proj)
+        assert L.oracle_allocate_from_depth(vol.engine, C.byref(vol.scene), C.byref(vol.rs), C.byref(hv), 0, 0) == 0
+        pre = vol.voxels.copy() if ref_check else None
+        L.oracle_integrate(vol.engine, C.byref(vol.scene), C.byref(vol.rs), C.byref(hv), 0)
+        if ref_check:
+            R = H.ref()
+            for p in vol.visiblePos[:vol.rs.noVisibleBlocks]:
+                idx = L.oracle_find_block(H.vptr(vol.hash), cfg.numBuckets, int(p[0]), int(p[1]), int(p[2]))
+                if idx < 0:
+                    continue
+                ptr = int(vol.hash[idx]["ptr"])
+                blk = pre[ptr * 512:(ptr + 1) * 512].copy()
+                pos = np.array(p, dtype=np.int16)
+                R.ref_integrate_block(H.vptr(blk), H.vptr(pos), C.byref(vol.scene), C.byref(hv))
+                assert blk.tobytes() == vol.voxels[ptr * 512:(ptr + 1) * 512].tobytes()
+        L.oracle_expected_depths(C.byref(vol.scene), C.byref(vol.rs), C.byref(cam))
+        L.oracle_icp_maps(C.byref(vol.scene), C.byref(vol.rs), C.byref(hv), H.vptr(vol.points), H.vptr(vol.normals), 0)
+        if ref_check and cfg.numBuckets == 0x100000:
+            pass
+        d = state_digests(vol.hash, vol.visType, vol.visiblePos[:vol.rs.noVisibleBlocks], vol.voxels, vol.allocationList,
+                          vol.minmax, vol.raycastResult, vol.raycastImage, vol.points, vol.normals,
+                          (vol.scene.lastFreeBlockId, vol.scene.lastFreeExcessListId, vol.rs.noVisibleBlocks))
+        if cfg.decay is not None:
+            L.oracle_decay(vol.engine, C.byref(vol.scene), C.byref(vol.rs), cfg.decay[0], cfg.decay[1], 0)
+            d["after_decay"] = {"hash.ptr": _sha(vol.hash["ptr"]), "hash.offset": _sha(vol.hash["offset"]), "voxels": _sha(vol.voxels),
+                                "allocationList": _sha(vol.allocationList), "visType": _sha(vol.visType),
+                                "lastFreeBlockId": int(vol.scene.lastFreeBlockId),
+                                "decayed": int(L.oracle_decayed_block_count(vol.engine))}
+        out.append(d)
+    return out
+
+
+def gpu_sequence_digests(cfg, device="cuda:0"):
+    pair = Pair(cfg, device)
+    out = []
+    for i, (depth, rgb, M, proj) in enumerate(frames_of(cfg)):
+        gv = E.View(torch.from_numpy(depth).to(pair.scene.device), torch.from_numpy(rgb).to(pair.scene.device), M, proj,
+                    depthWeighting=cfg.depthWeighting)
+        pair.reco.AllocateSceneFromDepth(pair.scene, gv, pair.rs)
+        pair.reco.IntegrateIntoScene(pair.scene, gv, pair.rs)
+        pair.vis.CreateExpectedDepths(E.make_camera(M, proj), pair.rs)
+        pair.vis.CreateICPMaps(gv, pair.rs, pair.points, pair.normals)
+        g, r = pair.scene.to_host(), pair.rs.to_host()
+        d = state_digests(g["hash"], r["visType"], r["visiblePos"], g["voxels"], g["allocationList"],
+                          pair.rs.renderingRangeImage.cpu().numpy(), pair.rs.raycastResult.cpu().numpy(),
+                          pair.rs.raycastImage.cpu().numpy(), pair.points.cpu().numpy(), pair.normals.cpu().numpy(),
+                          (g["lastFreeBlockId"], g["lastFreeExcessListId"], r["noVisibleBlocks"]))
+        if cfg.decay is not None:
+            pair.reco.Decay(pair.scene, pair.rs, cfg.decay[0], cfg.decay[1], False)
+            g, r = pair.scene.to_host(), pair.rs.to_host()
+            d["after_decay"] = {"hash.ptr": _sha(g["hash"]["ptr"]), "hash.offset": _sha(g["hash"]["offset"]), "voxels": _sha(g["voxels"]),
+                                "allocationList": _sha(g["allocationList"]), "visType": _sha(r["visType"]),
+                                "lastFreeBlockId": int(g["lastFreeBlockId"]), "decayed": int(pair.reco.GetDecayedBlockCount())}
+        out.append(d)
+    return out
