@@ -53,7 +53,7 @@ class ClockSampler(threading.Thread):
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "20",
                                           "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             for line in self.proc.stdout:
                 if self.stop_flag:
@@ -183,6 +183,39 @@ def run_reference(args, rank, world):
 
 
 # --------------------------------------------------------------------------------------------------
+# the same stream through the REAL ITMLib objects (oracle/itm_harness.cpp): unmodified reference CUDA
+# engines built for sm_100a vs. the B200 shim classes; pinned H2D of every frame inside the timing
+# --------------------------------------------------------------------------------------------------
+def run_itm_harness(frames, preroll, timed):
+    import torch
+    from tests import harnesslib as HL
+    if not HL.available():
+        return {"error": "oracle/_ref/libitmharness.so not built"}
+    n = min(len(frames), preroll + timed)
+    pinned = [(torch.from_numpy(f[0]).pin_memory(), torch.from_numpy(f[1]).pin_memory()) for f in frames[:n]]
+    out = {}
+    for name, impl in (("reference_cuda_build", HL.REFERENCE_CUDA), ("b200_itm_shim", HL.B200_SHIM)):
+        hs = HL.Harness(impl, synth.KITTI_W, synth.KITTI_H, frames[0][3], numBlocks=NUM_BLOCKS)
+        t0 = 0.0
+        for i in range(n):
+            if i == preroll:
+                hs.sync()
+                t0 = time.perf_counter()
+            hs.process_frame(pinned[i][0].numpy(), pinned[i][1].numpy(), frames[i][2], decay=DECAY)
+        hs.sync()
+        dt = time.perf_counter() - t0
+        c = hs.counters()
+        hs.close()
+        out[name] = {"value": (n - preroll) / dt, "unit": "frames/s", "ms_per_step": 1000.0 * dt / (n - preroll),
+                     "visible_blocks": c["noVisibleBlocks"], "frames": n - preroll}
+    out["what"] = ("per frame: pinned H2D of depth+RGB into the ITMView, then AllocateSceneFromDepth, IntegrateIntoScene, "
+                   "CreateExpectedDepths, CreateICPMaps, Decay through the abstract ITMLib interfaces (synchronous, as DynSLAM "
+                   f"calls them); {preroll}-frame pre-roll; reference = unmodified CUDA engines, nvcc sm_100a --use_fast_math")
+    out["speedup_shim_vs_reference_cuda"] = out["b200_itm_shim"]["value"] / out["reference_cuda_build"]["value"]
+    return out
+
+
+# --------------------------------------------------------------------------------------------------
 # own arm
 # --------------------------------------------------------------------------------------------------
 def run_own(args, rank, local_rank, world):
@@ -228,6 +261,8 @@ def run_own(args, rank, local_rank, world):
             if world > 1:
                 dist.gather(rs.raycastImage, gather_buf, dst=0)
 
+        sampler = ClockSampler(local_rank)
+        sampler.start()
         # ---- pre-roll: build the map to steady state (untimed set-up) ----
         idx = 0
         for _ in range(args.preroll):
@@ -241,9 +276,7 @@ def run_own(args, rank, local_rank, world):
         launches0 = eng.stats().launches
         blocks0 = eng.stats().totalIntegratedBlocks
         eng.set_timing(2)
-        sampler = ClockSampler(local_rank)
-        sampler.start()
-        time.sleep(0.3)
+        clk_first = len(sampler.rows)
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(dev)
@@ -267,8 +300,12 @@ def run_own(args, rank, local_rank, world):
         wall_ms -= flush_ms
         eng.sync(rs)
         st = eng.stats()
+        time.sleep(0.05)
         sampler.stop()
+        clk_all = len(sampler.rows)
+        sampler.rows = sampler.rows[max(clk_first - 1, 0):] or sampler.rows   # samples taken during the timed region
         clocks = sampler.summary()
+        clocks["samples_since_start"] = clk_all
         launches = st.launches - launches0
         blocks = st.totalIntegratedBlocks - blocks0
         int_ms, int_n = st.ring_ms_integrate, st.ring_count
@@ -345,6 +382,13 @@ def run_own(args, rank, local_rank, world):
         except Exception as ex:  # the baseline is reported, never required for the GPU numbers
             cpu = {"value": None, "unit": "frames/s", "cores": 0, "kind": "port", "sample": f"failed: {ex}"}
 
+    itm = None
+    if world == 1 and args.harness_frames > 0:
+        try:
+            itm = run_itm_harness(frames, args.harness_preroll, args.harness_frames)
+        except Exception as ex:
+            itm = {"error": str(ex)}
+
     line = {
         "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": Wm,
         "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
@@ -366,6 +410,7 @@ def run_own(args, rank, local_rank, world):
                      "peak_source": peak_src, "launches_timed": int_n, "mean_launch_us": 1000.0 * int_ms / max(int_n, 1),
                      "alg_bytes_per_launch": alg_bytes / max(int_n, 1)},
         "cpu_baseline": cpu,
+        "itmlib_harness": itm,
         "e2e": {"value": world * e2e_frames / t_e2e, "unit": "frames/s", "h2d_bytes_per_step": W * H_ * 8,
                 "d2h_bytes_per_step": W * H_ * 4, "steps": e2e_frames},
         "gpu_launches": int(launches_all),
@@ -379,7 +424,7 @@ def run_own(args, rank, local_rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--steps", type=int, default=400)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
     ap.add_argument("--preroll", type=int, default=230, help="untimed frames that build the map (> decay minAge)")
@@ -387,6 +432,8 @@ def main():
     ap.add_argument("--flush-l2", dest="flush_l2", action="store_true", default=True)
     ap.add_argument("--no-flush-l2", dest="flush_l2", action="store_false")
     ap.add_argument("--cpu-steps", type=int, default=6)
+    ap.add_argument("--harness-frames", type=int, default=100, help="frames timed through the real ITMLib objects (0 = skip)")
+    ap.add_argument("--harness-preroll", type=int, default=60)
     ap.add_argument("--cpu-preroll", type=int, default=12)
     ap.add_argument("--ref-preroll", type=int, default=12)
     args = ap.parse_args()

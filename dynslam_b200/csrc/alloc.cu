@@ -142,29 +142,48 @@ k_mark(const float *__restrict__ depth, const b200_hash_entry *__restrict__ tabl
 }
 
 // ------------------------------------------------------------------------------------------------
-// request ranking: exclusive prefix of popcounts over the bitmap words (one CTA, 1024 threads)
+// request ranking: exclusive prefix of popcounts over a bitmap (ordered, multi-CTA chained scan;
+// 1024 words = 32768 entries per tile, 128-bit loads). WHICH 0: all requests, 1: excess requests.
+// The second pass also commits the counters (every request decrements, served or not, :833, :857-858).
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024)
-k_request_scan(const unsigned *reqBits, const unsigned *req2Bits, unsigned *reqPrefix, unsigned *req2Prefix, int noWords,
-               DevCounters *ctr) {
+#define BMP_TILE 1024
+template <int WHICH>
+__global__ void __launch_bounds__(256)
+k_bitmap_prefix(const unsigned *__restrict__ bits, unsigned *prefix, int noWords, DevCounters *ctr, unsigned long long *scanDesc,
+                unsigned gen) {
   __shared__ unsigned sm[33];
-  const int per = (noWords + blockDim.x - 1) / blockDim.x;
-  const int beg = min(threadIdx.x * per, noWords), end = min(beg + per, noWords);
-  unsigned c1 = 0, c2 = 0;
-  for (int i = beg; i < end; ++i) { c1 += __popc(reqBits[i]); c2 += __popc(req2Bits[i]); }
-  unsigned t1, t2;
-  unsigned p1 = block_exclusive_scan(c1, sm, &t1);
-  unsigned p2 = block_exclusive_scan(c2, sm, &t2);
-  for (int i = beg; i < end; ++i) {
-    reqPrefix[i] = p1; req2Prefix[i] = p2;
-    p1 += __popc(reqBits[i]); p2 += __popc(req2Bits[i]);
-  }
-  if (threadIdx.x == 0) {
-    ctr->allocBaseVba = ctr->lastFreeBlockId;
-    ctr->allocBaseExl = ctr->lastFreeExcessListId;
-    ctr->noRequests = (int)t1; ctr->noRequestsExcess = (int)t2;
-    ctr->lastFreeBlockId -= (int)t1;       // every request decrements, served or not (:833, :857-858)
-    ctr->lastFreeExcessListId -= (int)t2;
+  __shared__ unsigned tileBase;
+  const int noTiles = (noWords + BMP_TILE - 1) / BMP_TILE;
+  for (int tile = blockIdx.x; tile < noTiles; tile += gridDim.x) {
+    const int first = tile * BMP_TILE + threadIdx.x * 4;
+    uint4 w = make_uint4(0, 0, 0, 0);
+    if (first + 4 <= noWords) w = *reinterpret_cast<const uint4 *>(bits + first);
+    else { if (first < noWords) w.x = bits[first]; if (first + 1 < noWords) w.y = bits[first + 1]; if (first + 2 < noWords) w.z = bits[first + 2]; }
+    const unsigned c0 = __popc(w.x), c1 = __popc(w.y), c2 = __popc(w.z), c3 = __popc(w.w);
+    unsigned total;
+    const unsigned local = block_exclusive_scan(c0 + c1 + c2 + c3, sm, &total);
+    if (threadIdx.x < 32) {
+      const unsigned ex = scan_lookback(scanDesc, gen, tile, total);
+      if (threadIdx.x == 0) {
+        tileBase = ex;
+        if (tile == noTiles - 1) {
+          const int t = (int)(ex + total);
+          if (WHICH == 0) { ctr->noRequests = t; }
+          else {
+            ctr->noRequestsExcess = t;
+            ctr->allocBaseVba = ctr->lastFreeBlockId;
+            ctr->allocBaseExl = ctr->lastFreeExcessListId;
+            ctr->lastFreeBlockId -= ctr->noRequests;
+            ctr->lastFreeExcessListId -= t;
+          }
+        }
+      }
+    }
+    __syncthreads();
+    const unsigned p = tileBase + local;
+    if (first + 4 <= noWords) *reinterpret_cast<uint4 *>(prefix + first) = make_uint4(p, p + c0, p + c0 + c1, p + c0 + c1 + c2);
+    else { if (first < noWords) prefix[first] = p; if (first + 1 < noWords) prefix[first + 1] = p + c0; if (first + 2 < noWords) prefix[first + 2] = p + c0 + c1; }
+    __syncthreads();
   }
 }
 
@@ -251,7 +270,8 @@ __device__ bool block_visible(int bx, int by, int bz, const Mat4 &M, const float
 
 // mode 0: reconstruction-engine list (types > 0, re-test type 3, writes the bytes back)
 // mode 1: free-view list (every entry with ptr >= 0 that passes the frustum test; bytes untouched)
-#define VIS_TILE (256 * 16)
+#define VIS_EPT 64                 // entries per thread (4 x 128-bit loads)
+#define VIS_TILE (256 * VIS_EPT)
 template <int MODE>
 __global__ void __launch_bounds__(256, 4)
 k_visible_list(const b200_hash_entry *__restrict__ table, int noTotal, uint8_t *visType, b200_vec3i *visiblePos, int capacity,
@@ -262,35 +282,39 @@ k_visible_list(const b200_hash_entry *__restrict__ table, int noTotal, uint8_t *
   const float proj[4] = {p0, p1, p2, p3};
   const int noTiles = (noTotal + VIS_TILE - 1) / VIS_TILE;
   for (int tile = blockIdx.x; tile < noTiles; tile += gridDim.x) {
-    const int first = tile * VIS_TILE + threadIdx.x * 16;
-    unsigned mask = 0;   // bit k: entry first+k goes to the list
+    const int first = tile * VIS_TILE + threadIdx.x * VIS_EPT;
+    unsigned long long mask = 0;   // bit k: entry first+k goes to the list
     if (MODE == 0) {
-      uint4 raw = make_uint4(0, 0, 0, 0);
-      if (first + 16 <= noTotal) raw = *reinterpret_cast<const uint4 *>(visType + first);
-      else for (int k = 0; k < 16; ++k) if (first + k < noTotal) reinterpret_cast<uint8_t *>(&raw)[k] = visType[first + k];
-      if (raw.x | raw.y | raw.z | raw.w) {
-        uint8_t *t = reinterpret_cast<uint8_t *>(&raw);
 #pragma unroll
-        for (int k = 0; k < 16; ++k) {
-          uint8_t v = t[k];
-          if (v == 3) {
-            Entry en = load_entry(table, first + k);
-            if (!block_visible(en.x, en.y, en.z, M, proj, voxelSize, w, h)) { v = 0; visType[first + k] = 0; }
+      for (int q = 0; q < VIS_EPT / 16; ++q) {
+        const int f16 = first + q * 16;
+        uint4 raw = make_uint4(0, 0, 0, 0);
+        if (f16 + 16 <= noTotal) raw = *reinterpret_cast<const uint4 *>(visType + f16);
+        else for (int k = 0; k < 16; ++k) if (f16 + k < noTotal) reinterpret_cast<uint8_t *>(&raw)[k] = visType[f16 + k];
+        if (raw.x | raw.y | raw.z | raw.w) {
+          uint8_t *t = reinterpret_cast<uint8_t *>(&raw);
+#pragma unroll
+          for (int k = 0; k < 16; ++k) {
+            uint8_t v = t[k];
+            if (v == 3) {
+              Entry en = load_entry(table, f16 + k);
+              if (!block_visible(en.x, en.y, en.z, M, proj, voxelSize, w, h)) { v = 0; visType[f16 + k] = 0; }
+            }
+            if (v > 0) mask |= 1ull << (q * 16 + k);
           }
-          if (v > 0) mask |= 1u << k;
         }
       }
     } else {
-      for (int k = 0; k < 16; ++k) {
+      for (int k = 0; k < VIS_EPT; ++k) {
         const int idx = first + k;
         if (idx < noTotal) {
           Entry en = load_entry(table, idx);
-          if (en.ptr >= 0 && block_visible(en.x, en.y, en.z, M, proj, voxelSize, w, h)) mask |= 1u << k;
+          if (en.ptr >= 0 && block_visible(en.x, en.y, en.z, M, proj, voxelSize, w, h)) mask |= 1ull << k;
         }
       }
     }
     unsigned total;
-    unsigned local = block_exclusive_scan(__popc(mask), sm, &total);
+    unsigned local = block_exclusive_scan(__popcll(mask), sm, &total);
     if (threadIdx.x < 32) {
       unsigned ex = scan_lookback(scanDesc, gen, tile, total);
       if (threadIdx.x == 0) {
@@ -301,7 +325,7 @@ k_visible_list(const b200_hash_entry *__restrict__ table, int noTotal, uint8_t *
     __syncthreads();
     unsigned o = tileBase + local;
     while (mask) {
-      const int k = __ffs(mask) - 1;
+      const int k = __ffsll((long long)mask) - 1;
       mask &= mask - 1;
       Entry en = load_entry(table, first + k);
       if ((int)o < capacity) { b200_vec3i p; p.x = en.x; p.y = en.y; p.z = en.z; visiblePos[o] = p; }
@@ -347,11 +371,14 @@ void launch_allocate(b200_engine *e, const SceneRef &s, const FrameGeom &g, cons
                                          frameTag);
   e->launches += 2;
   if (!onlyVisible) {
-    k_request_scan<<<1, 1024, 0, st>>>(e->d_reqBits, e->d_req2Bits, e->d_reqPrefix, e->d_req2Prefix, noWords, e->d_ctr);
+    const int bmpTiles = (noWords + BMP_TILE - 1) / BMP_TILE;
+    const int bmpGrid = persistent_grid(e, 2, bmpTiles);
+    k_bitmap_prefix<0><<<bmpGrid, 256, 0, st>>>(e->d_reqBits, e->d_reqPrefix, noWords, e->d_ctr, e->d_scanDesc, ++e->scanGen);
+    k_bitmap_prefix<1><<<bmpGrid, 256, 0, st>>>(e->d_req2Bits, e->d_req2Prefix, noWords, e->d_ctr, e->d_scanDesc, ++e->scanGen);
     k_request_apply<<<(noWords + 255) / 256, 256, 0, st>>>(depth, s.hash, s.numBuckets, s.visType, e->d_reqKey, e->d_reqBits,
                                                            e->d_req2Bits, e->d_reqPrefix, e->d_req2Prefix, noWords,
                                                            s.allocationList, s.excessList, e->d_ctr, g, frameIdx);
-    e->launches += 2;
+    e->launches += 3;
   }
   const int noTiles = (s.noTotal + VIS_TILE - 1) / VIS_TILE;
   const int grid = persistent_grid(e, 4, noTiles);

@@ -43,6 +43,8 @@ static FrameGeom frame_geom(const b200_scene *s, const b200_view *v) {
   g.w = v->depth_w; g.h = v->depth_h; g.rgb_w = v->rgb_w; g.rgb_h = v->rgb_h;
   g.voxelSize = s->voxelSize; g.mu = s->mu; g.maxW = s->maxW; g.vfmin = s->viewFrustum_min; g.vfmax = s->viewFrustum_max;
   g.depthWeighting = v->depthWeighting; g.stopMaxW = s->stopIntegratingAtMaxW; g.approx = !v->requiresFullRendering;
+  g.sameRgbCam = (memcmp(v->M_rgb, v->M_d, sizeof(v->M_d)) == 0 && memcmp(v->proj_rgb, v->proj_d, sizeof(v->proj_d)) == 0 &&
+                  v->rgb_w == v->depth_w && v->rgb_h == v->depth_h) ? 1 : 0;
   return g;
 }
 

@@ -10,6 +10,7 @@ struct FrameGeom {          // per-call constants handed to kernels by value
   int maxW;
   float vfmin, vfmax;
   int depthWeighting, stopMaxW, approx;
+  int sameRgbCam;           // M_rgb, proj_rgb, image size bitwise equal to the depth camera's: ix,iy are shared
 };
 
 struct SceneRef {           // raw device views of the caller-owned scene / render-state buffers
