@@ -43,17 +43,54 @@ void launch_reset(b200_engine *e, const SceneRef &s) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// prepare: setToType3 over the previous visible list + clear the request bitmaps
+// visibility test (DA/ITMSceneReconstructionEngine.h:315-397)
 // ------------------------------------------------------------------------------------------------
-__global__ void k_prepare(const b200_hash_entry *table, int numBuckets, const b200_vec3i *visiblePos, uint8_t *visType,
-                          const DevCounters *ctr, unsigned *reqBits, unsigned *req2Bits, int noWords) {
+DEV bool point_visible(const Mat4 &M, const float *proj, float x, float y, float z, int w, int h) {
+  Vec4 b = m4v4(M, x, y, z, 1.0f);
+  if (b.z < 1e-10f) return false;
+  float u = proj[0] * b.x / b.z + proj[2];
+  float v = proj[1] * b.y / b.z + proj[3];
+  return (u >= 0 && u < w && v >= 0 && v < h);
+}
+
+// checkBlockVisibility<false>: corner order and the incremental +=/-= updates are part of the arithmetic contract
+__device__ bool block_visible(int bx, int by, int bz, const Mat4 &M, const float *proj, float voxelSize, int w, int h) {
+  const float factor = (float)BS * voxelSize;
+  float x = (float)bx * factor, y = (float)by * factor, z = (float)bz * factor;
+  if (point_visible(M, proj, x, y, z, w, h)) return true;
+  z += factor; if (point_visible(M, proj, x, y, z, w, h)) return true;
+  y += factor; if (point_visible(M, proj, x, y, z, w, h)) return true;
+  x += factor; if (point_visible(M, proj, x, y, z, w, h)) return true;
+  z -= factor; if (point_visible(M, proj, x, y, z, w, h)) return true;
+  y -= factor; if (point_visible(M, proj, x, y, z, w, h)) return true;
+  x -= factor; y += factor; if (point_visible(M, proj, x, y, z, w, h)) return true;
+  x += factor; y -= factor; z += factor; if (point_visible(M, proj, x, y, z, w, h)) return true;
+  return false;
+}
+
+// Transient visibility codes, only alive between k_prepare and k_visible_list of ONE allocate call:
+// the reference marks every previously visible block 3 (setToType3) and re-tests the survivors'
+// frustum visibility inside the full-table sweep. Here the re-test is done eagerly, one previously
+// visible block per thread, and its verdict is parked in the byte; the sweep then only decodes it.
+#define VT_PREV_VISIBLE 5   // was 3, frustum test passed  -> ends as 3 unless re-observed (1)
+#define VT_PREV_HIDDEN 4    // was 3, frustum test failed  -> ends as 0 unless re-observed (1)
+
+// ------------------------------------------------------------------------------------------------
+// prepare: setToType3 over the previous visible list (+ eager frustum re-test) + clear the bitmaps
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_prepare(const b200_hash_entry *__restrict__ table, int numBuckets, const b200_vec3i *__restrict__ visiblePos, uint8_t *visType,
+          const DevCounters *ctr, unsigned *reqBits, unsigned *req2Bits, int noWords, Mat4 M, float p0, float p1, float p2, float p3,
+          float voxelSize, int w, int h, int capacity) {
   const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
   for (int i = tid; i < noWords; i += nth) { reqBits[i] = 0u; req2Bits[i] = 0u; }
-  const int n = ctr->noVisibleBlocks;
+  const float proj[4] = {p0, p1, p2, p3};
+  int n = ctr->noVisibleBlocks;
+  if (n > capacity) n = capacity;
   for (int i = tid; i < n; i += nth) {
-    b200_vec3i p = visiblePos[i];
-    int idx = find_block<false>(table, numBuckets, p.x, p.y, p.z);
-    if (idx >= 0) visType[idx] = 3;
+    const b200_vec3i p = visiblePos[i];
+    const int idx = find_block<false>(table, numBuckets, p.x, p.y, p.z);
+    if (idx >= 0) visType[idx] = block_visible(p.x, p.y, p.z, M, proj, voxelSize, w, h) ? VT_PREV_VISIBLE : VT_PREV_HIDDEN;
   }
 }
 
@@ -142,220 +179,227 @@ k_mark(const float *__restrict__ depth, const b200_hash_entry *__restrict__ tabl
 }
 
 // ------------------------------------------------------------------------------------------------
-// request ranking: exclusive prefix of popcounts over a bitmap (ordered, multi-CTA chained scan;
-// 1024 words = 32768 entries per tile, 128-bit loads). WHICH 0: all requests, 1: excess requests.
-// The second pass also commits the counters (every request decrements, served or not, :833, :857-858).
+// request server: ONE kernel ranks every request in ascending entry order (two chained scans over
+// the request bitmaps, 1024 words = 32768 entries per tile) and serves it:
+//   vbaIdx = lastFree - rank(all requests),  exlIdx = lastFreeExcess - rank(excess requests)
+// (every request decrements the counters, served or not — Reco_CUDA.cu:833, :857-858); the winning
+// pixel's ray is replayed up to its step to recover the block position.
 // ------------------------------------------------------------------------------------------------
 #define BMP_TILE 1024
-template <int WHICH>
 __global__ void __launch_bounds__(256)
-k_bitmap_prefix(const unsigned *__restrict__ bits, unsigned *prefix, int noWords, DevCounters *ctr, unsigned long long *scanDesc,
-                unsigned gen) {
+k_serve_requests(const float *__restrict__ depth, b200_hash_entry *table, int numBuckets, uint8_t *visType,
+                 const unsigned long long *__restrict__ reqKey, const unsigned *__restrict__ reqBits, const unsigned *__restrict__ req2Bits,
+                 int noWords, const int *__restrict__ allocList, const int *__restrict__ excessList, DevCounters *ctr, FrameGeom g,
+                 int currentFrame, unsigned long long *scanDesc, unsigned long long *scanDesc2, unsigned gen) {
   __shared__ unsigned sm[33];
-  __shared__ unsigned tileBase;
+  __shared__ unsigned tileBase, tileBase2;
   const int noTiles = (noWords + BMP_TILE - 1) / BMP_TILE;
+  const int baseVba = ctr->lastFreeBlockId, baseExl = ctr->lastFreeExcessListId;   // only the last tile updates them, at its very end
+  const float invfx = 1.0f / g.proj_d[0], invfy = 1.0f / g.proj_d[1];
+  const float oneOverVoxelSize = 1.0f / (g.voxelSize * BS);
   for (int tile = blockIdx.x; tile < noTiles; tile += gridDim.x) {
     const int first = tile * BMP_TILE + threadIdx.x * 4;
-    uint4 w = make_uint4(0, 0, 0, 0);
-    if (first + 4 <= noWords) w = *reinterpret_cast<const uint4 *>(bits + first);
-    else { if (first < noWords) w.x = bits[first]; if (first + 1 < noWords) w.y = bits[first + 1]; if (first + 2 < noWords) w.z = bits[first + 2]; }
-    const unsigned c0 = __popc(w.x), c1 = __popc(w.y), c2 = __popc(w.z), c3 = __popc(w.w);
-    unsigned total;
-    const unsigned local = block_exclusive_scan(c0 + c1 + c2 + c3, sm, &total);
+    unsigned wv[4] = {0, 0, 0, 0}, wx[4] = {0, 0, 0, 0};
+    if (first + 4 <= noWords) {
+      const uint4 a = *reinterpret_cast<const uint4 *>(reqBits + first), b = *reinterpret_cast<const uint4 *>(req2Bits + first);
+      wv[0] = a.x; wv[1] = a.y; wv[2] = a.z; wv[3] = a.w; wx[0] = b.x; wx[1] = b.y; wx[2] = b.z; wx[3] = b.w;
+    } else for (int k = 0; k < 4; ++k) if (first + k < noWords) { wv[k] = reqBits[first + k]; wx[k] = req2Bits[first + k]; }
+    const unsigned c = __popc(wv[0]) + __popc(wv[1]) + __popc(wv[2]) + __popc(wv[3]);
+    const unsigned c2 = __popc(wx[0]) + __popc(wx[1]) + __popc(wx[2]) + __popc(wx[3]);
+    unsigned total, total2;
+    unsigned rank = block_exclusive_scan(c, sm, &total);
+    unsigned rank2 = block_exclusive_scan(c2, sm, &total2);
     if (threadIdx.x < 32) {
       const unsigned ex = scan_lookback(scanDesc, gen, tile, total);
-      if (threadIdx.x == 0) {
-        tileBase = ex;
-        if (tile == noTiles - 1) {
-          const int t = (int)(ex + total);
-          if (WHICH == 0) { ctr->noRequests = t; }
-          else {
-            ctr->noRequestsExcess = t;
-            ctr->allocBaseVba = ctr->lastFreeBlockId;
-            ctr->allocBaseExl = ctr->lastFreeExcessListId;
-            ctr->lastFreeBlockId -= ctr->noRequests;
-            ctr->lastFreeExcessListId -= t;
-          }
+      const unsigned ex2 = scan_lookback(scanDesc2, gen, tile, total2);
+      if (threadIdx.x == 0) { tileBase = ex; tileBase2 = ex2; }
+    }
+    __syncthreads();
+    rank += tileBase; rank2 += tileBase2;
+    const bool last = (tile == noTiles - 1);
+    const unsigned grand = tileBase + total, grand2 = tileBase2 + total2;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      unsigned bits = wv[k];
+      while (bits) {
+        const int b = __ffs(bits) - 1;
+        bits &= bits - 1;
+        const int targetIdx = (first + k) * 32 + b;
+        const bool isExcess = (wx[k] >> b) & 1u;
+        const int vbaIdx = baseVba - (int)rank;
+        const int exlIdx = baseExl - (int)rank2;
+        rank++;
+        if (isExcess) rank2++;
+        if (vbaIdx < 0 || (isExcess && exlIdx < 0)) continue;   // exhausted: the counters still go negative
+        const unsigned long long key = reqKey[targetIdx];
+        const unsigned step = (unsigned)(key & ((1u << KEY_STEP_BITS) - 1));
+        const unsigned pixel = (unsigned)((key >> KEY_STEP_BITS) & ((1u << KEY_PIXEL_BITS) - 1));
+        const int x = pixel % g.w, y = pixel / g.w;
+        Ray r;
+        make_ray(r, x, y, __ldg(depth + pixel), g, invfx, invfy, oneOverVoxelSize);
+        float px = r.px, py = r.py, pz = r.pz;
+        for (unsigned i = 0; i < step; ++i) { px += r.dx; py += r.dy; pz += r.dz; }
+        const int bx = (short)(int)floorf(px), by = (short)(int)floorf(py), bz = (short)(int)floorf(pz);
+        int *ew;
+        if (!isExcess) {
+          ew = reinterpret_cast<int *>(table) + (size_t)targetIdx * 5;
+        } else {
+          const int exlOffset = excessList[exlIdx];
+          reinterpret_cast<int *>(table)[(size_t)targetIdx * 5 + 2] = exlOffset + 1;   // connect to child
+          ew = reinterpret_cast<int *>(table) + (size_t)(numBuckets + exlOffset) * 5;
+          visType[numBuckets + exlOffset] = 1;                                         // child visible
         }
+        ew[0] = (int)(((unsigned)bx & 0xffffu) | ((unsigned)by << 16));
+        ew[1] = (bz & 0xffff);
+        ew[2] = 0;
+        ew[3] = allocList[vbaIdx];
+        ew[4] = currentFrame;
       }
     }
     __syncthreads();
-    const unsigned p = tileBase + local;
-    if (first + 4 <= noWords) *reinterpret_cast<uint4 *>(prefix + first) = make_uint4(p, p + c0, p + c0 + c1, p + c0 + c1 + c2);
-    else { if (first < noWords) prefix[first] = p; if (first + 1 < noWords) prefix[first + 1] = p + c0; if (first + 2 < noWords) prefix[first + 2] = p + c0 + c1; }
-    __syncthreads();
-  }
-}
-
-// ------------------------------------------------------------------------------------------------
-// request server: one thread per bitmap word; ascending-entry-index slot assignment
-// ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-k_request_apply(const float *__restrict__ depth, b200_hash_entry *table, int numBuckets, uint8_t *visType,
-                const unsigned long long *reqKey, const unsigned *reqBits, const unsigned *req2Bits,
-                const unsigned *reqPrefix, const unsigned *req2Prefix, int noWords, const int *allocList,
-                const int *excessList, const DevCounters *ctr, FrameGeom g, int currentFrame) {
-  const int wIdx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (wIdx >= noWords) return;
-  unsigned bits = reqBits[wIdx];
-  if (!bits) return;
-  const unsigned bits2 = req2Bits[wIdx];
-  const int baseVba = ctr->allocBaseVba, baseExl = ctr->allocBaseExl;
-  unsigned rank = reqPrefix[wIdx], rank2 = req2Prefix[wIdx];
-  const float invfx = 1.0f / g.proj_d[0], invfy = 1.0f / g.proj_d[1];
-  const float oneOverVoxelSize = 1.0f / (g.voxelSize * BS);
-  while (bits) {
-    const int b = __ffs(bits) - 1;
-    bits &= bits - 1;
-    const int targetIdx = wIdx * 32 + b;
-    const bool isExcess = (bits2 >> b) & 1u;
-    const int vbaIdx = baseVba - (int)rank;
-    const int exlIdx = baseExl - (int)rank2;
-    rank++;
-    if (isExcess) rank2++;
-    if (vbaIdx < 0 || (isExcess && exlIdx < 0)) continue;   // exhausted: counters already went negative
-    // replay the winning ray up to its step to recover the requested block position
-    const unsigned long long key = reqKey[targetIdx];
-    const unsigned step = (unsigned)(key & ((1u << KEY_STEP_BITS) - 1));
-    const unsigned pixel = (unsigned)((key >> KEY_STEP_BITS) & ((1u << KEY_PIXEL_BITS) - 1));
-    const int x = pixel % g.w, y = pixel / g.w;
-    Ray r;
-    make_ray(r, x, y, __ldg(depth + pixel), g, invfx, invfy, oneOverVoxelSize);
-    float px = r.px, py = r.py, pz = r.pz;
-    for (unsigned i = 0; i < step; ++i) { px += r.dx; py += r.dy; pz += r.dz; }
-    const int bx = (short)(int)floorf(px), by = (short)(int)floorf(py), bz = (short)(int)floorf(pz);
-    int *ew;
-    if (!isExcess) {
-      ew = reinterpret_cast<int *>(table) + (size_t)targetIdx * 5;
-    } else {
-      const int exlOffset = excessList[exlIdx];
-      reinterpret_cast<int *>(table)[(size_t)targetIdx * 5 + 2] = exlOffset + 1;   // connect to child
-      ew = reinterpret_cast<int *>(table) + (size_t)(numBuckets + exlOffset) * 5;
-      visType[numBuckets + exlOffset] = 1;                                         // child visible
+    if (last && threadIdx.x == 0) {
+      ctr->allocBaseVba = baseVba; ctr->allocBaseExl = baseExl;
+      ctr->noRequests = (int)grand; ctr->noRequestsExcess = (int)grand2;
+      ctr->lastFreeBlockId = baseVba - (int)grand;
+      ctr->lastFreeExcessListId = baseExl - (int)grand2;
     }
-    ew[0] = (int)(((unsigned)bx & 0xffffu) | ((unsigned)by << 16));
-    ew[1] = (bz & 0xffff);
-    ew[2] = 0;
-    ew[3] = allocList[vbaIdx];
-    ew[4] = currentFrame;
   }
 }
 
 // ------------------------------------------------------------------------------------------------
-// visible list: frustum re-test of type-3 entries + ordered compaction of all types > 0
+// visible list (reconstruction engine): decode the visibility bytes and compact every entry with
+// type > 0 in ascending entry order — one pass over the 1.5 MB byte array with 128-bit accesses,
+// block scan + decoupled look-back for the global order, shared-memory compaction so that the
+// scattered 20-byte entry reads and the list writes are spread over all threads. The same pass
+// writes the snapshot for the decay queue into the ring (Reco_CUDA.cu:302-317 without the per-frame
+// cudaMalloc / blocking copies) and the resolved VBA pointer of every item (saves IntegrateIntoScene
+// and CreateExpectedDepths their hash lookups while the table is unchanged).
 // ------------------------------------------------------------------------------------------------
-DEV bool point_visible(const Mat4 &M, const float *proj, float x, float y, float z, int w, int h) {
-  Vec4 b = m4v4(M, x, y, z, 1.0f);
-  if (b.z < 1e-10f) return false;
-  float u = proj[0] * b.x / b.z + proj[2];
-  float v = proj[1] * b.y / b.z + proj[3];
-  return (u >= 0 && u < w && v >= 0 && v < h);
-}
-
-// checkBlockVisibility<false> — DA/ITMSceneReconstructionEngine.h:338-397 (corner order and the
-// incremental +=/-= updates are part of the arithmetic contract)
-__device__ bool block_visible(int bx, int by, int bz, const Mat4 &M, const float *proj, float voxelSize, int w, int h) {
-  const float factor = (float)BS * voxelSize;
-  float x = (float)bx * factor, y = (float)by * factor, z = (float)bz * factor;
-  if (point_visible(M, proj, x, y, z, w, h)) return true;
-  z += factor; if (point_visible(M, proj, x, y, z, w, h)) return true;
-  y += factor; if (point_visible(M, proj, x, y, z, w, h)) return true;
-  x += factor; if (point_visible(M, proj, x, y, z, w, h)) return true;
-  z -= factor; if (point_visible(M, proj, x, y, z, w, h)) return true;
-  y -= factor; if (point_visible(M, proj, x, y, z, w, h)) return true;
-  x -= factor; y += factor; if (point_visible(M, proj, x, y, z, w, h)) return true;
-  x += factor; y -= factor; z += factor; if (point_visible(M, proj, x, y, z, w, h)) return true;
-  return false;
-}
-
-// mode 0: reconstruction-engine list (types > 0, re-test type 3, writes the bytes back)
-// mode 1: free-view list (every entry with ptr >= 0 that passes the frustum test; bytes untouched)
-#define VIS_EPT 64                 // entries per thread (4 x 128-bit loads)
-#define VIS_TILE (256 * VIS_EPT)
-template <int MODE>
+#define VIS_EPT 32                 // entries per thread (2 x 128-bit loads)
+#define VIS_TILE (256 * VIS_EPT)   // 8192 entries per tile
 __global__ void __launch_bounds__(256, 4)
-k_visible_list(const b200_hash_entry *__restrict__ table, int noTotal, uint8_t *visType, b200_vec3i *visiblePos, int capacity,
-               DevCounters *ctr, unsigned long long *scanDesc, unsigned gen, Mat4 M, float p0, float p1, float p2, float p3,
-               float voxelSize, int w, int h) {
+k_visible_list(const b200_hash_entry *__restrict__ table, int numBuckets, int noTotal, uint8_t *visType, b200_vec3i *visiblePos,
+               int *visiblePtr, int capacity, DevCounters *ctr, unsigned long long *scanDesc, unsigned gen, Mat4 M, float p0, float p1,
+               float p2, float p3, float voxelSize, int w, int h, b200_vec3i *ring, long long ringCap, long long *snapStart,
+               int *snapCount, int slot, int oldestSlot) {
   __shared__ unsigned sm[33];
   __shared__ unsigned tileBase;
+  __shared__ int hits[VIS_TILE];
   const float proj[4] = {p0, p1, p2, p3};
+  const long long ringStart = ctr->ringHead;   // advanced by the last tile only, at its very end
   const int noTiles = (noTotal + VIS_TILE - 1) / VIS_TILE;
   for (int tile = blockIdx.x; tile < noTiles; tile += gridDim.x) {
     const int first = tile * VIS_TILE + threadIdx.x * VIS_EPT;
-    unsigned long long mask = 0;   // bit k: entry first+k goes to the list
-    if (MODE == 0) {
+    unsigned mask = 0;   // bit k: entry first+k goes to the list
 #pragma unroll
-      for (int q = 0; q < VIS_EPT / 16; ++q) {
-        const int f16 = first + q * 16;
-        uint4 raw = make_uint4(0, 0, 0, 0);
-        if (f16 + 16 <= noTotal) raw = *reinterpret_cast<const uint4 *>(visType + f16);
-        else for (int k = 0; k < 16; ++k) if (f16 + k < noTotal) reinterpret_cast<uint8_t *>(&raw)[k] = visType[f16 + k];
-        if (raw.x | raw.y | raw.z | raw.w) {
-          uint8_t *t = reinterpret_cast<uint8_t *>(&raw);
+    for (int q = 0; q < VIS_EPT / 16; ++q) {
+      const int f16 = first + q * 16;
+      if (f16 >= noTotal) break;
+      uint4 raw = *reinterpret_cast<const uint4 *>(visType + f16);   // noTotal is a multiple of 32
+      if (raw.x | raw.y | raw.z | raw.w) {
+        uint8_t *t = reinterpret_cast<uint8_t *>(&raw);
+        bool dirty = false;
 #pragma unroll
-          for (int k = 0; k < 16; ++k) {
-            uint8_t v = t[k];
-            if (v == 3) {
-              Entry en = load_entry(table, f16 + k);
-              if (!block_visible(en.x, en.y, en.z, M, proj, voxelSize, w, h)) { v = 0; visType[f16 + k] = 0; }
-            }
-            if (v > 0) mask |= 1ull << (q * 16 + k);
+        for (int k = 0; k < 16; ++k) {
+          uint8_t v = t[k];
+          if (v == VT_PREV_VISIBLE) { v = 3; dirty = true; }
+          else if (v == VT_PREV_HIDDEN) { v = 0; dirty = true; }
+          else if (v == 3) {   // a 3 this frame's k_prepare did not produce (decay moved it, Reco_CUDA.cu:1109): test it now
+            Entry en = load_entry(table, f16 + k);
+            if (!block_visible(en.x, en.y, en.z, M, proj, voxelSize, w, h)) { v = 0; dirty = true; }
           }
+          t[k] = v;
+          if (v > 0) mask |= 1u << (q * 16 + k);
         }
-      }
-    } else {
-      for (int k = 0; k < VIS_EPT; ++k) {
-        const int idx = first + k;
-        if (idx < noTotal) {
-          Entry en = load_entry(table, idx);
-          if (en.ptr >= 0 && block_visible(en.x, en.y, en.z, M, proj, voxelSize, w, h)) mask |= 1ull << k;
-        }
+        if (dirty) *reinterpret_cast<uint4 *>(visType + f16) = raw;
       }
     }
     unsigned total;
-    unsigned local = block_exclusive_scan(__popcll(mask), sm, &total);
+    const unsigned local = block_exclusive_scan(__popc(mask), sm, &total);
     if (threadIdx.x < 32) {
-      unsigned ex = scan_lookback(scanDesc, gen, tile, total);
-      if (threadIdx.x == 0) {
-        tileBase = ex;
-        if (tile == noTiles - 1) ctr->noVisibleBlocks = (int)(ex + total);
+      const unsigned ex = scan_lookback(scanDesc, gen, tile, total);
+      if (threadIdx.x == 0) tileBase = ex;
+    }
+    unsigned o = local;
+    while (mask) {
+      const int k = __ffs(mask) - 1;
+      mask &= mask - 1;
+      hits[o++] = first + k;
+    }
+    __syncthreads();
+    const unsigned base = tileBase;
+    for (unsigned t = threadIdx.x; t < total; t += blockDim.x) {
+      const int idx = hits[t];
+      const Entry en = load_entry(table, idx);
+      const long long out = (long long)base + t;
+      if (out < capacity) {
+        b200_vec3i p; p.x = en.x; p.y = en.y; p.z = en.z;
+        visiblePos[out] = p;
+        ring[(ringStart + out) % ringCap] = p;
+        int ptr = en.ptr;
+        if (ptr < 0) { if (find_block<false>(table, numBuckets, en.x, en.y, en.z, &ptr) < 0) ptr = -1; }   // stale entry: what findBlock(pos) would hit
+        visiblePtr[out] = ptr;
       }
     }
     __syncthreads();
-    unsigned o = tileBase + local;
-    while (mask) {
-      const int k = __ffsll((long long)mask) - 1;
-      mask &= mask - 1;
-      Entry en = load_entry(table, first + k);
-      if ((int)o < capacity) { b200_vec3i p; p.x = en.x; p.y = en.y; p.z = en.z; visiblePos[o] = p; }
-      o++;
+    if (tile == noTiles - 1 && threadIdx.x == 0) {
+      const int n = (int)(base + total);
+      ctr->noVisibleBlocks = n;
+      const int kept = n < capacity ? n : capacity;
+      if (oldestSlot >= 0) { if (ringStart + kept - snapStart[oldestSlot] > ringCap) ctr->errorFlags |= 1; }
+      else if (kept > ringCap) ctr->errorFlags |= 1;
+      snapStart[slot] = ringStart;
+      snapCount[slot] = kept;
+      ctr->ringHead = ringStart + kept;
     }
-    __syncthreads();
   }
 }
 
-// snapshot of the visible list into the decay ring (Reco_CUDA.cu:302-317 without the per-frame
-// cudaMalloc / blocking copies): one bump allocation on the device + a coalesced copy
-__global__ void k_snapshot(const b200_vec3i *visiblePos, int capacity, DevCounters *ctr, b200_vec3i *ring, long long ringCap,
-                           long long *snapStart, int *snapCount, int slot, int oldestSlot) {
-  __shared__ long long start;
-  int n = ctr->noVisibleBlocks;
-  if (n > capacity) n = capacity;
-  if (threadIdx.x == 0) {
-    // single CTA: plain read-modify-write of the cursor
-    start = ctr->ringHead;
-    if (oldestSlot >= 0) {
-      long long live = start + n - snapStart[oldestSlot];
-      if (live > ringCap) ctr->errorFlags |= 1;
-    } else if (n > ringCap) ctr->errorFlags |= 1;
-    ctr->ringHead = start + n;
-    snapStart[slot] = start;
-    snapCount[slot] = n;
+// free-view visible list (FindVisibleBlocks, Vis_CUDA.cu:151-180, :536-569): every entry with ptr >= 0
+// that passes the frustum test, ascending entry order; the visibility bytes are not touched.
+#define FV_EPT 16
+#define FV_TILE (256 * FV_EPT)
+__global__ void __launch_bounds__(256, 4)
+k_freeview_list(const b200_hash_entry *__restrict__ table, int noTotal, b200_vec3i *visiblePos, int capacity, DevCounters *ctr,
+                unsigned long long *scanDesc, unsigned gen, Mat4 M, float p0, float p1, float p2, float p3, float voxelSize, int w, int h) {
+  __shared__ unsigned sm[33];
+  __shared__ unsigned tileBase;
+  const float proj[4] = {p0, p1, p2, p3};
+  const int noTiles = (noTotal + FV_TILE - 1) / FV_TILE;
+  for (int tile = blockIdx.x; tile < noTiles; tile += gridDim.x) {
+    // strided assignment inside the tile keeps the 20-byte entry reads of a warp adjacent
+    unsigned mask = 0;
+    for (int k = 0; k < FV_EPT; ++k) {
+      const int idx = tile * FV_TILE + k * 256 + threadIdx.x;
+      if (idx < noTotal) {
+        Entry en = load_entry(table, idx);
+        if (en.ptr >= 0 && block_visible(en.x, en.y, en.z, M, proj, voxelSize, w, h)) mask |= 1u << k;
+      }
+    }
+    // order inside the tile must be ascending entry index: rank = sum over k' < k of count(k') + rank within row k
+    unsigned total = 0;
+    unsigned offs[FV_EPT];
+#pragma unroll
+    for (int k = 0; k < FV_EPT; ++k) {
+      unsigned rowTotal;
+      const unsigned r = block_exclusive_scan((mask >> k) & 1u, sm, &rowTotal);
+      offs[k] = total + r;
+      total += rowTotal;
+    }
+    if (threadIdx.x < 32) {
+      const unsigned ex = scan_lookback(scanDesc, gen, tile, total);
+      if (threadIdx.x == 0) { tileBase = ex; if (tile == noTiles - 1) ctr->noVisibleBlocks = (int)(ex + total); }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < FV_EPT; ++k) if ((mask >> k) & 1u) {
+      const int idx = tile * FV_TILE + k * 256 + threadIdx.x;
+      const Entry en = load_entry(table, idx);
+      const unsigned o = tileBase + offs[k];
+      if ((int)o < capacity) { b200_vec3i p; p.x = en.x; p.y = en.y; p.z = en.z; visiblePos[o] = p; }
+    }
+    __syncthreads();
   }
-  __syncthreads();
-  const long long s0 = start;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) ring[(s0 + i) % ringCap] = visiblePos[i];
 }
 
 void launch_allocate(b200_engine *e, const SceneRef &s, const FrameGeom &g, const float *depth, bool onlyVisible, int frameIdx,
@@ -364,38 +408,33 @@ void launch_allocate(b200_engine *e, const SceneRef &s, const FrameGeom &g, cons
   const int noWords = e->noWords;
   const unsigned frameTag = (unsigned)(frameIdx + 1) & 0xffffffu;
   if (frameTag == 0) cudaMemsetAsync(e->d_reqKey, 0, sizeof(unsigned long long) * (size_t)s.noTotal, st);
-  k_prepare<<<e->smCount * 4, 256, 0, st>>>(s.hash, s.numBuckets, s.visiblePos, s.visType, e->d_ctr, e->d_reqBits, e->d_req2Bits,
-                                           noWords);
+  k_prepare<<<e->smCount * 2, 256, 0, st>>>(s.hash, s.numBuckets, s.visiblePos, s.visType, e->d_ctr, e->d_reqBits, e->d_req2Bits, noWords,
+                                           g.M_d, g.proj_d[0], g.proj_d[1], g.proj_d[2], g.proj_d[3], g.voxelSize, g.w, g.h, s.numBlocks);
   const int tiles = ((g.w + 7) / 8) * ((g.h + 3) / 4);
   k_mark<<<(tiles + 7) / 8, 256, 0, st>>>(depth, s.hash, s.numBuckets, s.visType, e->d_reqKey, e->d_reqBits, e->d_req2Bits, g,
                                          frameTag);
   e->launches += 2;
   if (!onlyVisible) {
     const int bmpTiles = (noWords + BMP_TILE - 1) / BMP_TILE;
-    const int bmpGrid = persistent_grid(e, 2, bmpTiles);
-    k_bitmap_prefix<0><<<bmpGrid, 256, 0, st>>>(e->d_reqBits, e->d_reqPrefix, noWords, e->d_ctr, e->d_scanDesc, ++e->scanGen);
-    k_bitmap_prefix<1><<<bmpGrid, 256, 0, st>>>(e->d_req2Bits, e->d_req2Prefix, noWords, e->d_ctr, e->d_scanDesc, ++e->scanGen);
-    k_request_apply<<<(noWords + 255) / 256, 256, 0, st>>>(depth, s.hash, s.numBuckets, s.visType, e->d_reqKey, e->d_reqBits,
-                                                           e->d_req2Bits, e->d_reqPrefix, e->d_req2Prefix, noWords,
-                                                           s.allocationList, s.excessList, e->d_ctr, g, frameIdx);
-    e->launches += 3;
+    const unsigned gen = ++e->scanGen;
+    k_serve_requests<<<persistent_grid(e, 2, bmpTiles), 256, 0, st>>>(depth, s.hash, s.numBuckets, s.visType, e->d_reqKey, e->d_reqBits,
+                                                                     e->d_req2Bits, noWords, s.allocationList, s.excessList, e->d_ctr,
+                                                                     g, frameIdx, e->d_scanDesc, e->d_scanDesc + e->scanDescCap / 2, gen);
+    e->launches += 1;
   }
   const int noTiles = (s.noTotal + VIS_TILE - 1) / VIS_TILE;
-  const int grid = persistent_grid(e, 4, noTiles);
-  k_visible_list<0><<<grid, 256, 0, st>>>(s.hash, s.noTotal, s.visType, s.visiblePos, s.numBlocks, e->d_ctr, e->d_scanDesc,
-                                         ++e->scanGen, g.M_d, g.proj_d[0], g.proj_d[1], g.proj_d[2], g.proj_d[3],
-                                         g.voxelSize, g.w, g.h);
   const int oldest = e->qSize > 0 ? (e->qHead % SNAP_SLOTS) : -1;
-  k_snapshot<<<1, 1024, 0, st>>>(s.visiblePos, s.numBlocks, e->d_ctr, e->d_ring, e->ringCap, e->d_snapStart, e->d_snapCount,
-                                 snapSlot, oldest);
-  e->launches += 2;
+  k_visible_list<<<persistent_grid(e, 2, noTiles), 256, 0, st>>>(s.hash, s.numBuckets, s.noTotal, s.visType, s.visiblePos, e->d_visiblePtr,
+                                                                s.numBlocks, e->d_ctr, e->d_scanDesc, ++e->scanGen, g.M_d, g.proj_d[0],
+                                                                g.proj_d[1], g.proj_d[2], g.proj_d[3], g.voxelSize, g.w, g.h, e->d_ring,
+                                                                e->ringCap, e->d_snapStart, e->d_snapCount, snapSlot, oldest);
+  e->launches += 1;
 }
 
 void launch_find_visible(b200_engine *e, const SceneRef &s, const Mat4 &M, const float proj[4], int w, int h, float voxelSize) {
-  const int noTiles = (s.noTotal + VIS_TILE - 1) / VIS_TILE;
-  const int grid = persistent_grid(e, 4, noTiles);
-  k_visible_list<1><<<grid, 256, 0, e->stream>>>(s.hash, s.noTotal, s.visType, s.visiblePos, s.numBlocks, e->d_ctr,
-                                                e->d_scanDesc, ++e->scanGen, M, proj[0], proj[1], proj[2], proj[3], voxelSize,
-                                                w, h);
+  const int noTiles = (s.noTotal + FV_TILE - 1) / FV_TILE;
+  k_freeview_list<<<persistent_grid(e, 4, noTiles), 256, 0, e->stream>>>(s.hash, s.noTotal, s.visiblePos, s.numBlocks, e->d_ctr,
+                                                                        e->d_scanDesc, ++e->scanGen, M, proj[0], proj[1], proj[2], proj[3],
+                                                                        voxelSize, w, h);
   e->launches++;
 }

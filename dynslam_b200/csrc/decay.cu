@@ -122,7 +122,75 @@ k_decay_rank(const int *itemPtr, const unsigned long long *delTag, unsigned gen,
   if (noTiles == 0 && blockIdx.x == 0 && threadIdx.x == 0) ctr->decayDeleted = 0;
 }
 
-// phase 3a: leader election per bucket chain (read-only on the table)
+// item position: MODE 0 = ring snapshot, MODE 1 = allocatedPos[VBA slot]
+DEV void item_pos(int mode, const b200_vec3i *ring, long long ringCap, long long s0, const short4 *allocatedPos, int item, int &x, int &y,
+                  int &z) {
+  if (mode == 0) { const b200_vec3i p = ring[(s0 + item) % ringCap]; x = p.x; y = p.y; z = p.z; }
+  else { const short4 p = allocatedPos[item]; x = p.x; y = p.y; z = p.z; }
+}
+
+// phase 3a: is deletion r the first (list order) deletion of its bucket chain? (read-only on the table)
+DEV bool chain_leader(const b200_hash_entry *table, int numBuckets, int x, int y, int z, int item, const unsigned long long *delTag,
+                      unsigned gen) {
+  int idx = hash_index(x, y, z, numBuckets - 1);
+  unsigned minItem = 0xffffffffu;
+  for (;;) {
+    const Entry en = load_entry_rw(table, idx);
+    if (en.ptr >= 0) {
+      const unsigned long long t = delTag[en.ptr];
+      if ((unsigned)(t >> 32) == gen) { const unsigned it = 0xffffffffu - (unsigned)(t & 0xffffffffu); if (it < minItem) minItem = it; }
+    }
+    if (en.offset < 1) break;
+    idx = numBuckets + en.offset - 1;
+  }
+  return minItem == (unsigned)item;
+}
+
+// phase 3b: the leader unlinks its chain's claimed blocks in list order — deleteBlock, Reco_CUDA.cu:1032-1111.
+// Serial order = ascending list position: repeatedly take the chain entry whose block was claimed by the
+// smallest item and unlink it on the evolving chain (findVoxel's idx / prev, :1032-1037).
+DEV void unlink_chain(b200_hash_entry *table, int numBuckets, uint8_t *visType, int head, const unsigned long long *delTag, unsigned gen) {
+  int *tw = reinterpret_cast<int *>(table);
+  for (;;) {
+    int found = -1, foundPrev = -1; unsigned best = 0xffffffffu;
+    for (int idx = head, prev = -1;;) {
+      const Entry en = load_entry_rw(table, idx);
+      if (en.ptr >= 0) {
+        const unsigned long long t = delTag[en.ptr];
+        if ((unsigned)(t >> 32) == gen) {
+          const unsigned it = 0xffffffffu - (unsigned)(t & 0xffffffffu);
+          if (it < best) { best = it; found = idx; foundPrev = prev; }
+        }
+      }
+      if (en.offset < 1) break;
+      prev = idx;
+      idx = numBuckets + en.offset - 1;
+    }
+    if (found < 0) break;
+    const int prev = foundPrev;
+    int *e = tw + (size_t)found * 5;
+    if (prev == -1) {
+      if (e[2] >= 1) {                       // ordered entry with a successor: pull the successor in
+        const int nextIdx = numBuckets + e[2] - 1;
+        int *nx = tw + (size_t)nextIdx * 5;
+        e[0] = nx[0]; e[1] = nx[1]; e[2] = nx[2]; e[3] = nx[3]; e[4] = nx[4];
+        visType[found] = visType[nextIdx];
+        visType[nextIdx] = 0;
+        nx[2] = 0; nx[3] = -2;
+      } else {                               // ordered entry, no successor
+        e[3] = -2;
+        visType[found] = 0;
+      }
+    } else {                                 // excess entry: predecessor inherits the link
+      int *pv = tw + (size_t)prev * 5;
+      pv[2] = e[2];
+      e[2] = 0; e[3] = -2;
+      visType[prev] = visType[found];        // (sic) reference quirk, :1109-1110
+      visType[found] = 0;
+    }
+  }
+}
+
 template <int MODE>
 __global__ void k_decay_elect(const b200_hash_entry *table, int numBuckets, const b200_vec3i *ring, long long ringCap,
                               const long long *snapStart, int slot, const short4 *allocatedPos, const int *delList,
@@ -132,77 +200,66 @@ __global__ void k_decay_elect(const b200_hash_entry *table, int numBuckets, cons
   for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < nDel; r += gridDim.x * blockDim.x) {
     const int item = delList[r];
     int x, y, z;
-    if (MODE == 0) { b200_vec3i p = ring[(s0 + item) % ringCap]; x = p.x; y = p.y; z = p.z; }
-    else { short4 p = allocatedPos[item]; x = p.x; y = p.y; z = p.z; }
-    int idx = hash_index(x, y, z, numBuckets - 1);
-    unsigned minItem = 0xffffffffu;
-    for (;;) {
-      Entry en = load_entry_rw(table, idx);
-      if (en.ptr >= 0) {
-        unsigned long long t = delTag[en.ptr];
-        if ((unsigned)(t >> 32) == gen) { unsigned it = 0xffffffffu - (unsigned)(t & 0xffffffffu); if (it < minItem) minItem = it; }
-      }
-      if (en.offset < 1) break;
-      idx = numBuckets + en.offset - 1;
-    }
-    isLeader[r] = (minItem == (unsigned)item) ? 1 : 0;
+    item_pos(MODE, ring, ringCap, s0, allocatedPos, item, x, y, z);
+    isLeader[r] = chain_leader(table, numBuckets, x, y, z, item, delTag, gen) ? 1 : 0;
   }
 }
 
-// phase 3b: leaders unlink their chain's blocks in list order — deleteBlock :1032-1111
 __global__ void k_decay_unlink(b200_hash_entry *table, int numBuckets, uint8_t *visType, const b200_vec3i *ring, long long ringCap,
                                const long long *snapStart, int slot, const short4 *allocatedPos, int mode, const int *delList,
                                const unsigned long long *delTag, unsigned gen, const uint8_t *isLeader, DevCounters *ctr) {
   const int nDel = ctr->decayDeleted;
   const long long s0 = (mode == 0) ? snapStart[slot] : 0;
-  int *tw = reinterpret_cast<int *>(table);
   for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < nDel; r += gridDim.x * blockDim.x) {
     if (!isLeader[r]) continue;
-    const int item0 = delList[r];
-    int x0, y0, z0;
-    if (mode == 0) { b200_vec3i p = ring[(s0 + item0) % ringCap]; x0 = p.x; y0 = p.y; z0 = p.z; }
-    else { short4 p = allocatedPos[item0]; x0 = p.x; y0 = p.y; z0 = p.z; }
-    const int head = hash_index(x0, y0, z0, numBuckets - 1);
-    // Serial order = ascending list position: repeatedly take the chain entry whose block was claimed
-    // by the smallest item and unlink it on the evolving chain (findVoxel's idx / prev, :1032-1037).
-    for (;;) {
-      int found = -1, foundPrev = -1; unsigned best = 0xffffffffu;
-      for (int idx = head, prev = -1;;) {
-        Entry en = load_entry_rw(table, idx);
-        if (en.ptr >= 0) {
-          unsigned long long t = delTag[en.ptr];
-          if ((unsigned)(t >> 32) == gen) {
-            unsigned it = 0xffffffffu - (unsigned)(t & 0xffffffffu);
-            if (it < best) { best = it; found = idx; foundPrev = prev; }
-          }
-        }
-        if (en.offset < 1) break;
-        prev = idx;
-        idx = numBuckets + en.offset - 1;
-      }
-      if (found < 0) break;
-      const int prev = foundPrev;
-      int *e = tw + (size_t)found * 5;
-      if (prev == -1) {
-        if (e[2] >= 1) {                       // ordered entry with a successor: pull the successor in
-          const int nextIdx = numBuckets + e[2] - 1;
-          int *nx = tw + (size_t)nextIdx * 5;
-          e[0] = nx[0]; e[1] = nx[1]; e[2] = nx[2]; e[3] = nx[3]; e[4] = nx[4];
-          visType[found] = visType[nextIdx];
-          visType[nextIdx] = 0;
-          nx[2] = 0; nx[3] = -2;
-        } else {                               // ordered entry, no successor
-          e[3] = -2;
-          visType[found] = 0;
-        }
-      } else {                                 // excess entry: predecessor inherits the link
-        int *pv = tw + (size_t)prev * 5;
-        pv[2] = e[2];
-        e[2] = 0; e[3] = -2;
-        visType[prev] = visType[found];        // (sic) reference quirk, :1109-1110
-        visType[found] = 0;
-      }
-    }
+    int x, y, z;
+    item_pos(mode, ring, ringCap, s0, allocatedPos, delList[r], x, y, z);
+    unlink_chain(table, numBuckets, visType, hash_index(x, y, z, numBuckets - 1), delTag, gen);
+  }
+}
+
+// phases 2 + 3 + counters of a PARTIAL decay in one single-CTA launch (a frame's list is a few thousand
+// items; four tiny dependent launches cost more than the work). Ordered compaction of the claims,
+// leader election, chain unlinking, counter update.
+__global__ void __launch_bounds__(1024)
+k_decay_commit(b200_hash_entry *table, int numBuckets, uint8_t *visType, const b200_vec3i *ring, long long ringCap,
+               const long long *snapStart, int slot, const int *itemPtr, const unsigned long long *delTag, unsigned gen, int *allocList,
+               int *delList, uint8_t *isLeader, DevCounters *ctr) {
+  __shared__ unsigned sm[33];
+  const int n = ctr->decayItems;
+  const int lastFree = ctr->lastFreeBlockId;
+  const long long s0 = snapStart[slot];
+  unsigned running = 0;
+  for (int base = 0; base < n; base += blockDim.x) {
+    const int item = base + threadIdx.x;
+    int ptr = -1;
+    if (item < n) { ptr = itemPtr[item]; if (ptr >= 0 && delTag[ptr] != del_tag(gen, (unsigned)item)) ptr = -1; }
+    unsigned total;
+    const unsigned r = running + block_exclusive_scan(ptr >= 0 ? 1u : 0u, sm, &total);
+    if (ptr >= 0) { allocList[lastFree + 1 + (int)r] = ptr; delList[r] = item; }   // free-list push by list position (:1072-1073)
+    running += total;
+  }
+  const int nDel = (int)running;
+  __syncthreads();
+  for (int r = threadIdx.x; r < nDel; r += blockDim.x) {
+    int x, y, z;
+    const int item = delList[r];
+    item_pos(0, ring, ringCap, s0, nullptr, item, x, y, z);
+    isLeader[r] = chain_leader(table, numBuckets, x, y, z, item, delTag, gen) ? 1 : 0;
+  }
+  __syncthreads();
+  for (int r = threadIdx.x; r < nDel; r += blockDim.x) {
+    if (!isLeader[r]) continue;
+    int x, y, z;
+    item_pos(0, ring, ringCap, s0, nullptr, delList[r], x, y, z);
+    unlink_chain(table, numBuckets, visType, hash_index(x, y, z, numBuckets - 1), delTag, gen);
+  }
+  if (threadIdx.x == 0) {
+    ctr->lastFreeBlockId = lastFree + nDel;
+    ctr->freedLastDecay = nDel;
+    ctr->totalDecayed += nDel;
+    ctr->decayDeleted = 0;
+    ctr->decayItems = 0;
   }
 }
 
@@ -236,15 +293,17 @@ static void decay_common(b200_engine *e, const SceneRef &s, int mode, int slot, 
     k_decay_blocks<1><<<grid1, 256, 0, st>>>(s.voxels, s.hash, s.numBuckets, e->d_ring, e->ringCap, e->d_snapStart, e->d_snapCount,
                                             slot, e->d_allocatedPos, s.numBlocks, minAge, maxWeight, frameIdx, gen, e->d_delTag,
                                             e->d_itemPtr, e->d_ctr);
+  if (mode == 0) {
+    k_decay_commit<<<1, 1024, 0, st>>>(s.hash, s.numBuckets, s.visType, e->d_ring, e->ringCap, e->d_snapStart, slot, e->d_itemPtr, e->d_delTag,
+                                       gen, s.allocationList, e->d_delList, e->d_isLeader, e->d_ctr);
+    e->launches += 2;
+    return;
+  }
   const int noTiles = (int)((items + DEC_TILE - 1) / DEC_TILE);
   k_decay_rank<<<persistent_grid(e, 4, noTiles), 256, 0, st>>>(e->d_itemPtr, e->d_delTag, gen, s.allocationList, e->d_delList,
                                                                e->d_ctr, e->d_scanDesc, ++e->scanGen);
-  if (mode == 0)
-    k_decay_elect<0><<<e->smCount, 128, 0, st>>>(s.hash, s.numBuckets, e->d_ring, e->ringCap, e->d_snapStart, slot, e->d_allocatedPos,
-                                                e->d_delList, e->d_delTag, gen, e->d_isLeader, e->d_ctr);
-  else
-    k_decay_elect<1><<<e->smCount, 128, 0, st>>>(s.hash, s.numBuckets, e->d_ring, e->ringCap, e->d_snapStart, slot, e->d_allocatedPos,
-                                                e->d_delList, e->d_delTag, gen, e->d_isLeader, e->d_ctr);
+  k_decay_elect<1><<<e->smCount, 128, 0, st>>>(s.hash, s.numBuckets, e->d_ring, e->ringCap, e->d_snapStart, slot, e->d_allocatedPos,
+                                              e->d_delList, e->d_delTag, gen, e->d_isLeader, e->d_ctr);
   k_decay_unlink<<<e->smCount, 128, 0, st>>>(s.hash, s.numBuckets, s.visType, e->d_ring, e->ringCap, e->d_snapStart, slot,
                                             e->d_allocatedPos, mode, e->d_delList, e->d_delTag, gen, e->d_isLeader, e->d_ctr);
   k_decay_finish<<<1, 1, 0, st>>>(e->d_ctr);

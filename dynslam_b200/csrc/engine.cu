@@ -43,6 +43,7 @@ static FrameGeom frame_geom(const b200_scene *s, const b200_view *v) {
   g.w = v->depth_w; g.h = v->depth_h; g.rgb_w = v->rgb_w; g.rgb_h = v->rgb_h;
   g.voxelSize = s->voxelSize; g.mu = s->mu; g.maxW = s->maxW; g.vfmin = s->viewFrustum_min; g.vfmax = s->viewFrustum_max;
   g.depthWeighting = v->depthWeighting; g.stopMaxW = s->stopIntegratingAtMaxW; g.approx = !v->requiresFullRendering;
+  { volatile float a = -1.0f, b = s->mu; g.negOneOverMu = a / b; }
   g.sameRgbCam = (memcmp(v->M_rgb, v->M_d, sizeof(v->M_d)) == 0 && memcmp(v->proj_rgb, v->proj_d, sizeof(v->proj_d)) == 0 &&
                   v->rgb_w == v->depth_w && v->rgb_h == v->depth_h) ? 1 : 0;
   return g;
@@ -129,6 +130,7 @@ b200_status b200_engine_create(const b200_engine_config *cfg, b200_engine **out)
   CK(cudaMemset(e->d_snapStart, 0, sizeof(long long) * SNAP_SLOTS));
   CK(cudaMalloc(&e->d_delTag, sizeof(unsigned long long) * (size_t)e->numBlocks));
   CK(cudaMemset(e->d_delTag, 0, sizeof(unsigned long long) * (size_t)e->numBlocks));
+  CK(cudaMalloc(&e->d_visiblePtr, sizeof(int) * (size_t)e->numBlocks));
   CK(cudaMalloc(&e->d_itemPtr, sizeof(int) * (size_t)e->numBlocks));
   CK(cudaMalloc(&e->d_delList, sizeof(int) * (size_t)e->numBlocks));
   CK(cudaMalloc(&e->d_isLeader, (size_t)e->numBlocks));
@@ -145,7 +147,7 @@ void b200_engine_destroy(b200_engine *e) {
   cudaSetDevice(e->device);
   if (e->stream) cudaStreamSynchronize(e->stream);
   cudaFree(e->d_ctr); cudaFreeHost(e->h_ctr); cudaFree(e->d_reqKey); cudaFree(e->d_reqBits); cudaFree(e->d_scanDesc);
-  cudaFree(e->d_ring); cudaFree(e->d_snapCount); cudaFree(e->d_snapStart); cudaFree(e->d_delTag); cudaFree(e->d_itemPtr);
+  cudaFree(e->d_ring); cudaFree(e->d_snapCount); cudaFree(e->d_snapStart); cudaFree(e->d_delTag); cudaFree(e->d_itemPtr); cudaFree(e->d_visiblePtr);
   cudaFree(e->d_delList); cudaFree(e->d_isLeader); cudaFree(e->d_allocatedPos); cudaFree(e->d_tileCounts);
   for (int i = 0; i < 8; ++i) if (e->ev[i]) cudaEventDestroy(e->ev[i]);
   if (e->ownStream && e->stream) cudaStreamDestroy(e->stream);
@@ -215,6 +217,7 @@ b200_status b200_reset_scene(b200_engine *e, b200_scene *s) {
   CK(cudaSetDevice(e->device));
   e->totalDecayed = 0;
   e->qHead += e->qSize; e->qSize = 0;          // clear the decay queue; frameIdx is NOT reset (Reco_CUDA.cu:150-155)
+  e->tableVersion++;
   launch_reset(e, scene_ref(s, nullptr));
   return download_sync(e, s, nullptr);
 }
@@ -229,7 +232,9 @@ static b200_status enqueue_allocate(b200_engine *e, b200_scene *s, b200_render_s
     return B200_ERR_INVALID;
   }
   const int slot = (e->qHead + e->qSize) % SNAP_SLOTS;
+  e->tableVersion++;
   launch_allocate(e, scene_ref(s, rs), frame_geom(s, v), v->d_depth, onlyVisible != 0, e->frameIdx, slot);
+  e->ptrListFor = rs->d_visibleBlockPositions; e->ptrListVersion = e->tableVersion;
   e->qSize++;
   e->frameIdx++;
   return B200_OK;
@@ -258,6 +263,7 @@ b200_status b200_integrate(b200_engine *e, b200_scene *s, b200_render_state *rs,
 
 static void enqueue_decay(b200_engine *e, b200_scene *s, b200_render_state *rs, int maxWeight, int minAge, int forceAll) {
   SceneRef r = scene_ref(s, rs);
+  e->tableVersion++;
   if (forceAll) launch_decay_full(e, r, minAge, maxWeight, e->frameIdx);
   else if ((long)e->qSize > minAge) {
     const int slot = e->qHead % SNAP_SLOTS;
@@ -280,6 +286,7 @@ b200_status b200_find_visible_blocks(b200_engine *e, const b200_scene *s, b200_r
   b200_status st = check_scene(e, s); if (st) return st;
   CK(cudaSetDevice(e->device));
   st = upload(e, s, rs); if (st) return st;
+  if (e->ptrListFor == (const void *)rs->d_visibleBlockPositions) e->ptrListFor = nullptr;   // list rebuilt without ptrs
   launch_find_visible(e, scene_ref(s, rs), to_mat(cam->M), cam->proj, rs->img_w, rs->img_h, s->voxelSize);
   return download_sync(e, nullptr, rs);
 }
@@ -385,6 +392,7 @@ b200_status b200_swap_out(b200_engine *e, b200_scene *s, b200_render_state *rs, 
   const int n = e->h_ctr->noNeededEntries;
   *noNeeded = n;
   if (n > 0) {
+    e->tableVersion++;
     launch_swap_move_out(e, r, tb->d_syncedVoxelBlocks, tb->d_hasSyncedData, tb->d_neededEntryIDs, n);
     st = download_sync(e, s, nullptr);
   }

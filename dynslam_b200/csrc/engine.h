@@ -10,6 +10,7 @@ struct FrameGeom {          // per-call constants handed to kernels by value
   int maxW;
   float vfmin, vfmax;
   int depthWeighting, stopMaxW, approx;
+  float negOneOverMu;       // -1.0f / mu, the quotient of every rejected voxel (eta == -1)
   int sameRgbCam;           // M_rgb, proj_rgb, image size bitwise equal to the depth camera's: ix,iy are shared
 };
 
@@ -49,6 +50,9 @@ struct b200_engine {
   long long *d_snapStart;
   int qHead, qSize;                   // host view of the queue (slots qHead .. qHead+qSize-1)
   unsigned long long *d_delTag;       // per VBA block: gen | ~itemIndex of the deleting item
+  int *d_visiblePtr;                  // VBA ptr of every item of the list built by the last allocate (or -1)
+  const void *ptrListFor;             // the visible list buffer d_visiblePtr describes
+  unsigned long long tableVersion, ptrListVersion;   // d_visiblePtr is valid while they are equal
   int *d_itemPtr;                     // per decay item: VBA ptr (or -1)
   unsigned *d_itemFlag;               // per decay item: 1 = deletes its block
   int *d_delList;                     // compacted deleting items (list order)
@@ -78,6 +82,9 @@ void launch_reset(b200_engine *e, const SceneRef &s);
 void launch_allocate(b200_engine *e, const SceneRef &s, const FrameGeom &g, const float *depth, bool onlyVisible,
                      int frameIdx, int snapSlot);
 void launch_integrate(b200_engine *e, const SceneRef &s, const FrameGeom &g, const float *depth, const b200_vec4u *rgb);
+static inline const int *fresh_ptr_list(const b200_engine *e, const SceneRef &s) {
+  return (e->ptrListFor == (const void *)s.visiblePos && e->ptrListVersion == e->tableVersion) ? e->d_visiblePtr : nullptr;
+}
 void launch_decay_partial(b200_engine *e, const SceneRef &s, int snapSlot, int minAge, int maxWeight, int frameIdx);
 void launch_decay_full(b200_engine *e, const SceneRef &s, int minAge, int maxWeight, int frameIdx);
 void launch_find_visible(b200_engine *e, const SceneRef &s, const Mat4 &M, const float proj[4], int w, int h, float voxelSize);

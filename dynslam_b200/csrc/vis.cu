@@ -53,24 +53,26 @@ DEV bool project_single_block(int bx, int by, int bz, const Mat4 &pose, const fl
   return true;
 }
 
-__global__ void __launch_bounds__(256)
-k_project_blocks(const b200_hash_entry *__restrict__ table, int numBuckets, const b200_vec3i *__restrict__ visiblePos, int capacity,
-                 DevCounters *ctr, Mat4 M, float p0, float p1, float p2, float p3, int w, int h, float voxelSize, float2 *minmax,
+#define PRJ_THREADS 64   // small CTAs: a frame has a few thousand visible blocks, spread them over many SMs
+__global__ void __launch_bounds__(PRJ_THREADS)
+k_project_blocks(const b200_hash_entry *__restrict__ table, int numBuckets, const b200_vec3i *__restrict__ visiblePos,
+                 const int *__restrict__ visiblePtr, int capacity, DevCounters *ctr, Mat4 M, float p0, float p1, float p2, float p3, int w, int h, float voxelSize, float2 *minmax,
                  unsigned long long *scanDesc, unsigned gen) {
   __shared__ unsigned sm[33];
   __shared__ unsigned tileBase;
   const float intr[4] = {p0, p1, p2, p3};
   int n = ctr->noVisibleBlocks;
   if (n > capacity) n = capacity;
-  const int noTiles = (n + 255) / 256;
+  const int noTiles = (n + PRJ_THREADS - 1) / PRJ_THREADS;
   const int lane = threadIdx.x & 31;
   for (int tile = blockIdx.x; tile < noTiles; tile += gridDim.x) {
-    const int item = tile * 256 + threadIdx.x;
+    const int item = tile * PRJ_THREADS + threadIdx.x;
     int ulx = 0, uly = 0, lrx = -1, lry = -1; float zmin = 0, zmax = 0;
     unsigned required = 0;
     if (item < n) {
       const b200_vec3i p = visiblePos[item];
-      if (find_block<false>(table, numBuckets, p.x, p.y, p.z) >= 0) {
+      const bool allocated = visiblePtr ? (visiblePtr[item] >= 0) : (find_block<false>(table, numBuckets, p.x, p.y, p.z) >= 0);
+      if (allocated) {
         if (project_single_block(p.x, p.y, p.z, M, intr, w, h, voxelSize, ulx, uly, lrx, lry, zmin, zmax)) {
           const int rx = (int)ceilf((float)(lrx - ulx + 1) / 16), ry = (int)ceilf((float)(lry - uly + 1) / 16);
           required = (unsigned)(rx * ry);
@@ -110,8 +112,9 @@ k_project_blocks(const b200_hash_entry *__restrict__ table, int numBuckets, cons
 void launch_expected_depths(b200_engine *e, const SceneRef &s, const Mat4 &M, const float proj[4], int w, int h, float voxelSize,
                             b200_vec2f *minmax) {
   k_minmax_init<<<e->smCount * 4, 256, 0, e->stream>>>((float2 *)minmax, w * h);
-  const int noTiles = (s.numBlocks + 255) / 256;
-  k_project_blocks<<<persistent_grid(e, 4, noTiles), 256, 0, e->stream>>>(s.hash, s.numBuckets, s.visiblePos, s.numBlocks, e->d_ctr, M,
+  const int noTiles = (s.numBlocks + PRJ_THREADS - 1) / PRJ_THREADS;
+  k_project_blocks<<<persistent_grid(e, 8, noTiles), PRJ_THREADS, 0, e->stream>>>(s.hash, s.numBuckets, s.visiblePos, fresh_ptr_list(e, s),
+                                                                                 s.numBlocks, e->d_ctr, M,
                                                                          proj[0], proj[1], proj[2], proj[3], w, h, voxelSize,
                                                                          (float2 *)minmax, e->d_scanDesc, ++e->scanGen);
   e->launches += 2;
@@ -121,25 +124,30 @@ void launch_expected_depths(b200_engine *e, const SceneRef &s, const Mat4 &M, co
 // voxel access with the one-entry IndexCache (DA/ITMRepresentationAccess.h:176-220,
 // Objects/ITMVoxelBlockHash.h:27-31)
 // ------------------------------------------------------------------------------------------------
+// The cache memoises the LAST block resolved, hit or miss (blockPtr = -1): the table is constant
+// during a raycast, so remembering a miss returns exactly what the reference's chain walk would.
 struct IdxCache { int bx, by, bz, blockPtr; };
 DEV void cache_init(IdxCache &c) { c.bx = c.by = c.bz = 0x7fffffff; c.blockPtr = -1; }
 
-// returns the voxel index in the VBA or -1
-DEV int voxel_index(const b200_hash_entry *__restrict__ table, int numBuckets, int px, int py, int pz, IdxCache &c) {
-  const int bx = floordiv8(px), by = floordiv8(py), bz = floordiv8(pz);
-  const int linearIdx = px + (py - bx) * BS + (pz - by) * BS * BS - bz * BS3;
-  if (bx == c.bx && by == c.by && bz == c.bz) return c.blockPtr + linearIdx;
+// resolves block (bx,by,bz): returns ptr*512 or -1
+DEV int block_base(const b200_hash_entry *__restrict__ table, int numBuckets, int bx, int by, int bz, IdxCache &c) {
+  if (bx == c.bx && by == c.by && bz == c.bz) return c.blockPtr;
   int hashIdx = hash_index(bx, by, bz, numBuckets - 1);
+  int res = -1;
   for (;;) {
-    Entry he = load_entry(table, hashIdx);
-    if (he.x == bx && he.y == by && he.z == bz && he.ptr >= 0) {
-      c.bx = bx; c.by = by; c.bz = bz; c.blockPtr = he.ptr * BS3;
-      return c.blockPtr + linearIdx;
-    }
+    const Entry he = load_entry(table, hashIdx);
+    if (he.x == bx && he.y == by && he.z == bz && he.ptr >= 0) { res = he.ptr * BS3; break; }
     if (he.offset < 1) break;
     hashIdx = numBuckets + he.offset - 1;
   }
-  return -1;
+  c.bx = bx; c.by = by; c.bz = bz; c.blockPtr = res;
+  return res;
+}
+
+// returns the voxel index in the VBA or -1 (pointToVoxelBlockPos: floor division by 8 == arithmetic shift)
+DEV int voxel_index(const b200_hash_entry *__restrict__ table, int numBuckets, int px, int py, int pz, IdxCache &c) {
+  const int base = block_base(table, numBuckets, px >> 3, py >> 3, pz >> 3, c);
+  return base < 0 ? -1 : base + (px & 7) + ((py & 7) << 3) + ((pz & 7) << 6);
 }
 
 DEV float sdf_raw(const b200_voxel *__restrict__ voxels, int vi) {   // (float)voxel.sdf, missing -> TVoxel() = 32767
@@ -150,21 +158,37 @@ DEV float rv_sdf(const b200_voxel *__restrict__ voxels, const b200_hash_entry *_
   return sdf_raw(voxels, voxel_index(table, nb, x, y, z, c));
 }
 
-// readFromSDF_float_interpolated — DA/ITMRepresentationAccess.h:252-278
+// readFromSDF_float_interpolated — DA/ITMRepresentationAccess.h:252-278. When the 2x2x2 neighbourhood
+// lies inside one block (7 of 8 positions per axis) the block is resolved once and the eight 2-byte
+// reads use constant offsets; the arithmetic is the reference's, operand for operand.
 DEV float sdf_interp(const b200_voxel *__restrict__ voxels, const b200_hash_entry *__restrict__ table, int nb, float px, float py, float pz,
                      IdxCache &c) {
   const float fx = floorf(px), fy = floorf(py), fz = floorf(pz);
   const float cx = px - fx, cy = py - fy, cz = pz - fz;
   const int x = (int)fx, y = (int)fy, z = (int)fz;
-  float res1, res2, v1, v2;
-  v1 = rv_sdf(voxels, table, nb, x, y, z, c); v2 = rv_sdf(voxels, table, nb, x + 1, y, z, c);
-  res1 = (1.0f - cx) * v1 + cx * v2;
-  v1 = rv_sdf(voxels, table, nb, x, y + 1, z, c); v2 = rv_sdf(voxels, table, nb, x + 1, y + 1, z, c);
-  res1 = (1.0f - cy) * res1 + cy * ((1.0f - cx) * v1 + cx * v2);
-  v1 = rv_sdf(voxels, table, nb, x, y, z + 1, c); v2 = rv_sdf(voxels, table, nb, x + 1, y, z + 1, c);
-  res2 = (1.0f - cx) * v1 + cx * v2;
-  v1 = rv_sdf(voxels, table, nb, x, y + 1, z + 1, c); v2 = rv_sdf(voxels, table, nb, x + 1, y + 1, z + 1, c);
-  res2 = (1.0f - cy) * res2 + cy * ((1.0f - cx) * v1 + cx * v2);
+  float v000, v100, v010, v110, v001, v101, v011, v111;
+  const int lx = x & 7, ly = y & 7, lz = z & 7;
+  if (lx < 7 && ly < 7 && lz < 7) {
+    const int base = block_base(table, nb, x >> 3, y >> 3, z >> 3, c);
+    if (base < 0) { v000 = v100 = v010 = v110 = v001 = v101 = v011 = v111 = 32767.0f; }
+    else {
+      const short *sp = reinterpret_cast<const short *>(voxels + base + lx + (ly << 3) + (lz << 6));   // 8-byte voxels: short stride 4
+      v000 = (float)__ldg(sp);            v100 = (float)__ldg(sp + 4);
+      v010 = (float)__ldg(sp + 32);       v110 = (float)__ldg(sp + 36);
+      v001 = (float)__ldg(sp + 256);      v101 = (float)__ldg(sp + 260);
+      v011 = (float)__ldg(sp + 288);      v111 = (float)__ldg(sp + 292);
+    }
+  } else {
+    v000 = rv_sdf(voxels, table, nb, x, y, z, c);         v100 = rv_sdf(voxels, table, nb, x + 1, y, z, c);
+    v010 = rv_sdf(voxels, table, nb, x, y + 1, z, c);     v110 = rv_sdf(voxels, table, nb, x + 1, y + 1, z, c);
+    v001 = rv_sdf(voxels, table, nb, x, y, z + 1, c);     v101 = rv_sdf(voxels, table, nb, x + 1, y, z + 1, c);
+    v011 = rv_sdf(voxels, table, nb, x, y + 1, z + 1, c); v111 = rv_sdf(voxels, table, nb, x + 1, y + 1, z + 1, c);
+  }
+  float res1, res2;
+  res1 = (1.0f - cx) * v000 + cx * v100;
+  res1 = (1.0f - cy) * res1 + cy * ((1.0f - cx) * v010 + cx * v110);
+  res2 = (1.0f - cx) * v001 + cx * v101;
+  res2 = (1.0f - cy) * res2 + cy * ((1.0f - cx) * v011 + cx * v111);
   return ((1.0f - cz) * res1 + cz * res2) / 32767.0f;
 }
 
