@@ -167,11 +167,17 @@ k_mark(const float *__restrict__ depth, const b200_hash_entry *__restrict__ tabl
         isExcess = true;
       }
       if (!isFound) {
-        atomicMax(&reqKey[hashIdx], make_key(frameTag, pixel, (unsigned)i));
-        const unsigned bit = 1u << (hashIdx & 31);
-        if (!(reqBits[hashIdx >> 5] & bit)) atomicOr(&reqBits[hashIdx >> 5], bit);
-        if (isExcess) { if (!(req2Bits[hashIdx >> 5] & bit)) atomicOr(&req2Bits[hashIdx >> 5], bit); }
-        else visType[hashIdx] = 1;
+        // Neighbouring rays miss the same block at the same step: the lanes of the warp that request the same
+        // entry elect the one with the largest key (lane order == raster order inside the 8x4 tile, the step
+        // is warp-uniform) and only that lane issues the atomics.
+        const unsigned peers = __match_any_sync(__activemask(), hashIdx);
+        if (lane == 31 - __clz(peers)) {
+          atomicMax(&reqKey[hashIdx], make_key(frameTag, pixel, (unsigned)i));
+          const unsigned bit = 1u << (hashIdx & 31);
+          if (!(reqBits[hashIdx >> 5] & bit)) atomicOr(&reqBits[hashIdx >> 5], bit);
+          if (isExcess) { if (!(req2Bits[hashIdx >> 5] & bit)) atomicOr(&req2Bits[hashIdx >> 5], bit); }
+          else visType[hashIdx] = 1;
+        }
       }
     }
     px += r.dx; py += r.dy; pz += r.dz;

@@ -135,6 +135,7 @@ b200_status b200_engine_create(const b200_engine_config *cfg, b200_engine **out)
   CK(cudaMalloc(&e->d_delList, sizeof(int) * (size_t)e->numBlocks));
   CK(cudaMalloc(&e->d_isLeader, (size_t)e->numBlocks));
   CK(cudaMalloc(&e->d_allocatedPos, sizeof(short4) * (size_t)e->numBlocks));
+  CK(cudaMalloc(&e->d_blockRecs, 16 * (size_t)e->numBlocks));
   CK(cudaMalloc(&e->d_tileCounts, sizeof(unsigned) * (size_t)(px > 0 ? px : 1)));
   for (int i = 0; i < 8; ++i) CK(cudaEventCreate(&e->ev[i]));
   e->hostAuthoritative = true;
@@ -148,7 +149,7 @@ void b200_engine_destroy(b200_engine *e) {
   if (e->stream) cudaStreamSynchronize(e->stream);
   cudaFree(e->d_ctr); cudaFreeHost(e->h_ctr); cudaFree(e->d_reqKey); cudaFree(e->d_reqBits); cudaFree(e->d_scanDesc);
   cudaFree(e->d_ring); cudaFree(e->d_snapCount); cudaFree(e->d_snapStart); cudaFree(e->d_delTag); cudaFree(e->d_itemPtr); cudaFree(e->d_visiblePtr);
-  cudaFree(e->d_delList); cudaFree(e->d_isLeader); cudaFree(e->d_allocatedPos); cudaFree(e->d_tileCounts);
+  cudaFree(e->d_delList); cudaFree(e->d_isLeader); cudaFree(e->d_allocatedPos); cudaFree(e->d_tileCounts); cudaFree(e->d_blockRecs);
   for (int i = 0; i < 8; ++i) if (e->ev[i]) cudaEventDestroy(e->ev[i]);
   if (e->ownStream && e->stream) cudaStreamDestroy(e->stream);
   delete e;

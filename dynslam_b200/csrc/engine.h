@@ -63,6 +63,7 @@ struct b200_engine {
   long long totalDecayed;
   // vis
   unsigned *d_tileCounts;
+  void *d_blockRecs;                  // expected depths: per visible block {bbox, z-range}, 16 B
   // timing / stats
   bool timing;
   cudaEvent_t ev[8];

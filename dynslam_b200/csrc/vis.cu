@@ -17,11 +17,6 @@
 // ------------------------------------------------------------------------------------------------
 // expected depths
 // ------------------------------------------------------------------------------------------------
-__global__ void k_minmax_init(float2 *minmax, int n) {
-  const float2 v = make_float2(B200_FAR_AWAY, B200_VERY_CLOSE);
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) minmax[i] = v;
-}
-
 // ProjectSingleBlock — DA/ITMVisualisationEngine.h:29-71
 DEV bool project_single_block(int bx, int by, int bz, const Mat4 &pose, const float *intr, int w, int h, float voxelSize,
                               int &ulx, int &uly, int &lrx, int &lry, float &zmin, float &zmax) {
@@ -53,18 +48,29 @@ DEV bool project_single_block(int bx, int by, int bz, const Mat4 &pose, const fl
   return true;
 }
 
-#define PRJ_THREADS 64   // small CTAs: a frame has a few thousand visible blocks, spread them over many SMs
+// Stage 1: project every visible block (one thread each, small CTAs so that a few thousand blocks spread over
+// many SMs), apply the MAX_RENDERING_BLOCKS rule from the list-order prefix of the tile counts (Vis_CUDA.cu:609)
+// and emit a 16-byte record {bbox, z-range}. Cells of a bounding box that lie outside the live 1/8-resolution
+// corner (the reference clamps boxes to the FULL-resolution bounds, DA/ITMVisualisationEngine.h:57-60) are
+// rasterised here with global atomics; they are rare and never read by the raycast.
+// Stage 2 (k_fill_minmax): the live corner is cut into 8x8-cell tiles, one CTA per tile; the CTA scans all
+// records, rasterises the boxes that overlap its tile into shared memory with shared-memory atomics and
+// writes the tile out with plain stores — no global atomics on the hot cells that hundreds of far blocks
+// cover, and no separate initialisation of the live corner.
+struct __align__(16) BlockRec { short ulx, uly, lrx, lry; float zmin, zmax; };
+
+#define PRJ_THREADS 64
 __global__ void __launch_bounds__(PRJ_THREADS)
 k_project_blocks(const b200_hash_entry *__restrict__ table, int numBuckets, const b200_vec3i *__restrict__ visiblePos,
-                 const int *__restrict__ visiblePtr, int capacity, DevCounters *ctr, Mat4 M, float p0, float p1, float p2, float p3, int w, int h, float voxelSize, float2 *minmax,
-                 unsigned long long *scanDesc, unsigned gen) {
+                 const int *__restrict__ visiblePtr, int capacity, DevCounters *ctr, Mat4 M, float p0, float p1, float p2, float p3, int w,
+                 int h, float voxelSize, float2 *minmax, BlockRec *recs, unsigned long long *scanDesc, unsigned gen) {
   __shared__ unsigned sm[33];
   __shared__ unsigned tileBase;
   const float intr[4] = {p0, p1, p2, p3};
   int n = ctr->noVisibleBlocks;
   if (n > capacity) n = capacity;
   const int noTiles = (n + PRJ_THREADS - 1) / PRJ_THREADS;
-  const int lane = threadIdx.x & 31;
+  const int liveX = (w - 1) / B200_MINMAX_SUBSAMPLE, liveY = (h - 1) / B200_MINMAX_SUBSAMPLE;   // last live cell
   for (int tile = blockIdx.x; tile < noTiles; tile += gridDim.x) {
     const int item = tile * PRJ_THREADS + threadIdx.x;
     int ulx = 0, uly = 0, lrx = -1, lry = -1; float zmin = 0, zmax = 0;
@@ -80,28 +86,23 @@ k_project_blocks(const b200_hash_entry *__restrict__ table, int numBuckets, cons
       }
     }
     unsigned total;
-    unsigned local = block_exclusive_scan(required, sm, &total);
+    const unsigned local = block_exclusive_scan(required, sm, &total);
     if (threadIdx.x < 32) {
-      unsigned ex = scan_lookback(scanDesc, gen, tile, total);
+      const unsigned ex = scan_lookback(scanDesc, gen, tile, total);
       if (threadIdx.x == 0) { tileBase = ex; if (tile == noTiles - 1) ctr->noRenderingBlocks = ex + total; }
     }
     __syncthreads();
     const unsigned out_offset = tileBase + local;
-    bool draw = required > 0 && (out_offset + required <= (unsigned)B200_MAX_RENDERING_BLOCKS);   // :609
-    // warp-cooperative rasterisation of each lane's bounding box
-    unsigned todo = __ballot_sync(0xffffffffu, draw);
-    while (todo) {
-      const int src = __ffs(todo) - 1;
-      todo &= todo - 1;
-      const int ax = __shfl_sync(0xffffffffu, ulx, src), ay = __shfl_sync(0xffffffffu, uly, src);
-      const int bx = __shfl_sync(0xffffffffu, lrx, src), by = __shfl_sync(0xffffffffu, lry, src);
-      const float zn = __shfl_sync(0xffffffffu, zmin, src), zx = __shfl_sync(0xffffffffu, zmax, src);
-      const int bw = bx - ax + 1, cnt = bw * (by - ay + 1);
-      for (int k = lane; k < cnt; k += 32) {
-        const int yy = ay + k / bw, xx = ax + k % bw;
-        float2 *px = &minmax[xx + yy * w];
-        atomic_min_posf(&px->x, zn);
-        atomic_max_posf(&px->y, zx);
+    const bool draw = required > 0 && (out_offset + required <= (unsigned)B200_MAX_RENDERING_BLOCKS);   // :609
+    if (item < n) {
+      BlockRec r;
+      if (draw) { r.ulx = (short)ulx; r.uly = (short)uly; r.lrx = (short)lrx; r.lry = (short)lry; r.zmin = zmin; r.zmax = zmax; }
+      else { r.ulx = 1; r.uly = 1; r.lrx = 0; r.lry = 0; r.zmin = 0; r.zmax = 0; }
+      recs[item] = r;
+      if (draw && (lrx > liveX || lry > liveY)) {   // the part of the box outside the live corner (dead cells)
+        for (int yy = uly; yy <= lry; ++yy)
+          for (int xx = ulx; xx <= lrx; ++xx)
+            if (xx > liveX || yy > liveY) { float2 *px = &minmax[xx + yy * w]; atomic_min_posf(&px->x, zmin); atomic_max_posf(&px->y, zmax); }
       }
     }
     __syncthreads();
@@ -109,15 +110,61 @@ k_project_blocks(const b200_hash_entry *__restrict__ table, int numBuckets, cons
   if (noTiles == 0 && blockIdx.x == 0 && threadIdx.x == 0) ctr->noRenderingBlocks = 0;
 }
 
+#define FILL_T 8          // tile edge in 1/8-resolution cells
+#define FILL_THREADS 128
+__global__ void __launch_bounds__(FILL_THREADS)
+k_fill_minmax(const BlockRec *__restrict__ recs, const DevCounters *ctr, int capacity, int w, int h, float2 *minmax) {
+  __shared__ int smin[FILL_T * FILL_T], smax[FILL_T * FILL_T];
+  const int liveX = (w - 1) / B200_MINMAX_SUBSAMPLE, liveY = (h - 1) / B200_MINMAX_SUBSAMPLE;
+  const int tx0 = blockIdx.x * FILL_T, ty0 = blockIdx.y * FILL_T;
+  const int tx1 = min(tx0 + FILL_T - 1, liveX), ty1 = min(ty0 + FILL_T - 1, liveY);
+  if (threadIdx.x < FILL_T * FILL_T) { smin[threadIdx.x] = __float_as_int(B200_FAR_AWAY); smax[threadIdx.x] = __float_as_int(B200_VERY_CLOSE); }
+  __syncthreads();
+  int n = ctr->noVisibleBlocks;
+  if (n > capacity) n = capacity;
+  const uint4 *r4 = reinterpret_cast<const uint4 *>(recs);
+  for (int i = threadIdx.x; i < n; i += FILL_THREADS) {
+    const uint4 q = __ldg(r4 + i);
+    const int ulx = (short)(q.x & 0xffff), uly = (short)(q.x >> 16), lrx = (short)(q.y & 0xffff), lry = (short)(q.y >> 16);
+    const int ax = max(ulx, tx0), bx = min(lrx, tx1), ay = max(uly, ty0), by = min(lry, ty1);
+    if (ax > bx || ay > by) continue;
+    const int zn = (int)q.z, zx = (int)q.w;   // positive floats: integer order == float order
+    for (int yy = ay; yy <= by; ++yy)
+      for (int xx = ax; xx <= bx; ++xx) {
+        const int c = (yy - ty0) * FILL_T + (xx - tx0);
+        atomicMin(&smin[c], zn);
+        atomicMax(&smax[c], zx);
+      }
+  }
+  __syncthreads();
+  if (threadIdx.x < FILL_T * FILL_T) {
+    const int xx = tx0 + (threadIdx.x % FILL_T), yy = ty0 + (threadIdx.x / FILL_T);
+    if (xx <= tx1 && yy <= ty1) minmax[xx + yy * w] = make_float2(__int_as_float(smin[threadIdx.x]), __int_as_float(smax[threadIdx.x]));
+  }
+}
+
+// initialises every cell OUTSIDE the live corner (the live corner is written in full by k_fill_minmax)
+__global__ void k_minmax_init_dead(float2 *minmax, int w, int h) {
+  const int liveX = (w - 1) / B200_MINMAX_SUBSAMPLE, liveY = (h - 1) / B200_MINMAX_SUBSAMPLE;
+  const float2 v = make_float2(B200_FAR_AWAY, B200_VERY_CLOSE);
+  const int n = w * h;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int y = i / w, x = i - y * w;
+    if (x > liveX || y > liveY) minmax[i] = v;
+  }
+}
+
 void launch_expected_depths(b200_engine *e, const SceneRef &s, const Mat4 &M, const float proj[4], int w, int h, float voxelSize,
                             b200_vec2f *minmax) {
-  k_minmax_init<<<e->smCount * 4, 256, 0, e->stream>>>((float2 *)minmax, w * h);
+  k_minmax_init_dead<<<e->smCount * 4, 256, 0, e->stream>>>((float2 *)minmax, w, h);
   const int noTiles = (s.numBlocks + PRJ_THREADS - 1) / PRJ_THREADS;
   k_project_blocks<<<persistent_grid(e, 8, noTiles), PRJ_THREADS, 0, e->stream>>>(s.hash, s.numBuckets, s.visiblePos, fresh_ptr_list(e, s),
-                                                                                 s.numBlocks, e->d_ctr, M,
-                                                                         proj[0], proj[1], proj[2], proj[3], w, h, voxelSize,
-                                                                         (float2 *)minmax, e->d_scanDesc, ++e->scanGen);
-  e->launches += 2;
+                                                                                 s.numBlocks, e->d_ctr, M, proj[0], proj[1], proj[2], proj[3],
+                                                                                 w, h, voxelSize, (float2 *)minmax, (BlockRec *)e->d_blockRecs,
+                                                                                 e->d_scanDesc, ++e->scanGen);
+  dim3 grid(((w - 1) / B200_MINMAX_SUBSAMPLE) / FILL_T + 1, ((h - 1) / B200_MINMAX_SUBSAMPLE) / FILL_T + 1);
+  k_fill_minmax<<<grid, FILL_THREADS, 0, e->stream>>>((const BlockRec *)e->d_blockRecs, e->d_ctr, s.numBlocks, w, h, (float2 *)minmax);
+  e->launches += 3;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -217,6 +264,14 @@ __device__ bool cast_ray(float4 &out, int x, int y, const b200_voxel *__restrict
     sdfValue = sdf_raw(voxels, vi) / 32767.0f;
     if (vi < 0) {
       stepLength = BS;
+      // Empty space is crossed in 8-voxel steps, each landing in a new block whose lookup is a dependent L2 read.
+      // The next positions are known now: touch their bucket heads so that those lookups hit L1.
+#pragma unroll
+      for (int a = 1; a <= 3; ++a) {
+        const float qx = px + (float)(a * BS) * dx, qy = py + (float)(a * BS) * dy, qz = pz + (float)(a * BS) * dz;   // hint only
+        const int hidx = hash_index(((int)round_(qx)) >> 3, ((int)round_(qy)) >> 3, ((int)round_(qz)) >> 3, nb - 1);
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(reinterpret_cast<const int *>(table) + (size_t)hidx * 5));
+      }
     } else {
       if ((sdfValue <= 20.0f) && (sdfValue >= -100.0f)) sdfValue = sdf_interp(voxels, table, nb, px, py, pz, cache);
       if (sdfValue <= 0.0f) break;
