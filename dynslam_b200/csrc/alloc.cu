@@ -351,6 +351,7 @@ k_visible_list(const b200_hash_entry *__restrict__ table, int numBuckets, int no
     if (tile == noTiles - 1 && threadIdx.x == 0) {
       const int n = (int)(base + total);
       ctr->noVisibleBlocks = n;
+      ctr->noIntegrated = 0;            // IntegrateIntoScene of this frame counts from zero (no separate memset)
       const int kept = n < capacity ? n : capacity;
       if (oldestSlot >= 0) { if (ringStart + kept - snapStart[oldestSlot] > ringCap) ctr->errorFlags |= 1; }
       else if (kept > ringCap) ctr->errorFlags |= 1;

@@ -267,20 +267,23 @@ __device__ bool cast_ray(float4 &out, int x, int y, const b200_voxel *__restrict
   IdxCache cache; cache_init(cache);
   float sdfValue = 1.0f, stepLength;
   while (totalLength < totalLengthMax) {
-    const int vi = voxel_index(table, nb, (int)round_(px), (int)round_(py), (int)round_(pz), cache);
-    sdfValue = sdf_raw(voxels, vi) / 32767.0f;
-    if (vi < 0) {
+    // readFromSDF_float_uninterpolated (:133): only its hash_found matters. When the block exists the value is
+    // re-read interpolated unconditionally (the [-100, 20] window at :141-145 contains every sdf in [-1, 1]), so the
+    // nearest voxel's 2-byte value is never consumed and is not loaded — one dependent memory latency less per step.
+    const int base = block_base(table, nb, ((int)round_(px)) >> 3, ((int)round_(py)) >> 3, ((int)round_(pz)) >> 3, cache);
+    if (base < 0) {
+      sdfValue = 1.0f;   // TVoxel() = 32767 / 32767
       stepLength = BS;
       // Empty space is crossed in 8-voxel steps, each landing in a new block whose lookup is a dependent L2 read.
       // The next positions are known now: touch their bucket heads so that those lookups hit L1.
 #pragma unroll
-      for (int a = 1; a <= 3; ++a) {
+      for (int a = 1; a <= 2; ++a) {
         const float qx = px + (float)(a * BS) * dx, qy = py + (float)(a * BS) * dy, qz = pz + (float)(a * BS) * dz;   // hint only
         const int hidx = hash_index(((int)round_(qx)) >> 3, ((int)round_(qy)) >> 3, ((int)round_(qz)) >> 3, nb - 1);
         asm volatile("prefetch.global.L1 [%0];" ::"l"(reinterpret_cast<const int *>(table) + (size_t)hidx * 5));
       }
     } else {
-      if ((sdfValue <= 20.0f) && (sdfValue >= -100.0f)) sdfValue = sdf_interp(voxels, table, nb, px, py, pz, cache);
+      sdfValue = sdf_interp(voxels, table, nb, px, py, pz, cache);
       if (sdfValue <= 0.0f) break;
       stepLength = maxf_(sdfValue * stepScale, 1.0f);
     }
@@ -300,104 +303,30 @@ __device__ bool cast_ray(float4 &out, int x, int y, const b200_voxel *__restrict
   return found;
 }
 
-// GenericRaycast (Vis_CUDA.cu:242-265, :672-684) as a ray-refill kernel. Rays of one warp need very different
-// numbers of march steps (a quarter of the KITTI rays have an empty range, the rest take 2..20 steps), so a
-// one-ray-per-thread kernel idles most lanes while the longest ray of the warp finishes. Here a warp owns four
-// 8x4-pixel tiles (128 rays); every loop iteration advances each live ray by ONE march step of castRay, and lanes
-// whose ray has finished take the next ray of the warp's chunk. The per-ray arithmetic is castRay's, unchanged.
-#define RC_TILES_PER_WARP 2   // default; B200_RC_TPW overrides (tuning knob)
+// GenericRaycast — Vis_CUDA.cu:242-265, :672-684. One ray per thread, 8x4-pixel warps (a warp's rays walk the same
+// voxel blocks). Measured on B200: the march is bound by the chain of dependent L2 reads per step, not by lane
+// utilisation — a ray-refill variant (fewer, longer-lived warps) was 1.1-3x slower (profiles/), so the kernel keeps
+// the maximum number of independent rays in flight and shortens the chain per step instead (see cast_ray).
 __global__ void __launch_bounds__(256)
 k_raycast(float4 *out, const b200_voxel *__restrict__ voxels, const b200_hash_entry *__restrict__ table, int nb, int w, int h, Mat4 invM,
-          float fx, float fy, float cxp, float cyp, float voxelSize, float mu, const float2 *__restrict__ minmax, int tilesPerWarp) {
-  const int tilesX = (w + 7) >> 3, tilesY = (h + 3) >> 2, totalTiles = tilesX * tilesY;
+          float fx, float fy, float cxp, float cyp, float voxelSize, float mu, const float2 *__restrict__ minmax) {
+  const int tilesX = (w + 7) >> 3, tilesY = (h + 3) >> 2;
   const int warpGlobal = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int firstTile = warpGlobal * tilesPerWarp;
-  if (firstTile >= totalTiles) return;
+  if (warpGlobal >= tilesX * tilesY) return;
   const int lane = threadIdx.x & 31;
-  const unsigned full = 0xffffffffu, lt = (1u << lane) - 1u;
-  const int nRays = min(tilesPerWarp, totalTiles - firstTile) * 32;
-  const float invfx = 1.0f / fx, invfy = 1.0f / fy, oneOverVoxelSize = 1.0f / voxelSize;
-  const float stepScale = mu * oneOverVoxelSize * 1.0f;
-  int next = 0;                      // warp-uniform: next unassigned ray of the chunk
-  bool active = false;
-  int locId = 0;
-  float px = 0, py = 0, pz = 0, dx = 0, dy = 0, dz = 0, totalLength = 0, totalLengthMax = 0;
-  IdxCache cache; cache_init(cache);
-  for (;;) {
-    const unsigned idle = __ballot_sync(full, !active);
-    if (idle && next < nRays && (__popc(idle) >= 8 || idle == full)) {
-      if (!active) {
-        const int r = next + __popc(idle & lt);
-        if (r < nRays) {
-          const int tile = firstTile + (r >> 5), within = r & 31;
-          const int x = (tile % tilesX) * 8 + (within & 7), y = (tile / tilesX) * 4 + (within >> 3);
-          if (x < w && y < h) {
-            // ray set-up — DA/ITMVisualisationEngine.h:108-128
-            const int locId2 = (int)floorf((float)x / B200_MINMAX_SUBSAMPLE) + (int)floorf((float)y / B200_MINMAX_SUBSAMPLE) * w;
-            const float2 mm = __ldg(minmax + locId2);
-            float cz = mm.x;
-            float cx = cz * (((float)x - cxp) * invfx), cy = cz * (((float)y - cyp) * invfy);
-            totalLength = sqrtf(cx * cx + cy * cy + cz * cz) * oneOverVoxelSize;
-            Vec4 rr = m4v4(invM, cx, cy, cz, 1.0f);
-            const float sx = rr.x * oneOverVoxelSize, sy = rr.y * oneOverVoxelSize, sz = rr.z * oneOverVoxelSize;
-            cz = mm.y;
-            cx = cz * (((float)x - cxp) * invfx); cy = cz * (((float)y - cyp) * invfy);
-            totalLengthMax = sqrtf(cx * cx + cy * cy + cz * cz) * oneOverVoxelSize;
-            rr = m4v4(invM, cx, cy, cz, 1.0f);
-            dx = rr.x * oneOverVoxelSize - sx; dy = rr.y * oneOverVoxelSize - sy; dz = rr.z * oneOverVoxelSize - sz;
-            const float direction_norm = 1.0f / sqrtf(dx * dx + dy * dy + dz * dz);
-            dx *= direction_norm; dy *= direction_norm; dz *= direction_norm;
-            px = sx; py = sy; pz = sz;
-            cache_init(cache);
-            locId = x + y * w;
-            active = true;
-          }
-        }
-      }
-      next += __popc(idle);
-    }
-    if (!__any_sync(full, active)) { if (next >= nRays) break; continue; }
-    if (active) {
-      if (!(totalLength < totalLengthMax)) {                       // range exhausted: no surface (sdfValue > 0)
-        out[locId] = make_float4(px, py, pz, 0.0f);
-        active = false;
-      } else {
-        const int vi = voxel_index(table, nb, (int)round_(px), (int)round_(py), (int)round_(pz), cache);
-        float sdfValue = sdf_raw(voxels, vi) / 32767.0f;
-        float stepLength;
-        bool hit = false;
-        if (vi < 0) {
-          stepLength = BS;
-        } else {
-          if ((sdfValue <= 20.0f) && (sdfValue >= -100.0f)) sdfValue = sdf_interp(voxels, table, nb, px, py, pz, cache);
-          if (sdfValue <= 0.0f) hit = true;
-          else stepLength = maxf_(sdfValue * stepScale, 1.0f);
-        }
-        if (hit) {                                                  // zero crossing: two interpolated refinements, :163-171
-          stepLength = sdfValue * stepScale;
-          px += stepLength * dx; py += stepLength * dy; pz += stepLength * dz;
-          sdfValue = sdf_interp(voxels, table, nb, px, py, pz, cache);
-          stepLength = sdfValue * stepScale;
-          px += stepLength * dx; py += stepLength * dy; pz += stepLength * dz;
-          out[locId] = make_float4(px, py, pz, 1.0f);
-          active = false;
-        } else {
-          px += stepLength * dx; py += stepLength * dy; pz += stepLength * dz;
-          totalLength += stepLength;
-        }
-      }
-    }
-  }
+  const int x = (warpGlobal % tilesX) * 8 + (lane & 7), y = (warpGlobal / tilesX) * 4 + (lane >> 3);
+  if (x >= w || y >= h) return;
+  const int locId2 = (int)floorf((float)x / B200_MINMAX_SUBSAMPLE) + (int)floorf((float)y / B200_MINMAX_SUBSAMPLE) * w;
+  float4 o;
+  cast_ray(o, x, y, voxels, table, nb, invM, 1.0f / fx, 1.0f / fy, cxp, cyp, 1.0f / voxelSize, mu, __ldg(minmax + locId2));
+  out[x + y * w] = o;
 }
 
 void launch_raycast(b200_engine *e, const SceneRef &s, const Mat4 &invM, const float proj[4], int w, int h, float voxelSize, float mu,
                     const b200_vec2f *minmax, b200_vec4f *out) {
   const int tiles = ((w + 7) / 8) * ((h + 3) / 4);
-  static int tpw = 0;
-  if (!tpw) { const char *v = getenv("B200_RC_TPW"); tpw = v ? atoi(v) : RC_TILES_PER_WARP; if (tpw < 1) tpw = 1; }
-  const int warps = (tiles + tpw - 1) / tpw;
-  k_raycast<<<(warps + 7) / 8, 256, 0, e->stream>>>((float4 *)out, s.voxels, s.hash, s.numBuckets, w, h, invM, proj[0], proj[1], proj[2],
-                                                   proj[3], voxelSize, mu, (const float2 *)minmax, tpw);
+  k_raycast<<<(tiles + 7) / 8, 256, 0, e->stream>>>((float4 *)out, s.voxels, s.hash, s.numBuckets, w, h, invM, proj[0], proj[1], proj[2],
+                                                   proj[3], voxelSize, mu, (const float2 *)minmax);
   e->launches++;
 }
 

@@ -54,8 +54,8 @@ def test_config1_plane_8mm():
     assert pair.rs.noVisibleBlocks > 1000
 
 
-def test_integrate_tma_variant_matches():
-    os.environ["B200_INTEGRATE_IMPL"] = "tma"
+def test_integrate_ldg_variant_matches():
+    os.environ["B200_INTEGRATE_IMPL"] = "ldg"
     try:
         pair, _ = P.run_sequence(P.Cfg(frames=5, raycast=False, decay=(1, 2)))
     finally:
