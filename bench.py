@@ -7,8 +7,9 @@
 A step is one frame through {AllocateSceneFromDepth, IntegrateIntoScene, CreateExpectedDepths,
 CreateICPMaps (raycast), Decay(partial)} on one ITMScene volume (BASELINE.json configs[1]).
 value  = frames/s with the frames already resident in HBM (whole job: all ranks' frames / max time)
-e2e    = frames/s through b200_process_frame_host: per frame the depth+RGB are copied from pinned
-         host memory and the grey raycast image is copied back, inside the timed region
+e2e    = frames/s through b200_host_frame_submit/_wait (host buffers in, host image out): every frame's
+         depth+RGB are copied from pinned host memory and its grey raycast image is copied back inside the
+         timed region; the copies of neighbouring frames overlap the kernels (two staging slots)
 roofline = IntegrateIntoScene: algorithmic bytes (8224 B per integrated block + w*h*8 B of images
          per launch) / mean launch duration from CUDA events around every launch of the timed region
 cpu_baseline = the CPU oracle (oracle/tsdf_oracle.c, OpenMP at the reference's own pragma sites)
@@ -326,23 +327,26 @@ def run_own(args, rank, local_rank, world):
         # ---- e2e: host buffers -> H2D -> frame -> D2H image, every step ----
         h_depth = [torch.from_numpy(frames[idx + i][0]).pin_memory() for i in range(n_e2e)]
         h_rgb = [torch.from_numpy(frames[idx + i][1]).pin_memory() for i in range(n_e2e)]
-        h_out = torch.zeros(H_ * W * 4, dtype=torch.uint8).pin_memory()
-        d_depth_stage = torch.zeros(H_ * W, dtype=torch.float32, device=dev)
-        d_rgb_stage = torch.zeros(H_ * W * 4, dtype=torch.uint8, device=dev)
-        ev = E.View(d_depth_stage.view(H_, W), d_rgb_stage.view(H_, W, 4), frames[idx][2], frames[idx][3])
+        h_out = [torch.zeros(H_ * W * 4, dtype=torch.uint8).pin_memory() for _ in range(2)]
+        ev = E.View(torch.zeros((H_, W), dtype=torch.float32, device=dev), torch.zeros((H_, W, 4), dtype=torch.uint8, device=dev),
+                    frames[idx][2], frames[idx][3])
         e2e_warm = min(3, n_e2e // 2)
         t_e2e = 0.0
         for i in range(n_e2e):
             if i == e2e_warm:
+                eng.host_frame_wait(0); eng.host_frame_wait(1)
                 torch.cuda.synchronize(dev)
                 if world > 1:
                     dist.barrier()
                 t_e2e = time.perf_counter()
+            slot = i & 1
+            eng.host_frame_wait(slot)          # frame i-2 (same staging slot) has delivered its image
             ev.set_pose(frames[idx + i][2])
-            eng.process_frame_host(rs, ev, h_depth[i], h_rgb[i], d_depth_stage, d_rgb_stage, points, normals, decay=DECAY,
-                                   h_out=h_out)
+            # public API: host depth+RGB in, grey raycast image out; copies of neighbouring frames overlap the kernels
+            eng.host_frame_submit(rs, ev, h_depth[i], h_rgb[i], points, normals, decay=DECAY, h_out=h_out[slot], slot=slot)
             if world > 1:
                 dist.gather(rs.raycastImage, gather_buf, dst=0)
+        eng.host_frame_wait(0); eng.host_frame_wait(1)
         torch.cuda.synchronize(dev)
         if world > 1:
             dist.barrier()
@@ -428,7 +432,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
     ap.add_argument("--preroll", type=int, default=230, help="untimed frames that build the map (> decay minAge)")
-    ap.add_argument("--e2e-steps", type=int, default=23)
+    ap.add_argument("--e2e-steps", type=int, default=103)
     ap.add_argument("--flush-l2", dest="flush_l2", action="store_true", default=True)
     ap.add_argument("--no-flush-l2", dest="flush_l2", action="store_false")
     ap.add_argument("--cpu-steps", type=int, default=6)

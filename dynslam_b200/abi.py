@@ -94,7 +94,7 @@ EXPORTS = [
     "b200_find_visible_blocks", "b200_expected_depths", "b200_find_surface", "b200_render_image",
     "b200_icp_maps", "b200_forward_render", "b200_point_cloud", "b200_swap_list_in",
     "b200_swap_integrate_in", "b200_swap_out", "b200_process_frame_async", "b200_sync",
-    "b200_process_frame_host", "b200_set_timing", "b200_get_stats",
+    "b200_process_frame_host", "b200_set_timing", "b200_get_stats", "b200_host_frame_submit", "b200_host_frame_wait",
 ]
 
 _lib = None
@@ -144,6 +144,8 @@ def load_library():
     lib.b200_sync.argtypes = [vp, P(Scene), P(RenderState)]
     lib.b200_process_frame_host.argtypes = [vp, P(Scene), P(RenderState), P(View), vp, vp, vp, vp, vp, vp,
                                             P(FrameOpts), vp]
+    lib.b200_host_frame_submit.argtypes = [vp, P(Scene), P(RenderState), P(View), vp, vp, vp, vp, P(FrameOpts), vp, C.c_int]
+    lib.b200_host_frame_wait.argtypes = [vp, C.c_int]
     lib.b200_set_timing.argtypes = [vp, C.c_int]
     lib.b200_set_timing.restype = None
     lib.b200_get_stats.argtypes = [vp, P(FrameStats)]

@@ -81,9 +81,14 @@ __device__ bool block_visible(int bx, int by, int bz, const Mat4 &M, const float
 __global__ void __launch_bounds__(256)
 k_prepare(const b200_hash_entry *__restrict__ table, int numBuckets, const b200_vec3i *__restrict__ visiblePos, uint8_t *visType,
           const DevCounters *ctr, unsigned *reqBits, unsigned *req2Bits, int noWords, Mat4 M, float p0, float p1, float p2, float p3,
-          float voxelSize, int w, int h, int capacity) {
+          float voxelSize, int w, int h, int capacity, float2 *minmaxDead, int mw, int mh) {
   const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
   for (int i = tid; i < noWords; i += nth) { reqBits[i] = 0u; req2Bits[i] = 0u; }
+  if (minmaxDead) {   // fused frame: initialise the cells of the expected-depth image outside its live 1/8-res corner here
+    const int liveX = (mw - 1) / B200_MINMAX_SUBSAMPLE, liveY = (mh - 1) / B200_MINMAX_SUBSAMPLE;
+    const float2 v = make_float2(B200_FAR_AWAY, B200_VERY_CLOSE);
+    for (int i = tid; i < mw * mh; i += nth) { const int y = i / mw, x = i - y * mw; if (x > liveX || y > liveY) minmaxDead[i] = v; }
+  }
   const float proj[4] = {p0, p1, p2, p3};
   int n = ctr->noVisibleBlocks;
   if (n > capacity) n = capacity;
@@ -410,13 +415,14 @@ k_freeview_list(const b200_hash_entry *__restrict__ table, int noTotal, b200_vec
 }
 
 void launch_allocate(b200_engine *e, const SceneRef &s, const FrameGeom &g, const float *depth, bool onlyVisible, int frameIdx,
-                     int snapSlot) {
+                     int snapSlot, b200_vec2f *minmaxDead, int mw, int mh) {
   cudaStream_t st = e->stream;
   const int noWords = e->noWords;
   const unsigned frameTag = (unsigned)(frameIdx + 1) & 0xffffffu;
   if (frameTag == 0) cudaMemsetAsync(e->d_reqKey, 0, sizeof(unsigned long long) * (size_t)s.noTotal, st);
-  k_prepare<<<e->smCount * 2, 256, 0, st>>>(s.hash, s.numBuckets, s.visiblePos, s.visType, e->d_ctr, e->d_reqBits, e->d_req2Bits, noWords,
-                                           g.M_d, g.proj_d[0], g.proj_d[1], g.proj_d[2], g.proj_d[3], g.voxelSize, g.w, g.h, s.numBlocks);
+  k_prepare<<<e->smCount * 4, 256, 0, st>>>(s.hash, s.numBuckets, s.visiblePos, s.visType, e->d_ctr, e->d_reqBits, e->d_req2Bits, noWords,
+                                           g.M_d, g.proj_d[0], g.proj_d[1], g.proj_d[2], g.proj_d[3], g.voxelSize, g.w, g.h, s.numBlocks,
+                                           (float2 *)minmaxDead, mw, mh);
   const int tiles = ((g.w + 7) / 8) * ((g.h + 3) / 4);
   k_mark<<<(tiles + 7) / 8, 256, 0, st>>>(depth, s.hash, s.numBuckets, s.visType, e->d_reqKey, e->d_reqBits, e->d_req2Bits, g,
                                          frameTag);

@@ -152,6 +152,12 @@ void b200_engine_destroy(b200_engine *e) {
   cudaFree(e->d_ring); cudaFree(e->d_snapCount); cudaFree(e->d_snapStart); cudaFree(e->d_delTag); cudaFree(e->d_itemPtr); cudaFree(e->d_visiblePtr);
   cudaFree(e->d_delList); cudaFree(e->d_isLeader); cudaFree(e->d_allocatedPos); cudaFree(e->d_tileCounts); cudaFree(e->d_blockRecs);
   for (int i = 0; i < 8; ++i) if (e->ev[i]) cudaEventDestroy(e->ev[i]);
+  if (e->copyStream) {
+    cudaStreamSynchronize(e->copyStream);
+    for (int i = 0; i < 2; ++i) { cudaFree(e->d_stageDepth[i]); cudaFree(e->d_stageRgb[i]); cudaFree(e->d_stageOut[i]);
+      cudaEventDestroy(e->evH2D[i]); cudaEventDestroy(e->evCompute[i]); cudaEventDestroy(e->evD2H[i]); }
+    cudaStreamDestroy(e->copyStream);
+  }
   if (e->ownStream && e->stream) cudaStreamDestroy(e->stream);
   delete e;
 }
@@ -224,7 +230,8 @@ b200_status b200_reset_scene(b200_engine *e, b200_scene *s) {
   return download_sync(e, s, nullptr);
 }
 
-static b200_status enqueue_allocate(b200_engine *e, b200_scene *s, b200_render_state *rs, const b200_view *v, int onlyVisible) {
+static b200_status enqueue_allocate(b200_engine *e, b200_scene *s, b200_render_state *rs, const b200_view *v, int onlyVisible,
+                                    bool fuseDeadInit = false) {
   if (e->qSize >= SNAP_SLOTS - 1) {
     snprintf(e->err, sizeof(e->err), "decay queue deeper than %d frames", SNAP_SLOTS);
     return B200_ERR_DECAY_RING_FULL;
@@ -235,7 +242,8 @@ static b200_status enqueue_allocate(b200_engine *e, b200_scene *s, b200_render_s
   }
   const int slot = (e->qHead + e->qSize) % SNAP_SLOTS;
   e->tableVersion++;
-  launch_allocate(e, scene_ref(s, rs), frame_geom(s, v), v->d_depth, onlyVisible != 0, e->frameIdx, slot);
+  launch_allocate(e, scene_ref(s, rs), frame_geom(s, v), v->d_depth, onlyVisible != 0, e->frameIdx, slot,
+                  fuseDeadInit ? rs->d_minmax : nullptr, rs->img_w, rs->img_h);
   e->ptrListFor = rs->d_visibleBlockPositions; e->ptrListVersion = e->tableVersion;
   e->qSize++;
   e->frameIdx++;
@@ -409,7 +417,8 @@ b200_status b200_process_frame_async(b200_engine *e, b200_scene *s, b200_render_
   CK(cudaSetDevice(e->device));
   if (e->hostAuthoritative) { st = upload(e, s, rs); if (st) return st; e->hostAuthoritative = false; }
   if (e->timing) CK(cudaEventRecord(e->ev[0], e->stream));
-  st = enqueue_allocate(e, s, rs, v, 0); if (st) return st;
+  const bool doRay = (!opts || opts->doRaycast);
+  st = enqueue_allocate(e, s, rs, v, 0, doRay); if (st) return st;
   if (e->timing) CK(cudaEventRecord(e->ev[1], e->stream));
   SceneRef r = scene_ref(s, rs);
   FrameGeom g = frame_geom(s, v);
@@ -418,8 +427,8 @@ b200_status b200_process_frame_async(b200_engine *e, b200_scene *s, b200_render_
   launch_integrate(e, r, g, v->d_depth, v->d_rgb);
   if (ring) { CK(cudaEventRecord(e->evRing[2 * e->evRingCount + 1], e->stream)); e->evRingCount++; }
   if (e->timing) CK(cudaEventRecord(e->ev[2], e->stream));
-  if (!opts || opts->doRaycast) {
-    launch_expected_depths(e, r, g.M_d, g.proj_d, rs->img_w, rs->img_h, s->voxelSize, rs->d_minmax);
+  if (doRay) {
+    launch_expected_depths(e, r, g.M_d, g.proj_d, rs->img_w, rs->img_h, s->voxelSize, rs->d_minmax, true);
     if (e->timing) CK(cudaEventRecord(e->ev[3], e->stream));
     launch_raycast(e, r, g.invM_d, g.proj_d, rs->img_w, rs->img_h, s->voxelSize, s->mu, rs->d_minmax, rs->d_raycastResult);
     launch_icp(e, g.invM_d, rs->img_w, rs->img_h, s->voxelSize, rs->d_raycastResult, rs->d_raycastImage, d_points, d_normals);
@@ -449,6 +458,65 @@ b200_status b200_process_frame_host(b200_engine *e, b200_scene *s, b200_render_s
   b200_status st = b200_process_frame_async(e, s, rs, v, d_points, d_normals, opts); if (st) return st;
   if (h_outImage) CK(cudaMemcpyAsync(h_outImage, rs->d_raycastImage, (size_t)rs->img_w * rs->img_h * sizeof(b200_vec4u), cudaMemcpyDeviceToHost, e->stream));
   return b200_sync(e, s, rs);
+}
+
+static b200_status ensure_pipeline(b200_engine *e, size_t pixels) {
+  if (e->copyStream && e->stagePixels >= pixels) return B200_OK;
+  if (!e->copyStream) {
+    CK(cudaStreamCreateWithFlags(&e->copyStream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+      CK(cudaEventCreateWithFlags(&e->evH2D[i], cudaEventDisableTiming));
+      CK(cudaEventCreateWithFlags(&e->evCompute[i], cudaEventDisableTiming));
+      CK(cudaEventCreateWithFlags(&e->evD2H[i], cudaEventDisableTiming));
+    }
+  }
+  for (int i = 0; i < 2; ++i) {
+    cudaFree(e->d_stageDepth[i]); cudaFree(e->d_stageRgb[i]); cudaFree(e->d_stageOut[i]);
+    CK(cudaMalloc(&e->d_stageDepth[i], pixels * sizeof(float)));
+    CK(cudaMalloc(&e->d_stageRgb[i], pixels * sizeof(b200_vec4u)));
+    CK(cudaMalloc(&e->d_stageOut[i], pixels * sizeof(b200_vec4u)));
+    e->slotBusy[i] = false;
+  }
+  e->stagePixels = pixels;
+  return B200_OK;
+}
+
+b200_status b200_host_frame_submit(b200_engine *e, b200_scene *s, b200_render_state *rs, b200_view *v, const float *h_depth,
+                                   const b200_vec4u *h_rgb, b200_vec4f *d_points, b200_vec4f *d_normals, const b200_frame_opts *opts,
+                                   b200_vec4u *h_outImage, int slot) {
+  if (slot < 0 || slot > 1) { snprintf(e->err, sizeof(e->err), "slot must be 0 or 1"); return B200_ERR_INVALID; }
+  CK(cudaSetDevice(e->device));
+  const size_t nd = (size_t)v->depth_w * v->depth_h, nc = (size_t)v->rgb_w * v->rgb_h, no = (size_t)rs->img_w * rs->img_h;
+  size_t px = nd > nc ? nd : nc; if (no > px) px = no;
+  b200_status st = ensure_pipeline(e, px); if (st) return st;
+  if (e->slotBusy[slot]) { snprintf(e->err, sizeof(e->err), "slot %d resubmitted before b200_host_frame_wait", slot); return B200_ERR_INVALID; }
+  // H2D on the copy stream (the slot's previous frame was waited for, so its staging buffers are free)
+  CK(cudaMemcpyAsync(e->d_stageDepth[slot], h_depth, nd * sizeof(float), cudaMemcpyHostToDevice, e->copyStream));
+  CK(cudaMemcpyAsync(e->d_stageRgb[slot], h_rgb, nc * sizeof(b200_vec4u), cudaMemcpyHostToDevice, e->copyStream));
+  CK(cudaEventRecord(e->evH2D[slot], e->copyStream));
+  // the frame on the compute stream
+  CK(cudaStreamWaitEvent(e->stream, e->evH2D[slot], 0));
+  v->d_depth = e->d_stageDepth[slot]; v->d_rgb = e->d_stageRgb[slot];
+  st = b200_process_frame_async(e, s, rs, v, d_points, d_normals, opts); if (st) return st;
+  if (h_outImage) {
+    CK(cudaMemcpyAsync(e->d_stageOut[slot], rs->d_raycastImage, no * sizeof(b200_vec4u), cudaMemcpyDeviceToDevice, e->stream));
+    CK(cudaEventRecord(e->evCompute[slot], e->stream));
+    CK(cudaStreamWaitEvent(e->copyStream, e->evCompute[slot], 0));
+    CK(cudaMemcpyAsync(h_outImage, e->d_stageOut[slot], no * sizeof(b200_vec4u), cudaMemcpyDeviceToHost, e->copyStream));
+    CK(cudaEventRecord(e->evD2H[slot], e->copyStream));
+  } else {
+    CK(cudaEventRecord(e->evD2H[slot], e->stream));
+  }
+  e->slotBusy[slot] = true;
+  return B200_OK;
+}
+
+b200_status b200_host_frame_wait(b200_engine *e, int slot) {
+  if (slot < 0 || slot > 1 || !e->copyStream) { snprintf(e->err, sizeof(e->err), "no frame submitted on slot %d", slot); return B200_ERR_INVALID; }
+  if (!e->slotBusy[slot]) return B200_OK;
+  CK(cudaEventSynchronize(e->evD2H[slot]));
+  e->slotBusy[slot] = false;
+  return B200_OK;
 }
 
 b200_status b200_get_stats(b200_engine *e, b200_frame_stats *out) {

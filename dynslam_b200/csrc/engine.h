@@ -67,6 +67,11 @@ struct b200_engine {
   // timing / stats
   bool timing;
   cudaEvent_t ev[8];
+  // pipelined host frames: copy stream, two staging slots
+  cudaStream_t copyStream;
+  float *d_stageDepth[2]; b200_vec4u *d_stageRgb[2]; b200_vec4u *d_stageOut[2];
+  cudaEvent_t evH2D[2], evCompute[2], evD2H[2];
+  bool slotBusy[2]; size_t stagePixels;
   cudaEvent_t *evRing;                // timing mode 2: event pairs around every integrate launch
   int evRingCap, evRingCount, timingMode;
   long long launches;
@@ -81,7 +86,7 @@ struct b200_engine {
 // launchers (each enqueues on e->stream and bumps e->launches)
 void launch_reset(b200_engine *e, const SceneRef &s);
 void launch_allocate(b200_engine *e, const SceneRef &s, const FrameGeom &g, const float *depth, bool onlyVisible,
-                     int frameIdx, int snapSlot);
+                     int frameIdx, int snapSlot, b200_vec2f *minmaxDead, int mw, int mh);
 void launch_integrate(b200_engine *e, const SceneRef &s, const FrameGeom &g, const float *depth, const b200_vec4u *rgb);
 static inline const int *fresh_ptr_list(const b200_engine *e, const SceneRef &s) {
   return (e->ptrListFor == (const void *)s.visiblePos && e->ptrListVersion == e->tableVersion) ? e->d_visiblePtr : nullptr;
@@ -90,7 +95,7 @@ void launch_decay_partial(b200_engine *e, const SceneRef &s, int snapSlot, int m
 void launch_decay_full(b200_engine *e, const SceneRef &s, int minAge, int maxWeight, int frameIdx);
 void launch_find_visible(b200_engine *e, const SceneRef &s, const Mat4 &M, const float proj[4], int w, int h, float voxelSize);
 void launch_expected_depths(b200_engine *e, const SceneRef &s, const Mat4 &M, const float proj[4], int w, int h,
-                            float voxelSize, b200_vec2f *minmax);
+                            float voxelSize, b200_vec2f *minmax, bool deadInitDone = false);
 void launch_raycast(b200_engine *e, const SceneRef &s, const Mat4 &invM, const float proj[4], int w, int h, float voxelSize,
                     float mu, const b200_vec2f *minmax, b200_vec4f *out);
 void launch_shade(b200_engine *e, const SceneRef &s, const Mat4 &M, const Mat4 &invM, int w, int h, float voxelSize, int maxW,

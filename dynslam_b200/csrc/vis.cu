@@ -60,7 +60,7 @@ DEV bool project_single_block(int bx, int by, int bz, const Mat4 &pose, const fl
 // cover, and no separate initialisation of the live corner.
 struct __align__(16) BlockRec { short ulx, uly, lrx, lry; float zmin, zmax; };
 
-#define PRJ_THREADS 64
+#define PRJ_THREADS 256
 __global__ void __launch_bounds__(PRJ_THREADS)
 k_project_blocks(const b200_hash_entry *__restrict__ table, int numBuckets, const b200_vec3i *__restrict__ visiblePos,
                  const int *__restrict__ visiblePtr, int capacity, DevCounters *ctr, Mat4 M, float p0, float p1, float p2, float p3, int w,
@@ -72,6 +72,7 @@ k_project_blocks(const b200_hash_entry *__restrict__ table, int numBuckets, cons
   if (n > capacity) n = capacity;
   const int noTiles = (n + PRJ_THREADS - 1) / PRJ_THREADS;
   const int liveX = (w - 1) / B200_MINMAX_SUBSAMPLE, liveY = (h - 1) / B200_MINMAX_SUBSAMPLE;   // last live cell
+  const int lane = threadIdx.x & 31;
   for (int tile = blockIdx.x; tile < noTiles; tile += gridDim.x) {
     const int item = tile * PRJ_THREADS + threadIdx.x;
     int ulx = 0, uly = 0, lrx = -1, lry = -1; float zmin = 0, zmax = 0;
@@ -100,10 +101,19 @@ k_project_blocks(const b200_hash_entry *__restrict__ table, int numBuckets, cons
       if (draw) { r.ulx = (short)ulx; r.uly = (short)uly; r.lrx = (short)lrx; r.lry = (short)lry; r.zmin = zmin; r.zmax = zmax; }
       else { r.ulx = 1; r.uly = 1; r.lrx = 0; r.lry = 0; r.zmin = 0; r.zmax = 0; }
       recs[item] = r;
-      if (draw && (lrx > liveX || lry > liveY)) {   // the part of the box outside the live corner (dead cells)
-        for (int yy = uly; yy <= lry; ++yy)
-          for (int xx = ulx; xx <= lrx; ++xx)
-            if (xx > liveX || yy > liveY) { float2 *px = &minmax[xx + yy * w]; atomic_min_posf(&px->x, zmin); atomic_max_posf(&px->y, zmax); }
+    }
+    // the part of a box outside the live corner (dead cells): warp-cooperative, one box at a time
+    unsigned todo = __ballot_sync(0xffffffffu, item < n && draw && (lrx > liveX || lry > liveY));
+    while (todo) {
+      const int src = __ffs(todo) - 1;
+      todo &= todo - 1;
+      const int ax = __shfl_sync(0xffffffffu, ulx, src), ay = __shfl_sync(0xffffffffu, uly, src);
+      const int bx = __shfl_sync(0xffffffffu, lrx, src), by = __shfl_sync(0xffffffffu, lry, src);
+      const float zn = __shfl_sync(0xffffffffu, zmin, src), zx = __shfl_sync(0xffffffffu, zmax, src);
+      const int bw = bx - ax + 1, cnt = bw * (by - ay + 1);
+      for (int k = lane; k < cnt; k += 32) {
+        const int yy = ay + k / bw, xx = ax + k % bw;
+        if (xx > liveX || yy > liveY) { float2 *px = &minmax[xx + yy * w]; atomic_min_posf(&px->x, zn); atomic_max_posf(&px->y, zx); }
       }
     }
     __syncthreads();
@@ -162,16 +172,16 @@ __global__ void k_minmax_init_dead(float2 *minmax, int w, int h) {
 }
 
 void launch_expected_depths(b200_engine *e, const SceneRef &s, const Mat4 &M, const float proj[4], int w, int h, float voxelSize,
-                            b200_vec2f *minmax) {
-  k_minmax_init_dead<<<e->smCount * 4, 256, 0, e->stream>>>((float2 *)minmax, w, h);
+                            b200_vec2f *minmax, bool deadInitDone) {
+  if (!deadInitDone) { k_minmax_init_dead<<<e->smCount * 4, 256, 0, e->stream>>>((float2 *)minmax, w, h); e->launches++; }
   const int noTiles = (s.numBlocks + PRJ_THREADS - 1) / PRJ_THREADS;
-  k_project_blocks<<<persistent_grid(e, 8, noTiles), PRJ_THREADS, 0, e->stream>>>(s.hash, s.numBuckets, s.visiblePos, fresh_ptr_list(e, s),
+  k_project_blocks<<<persistent_grid(e, 2, noTiles), PRJ_THREADS, 0, e->stream>>>(s.hash, s.numBuckets, s.visiblePos, fresh_ptr_list(e, s),
                                                                                  s.numBlocks, e->d_ctr, M, proj[0], proj[1], proj[2], proj[3],
                                                                                  w, h, voxelSize, (float2 *)minmax, (BlockRec *)e->d_blockRecs,
                                                                                  e->d_scanDesc, ++e->scanGen);
   dim3 grid(((w - 1) / B200_MINMAX_SUBSAMPLE) / FILL_T + 1, ((h - 1) / B200_MINMAX_SUBSAMPLE) / FILL_T + 1);
   k_fill_minmax<<<grid, FILL_THREADS, 0, e->stream>>>((const BlockRec *)e->d_blockRecs, e->d_ctr, s.numBlocks, w, h, (float2 *)minmax);
-  e->launches += 3;
+  e->launches += 2;
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -231,6 +231,20 @@ class Engine:
                                                      _ptr(points), _ptr(normals), C.byref(o), _ptr(h_out)))
 
 
+    def host_frame_submit(self, renderState, view, h_depth, h_rgb, points=None, normals=None, decay=None, raycast=True, h_out=None,
+                          slot=0):
+        """Pipelined host frames: H2D, fused frame and D2H of the grey image are enqueued without blocking."""
+        o = abi.FrameOpts()
+        o.doRaycast = int(raycast)
+        if decay is not None:
+            o.doDecay, o.decayMaxWeight, o.decayMinAge = 1, decay[0], decay[1]
+        self.check(self.lib.b200_host_frame_submit(self.h, C.byref(self.scene.c), C.byref(renderState.c), C.byref(view.c),
+                                                    _ptr(h_depth), _ptr(h_rgb), _ptr(points), _ptr(normals), C.byref(o), _ptr(h_out), slot))
+
+    def host_frame_wait(self, slot):
+        self.check(self.lib.b200_host_frame_wait(self.h, slot))
+
+
 class SceneReconstructionEngine:
     """ITMSceneReconstructionEngine<ITMVoxel, ITMVoxelBlockHash> (B200 back-end)."""
 

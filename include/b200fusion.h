@@ -248,6 +248,16 @@ b200_status b200_process_frame_host(b200_engine *e, b200_scene *scene, b200_rend
                                     b200_vec4f *d_normals, const b200_frame_opts *opts,
                                     b200_vec4u *h_outImage);
 
+/* Pipelined variant for streams of host frames: two staging slots and a copy stream inside the engine, so that the
+   H2D copy of frame f+1 and the D2H copy of frame f's image overlap the kernels of the neighbouring frames.
+   b200_host_frame_submit(slot) enqueues {H2D depth+RGB from (pinned) host memory, the fused frame, D2H of the grey raycast
+   image into h_outImage} without blocking; b200_host_frame_wait(slot) blocks until that slot's image has landed.
+   A slot may be resubmitted only after it has been waited for. Host counters are refreshed by b200_sync(). */
+b200_status b200_host_frame_submit(b200_engine *e, b200_scene *scene, b200_render_state *rs, b200_view *view,
+                                   const float *h_depth, const b200_vec4u *h_rgb, b200_vec4f *d_points, b200_vec4f *d_normals,
+                                   const b200_frame_opts *opts, b200_vec4u *h_outImage, int slot);
+b200_status b200_host_frame_wait(b200_engine *e, int slot);
+
 /* ---- introspection used by bench.py / tests -------------------------------------------------- */
 
 typedef struct {

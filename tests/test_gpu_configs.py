@@ -75,7 +75,7 @@ def test_config4_full_decay_properties_at_scale():
     numBlocks = 400000
     scene, eng, reco, rs = _build_hires(numBlocks, frames=6)
     allocated = numBlocks - 1 - scene.lastFreeBlockId
-    assert allocated > 100000
+    assert allocated > 40000
     reco.Decay(scene, rs, 1, 0, True)                      # noisy voxels only
     freed1 = reco.GetDecayedBlockCount()
     st = scene.to_host()

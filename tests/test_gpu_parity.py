@@ -167,3 +167,30 @@ def test_fused_async_path_equals_stepwise():
     P._cmp("fused visible", ra["visiblePos"], rb["visiblePos"])
     P._cmp("fused image", pair.rs.raycastImage.cpu().numpy(), stepwise.rs.raycastImage.cpu().numpy())
     assert pair.reco.GetDecayedBlockCount() == stepwise.reco.GetDecayedBlockCount()
+
+
+def test_pipelined_host_frames_equal_stepwise():
+    """b200_host_frame_submit/_wait (H2D, fused frame and D2H overlapped over two slots) == the call-by-call path."""
+    cfg = P.Cfg(frames=7, decay=(1, 2))
+    stepwise, _ = P.run_sequence(cfg)
+    pair = P.Pair(cfg)
+    outs = [torch.zeros(pair.h * pair.w * 4, dtype=torch.uint8).pin_memory() for _ in range(2)]
+    view = None
+    keep = []
+    for i, (depth, rgb, M, proj) in enumerate(P.frames_of(cfg)):
+        hd, hc = torch.from_numpy(depth).pin_memory(), torch.from_numpy(rgb).pin_memory()
+        keep.append((hd, hc))
+        if view is None:
+            view = E.View(torch.zeros_like(hd, device="cuda"), torch.zeros_like(hc, device="cuda"), M, proj)
+        view.set_pose(M)
+        pair.eng.host_frame_wait(i & 1)
+        pair.eng.host_frame_submit(pair.rs, view, hd, hc, pair.points, pair.normals, decay=cfg.decay, h_out=outs[i & 1], slot=i & 1)
+    pair.eng.host_frame_wait(0)
+    pair.eng.host_frame_wait(1)
+    pair.eng.sync(pair.rs)
+    a, b = pair.scene.to_host(), stepwise.scene.to_host()
+    for k in ("hash", "voxels", "allocationList"):
+        P._cmp("pipelined " + k, a[k], b[k])
+    last = outs[(cfg.frames - 1) & 1].numpy()
+    P._cmp("pipelined image", last, stepwise.rs.raycastImage.cpu().numpy())
+    assert pair.reco.GetDecayedBlockCount() == stepwise.reco.GetDecayedBlockCount()
