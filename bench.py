@@ -148,10 +148,19 @@ def cpu_run(seed, preroll, warmup, steps, length_m, omp=True):
         L.oracle_decay(vol.engine, C.byref(vol.scene), C.byref(vol.rs), DECAY[0], DECAY[1], 0)
         return n
 
+    ncpu = os.cpu_count() or 1
+    cands = sorted({c for c in (4, 8, 16, 32, 64, ncpu) if c <= ncpu}) if omp else [1]
+    best = None
     for i, fr in enumerate(frames):
+        if omp and preroll >= len(cands) + 1 and 1 <= i <= len(cands):
+            L.oracle_set_threads(cands[i - 1])     # calibration during the pre-roll: one frame per thread count
+        elif omp and i == len(cands) + 1 and best is not None:
+            L.oracle_set_threads(best[1])
         t0 = time.perf_counter()
         n = one(fr)
         dt = time.perf_counter() - t0
+        if omp and preroll >= len(cands) + 1 and 1 <= i <= len(cands) and (best is None or dt < best[0]):
+            best = (dt, cands[i - 1])
         if i >= preroll + warmup:
             times.append(dt)
             vox += n * 512

@@ -512,8 +512,8 @@ b200_status b200_host_frame_submit(b200_engine *e, b200_scene *s, b200_render_st
 }
 
 b200_status b200_host_frame_wait(b200_engine *e, int slot) {
-  if (slot < 0 || slot > 1 || !e->copyStream) { snprintf(e->err, sizeof(e->err), "no frame submitted on slot %d", slot); return B200_ERR_INVALID; }
-  if (!e->slotBusy[slot]) return B200_OK;
+  if (slot < 0 || slot > 1) { snprintf(e->err, sizeof(e->err), "slot must be 0 or 1"); return B200_ERR_INVALID; }
+  if (!e->copyStream || !e->slotBusy[slot]) return B200_OK;   // nothing in flight on this slot
   CK(cudaEventSynchronize(e->evD2H[slot]));
   e->slotBusy[slot] = false;
   return B200_OK;

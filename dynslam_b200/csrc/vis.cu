@@ -222,9 +222,26 @@ DEV float rv_sdf(const b200_voxel *__restrict__ voxels, const b200_hash_entry *_
   return sdf_raw(voxels, voxel_index(table, nb, x, y, z, c));
 }
 
-// readFromSDF_float_interpolated — DA/ITMRepresentationAccess.h:252-278. When the 2x2x2 neighbourhood
-// lies inside one block (7 of 8 positions per axis) the block is resolved once and the eight 2-byte
-// reads use constant offsets; the arithmetic is the reference's, operand for operand.
+// uncached chain walk: ptr*512 or -1
+DEV int block_lookup(const b200_hash_entry *__restrict__ table, int numBuckets, int bx, int by, int bz) {
+  int hashIdx = hash_index(bx, by, bz, numBuckets - 1);
+  for (;;) {
+    const Entry he = load_entry(table, hashIdx);
+    if (he.x == bx && he.y == by && he.z == bz && he.ptr >= 0) return he.ptr * BS3;
+    if (he.offset < 1) return -1;
+    hashIdx = numBuckets + he.offset - 1;
+  }
+}
+
+DEV float sdf_at(const b200_voxel *__restrict__ voxels, int base, int off) {   // (float)voxel.sdf or TVoxel() when the block is missing
+  return base >= 0 ? (float)__ldg(reinterpret_cast<const short *>(voxels + base + off)) : 32767.0f;
+}
+
+// readFromSDF_float_interpolated — DA/ITMRepresentationAccess.h:252-278. The eight taps are the reference's, operand
+// for operand; only the addressing differs. 67% of the positions have their 2x2x2 neighbourhood inside one block
+// (one resolve, eight constant-offset 2-byte reads), 29% straddle exactly one block face (two resolves), the rest
+// take the general per-tap walk. (A warp almost always contains straddling lanes, so the straddling paths must be
+// cheap: the per-tap walk through a one-entry cache re-hashes on every tap.)
 DEV float sdf_interp(const b200_voxel *__restrict__ voxels, const b200_hash_entry *__restrict__ table, int nb, float px, float py, float pz,
                      IdxCache &c) {
   const float fx = floorf(px), fy = floorf(py), fz = floorf(pz);
@@ -232,16 +249,27 @@ DEV float sdf_interp(const b200_voxel *__restrict__ voxels, const b200_hash_entr
   const int x = (int)fx, y = (int)fy, z = (int)fz;
   float v000, v100, v010, v110, v001, v101, v011, v111;
   const int lx = x & 7, ly = y & 7, lz = z & 7;
-  if (lx < 7 && ly < 7 && lz < 7) {
-    const int base = block_base(table, nb, x >> 3, y >> 3, z >> 3, c);
-    if (base < 0) { v000 = v100 = v010 = v110 = v001 = v101 = v011 = v111 = 32767.0f; }
-    else {
-      const short *sp = reinterpret_cast<const short *>(voxels + base + lx + (ly << 3) + (lz << 6));   // 8-byte voxels: short stride 4
-      v000 = (float)__ldg(sp);            v100 = (float)__ldg(sp + 4);
-      v010 = (float)__ldg(sp + 32);       v110 = (float)__ldg(sp + 36);
-      v001 = (float)__ldg(sp + 256);      v101 = (float)__ldg(sp + 260);
-      v011 = (float)__ldg(sp + 288);      v111 = (float)__ldg(sp + 292);
+  const int m = (lx == 7 ? 1 : 0) | (ly == 7 ? 2 : 0) | (lz == 7 ? 4 : 0);   // block faces crossed
+  if ((m & (m - 1)) == 0) {
+    // no face or exactly one face crossed
+    const int bx = x >> 3, by = y >> 3, bz = z >> 3;
+    const int base0 = block_base(table, nb, bx, by, bz, c);
+    const int local = lx + (ly << 3) + (lz << 6);
+    int far = base0, farAdj = 0;                     // block of the taps beyond the crossed face, and their index correction
+    if (m) {
+      far = block_lookup(table, nb, bx + (m & 1), by + ((m >> 1) & 1), bz + (m >> 2));
+      farAdj = (m & 1) ? -8 : ((m & 2) ? -64 : -512);   // (l + 1) & 7 == 0 on that axis: undo the carry of the tap offset
     }
+#define TAP(bits, off) (((bits) & m) ? sdf_at(voxels, far, local + (off) + farAdj) : sdf_at(voxels, base0, local + (off)))
+    v000 = sdf_at(voxels, base0, local);
+    v100 = TAP(1, 1);
+    v010 = TAP(2, 8);
+    v110 = TAP(3, 9);
+    v001 = TAP(4, 64);
+    v101 = TAP(5, 65);
+    v011 = TAP(6, 72);
+    v111 = TAP(7, 73);
+#undef TAP
   } else {
     v000 = rv_sdf(voxels, table, nb, x, y, z, c);         v100 = rv_sdf(voxels, table, nb, x + 1, y, z, c);
     v010 = rv_sdf(voxels, table, nb, x, y + 1, z, c);     v110 = rv_sdf(voxels, table, nb, x + 1, y + 1, z, c);

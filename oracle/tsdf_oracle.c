@@ -1212,6 +1212,14 @@ int oracle_swap_out(b200_scene *s, const b200_render_state *rs, b200_voxel *sync
   return n;
 }
 
+void oracle_set_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
+
 int oracle_num_threads(void) {
 #ifdef _OPENMP
   return omp_get_max_threads();

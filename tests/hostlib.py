@@ -68,6 +68,8 @@ def oracle():
     L.oracle_swap_integrate_in.restype = None
     L.oracle_swap_out.argtypes = [P(abi.Scene), P(abi.RenderState), vp, vp, vp]
     L.oracle_num_threads.restype = C.c_int
+    L.oracle_set_threads.argtypes = [C.c_int]
+    L.oracle_set_threads.restype = None
     _oracle = L
     return L
 
