@@ -226,6 +226,52 @@ def run_itm_harness(frames, preroll, timed):
 
 
 # --------------------------------------------------------------------------------------------------
+# roofline stress (BASELINE.json configs[4]): 4 mm voxels, mu 16 mm — the same street at
+# 12.5x finer voxels makes the visible list two orders of magnitude longer, so IntegrateIntoScene runs for
+# hundreds of microseconds and its bandwidth fraction can be read without launch effects.
+# --------------------------------------------------------------------------------------------------
+def run_hires(local_rank, frames_n):
+    import torch
+    from dynslam_b200 import engine as E
+    dev = torch.device("cuda", local_rank)
+    W, H_ = synth.KITTI_W, synth.KITTI_H
+    nb, nbk, nex = 3000000, 0x400000, 0x100000
+    frames = gen_frames_hires(5, frames_n)
+    scene = E.Scene(E.SceneParams(voxelSize=0.004, mu=0.016, maxW=50), nb, nbk, nex, device=f"cuda:{local_rank}")
+    eng = E.Engine(scene, (W, H_), decayRingItems=4 * nb)
+    reco = E.SceneReconstructionEngine(eng)
+    rs = E.VisualisationEngine(eng, scene).CreateRenderState((W, H_))
+    reco.ResetScene(scene)
+    views = [E.View(torch.from_numpy(f[0]).to(dev), torch.from_numpy(f[1]).to(dev), f[2], f[3]) for f in frames]
+    torch.cuda.synchronize(dev)
+    half = frames_n // 2
+    for v in views[:half]:
+        eng.process_frame_async(rs, v, None, None, decay=None, raycast=False)
+    eng.sync(rs)
+    b0 = eng.stats().totalIntegratedBlocks
+    eng.set_timing(2)
+    for v in views[half:]:
+        eng.process_frame_async(rs, v, None, None, decay=None, raycast=False)
+    eng.sync(rs)
+    st = eng.stats()
+    blocks, ms, n = st.totalIntegratedBlocks - b0, st.ring_ms_integrate, st.ring_count
+    peak, _ = peaks()
+    alg = blocks * BYTES_PER_BLOCK + n * W * H_ * 8
+    out = {"workload": "4 mm voxels, mu 16 mm, depth clamp 8 m, same street (configs[4])", "frames": n,
+           "visible_blocks": rs.noVisibleBlocks, "allocated_blocks": nb - 1 - scene.lastFreeBlockId,
+           "mean_launch_us": 1000.0 * ms / max(n, 1), "achieved": alg / (ms / 1000.0) / 1e9 if ms > 0 else 0.0, "unit": "GB/s",
+           "peak": peak, "mvoxels_per_s": blocks * 512 / (ms / 1000.0) / 1e6 if ms > 0 else 0.0}
+    out["frac"] = out["achieved"] / peak
+    eng.close()
+    return out
+
+
+def gen_frames_hires(seed, count):
+    scene = synth.StreetScene(seed=seed, length_m=60.0)
+    return [synth.kitti_frame(scene, f, zmax=8.0) for f in range(count)]
+
+
+# --------------------------------------------------------------------------------------------------
 # own arm
 # --------------------------------------------------------------------------------------------------
 def run_own(args, rank, local_rank, world):
@@ -402,6 +448,13 @@ def run_own(args, rank, local_rank, world):
         except Exception as ex:
             itm = {"error": str(ex)}
 
+    hires = None
+    if world == 1 and args.hires_frames > 0:
+        try:
+            hires = run_hires(local_rank, args.hires_frames)
+        except Exception as ex:
+            hires = {"error": str(ex)}
+
     line = {
         "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": Wm,
         "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
@@ -422,6 +475,7 @@ def run_own(args, rank, local_rank, world):
                      "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None, "traffic": ncu_traffic(),
                      "peak_source": peak_src, "launches_timed": int_n, "mean_launch_us": 1000.0 * int_ms / max(int_n, 1),
                      "alg_bytes_per_launch": alg_bytes / max(int_n, 1)},
+        "roofline_hires": hires,
         "cpu_baseline": cpu,
         "itmlib_harness": itm,
         "e2e": {"value": world * e2e_frames / t_e2e, "unit": "frames/s", "h2d_bytes_per_step": W * H_ * 8,
@@ -447,6 +501,7 @@ def main():
     ap.add_argument("--cpu-steps", type=int, default=6)
     ap.add_argument("--harness-frames", type=int, default=100, help="frames timed through the real ITMLib objects (0 = skip)")
     ap.add_argument("--harness-preroll", type=int, default=60)
+    ap.add_argument("--hires-frames", type=int, default=24, help="frames of the 4 mm roofline-stress stream (0 = skip)")
     ap.add_argument("--cpu-preroll", type=int, default=12)
     ap.add_argument("--ref-preroll", type=int, default=12)
     args = ap.parse_args()

@@ -138,6 +138,11 @@ b200_status b200_engine_create(const b200_engine_config *cfg, b200_engine **out)
   CK(cudaMalloc(&e->d_blockRecs, 16 * (size_t)e->numBlocks));
   CK(cudaMalloc(&e->d_tileCounts, sizeof(unsigned) * (size_t)(px > 0 ? px : 1)));
   for (int i = 0; i < 8; ++i) CK(cudaEventCreate(&e->ev[i]));
+  if (!getenv("B200_NO_OVERLAP")) {
+    CK(cudaStreamCreateWithFlags(&e->sideStream, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&e->evFork, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&e->evJoin, cudaEventDisableTiming));
+  }
   e->hostAuthoritative = true;
   // default: TMA variant (measured faster); B200_INTEGRATE_IMPL=ldg selects the simple one
   { const char *v = getenv("B200_INTEGRATE_IMPL"); e->integrateImpl = (v && v[0] == 'l') ? 0 : 1; }
@@ -158,6 +163,7 @@ void b200_engine_destroy(b200_engine *e) {
       cudaEventDestroy(e->evH2D[i]); cudaEventDestroy(e->evCompute[i]); cudaEventDestroy(e->evD2H[i]); }
     cudaStreamDestroy(e->copyStream);
   }
+  if (e->sideStream) { cudaStreamSynchronize(e->sideStream); cudaEventDestroy(e->evFork); cudaEventDestroy(e->evJoin); cudaStreamDestroy(e->sideStream); }
   if (e->ownStream && e->stream) cudaStreamDestroy(e->stream);
   delete e;
 }
@@ -424,17 +430,40 @@ b200_status b200_process_frame_async(b200_engine *e, b200_scene *s, b200_render_
   FrameGeom g = frame_geom(s, v);
   const bool ring = e->timingMode >= 2 && e->evRingCount < e->evRingCap;
   if (ring) CK(cudaEventRecord(e->evRing[2 * e->evRingCount], e->stream));
+  // Fork: the expected-depth kernels only need the visible list (+ its ptr list), not the voxels IntegrateIntoScene is
+  // about to rewrite; they are small latency-bound launches, so they run on the side stream underneath the integrate kernel.
+  cudaStream_t mainStream = e->stream;
+  const bool overlap = doRay && e->sideStream != nullptr;
+  if (overlap) {
+    CK(cudaEventRecord(e->evFork, mainStream));
+    CK(cudaStreamWaitEvent(e->sideStream, e->evFork, 0));
+    e->stream = e->sideStream;
+    launch_expected_depths(e, r, g.M_d, g.proj_d, rs->img_w, rs->img_h, s->voxelSize, rs->d_minmax, true);
+    e->stream = mainStream;
+    CK(cudaEventRecord(e->evJoin, e->sideStream));
+  }
   launch_integrate(e, r, g, v->d_depth, v->d_rgb);
   if (ring) { CK(cudaEventRecord(e->evRing[2 * e->evRingCount + 1], e->stream)); e->evRingCount++; }
   if (e->timing) CK(cudaEventRecord(e->ev[2], e->stream));
   if (doRay) {
-    launch_expected_depths(e, r, g.M_d, g.proj_d, rs->img_w, rs->img_h, s->voxelSize, rs->d_minmax, true);
+    if (overlap) CK(cudaStreamWaitEvent(mainStream, e->evJoin, 0));
+    else launch_expected_depths(e, r, g.M_d, g.proj_d, rs->img_w, rs->img_h, s->voxelSize, rs->d_minmax, true);
     if (e->timing) CK(cudaEventRecord(e->ev[3], e->stream));
     launch_raycast(e, r, g.invM_d, g.proj_d, rs->img_w, rs->img_h, s->voxelSize, s->mu, rs->d_minmax, rs->d_raycastResult);
-    launch_icp(e, g.invM_d, rs->img_w, rs->img_h, s->voxelSize, rs->d_raycastResult, rs->d_raycastImage, d_points, d_normals);
+    if (overlap) {   // the ICP-map pass (image space) runs beside the decay sweep (voxel space)
+      CK(cudaEventRecord(e->evFork, mainStream));
+      CK(cudaStreamWaitEvent(e->sideStream, e->evFork, 0));
+      e->stream = e->sideStream;
+      launch_icp(e, g.invM_d, rs->img_w, rs->img_h, s->voxelSize, rs->d_raycastResult, rs->d_raycastImage, d_points, d_normals);
+      e->stream = mainStream;
+      CK(cudaEventRecord(e->evJoin, e->sideStream));
+    } else {
+      launch_icp(e, g.invM_d, rs->img_w, rs->img_h, s->voxelSize, rs->d_raycastResult, rs->d_raycastImage, d_points, d_normals);
+    }
   } else if (e->timing) CK(cudaEventRecord(e->ev[3], e->stream));
   if (e->timing) CK(cudaEventRecord(e->ev[4], e->stream));
   if (opts && opts->doDecay) enqueue_decay(e, s, rs, opts->decayMaxWeight, opts->decayMinAge, 0);
+  if (overlap) CK(cudaStreamWaitEvent(mainStream, e->evJoin, 0));   // join: the frame is complete on the main stream
   if (e->timing) CK(cudaEventRecord(e->ev[5], e->stream));
   return B200_OK;
 }

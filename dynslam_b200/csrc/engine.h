@@ -68,6 +68,8 @@ struct b200_engine {
   bool timing;
   cudaEvent_t ev[8];
   // pipelined host frames: copy stream, two staging slots
+  cudaStream_t sideStream;            // fused frame: small launches overlapped with the big ones
+  cudaEvent_t evFork, evJoin;
   cudaStream_t copyStream;
   float *d_stageDepth[2]; b200_vec4u *d_stageRgb[2]; b200_vec4u *d_stageOut[2];
   cudaEvent_t evH2D[2], evCompute[2], evD2H[2];
