@@ -345,7 +345,9 @@ __device__ bool cast_ray(float4 &out, int x, int y, const b200_voxel *__restrict
 // voxel blocks). Measured on B200: the march is bound by the chain of dependent L2 reads per step, not by lane
 // utilisation — a ray-refill variant (fewer, longer-lived warps) was 1.1-3x slower (profiles/), so the kernel keeps
 // the maximum number of independent rays in flight and shortens the chain per step instead (see cast_ray).
-__global__ void __launch_bounds__(256)
+// 64-thread CTAs: rays finish at very different times, small CTAs hand their SM slots back sooner.
+#define RC_THREADS 64
+__global__ void __launch_bounds__(RC_THREADS)
 k_raycast(float4 *out, const b200_voxel *__restrict__ voxels, const b200_hash_entry *__restrict__ table, int nb, int w, int h, Mat4 invM,
           float fx, float fy, float cxp, float cyp, float voxelSize, float mu, const float2 *__restrict__ minmax) {
   const int tilesX = (w + 7) >> 3, tilesY = (h + 3) >> 2;
@@ -363,8 +365,10 @@ k_raycast(float4 *out, const b200_voxel *__restrict__ voxels, const b200_hash_en
 void launch_raycast(b200_engine *e, const SceneRef &s, const Mat4 &invM, const float proj[4], int w, int h, float voxelSize, float mu,
                     const b200_vec2f *minmax, b200_vec4f *out) {
   const int tiles = ((w + 7) / 8) * ((h + 3) / 4);
-  k_raycast<<<(tiles + 7) / 8, 256, 0, e->stream>>>((float4 *)out, s.voxels, s.hash, s.numBuckets, w, h, invM, proj[0], proj[1], proj[2],
-                                                   proj[3], voxelSize, mu, (const float2 *)minmax);
+  const int warpsPerCta = RC_THREADS / 32;
+  k_raycast<<<(tiles + warpsPerCta - 1) / warpsPerCta, RC_THREADS, 0, e->stream>>>((float4 *)out, s.voxels, s.hash, s.numBuckets, w, h, invM,
+                                                                                  proj[0], proj[1], proj[2], proj[3], voxelSize, mu,
+                                                                                  (const float2 *)minmax);
   e->launches++;
 }
 
