@@ -349,12 +349,14 @@ __device__ bool cast_ray(float4 &out, int x, int y, const b200_voxel *__restrict
 #define RC_THREADS 64
 __global__ void __launch_bounds__(RC_THREADS)
 k_raycast(float4 *out, const b200_voxel *__restrict__ voxels, const b200_hash_entry *__restrict__ table, int nb, int w, int h, Mat4 invM,
-          float fx, float fy, float cxp, float cyp, float voxelSize, float mu, const float2 *__restrict__ minmax) {
-  const int tilesX = (w + 7) >> 3, tilesY = (h + 3) >> 2;
+          float fx, float fy, float cxp, float cyp, float voxelSize, float mu, const float2 *__restrict__ minmax, int twLog2) {
+  // warp tile: (1 << twLog2) x (32 >> twLog2) pixels
+  const int tw = 1 << twLog2, th = 32 >> twLog2;
+  const int tilesX = (w + tw - 1) >> twLog2, tilesY = (h + th - 1) / th;
   const int warpGlobal = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (warpGlobal >= tilesX * tilesY) return;
   const int lane = threadIdx.x & 31;
-  const int x = (warpGlobal % tilesX) * 8 + (lane & 7), y = (warpGlobal / tilesX) * 4 + (lane >> 3);
+  const int x = (warpGlobal % tilesX) * tw + (lane & (tw - 1)), y = (warpGlobal / tilesX) * th + (lane >> twLog2);
   if (x >= w || y >= h) return;
   const int locId2 = (int)floorf((float)x / B200_MINMAX_SUBSAMPLE) + (int)floorf((float)y / B200_MINMAX_SUBSAMPLE) * w;
   float4 o;
@@ -364,11 +366,14 @@ k_raycast(float4 *out, const b200_voxel *__restrict__ voxels, const b200_hash_en
 
 void launch_raycast(b200_engine *e, const SceneRef &s, const Mat4 &invM, const float proj[4], int w, int h, float voxelSize, float mu,
                     const b200_vec2f *minmax, b200_vec4f *out) {
-  const int tiles = ((w + 7) / 8) * ((h + 3) / 4);
+  static int twLog2 = -1;
+  if (twLog2 < 0) { const char *v = getenv("B200_RC_TILE"); twLog2 = v ? atoi(v) : 3; if (twLog2 < 0 || twLog2 > 5) twLog2 = 3; }   // 3: 8x4 (default)
+  const int tw = 1 << twLog2, th = 32 >> twLog2;
+  const int tiles = ((w + tw - 1) / tw) * ((h + th - 1) / th);
   const int warpsPerCta = RC_THREADS / 32;
   k_raycast<<<(tiles + warpsPerCta - 1) / warpsPerCta, RC_THREADS, 0, e->stream>>>((float4 *)out, s.voxels, s.hash, s.numBuckets, w, h, invM,
                                                                                   proj[0], proj[1], proj[2], proj[3], voxelSize, mu,
-                                                                                  (const float2 *)minmax);
+                                                                                  (const float2 *)minmax, twLog2);
   e->launches++;
 }
 
