@@ -162,6 +162,7 @@ void b200_engine_destroy(b200_engine *e) {
     for (int i = 0; i < 2; ++i) { cudaFree(e->d_stageDepth[i]); cudaFree(e->d_stageRgb[i]); cudaFree(e->d_stageOut[i]);
       cudaEventDestroy(e->evH2D[i]); cudaEventDestroy(e->evCompute[i]); cudaEventDestroy(e->evD2H[i]); }
     cudaStreamDestroy(e->copyStream);
+    if (e->d2hStream) { cudaStreamSynchronize(e->d2hStream); cudaStreamDestroy(e->d2hStream); }
   }
   if (e->sideStream) { cudaStreamSynchronize(e->sideStream); cudaEventDestroy(e->evFork); cudaEventDestroy(e->evJoin); cudaStreamDestroy(e->sideStream); }
   if (e->ownStream && e->stream) cudaStreamDestroy(e->stream);
@@ -493,6 +494,7 @@ static b200_status ensure_pipeline(b200_engine *e, size_t pixels) {
   if (e->copyStream && e->stagePixels >= pixels) return B200_OK;
   if (!e->copyStream) {
     CK(cudaStreamCreateWithFlags(&e->copyStream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&e->d2hStream, cudaStreamNonBlocking));
     for (int i = 0; i < 2; ++i) {
       CK(cudaEventCreateWithFlags(&e->evH2D[i], cudaEventDisableTiming));
       CK(cudaEventCreateWithFlags(&e->evCompute[i], cudaEventDisableTiming));
@@ -530,9 +532,9 @@ b200_status b200_host_frame_submit(b200_engine *e, b200_scene *s, b200_render_st
   if (h_outImage) {
     CK(cudaMemcpyAsync(e->d_stageOut[slot], rs->d_raycastImage, no * sizeof(b200_vec4u), cudaMemcpyDeviceToDevice, e->stream));
     CK(cudaEventRecord(e->evCompute[slot], e->stream));
-    CK(cudaStreamWaitEvent(e->copyStream, e->evCompute[slot], 0));
-    CK(cudaMemcpyAsync(h_outImage, e->d_stageOut[slot], no * sizeof(b200_vec4u), cudaMemcpyDeviceToHost, e->copyStream));
-    CK(cudaEventRecord(e->evD2H[slot], e->copyStream));
+    CK(cudaStreamWaitEvent(e->d2hStream, e->evCompute[slot], 0));
+    CK(cudaMemcpyAsync(h_outImage, e->d_stageOut[slot], no * sizeof(b200_vec4u), cudaMemcpyDeviceToHost, e->d2hStream));
+    CK(cudaEventRecord(e->evD2H[slot], e->d2hStream));
   } else {
     CK(cudaEventRecord(e->evD2H[slot], e->stream));
   }

@@ -70,7 +70,8 @@ struct b200_engine {
   // pipelined host frames: copy stream, two staging slots
   cudaStream_t sideStream;            // fused frame: small launches overlapped with the big ones
   cudaEvent_t evFork, evJoin;
-  cudaStream_t copyStream;
+  cudaStream_t copyStream;     // H2D of the next frame's depth + RGB
+  cudaStream_t d2hStream;      // D2H of the previous frame's image (own stream so it never holds up the next upload)
   float *d_stageDepth[2]; b200_vec4u *d_stageRgb[2]; b200_vec4u *d_stageOut[2];
   cudaEvent_t evH2D[2], evCompute[2], evD2H[2];
   bool slotBusy[2]; size_t stagePixels;
