@@ -79,6 +79,12 @@ class FrameOpts(C.Structure):
                 ("doRaycast", C.c_int32)]
 
 
+class ViewCalib(C.Structure):
+    """b200_view_calib: ITMDisparityCalib + depth intrinsics + the two ITMLibSettings switches UpdateView reads."""
+    _fields_ = [("trafoType", C.c_int32), ("params", C.c_float * 2), ("fx_depth", C.c_float),
+                ("intrinsics_d", C.c_float * 4), ("useBilateralFilter", C.c_int32), ("modelSensorNoise", C.c_int32)]
+
+
 class FrameStats(C.Structure):
     _fields_ = [("ms_allocate", C.c_float), ("ms_integrate", C.c_float), ("ms_expected", C.c_float),
                 ("ms_raycast", C.c_float), ("ms_decay", C.c_float), ("ms_total", C.c_float),
@@ -95,6 +101,8 @@ EXPORTS = [
     "b200_icp_maps", "b200_forward_render", "b200_point_cloud", "b200_swap_list_in",
     "b200_swap_integrate_in", "b200_swap_out", "b200_process_frame_async", "b200_sync",
     "b200_process_frame_host", "b200_set_timing", "b200_get_stats", "b200_host_frame_submit", "b200_host_frame_wait",
+    "b200_convert_disparity_to_depth", "b200_convert_depth_affine_to_float", "b200_depth_filtering",
+    "b200_compute_normal_and_weights", "b200_update_view", "b200_update_view_async", "b200_host_frame_submit_raw",
 ]
 
 _lib = None
@@ -146,6 +154,14 @@ def load_library():
                                             P(FrameOpts), vp]
     lib.b200_host_frame_submit.argtypes = [vp, P(Scene), P(RenderState), P(View), vp, vp, vp, vp, P(FrameOpts), vp, C.c_int]
     lib.b200_host_frame_wait.argtypes = [vp, C.c_int]
+    lib.b200_convert_disparity_to_depth.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float]
+    lib.b200_convert_depth_affine_to_float.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_float, C.c_float]
+    lib.b200_depth_filtering.argtypes = [vp, vp, vp, C.c_int, C.c_int]
+    lib.b200_compute_normal_and_weights.argtypes = [vp, vp, vp, vp, C.c_int, C.c_int, P(C.c_float)]
+    lib.b200_update_view.argtypes = [vp, vp, C.c_int, C.c_int, P(ViewCalib), vp, vp, vp]
+    lib.b200_update_view_async.argtypes = [vp, vp, C.c_int, C.c_int, P(ViewCalib), vp, vp, vp]
+    lib.b200_host_frame_submit_raw.argtypes = [vp, P(Scene), P(RenderState), P(View), vp, vp, P(ViewCalib), vp, vp, P(FrameOpts),
+                                               vp, C.c_int]
     lib.b200_set_timing.argtypes = [vp, C.c_int]
     lib.b200_set_timing.restype = None
     lib.b200_get_stats.argtypes = [vp, P(FrameStats)]

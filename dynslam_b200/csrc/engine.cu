@@ -159,7 +159,7 @@ void b200_engine_destroy(b200_engine *e) {
   for (int i = 0; i < 8; ++i) if (e->ev[i]) cudaEventDestroy(e->ev[i]);
   if (e->copyStream) {
     cudaStreamSynchronize(e->copyStream);
-    for (int i = 0; i < 2; ++i) { cudaFree(e->d_stageDepth[i]); cudaFree(e->d_stageRgb[i]); cudaFree(e->d_stageOut[i]);
+    for (int i = 0; i < 2; ++i) { cudaFree(e->d_stageDepth[i]); cudaFree(e->d_stageRgb[i]); cudaFree(e->d_stageOut[i]); cudaFree(e->d_stageRaw[i]);
       cudaEventDestroy(e->evH2D[i]); cudaEventDestroy(e->evCompute[i]); cudaEventDestroy(e->evD2H[i]); }
     cudaStreamDestroy(e->copyStream);
     if (e->d2hStream) { cudaStreamSynchronize(e->d2hStream); cudaStreamDestroy(e->d2hStream); }
@@ -502,8 +502,9 @@ static b200_status ensure_pipeline(b200_engine *e, size_t pixels) {
     }
   }
   for (int i = 0; i < 2; ++i) {
-    cudaFree(e->d_stageDepth[i]); cudaFree(e->d_stageRgb[i]); cudaFree(e->d_stageOut[i]);
+    cudaFree(e->d_stageDepth[i]); cudaFree(e->d_stageRgb[i]); cudaFree(e->d_stageOut[i]); cudaFree(e->d_stageRaw[i]);
     CK(cudaMalloc(&e->d_stageDepth[i], pixels * sizeof(float)));
+    CK(cudaMalloc(&e->d_stageRaw[i], pixels * sizeof(int16_t)));
     CK(cudaMalloc(&e->d_stageRgb[i], pixels * sizeof(b200_vec4u)));
     CK(cudaMalloc(&e->d_stageOut[i], pixels * sizeof(b200_vec4u)));
     e->slotBusy[i] = false;
@@ -512,9 +513,70 @@ static b200_status ensure_pipeline(b200_engine *e, size_t pixels) {
   return B200_OK;
 }
 
-b200_status b200_host_frame_submit(b200_engine *e, b200_scene *s, b200_render_state *rs, b200_view *v, const float *h_depth,
-                                   const b200_vec4u *h_rgb, b200_vec4f *d_points, b200_vec4f *d_normals, const b200_frame_opts *opts,
-                                   b200_vec4u *h_outImage, int slot) {
+// ---- view builder (view.cu) -------------------------------------------------------------------------
+static b200_status check_image(b200_engine *e, const void *a, const void *b, int w, int h) {
+  if (!a || !b || w < 5 || h < 5) { snprintf(e->err, sizeof(e->err), "view builder: null image or image smaller than 5x5"); return B200_ERR_INVALID; }
+  return B200_OK;
+}
+
+b200_status b200_convert_disparity_to_depth(b200_engine *e, float *d_out, const int16_t *d_in, int w, int h, float p0, float p1,
+                                            float fx_depth) {
+  b200_status st = check_image(e, d_out, d_in, w, h); if (st) return st;
+  CK(cudaSetDevice(e->device));
+  launch_view_convert(e, d_in, d_out, w, h, 0, p0, p1, fx_depth);
+  CK(cudaStreamSynchronize(e->stream)); CK(cudaGetLastError());
+  return B200_OK;
+}
+
+b200_status b200_convert_depth_affine_to_float(b200_engine *e, float *d_out, const int16_t *d_in, int w, int h, float p0, float p1) {
+  b200_status st = check_image(e, d_out, d_in, w, h); if (st) return st;
+  CK(cudaSetDevice(e->device));
+  launch_view_convert(e, d_in, d_out, w, h, 1, p0, p1, 0.0f);
+  CK(cudaStreamSynchronize(e->stream)); CK(cudaGetLastError());
+  return B200_OK;
+}
+
+b200_status b200_depth_filtering(b200_engine *e, float *d_out, const float *d_in, int w, int h) {
+  b200_status st = check_image(e, d_out, d_in, w, h); if (st) return st;
+  if (d_out == d_in) { snprintf(e->err, sizeof(e->err), "DepthFiltering cannot run in place"); return B200_ERR_INVALID; }
+  CK(cudaSetDevice(e->device));
+  launch_view_filter_pass(e, d_in, d_out, w, h);
+  CK(cudaStreamSynchronize(e->stream)); CK(cudaGetLastError());
+  return B200_OK;
+}
+
+b200_status b200_compute_normal_and_weights(b200_engine *e, b200_vec4f *d_normal, float *d_sigmaZ, const float *d_depth, int w, int h,
+                                            const float intrinsic[4]) {
+  b200_status st = check_image(e, d_normal, d_depth, w, h); if (st) return st;
+  if (!d_sigmaZ) { snprintf(e->err, sizeof(e->err), "sigmaZ image missing"); return B200_ERR_INVALID; }
+  CK(cudaSetDevice(e->device));
+  launch_view_normals(e, d_depth, d_normal, d_sigmaZ, w, h, intrinsic);
+  CK(cudaStreamSynchronize(e->stream)); CK(cudaGetLastError());
+  return B200_OK;
+}
+
+b200_status b200_update_view_async(b200_engine *e, const int16_t *d_rawDepth, int w, int h, const b200_view_calib *c, float *d_depth,
+                                   b200_vec4f *d_depthNormal, float *d_depthUncertainty) {
+  b200_status st = check_image(e, d_depth, d_rawDepth, w, h); if (st) return st;
+  if (c->trafoType != 0 && c->trafoType != 1) { snprintf(e->err, sizeof(e->err), "unknown disparity calibration type %d", c->trafoType); return B200_ERR_INVALID; }
+  if (c->modelSensorNoise && (!d_depthNormal || !d_depthUncertainty)) { snprintf(e->err, sizeof(e->err), "modelSensorNoise needs depthNormal and depthUncertainty"); return B200_ERR_INVALID; }
+  CK(cudaSetDevice(e->device));
+  launch_update_view(e, d_rawDepth, nullptr, d_depth, w, h, c->trafoType, c->params[0], c->params[1], c->fx_depth, c->useBilateralFilter != 0);
+  if (c->modelSensorNoise) launch_view_normals(e, d_depth, d_depthNormal, d_depthUncertainty, w, h, c->intrinsics_d);
+  return B200_OK;
+}
+
+b200_status b200_update_view(b200_engine *e, const int16_t *d_rawDepth, int w, int h, const b200_view_calib *c, float *d_depth,
+                             b200_vec4f *d_depthNormal, float *d_depthUncertainty) {
+  b200_status st = b200_update_view_async(e, d_rawDepth, w, h, c, d_depth, d_depthNormal, d_depthUncertainty); if (st) return st;
+  CK(cudaStreamSynchronize(e->stream)); CK(cudaGetLastError());
+  return B200_OK;
+}
+
+// ---- pipelined host frames ----------------------------------------------------------------------------
+static b200_status host_frame_submit(b200_engine *e, b200_scene *s, b200_render_state *rs, b200_view *v, const float *h_depth,
+                                     const int16_t *h_raw, const b200_view_calib *calib, const b200_vec4u *h_rgb, b200_vec4f *d_points,
+                                     b200_vec4f *d_normals, const b200_frame_opts *opts, b200_vec4u *h_outImage, int slot) {
   if (slot < 0 || slot > 1) { snprintf(e->err, sizeof(e->err), "slot must be 0 or 1"); return B200_ERR_INVALID; }
   CK(cudaSetDevice(e->device));
   const size_t nd = (size_t)v->depth_w * v->depth_h, nc = (size_t)v->rgb_w * v->rgb_h, no = (size_t)rs->img_w * rs->img_h;
@@ -522,11 +584,16 @@ b200_status b200_host_frame_submit(b200_engine *e, b200_scene *s, b200_render_st
   b200_status st = ensure_pipeline(e, px); if (st) return st;
   if (e->slotBusy[slot]) { snprintf(e->err, sizeof(e->err), "slot %d resubmitted before b200_host_frame_wait", slot); return B200_ERR_INVALID; }
   // H2D on the copy stream (the slot's previous frame was waited for, so its staging buffers are free)
-  CK(cudaMemcpyAsync(e->d_stageDepth[slot], h_depth, nd * sizeof(float), cudaMemcpyHostToDevice, e->copyStream));
+  if (h_raw) CK(cudaMemcpyAsync(e->d_stageRaw[slot], h_raw, nd * sizeof(int16_t), cudaMemcpyHostToDevice, e->copyStream));
+  else CK(cudaMemcpyAsync(e->d_stageDepth[slot], h_depth, nd * sizeof(float), cudaMemcpyHostToDevice, e->copyStream));
   CK(cudaMemcpyAsync(e->d_stageRgb[slot], h_rgb, nc * sizeof(b200_vec4u), cudaMemcpyHostToDevice, e->copyStream));
   CK(cudaEventRecord(e->evH2D[slot], e->copyStream));
   // the frame on the compute stream
   CK(cudaStreamWaitEvent(e->stream, e->evH2D[slot], 0));
+  if (h_raw) {
+    st = b200_update_view_async(e, e->d_stageRaw[slot], v->depth_w, v->depth_h, calib, e->d_stageDepth[slot], nullptr, nullptr);
+    if (st) return st;
+  }
   v->d_depth = e->d_stageDepth[slot]; v->d_rgb = e->d_stageRgb[slot];
   st = b200_process_frame_async(e, s, rs, v, d_points, d_normals, opts); if (st) return st;
   if (h_outImage) {
@@ -540,6 +607,20 @@ b200_status b200_host_frame_submit(b200_engine *e, b200_scene *s, b200_render_st
   }
   e->slotBusy[slot] = true;
   return B200_OK;
+}
+
+b200_status b200_host_frame_submit(b200_engine *e, b200_scene *s, b200_render_state *rs, b200_view *v, const float *h_depth,
+                                   const b200_vec4u *h_rgb, b200_vec4f *d_points, b200_vec4f *d_normals, const b200_frame_opts *opts,
+                                   b200_vec4u *h_outImage, int slot) {
+  return host_frame_submit(e, s, rs, v, h_depth, nullptr, nullptr, h_rgb, d_points, d_normals, opts, h_outImage, slot);
+}
+
+b200_status b200_host_frame_submit_raw(b200_engine *e, b200_scene *s, b200_render_state *rs, b200_view *v, const int16_t *h_rawDepth,
+                                       const b200_vec4u *h_rgb, const b200_view_calib *calib, b200_vec4f *d_points, b200_vec4f *d_normals,
+                                       const b200_frame_opts *opts, b200_vec4u *h_outImage, int slot) {
+  if (!h_rawDepth || !calib) { snprintf(e->err, sizeof(e->err), "raw depth / calibration missing"); return B200_ERR_INVALID; }
+  if (calib->modelSensorNoise) { snprintf(e->err, sizeof(e->err), "modelSensorNoise is not available on the pipelined path; call b200_update_view"); return B200_ERR_INVALID; }
+  return host_frame_submit(e, s, rs, v, nullptr, h_rawDepth, calib, h_rgb, d_points, d_normals, opts, h_outImage, slot);
 }
 
 b200_status b200_host_frame_wait(b200_engine *e, int slot) {

@@ -72,7 +72,7 @@ struct b200_engine {
   cudaEvent_t evFork, evJoin;
   cudaStream_t copyStream;     // H2D of the next frame's depth + RGB
   cudaStream_t d2hStream;      // D2H of the previous frame's image (own stream so it never holds up the next upload)
-  float *d_stageDepth[2]; b200_vec4u *d_stageRgb[2]; b200_vec4u *d_stageOut[2];
+  float *d_stageDepth[2]; b200_vec4u *d_stageRgb[2]; b200_vec4u *d_stageOut[2]; int16_t *d_stageRaw[2];
   cudaEvent_t evH2D[2], evCompute[2], evD2H[2];
   bool slotBusy[2]; size_t stagePixels;
   cudaEvent_t *evRing;                // timing mode 2: event pairs around every integrate launch
@@ -113,6 +113,12 @@ void launch_swap_list_in(b200_engine *e, const SceneRef &s, int *needed);
 void launch_swap_integrate_in(b200_engine *e, const SceneRef &s, const b200_voxel *synced, const int *needed, int n, int maxW);
 void launch_swap_list_out(b200_engine *e, const SceneRef &s, int *needed);
 void launch_swap_move_out(b200_engine *e, const SceneRef &s, b200_voxel *synced, uint8_t *hasSynced, const int *needed, int n);
+
+void launch_view_convert(b200_engine *e, const int16_t *raw, float *out, int w, int h, int type, float p0, float p1, float fx);
+void launch_view_filter_pass(b200_engine *e, const float *in, float *out, int w, int h);
+void launch_update_view(b200_engine *e, const int16_t *raw, const float *depthIn, float *out, int w, int h, int type, float p0,
+                        float p1, float fx, bool filter);
+void launch_view_normals(b200_engine *e, const float *depth, b200_vec4f *normal, float *sigmaZ, int w, int h, const float intr[4]);
 
 static inline int persistent_grid(const b200_engine *e, int ctasPerSm, long long workItems) {
   long long g = (long long)e->smCount * ctasPerSm;

@@ -1,0 +1,204 @@
+// view.cu — the view builder that feeds the fusion path.
+//
+// Replaces ITMViewBuilder_CUDA::UpdateView (Engine/DeviceSpecific/CUDA/ITMViewBuilder_CUDA.cu:33-84):
+// raw short depth -> float metres (convertDepthAffineToFloat / convertDisparityToDepth,
+// DeviceAgnostic/ITMViewBuilder.h:7-28), five passes of the 5x5 bilateral filter (filterDepth, :30-56,
+// ping-ponging view->depth <-> floatImage, then a device-to-device copy back) and, for the weighted-ICP
+// tracker, ComputeNormalAndWeights (:59-114).
+//
+// B200 design: ONE kernel for convert + 5 passes + copy. A CTA owns a 64x32 output tile, converts the
+// (64+20)x(32+20) raw neighbourhood into shared memory once, and runs the passes between two shared
+// buffers; every pass shrinks the valid region by the filter radius, the fifth writes straight to global.
+// 2 B/pixel are read and 4 B/pixel written instead of 2 + 5*(4+4) + 8; the six launch gaps disappear.
+// The kernel is bound by the 25 exp() per pixel and pass, not by memory.
+//
+// Border semantics are the CUDA reference's, not the CPU twin's (which clears the target of every pass,
+// CPU/ITMViewBuilder_CPU.cpp:116-127): filterDepth_device leaves the two outermost rows/columns of its
+// TARGET untouched (ITMViewBuilder_CUDA.cu:196-209), so
+//   * floatImage's border is the zero MemoryBlock's constructor put there and is never written
+//     (passes 1, 3, 5 write floatImage) -> the final depth image has a 2-pixel border of 0,
+//   * view->depth's border still holds the converted raw values when passes 3 and 5 read it,
+//   * those border values ARE read as taps by the neighbouring inner pixels (0 is not < 0).
+//
+// Arithmetic: the expressions keep the reference's operation order; the library is compiled without
+// contraction, division and sqrt are IEEE. exp()/acos() are the CUDA math library's (<= 2 ulp) where the
+// oracle uses the host libm, so this file is compared within a stated tolerance (tests/test_gpu_view.py),
+// not bit for bit; the reference's own CUDA build uses --use_fast_math here.
+#include "engine.h"
+
+namespace {
+
+constexpr float MEAN_SIGMA_L = 1.2232f;   // DeviceAgnostic/ITMViewBuilder.h:30
+
+// convertDepthAffineToFloat (DA/ITMViewBuilder.h:22-28)
+__device__ __forceinline__ float convert_affine(short d, float p0, float p1) {
+  return ((d <= 0) || (d > 32000)) ? -1.0f : (float)d * p0 + p1;
+}
+
+// convertDisparityToDepth (DA/ITMViewBuilder.h:7-20)
+__device__ __forceinline__ float convert_disparity(short disparity, float p0, float p1, float fx) {
+  const float disparity_tmp = p0 - (float)disparity;
+  float depth;
+  if (disparity_tmp == 0) depth = 0.0f;
+  else depth = 8.0f * p1 * fx / disparity_tmp;
+  return (depth > 0) ? depth : -1.0f;
+}
+
+// filterDepth (DA/ITMViewBuilder.h:31-56) for the pixel at *c; rows are `stride` floats apart.
+__device__ __forceinline__ float filter_depth_at(const float *c, int stride) {
+  const float z = c[0];
+  if (z < 0.0f) return -1.0f;
+  const float sigma_z = 1.0f / (0.0012f + 0.0019f * (z - 0.4f) * (z - 0.4f) + 0.0001f / sqrtf(z) * 0.25f);
+  float final_depth = 0.0f, w_sum = 0.0f;
+#pragma unroll
+  for (int i = -2; i <= 2; i++) {
+#pragma unroll
+    for (int j = -2; j <= 2; j++) {
+      const float tmpz = c[i * stride + j];
+      if (tmpz < 0.0f) continue;
+      float dz = (tmpz - z); dz *= dz;
+      const int a = (i < 0 ? -i : i) + (j < 0 ? -j : j);
+      const float w = expf(-0.5f * ((float)a * MEAN_SIGMA_L * MEAN_SIGMA_L + dz * sigma_z * sigma_z));
+      w_sum += w;
+      final_depth += w * tmpz;
+    }
+  }
+  return final_depth / w_sum;
+}
+
+__device__ __forceinline__ bool on_border(int x, int y, int w, int h) { return x < 2 || x >= w - 2 || y < 2 || y >= h - 2; }
+
+// ---- stand-alone stages (interface completeness: ITMViewBuilder::ConvertDisparityToDepth,
+// ConvertDepthAffineToFloat, DepthFiltering) ---------------------------------------------------------
+__global__ void k_convert(const short *__restrict__ in, float *__restrict__ out, int n, int type, float p0, float p1, float fx) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  out[i] = type == 0 ? convert_disparity(in[i], p0, p1, fx) : convert_affine(in[i], p0, p1);
+}
+
+__global__ void k_filter_pass(const float *__restrict__ in, float *__restrict__ out, int w, int h) {
+  const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
+  if (x >= w || y >= h || on_border(x, y, w, h)) return;          // target border untouched
+  out[x + y * w] = filter_depth_at(in + x + y * w, w);
+}
+
+// ---- fused UpdateView ------------------------------------------------------------------------------
+constexpr int VB_TW = 64, VB_TH = 32, VB_HALO = 10, VB_THREADS = 256;
+constexpr int VB_SW = VB_TW + 2 * VB_HALO, VB_SH = VB_TH + 2 * VB_HALO;
+
+template <bool RAW>
+__global__ void __launch_bounds__(VB_THREADS) k_update_view(const short *__restrict__ raw, const float *__restrict__ depthIn,
+                                                            float *__restrict__ out, int w, int h, int type, float p0, float p1,
+                                                            float fx, int filter) {
+  __shared__ float bufA[VB_SH * VB_SW];   // plays view->depth
+  __shared__ float bufB[VB_SH * VB_SW];   // plays floatImage
+  const int x0 = blockIdx.x * VB_TW - VB_HALO, y0 = blockIdx.y * VB_TH - VB_HALO;   // image coords of smem cell (0,0)
+
+  if (!filter) {   // conversion only
+    for (int c = threadIdx.x; c < VB_TW * VB_TH; c += VB_THREADS) {
+      const int gx = x0 + VB_HALO + c % VB_TW, gy = y0 + VB_HALO + c / VB_TW;
+      if (gx < w && gy < h) {
+        const int g = gx + gy * w;
+        out[g] = RAW ? (type == 0 ? convert_disparity(raw[g], p0, p1, fx) : convert_affine(raw[g], p0, p1)) : depthIn[g];
+      }
+    }
+    return;
+  }
+
+  for (int c = threadIdx.x; c < VB_SW * VB_SH; c += VB_THREADS) {
+    const int gx = x0 + c % VB_SW, gy = y0 + c / VB_SW;
+    float v = 0.0f;
+    if (gx >= 0 && gx < w && gy >= 0 && gy < h) {
+      const int g = gx + gy * w;
+      v = RAW ? (type == 0 ? convert_disparity(raw[g], p0, p1, fx) : convert_affine(raw[g], p0, p1)) : depthIn[g];
+    }
+    bufA[c] = v;
+  }
+  __syncthreads();
+
+#pragma unroll 1
+  for (int pass = 1; pass <= 5; ++pass) {
+    const int halo = VB_HALO - 2 * pass;                 // valid region after this pass: tile + halo
+    const int rw = VB_TW + 2 * halo, rh = VB_TH + 2 * halo, off = VB_HALO - halo;
+    const float *src = (pass & 1) ? bufA : bufB;
+    float *dst = (pass & 1) ? bufB : bufA;
+    for (int c = threadIdx.x; c < rw * rh; c += VB_THREADS) {
+      const int sx = off + c % rw, sy = off + c / rw;
+      const int gx = x0 + sx, gy = y0 + sy;
+      if (gx < 0 || gx >= w || gy < 0 || gy >= h) continue;
+      const int s = sx + sy * VB_SW;
+      if (on_border(gx, gy, w, h)) {
+        // odd passes write floatImage, whose border is the constructor's 0; even passes write view->depth,
+        // whose border keeps the converted value (bufA still holds it)
+        if (pass == 5) out[gx + gy * w] = 0.0f;
+        else if (pass & 1) dst[s] = 0.0f;
+        continue;
+      }
+      const float r = filter_depth_at(src + s, VB_SW);
+      if (pass == 5) out[gx + gy * w] = r; else dst[s] = r;
+    }
+    __syncthreads();
+  }
+}
+
+// ---- ComputeNormalAndWeights (ITMViewBuilder_CUDA.cu:211-227, DA/ITMViewBuilder.h:59-114) -----------
+// In-image threads only: the reference's kernel also lets its out-of-image threads (x >= w in the last
+// column of 16x16 CTAs) write w=-1 through idx = x + y*w, which aliases pixels of the next row and races
+// with their owners; that write is not reproduced (documented deviation).
+__global__ void k_normal_weight(const float *__restrict__ depth_in, float4 *__restrict__ normal_out, float *__restrict__ sigmaZ_out,
+                                int w, int h, float ix, float iy, float iz, float iw) {
+  const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
+  if (x >= w || y >= h) return;
+  const int idx = x + y * w;
+  if (x < 2 || x > w - 2 || y < 2 || y > h - 2) { normal_out[idx].w = -1.0f; sigmaZ_out[idx] = -1; return; }
+  const float z = depth_in[idx];
+  if (z < 0.0f) { normal_out[idx].w = -1.0f; sigmaZ_out[idx] = -1; return; }
+  const float zxp = depth_in[(x + 1) + y * w], zyp = depth_in[x + (y + 1) * w];
+  const float zxm = depth_in[(x - 1) + y * w], zym = depth_in[x + (y - 1) * w];
+  if (zxp <= 0 || zyp <= 0 || zxm <= 0 || zym <= 0) { normal_out[idx].w = -1.0f; sigmaZ_out[idx] = -1; return; }
+  // unprojected neighbours (the reference multiplies by intrinparam.x/.y, i.e. fx/fy, as written)
+  const float xp1_x = zxp * ((x + 1.0f) - iz) * ix, xp1_y = zxp * (y - iw) * iy;
+  const float xm1_x = zxm * ((x - 1.0f) - iz) * ix, xm1_y = zxm * (y - iw) * iy;
+  const float yp1_x = zyp * (x - iz) * ix, yp1_y = zyp * ((y + 1.0f) - iw) * iy;
+  const float ym1_x = zym * (x - iz) * ix, ym1_y = zym * ((y - 1.0f) - iw) * iy;
+  const float dxx = xp1_x - xm1_x, dxy = xp1_y - xm1_y, dxz = zxp - zxm;
+  const float dyx = yp1_x - ym1_x, dyy = yp1_y - ym1_y, dyz = zyp - zym;
+  float nx = (dxy * dyz - dxz * dyy);
+  float ny = (dxz * dyx - dxx * dyz);
+  float nz = (dxx * dyy - dxy * dyx);
+  if (nx == 0.0f && ny == 0 && nz == 0) { normal_out[idx].w = -1.0f; sigmaZ_out[idx] = -1; return; }
+  const float norm = 1.0f / sqrtf(nx * nx + ny * ny + nz * nz);
+  nx *= norm; ny *= norm; nz *= norm;
+  normal_out[idx] = make_float4(nx, ny, nz, 1.0f);
+  const float theta = acosf(nz);
+  const float theta_diff = theta / (3.1415926535897932384626433832795f * 0.5f - theta);
+  sigmaZ_out[idx] = (0.0012f + 0.0019f * (z - 0.4f) * (z - 0.4f) + 0.0001f / sqrtf(z) * theta_diff * theta_diff);
+}
+
+}  // namespace
+
+void launch_view_convert(b200_engine *e, const int16_t *raw, float *out, int w, int h, int type, float p0, float p1, float fx) {
+  const int n = w * h;
+  k_convert<<<(n + 255) / 256, 256, 0, e->stream>>>((const short *)raw, out, n, type, p0, p1, fx);
+  e->launches++;
+}
+
+void launch_view_filter_pass(b200_engine *e, const float *in, float *out, int w, int h) {
+  dim3 grid((w + 31) / 32, (h + 7) / 8);
+  k_filter_pass<<<grid, 256, 0, e->stream>>>(in, out, w, h);
+  e->launches++;
+}
+
+void launch_update_view(b200_engine *e, const int16_t *raw, const float *depthIn, float *out, int w, int h, int type, float p0,
+                        float p1, float fx, bool filter) {
+  dim3 grid((w + VB_TW - 1) / VB_TW, (h + VB_TH - 1) / VB_TH);
+  if (raw) k_update_view<true><<<grid, VB_THREADS, 0, e->stream>>>((const short *)raw, nullptr, out, w, h, type, p0, p1, fx, filter ? 1 : 0);
+  else k_update_view<false><<<grid, VB_THREADS, 0, e->stream>>>(nullptr, depthIn, out, w, h, type, p0, p1, fx, filter ? 1 : 0);
+  e->launches++;
+}
+
+void launch_view_normals(b200_engine *e, const float *depth, b200_vec4f *normal, float *sigmaZ, int w, int h, const float intr[4]) {
+  dim3 grid((w + 31) / 32, (h + 7) / 8);
+  k_normal_weight<<<grid, 256, 0, e->stream>>>(depth, (float4 *)normal, sigmaZ, w, h, intr[0], intr[1], intr[2], intr[3]);
+  e->launches++;
+}

@@ -241,8 +241,72 @@ class Engine:
         self.check(self.lib.b200_host_frame_submit(self.h, C.byref(self.scene.c), C.byref(renderState.c), C.byref(view.c),
                                                     _ptr(h_depth), _ptr(h_rgb), _ptr(points), _ptr(normals), C.byref(o), _ptr(h_out), slot))
 
+    def host_frame_submit_raw(self, renderState, view, h_raw, h_rgb, calib, points=None, normals=None, decay=None, raycast=True,
+                              h_out=None, slot=0):
+        """As host_frame_submit, from a RAW int16 depth frame: UpdateView (conversion + bilateral filter) runs on the device."""
+        o = abi.FrameOpts()
+        o.doRaycast = int(raycast)
+        if decay is not None:
+            o.doDecay, o.decayMaxWeight, o.decayMinAge = 1, decay[0], decay[1]
+        self.check(self.lib.b200_host_frame_submit_raw(self.h, C.byref(self.scene.c), C.byref(renderState.c), C.byref(view.c),
+                                                        _ptr(h_raw), _ptr(h_rgb), C.byref(calib), _ptr(points), _ptr(normals),
+                                                        C.byref(o), _ptr(h_out), slot))
+
     def host_frame_wait(self, slot):
         self.check(self.lib.b200_host_frame_wait(self.h, slot))
+
+
+def make_view_calib(trafoType=1, params=(1.0 / 1000.0, 0.0), fx_depth=0.0, intrinsics_d=(0.0, 0.0, 0.0, 0.0), useBilateralFilter=True,
+                    modelSensorNoise=False):
+    """b200_view_calib. Defaults: ITMDisparityCalib() = affine mm -> m (Objects/ITMDisparityCalib.h:40-45),
+    useBilateralFilter true, modelSensorNoise false (Utils/ITMLibSettings.cpp:63, :74)."""
+    c = abi.ViewCalib()
+    c.trafoType = int(trafoType)
+    c.params = (C.c_float * 2)(float(params[0]), float(params[1]))
+    c.fx_depth = float(fx_depth)
+    c.intrinsics_d = (C.c_float * 4)(*[float(x) for x in intrinsics_d])
+    c.useBilateralFilter, c.modelSensorNoise = int(useBilateralFilter), int(modelSensorNoise)
+    return c
+
+
+class ViewBuilder:
+    """ITMViewBuilder (B200 back-end, Engine/ITMViewBuilder.h:19-58). Images are torch CUDA tensors."""
+
+    def __init__(self, engine, calib):
+        self.e, self.calib = engine, calib
+
+    @staticmethod
+    def _inputs_ready():
+        # the images are torch tensors produced on torch's stream; the engine works on its own stream
+        torch.cuda.current_stream().synchronize()
+
+    def ConvertDisparityToDepth(self, depth_out, disp_in, fx_depth, params):
+        self._inputs_ready()
+        h, w = disp_in.shape
+        self.e.check(self.e.lib.b200_convert_disparity_to_depth(self.e.h, _ptr(depth_out), _ptr(disp_in), w, h, params[0], params[1], fx_depth))
+
+    def ConvertDepthAffineToFloat(self, depth_out, depth_in, params):
+        self._inputs_ready()
+        h, w = depth_in.shape
+        self.e.check(self.e.lib.b200_convert_depth_affine_to_float(self.e.h, _ptr(depth_out), _ptr(depth_in), w, h, params[0], params[1]))
+
+    def DepthFiltering(self, image_out, image_in):
+        self._inputs_ready()
+        h, w = image_in.shape
+        self.e.check(self.e.lib.b200_depth_filtering(self.e.h, _ptr(image_out), _ptr(image_in), w, h))
+
+    def ComputeNormalAndWeights(self, normal_out, sigmaZ_out, depth_in, intrinsic):
+        self._inputs_ready()
+        h, w = depth_in.shape
+        self.e.check(self.e.lib.b200_compute_normal_and_weights(self.e.h, _ptr(normal_out), _ptr(sigmaZ_out), _ptr(depth_in), w, h,
+                                                                (C.c_float * 4)(*[float(x) for x in intrinsic])))
+
+    def UpdateView(self, depth_out, rawDepth, depthNormal=None, depthUncertainty=None, sync=True):
+        """UpdateView(view, rgb, rawDepth, useBilateralFilter, modelSensorNoise) on device-resident images."""
+        self._inputs_ready()
+        h, w = rawDepth.shape
+        f = self.e.lib.b200_update_view if sync else self.e.lib.b200_update_view_async
+        self.e.check(f(self.e.h, _ptr(rawDepth), w, h, C.byref(self.calib), _ptr(depth_out), _ptr(depthNormal), _ptr(depthUncertainty)))
 
 
 class SceneReconstructionEngine:

@@ -258,6 +258,47 @@ b200_status b200_host_frame_submit(b200_engine *e, b200_scene *scene, b200_rende
                                    const b200_frame_opts *opts, b200_vec4u *h_outImage, int slot);
 b200_status b200_host_frame_wait(b200_engine *e, int slot);
 
+/* ---- view builder: the step immediately before fusion ------------------------
+   Replaces ITMViewBuilder_CUDA (Engine/DeviceSpecific/CUDA/ITMViewBuilder_CUDA.cu). All images are
+   device pointers, row-major, w*h elements. Border semantics are the CUDA reference's (the filter leaves
+   the two outermost rows/columns of its TARGET untouched, :196-209). */
+
+typedef struct {
+  int32_t trafoType;           /* ITMDisparityCalib::TrafoType (Objects/ITMDisparityCalib.h:24-29): 0 TRAFO_KINECT, 1 TRAFO_AFFINE */
+  float params[2];             /* disparityCalib.params */
+  float fx_depth;              /* intrinsics_d.projectionParamsSimple.fx (TRAFO_KINECT only) */
+  float intrinsics_d[4];       /* intrinsics_d.projectionParamsSimple.all, for ComputeNormalAndWeights */
+  int32_t useBilateralFilter;  /* ITMLibSettings::useBilateralFilter (default true, Utils/ITMLibSettings.cpp:63) */
+  int32_t modelSensorNoise;    /* ITMLibSettings::modelSensorNoise (TRACKER_WICP only, :74-75) */
+} b200_view_calib;
+
+/* ITMViewBuilder::ConvertDisparityToDepth (ITMViewBuilder_CUDA.cu:120-135, DA/ITMViewBuilder.h:7-20) */
+b200_status b200_convert_disparity_to_depth(b200_engine *e, float *d_out, const int16_t *d_in, int w, int h,
+                                            float p0, float p1, float fx_depth);
+/* ITMViewBuilder::ConvertDepthAffineToFloat (ITMViewBuilder_CUDA.cu:137-148, DA/ITMViewBuilder.h:22-28) */
+b200_status b200_convert_depth_affine_to_float(b200_engine *e, float *d_out, const int16_t *d_in, int w, int h,
+                                               float p0, float p1);
+/* ITMViewBuilder::DepthFiltering — ONE pass (ITMViewBuilder_CUDA.cu:150-161, :196-209, DA/ITMViewBuilder.h:31-56);
+   d_out's 2-pixel border is left untouched */
+b200_status b200_depth_filtering(b200_engine *e, float *d_out, const float *d_in, int w, int h);
+/* ITMViewBuilder::ComputeNormalAndWeights (ITMViewBuilder_CUDA.cu:163-178, :211-227, DA/ITMViewBuilder.h:59-114) */
+b200_status b200_compute_normal_and_weights(b200_engine *e, b200_vec4f *d_normal, float *d_sigmaZ, const float *d_depth,
+                                            int w, int h, const float intrinsic[4]);
+/* ITMViewBuilder::UpdateView(view, rgb, rawDepth, useBilateralFilter, modelSensorNoise) without its two H2D
+   copies (ITMViewBuilder_CUDA.cu:33-84): conversion + five filter passes + copy back in one kernel.
+   d_depthNormal / d_depthUncertainty are used only with modelSensorNoise. The _async form only enqueues
+   on the engine stream (the fused frame that follows is ordered behind it). */
+b200_status b200_update_view(b200_engine *e, const int16_t *d_rawDepth, int w, int h, const b200_view_calib *calib,
+                             float *d_depth, b200_vec4f *d_depthNormal, float *d_depthUncertainty);
+b200_status b200_update_view_async(b200_engine *e, const int16_t *d_rawDepth, int w, int h, const b200_view_calib *calib,
+                                   float *d_depth, b200_vec4f *d_depthNormal, float *d_depthUncertainty);
+/* b200_host_frame_submit for a RAW sensor frame: h_rawDepth (int16, e.g. millimetres) and h_rgb are copied H2D,
+   UpdateView runs on the device into the slot's float depth image, then the fused frame. Halves the depth upload. */
+b200_status b200_host_frame_submit_raw(b200_engine *e, b200_scene *scene, b200_render_state *rs, b200_view *view,
+                                       const int16_t *h_rawDepth, const b200_vec4u *h_rgb, const b200_view_calib *calib,
+                                       b200_vec4f *d_points, b200_vec4f *d_normals, const b200_frame_opts *opts,
+                                       b200_vec4u *h_outImage, int slot);
+
 /* ---- introspection used by bench.py / tests -------------------------------------------------- */
 
 typedef struct {

@@ -24,7 +24,7 @@ NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 LIBB200="$HERE/../dynslam_b200/csrc/libb200fusion.so"
 if [ ! -f "$LIBB200" ]; then echo "libb200fusion.so missing; skipping harness" >&2; exit 0; fi
 OBJ="$HERE/_ref/obj"; mkdir -p "$OBJ"
-CU="ITMLib/Engine/DeviceSpecific/CUDA/ITMSceneReconstructionEngine_CUDA.cu ITMLib/Engine/DeviceSpecific/CUDA/ITMVisualisationEngine_CUDA.cu ITMLib/Engine/DeviceSpecific/CUDA/ITMMeshingEngine_CUDA.cu"
+CU="ITMLib/Engine/DeviceSpecific/CUDA/ITMSceneReconstructionEngine_CUDA.cu ITMLib/Engine/DeviceSpecific/CUDA/ITMVisualisationEngine_CUDA.cu ITMLib/Engine/DeviceSpecific/CUDA/ITMMeshingEngine_CUDA.cu ITMLib/Engine/DeviceSpecific/CUDA/ITMViewBuilder_CUDA.cu"
 CPP="ITMLib/Utils/ITMLibSettings.cpp ITMLib/Objects/ITMPose.cpp ITMLib/Engine/ITMVisualisationEngine.cpp ORUtils/CUDADefines.cpp"
 pids=""
 for f in $CU; do

@@ -25,7 +25,12 @@
 #include "ITMLib/Objects/ITMView.h"
 #include "ITMLib/Utils/ITMLibSettings.h"
 
+#include "ITMLib/Engine/DeviceSpecific/CUDA/ITMViewBuilder_CUDA.h"
+
 #include "ITMEngines_B200.h"
+#include "ITMViewBuilder_B200.h"
+
+#include <chrono>
 
 using namespace ITMLib::Engine;
 using namespace ITMLib::Objects;
@@ -145,6 +150,86 @@ void harness_download(Harness *H, void *hashOut, void *voxelsOut, void *rayOut, 
   const size_t n = (size_t)H->imgSize.x * H->imgSize.y;
   if (rayOut) ORcudaSafeCall(cudaMemcpy(rayOut, H->renderState->raycastResult->GetData(MEMORYDEVICE_CUDA), n * sizeof(Vector4f), cudaMemcpyDeviceToHost));
   if (imgOut) ORcudaSafeCall(cudaMemcpy(imgOut, H->renderState->raycastImage->GetData(MEMORYDEVICE_CUDA), n * 4, cudaMemcpyDeviceToHost));
+}
+
+// ---- view builder: ITMViewBuilder_CUDA (impl 0) vs ITMViewBuilder_B200 (impl 1) ----
+struct VBHarness {
+  int impl;
+  ITMRGBDCalib calib;
+  ITMViewBuilder *vb;
+  ITMView *view;
+  ITMUChar4Image *rgb;
+  ITMShortImage *raw;
+  ITMFloatImage *scratch;      // device-only timing of the reference: stands in for its floatImage
+  std::shared_ptr<B200EngineHandle> handle;
+  Vector2i imgSize;
+};
+
+VBHarness *vbh_create(int impl, int w, int h, float fx, float fy, float cx, float cy) {
+  VBHarness *V = new VBHarness();
+  V->impl = impl; V->imgSize = Vector2i(w, h); V->view = NULL;
+  V->calib.intrinsics_d.SetFrom(fx, fy, cx, cy, (float)w, (float)h);
+  V->calib.intrinsics_rgb.SetFrom(fx, fy, cx, cy, (float)w, (float)h);     // disparityCalib default: affine mm -> m
+  if (impl == 0) V->vb = new ITMViewBuilder_CUDA(&V->calib);
+  else { V->handle = std::make_shared<B200EngineHandle>(0, 2048, V->imgSize); V->vb = new ITMViewBuilder_B200(&V->calib, V->handle); }
+  V->rgb = new ITMUChar4Image(V->imgSize, true, false);
+  V->raw = new ITMShortImage(V->imgSize, true, false);
+  V->scratch = new ITMFloatImage(V->imgSize, true, true);
+  return V;
+}
+
+void vbh_destroy(VBHarness *V) { delete V->view; delete V->vb; delete V->rgb; delete V->raw; delete V->scratch; delete V; }
+
+// ITMMainEngine::ProcessFrame's call (Engine/ITMMainEngine.cpp:152): host images in, view on the device
+void vbh_update_view(VBHarness *V, const short *raw, const unsigned char *rgba, int useBilateralFilter, int modelSensorNoise) {
+  const size_t n = (size_t)V->imgSize.x * V->imgSize.y;
+  memcpy(V->raw->GetData(MEMORYDEVICE_CPU), raw, n * sizeof(short));
+  memcpy(V->rgb->GetData(MEMORYDEVICE_CPU), rgba, n * 4);
+  V->vb->UpdateView(&V->view, V->rgb, V->raw, useBilateralFilter != 0, modelSensorNoise != 0);
+  ORcudaSafeCall(cudaDeviceSynchronize());
+}
+
+// wall-clock milliseconds per UpdateView (host images already in ITMLib's host buffers), device synchronised
+double vbh_time_update_view(VBHarness *V, int useBilateralFilter, int iters) {
+  ORcudaSafeCall(cudaDeviceSynchronize());
+  auto t0 = std::chrono::steady_clock::now();
+  for (int i = 0; i < iters; ++i) V->vb->UpdateView(&V->view, V->rgb, V->raw, useBilateralFilter != 0, false);
+  ORcudaSafeCall(cudaDeviceSynchronize());
+  return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count() / iters;
+}
+
+// device part only: for the reference its own public stages in UpdateView's order on the device-resident short image
+// (ITMViewBuilder_CUDA.cu:56-79); for the B200 builder the fused kernel. Milliseconds per call.
+double vbh_time_device_only(VBHarness *V, int iters) {
+  if (!V->view) return -1.0;
+  ITMShortImage dshort(V->imgSize, true, true);
+  dshort.SetFrom(V->raw, ORUtils::MemoryBlock<short>::CPU_TO_CUDA);
+  ORcudaSafeCall(cudaDeviceSynchronize());
+  auto t0 = std::chrono::steady_clock::now();
+  for (int i = 0; i < iters; ++i) {
+    if (V->impl == 0) {
+      V->vb->ConvertDepthAffineToFloat(V->view->depth, &dshort, V->calib.disparityCalib.params);
+      V->vb->DepthFiltering(V->scratch, V->view->depth);
+      V->vb->DepthFiltering(V->view->depth, V->scratch);
+      V->vb->DepthFiltering(V->scratch, V->view->depth);
+      V->vb->DepthFiltering(V->view->depth, V->scratch);
+      V->vb->DepthFiltering(V->scratch, V->view->depth);
+      V->view->depth->SetFrom(V->scratch, ORUtils::MemoryBlock<float>::CUDA_TO_CUDA);
+    } else {
+      b200_view_calib c{};
+      c.trafoType = 1; c.params[0] = V->calib.disparityCalib.params.x; c.params[1] = V->calib.disparityCalib.params.y;
+      c.useBilateralFilter = 1;
+      V->handle->check(b200_update_view_async(V->handle->e, dshort.GetData(MEMORYDEVICE_CUDA), V->imgSize.x, V->imgSize.y, &c,
+                                              V->view->depth->GetData(MEMORYDEVICE_CUDA), nullptr, nullptr));
+    }
+  }
+  ORcudaSafeCall(cudaDeviceSynchronize());
+  return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count() / iters;
+}
+
+void vbh_download(VBHarness *V, float *depthOut) {
+  ORcudaSafeCall(cudaDeviceSynchronize());
+  ORcudaSafeCall(cudaMemcpy(depthOut, V->view->depth->GetData(MEMORYDEVICE_CUDA), (size_t)V->imgSize.x * V->imgSize.y * sizeof(float), cudaMemcpyDeviceToHost));
 }
 
 }  // extern "C"

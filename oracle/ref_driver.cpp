@@ -17,6 +17,7 @@
 #include "ITMLib/Engine/DeviceAgnostic/ITMVisualisationEngine.h"
 #include "ITMLib/Engine/DeviceAgnostic/ITMSwappingEngine.h"
 #include "ITMLib/Engine/DeviceAgnostic/ITMRepresentationAccess.h"
+#include "ITMLib/Engine/DeviceAgnostic/ITMViewBuilder.h"
 
 #include "../include/b200fusion.h"
 
@@ -164,6 +165,29 @@ void ref_combine_block(const b200_voxel *src, b200_voxel *dst, int maxW) {
 
 int ref_forward_project_pixel(const float *px, const float *M, const float *proj, int w, int h) {
   return forwardProjectPixel(V4(px), M4(M), V4(proj), Vector2i(w, h));
+}
+
+// ---- view builder (DeviceAgnostic/ITMViewBuilder.h); the loops are the CUDA build's index ranges ----
+void ref_view_convert_disparity(float *out, const short *in, int w, int h, float p0, float p1, float fx) {
+  for (int y = 0; y < h; y++) for (int x = 0; x < w; x++) convertDisparityToDepth(out, x, y, in, Vector2f(p0, p1), fx, Vector2i(w, h));
+}
+
+void ref_view_convert_affine(float *out, const short *in, int w, int h, float p0, float p1) {
+  for (int y = 0; y < h; y++) for (int x = 0; x < w; x++) convertDepthAffineToFloat(out, x, y, in, Vector2i(w, h), Vector2f(p0, p1));
+}
+
+// filterDepth_device's guard (ITMViewBuilder_CUDA.cu:196-209): the target's 2-pixel border is not written
+void ref_view_filter_pass(float *out, const float *in, int w, int h) {
+  for (int y = 2; y < h - 2; y++) for (int x = 2; x < w - 2; x++) filterDepth(out, in, x, y, Vector2i(w, h));
+}
+
+// ComputeNormalAndWeight_device's guard (ITMViewBuilder_CUDA.cu:211-227), in-image threads
+void ref_view_normal_weight(const float *depth, b200_vec4f *normal, float *sigmaZ, int w, int h, const float *intr) {
+  for (int y = 0; y < h; y++) for (int x = 0; x < w; x++) {
+    int idx = x + y * w;
+    if (x < 2 || x > w - 2 || y < 2 || y > h - 2) { ((Vector4f *)normal)[idx].w = -1.0f; sigmaZ[idx] = -1; }
+    else computeNormalAndWeight(depth, (Vector4f *)normal, sigmaZ, x, y, Vector2i(w, h), V4(intr));
+  }
 }
 
 } // extern "C"

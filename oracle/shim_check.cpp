@@ -1,6 +1,7 @@
 // Compile-only check (TEST INFRASTRUCTURE): instantiates the ITMLib shim classes against the
 // unmodified reference headers, proving the drop-in compiles behind the real virtual interfaces.
 #include "ITMEngines_B200.h"
+#include "ITMViewBuilder_B200.h"
 
 using namespace ITMLib::Engine;
 
@@ -15,6 +16,7 @@ void *make_engines(ITMScene<ITMVoxel, ITMVoxelIndex> *scene, const ITMLibSetting
   ITMSceneReconstructionEngine<ITMVoxel, ITMVoxelIndex> *reco = new ITMSceneReconstructionEngine_B200<ITMVoxel, ITMVoxelIndex>(h);
   IITMVisualisationEngine *vis = new ITMVisualisationEngine_B200<ITMVoxel, ITMVoxelIndex>(scene, settings, h);
   ITMSwappingEngine<ITMVoxel, ITMVoxelIndex> *swap = new ITMSwappingEngine_B200<ITMVoxel, ITMVoxelIndex>(h);
-  (void)vis; (void)swap;
+  ITMViewBuilder *vb = new ITMViewBuilder_B200(nullptr, h);   // Engine/ITMMainEngine.cpp:24-54 picks the view builder
+  (void)vis; (void)swap; (void)vb;
   return reco;
 }

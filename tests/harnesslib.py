@@ -42,8 +42,48 @@ def lib():
         L.harness_counters.restype = None
         L.harness_download.argtypes = [vp, vp, vp, vp, vp]
         L.harness_download.restype = None
+        L.vbh_create.restype = vp
+        L.vbh_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float]
+        L.vbh_destroy.argtypes = [vp]
+        L.vbh_destroy.restype = None
+        L.vbh_update_view.argtypes = [vp, vp, vp, C.c_int, C.c_int]
+        L.vbh_update_view.restype = None
+        L.vbh_time_update_view.argtypes = [vp, C.c_int, C.c_int]
+        L.vbh_time_update_view.restype = C.c_double
+        L.vbh_time_device_only.argtypes = [vp, C.c_int]
+        L.vbh_time_device_only.restype = C.c_double
+        L.vbh_download.argtypes = [vp, vp]
+        L.vbh_download.restype = None
         _L = L
     return _L
+
+
+class ViewBuilderHarness:
+    """ITMViewBuilder_CUDA (impl 0) or ITMViewBuilder_B200 (impl 1) behind the abstract ITMViewBuilder."""
+
+    def __init__(self, impl, w, h, proj):
+        self.L = lib()
+        self.w, self.h = w, h
+        self.h_ = self.L.vbh_create(impl, w, h, float(proj[0]), float(proj[1]), float(proj[2]), float(proj[3]))
+
+    def update_view(self, raw, rgb, useBilateralFilter=True, modelSensorNoise=False):
+        raw = np.ascontiguousarray(raw, dtype=np.int16)
+        rgb = np.ascontiguousarray(rgb, dtype=np.uint8)
+        self.L.vbh_update_view(self.h_, raw.ctypes.data, rgb.ctypes.data, int(useBilateralFilter), int(modelSensorNoise))
+        out = np.zeros((self.h, self.w), dtype=np.float32)
+        self.L.vbh_download(self.h_, out.ctypes.data)
+        return out
+
+    def time_update_view(self, iters=50, useBilateralFilter=True):
+        return self.L.vbh_time_update_view(self.h_, int(useBilateralFilter), iters)
+
+    def time_device_only(self, iters=50):
+        return self.L.vbh_time_device_only(self.h_, iters)
+
+    def close(self):
+        if self.h_:
+            self.L.vbh_destroy(self.h_)
+            self.h_ = None
 
 
 class Harness:

@@ -26,8 +26,8 @@ def oracle():
     global _oracle
     if _oracle is not None:
         return _oracle
-    src = os.path.join(ROOT, "oracle", "tsdf_oracle.c")
-    if not os.path.exists(ORACLE_SO) or os.path.getmtime(ORACLE_SO) < os.path.getmtime(src):
+    srcs = [os.path.join(ROOT, "oracle", f) for f in ("tsdf_oracle.c", "view_oracle.c")]
+    if not os.path.exists(ORACLE_SO) or os.path.getmtime(ORACLE_SO) < max(os.path.getmtime(s) for s in srcs):
         build_oracle()
     L = C.CDLL(ORACLE_SO)
     P, vp = C.POINTER, C.c_void_p
@@ -67,6 +67,16 @@ def oracle():
     L.oracle_swap_integrate_in.argtypes = [P(abi.Scene), vp, vp, C.c_int]
     L.oracle_swap_integrate_in.restype = None
     L.oracle_swap_out.argtypes = [P(abi.Scene), P(abi.RenderState), vp, vp, vp]
+    L.oracle_convert_disparity_to_depth.argtypes = [vp, vp, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float]
+    L.oracle_convert_disparity_to_depth.restype = None
+    L.oracle_convert_depth_affine_to_float.argtypes = [vp, vp, C.c_int, C.c_int, C.c_float, C.c_float]
+    L.oracle_convert_depth_affine_to_float.restype = None
+    L.oracle_depth_filtering.argtypes = [vp, vp, C.c_int, C.c_int]
+    L.oracle_depth_filtering.restype = None
+    L.oracle_compute_normal_and_weights.argtypes = [vp, vp, vp, C.c_int, C.c_int, P(C.c_float)]
+    L.oracle_compute_normal_and_weights.restype = None
+    L.oracle_update_view.argtypes = [vp, C.c_int, C.c_int, P(abi.ViewCalib), vp, vp, vp, vp]
+    L.oracle_update_view.restype = None
     L.oracle_num_threads.restype = C.c_int
     L.oracle_set_threads.argtypes = [C.c_int]
     L.oracle_set_threads.restype = None
@@ -105,6 +115,14 @@ def ref():
     L.ref_combine_block.argtypes = [vp, vp, C.c_int]
     L.ref_combine_block.restype = None
     L.ref_forward_project_pixel.argtypes = [P(C.c_float), P(C.c_float), P(C.c_float), C.c_int, C.c_int]
+    L.ref_view_convert_disparity.argtypes = [vp, vp, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float]
+    L.ref_view_convert_disparity.restype = None
+    L.ref_view_convert_affine.argtypes = [vp, vp, C.c_int, C.c_int, C.c_float, C.c_float]
+    L.ref_view_convert_affine.restype = None
+    L.ref_view_filter_pass.argtypes = [vp, vp, C.c_int, C.c_int]
+    L.ref_view_filter_pass.restype = None
+    L.ref_view_normal_weight.argtypes = [vp, vp, vp, C.c_int, C.c_int, P(C.c_float)]
+    L.ref_view_normal_weight.restype = None
     _ref = L
     return L
 

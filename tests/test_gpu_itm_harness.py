@@ -97,3 +97,33 @@ def test_reference_cuda_build_agrees_on_order_free_invariants():
     assert (found_r == found_o).mean() > 0.98
     both = found_r & found_o
     assert np.abs(ref["rays"][both][:, :3] - own["rays"][both][:, :3]).max(axis=1).mean() < 0.05   # voxel units
+
+
+def test_view_builder_through_itmlib_objects():
+    """ITMViewBuilder_B200 behind the abstract ITMViewBuilder, called the way ITMMainEngine::ProcessFrame calls it
+    (host ITMUChar4Image / ITMShortImage in): close to the oracle (libm vs CUDA exp), zero border exactly; the
+    reference's ITMViewBuilder_CUDA (fast-math exp and division) agrees within 1e-4 relative."""
+    from tests import viewlib
+    raw, rgb = viewlib.raw_kitti_frame(scale=0.5)
+    h, w = raw.shape
+    proj = (353.5, 353.5, w / 2.0, h / 2.0)
+    L = H.oracle()
+    calib = abi.ViewCalib()
+    calib.trafoType, calib.useBilateralFilter = 1, 1
+    calib.params = (C.c_float * 2)(1.0 / 1000.0, 0.0)
+    want, scratch = np.zeros((h, w), np.float32), np.zeros((h, w), np.float32)
+    L.oracle_update_view(H.vptr(raw), w, h, C.byref(calib), H.vptr(want), H.vptr(scratch), None, None)
+    got = {}
+    for impl in (HL.B200_SHIM, HL.REFERENCE_CUDA):
+        vb = HL.ViewBuilderHarness(impl, w, h, proj)
+        first = vb.update_view(raw, rgb)
+        again = vb.update_view(raw, rgb)                    # second frame through the same builder: same result
+        assert np.array_equal(first, again)
+        got[impl] = first
+        vb.close()
+    for impl, tol in ((HL.B200_SHIM, 2e-6), (HL.REFERENCE_CUDA, 1e-4)):
+        g = got[impl]
+        assert ((g == -1.0) == (want == -1.0)).all()
+        err = np.abs(g.astype(np.float64) - want) / np.maximum(1.0, np.abs(want))
+        assert err.max() <= tol, (impl, err.max())
+        assert (g[:2] == 0).all() and (g[-2:] == 0).all() and (g[:, :2] == 0).all() and (g[:, -2:] == 0).all()

@@ -191,3 +191,61 @@ def test_combine_voxels(seq):
         L.oracle_combine_block(H.vptr(a), H.vptr(d1), 50)
         R.ref_combine_block(H.vptr(a), H.vptr(d2), 50)
         assert d1.tobytes() == d2.tobytes()
+
+
+# ---- view builder (oracle/view_oracle.c vs DeviceAgnostic/ITMViewBuilder.h) ---------------------------
+def _vb_inputs():
+    from tests import viewlib
+    raw, _ = viewlib.raw_kitti_frame(scale=0.25)
+    return [raw, viewlib.raw_noise_frame()]
+
+
+def test_view_convert_bit_exact():
+    L, R = H.oracle(), H.ref()
+    for raw in _vb_inputs():
+        h, w = raw.shape
+        a, b = np.zeros((h, w), np.float32), np.zeros((h, w), np.float32)
+        L.oracle_convert_depth_affine_to_float(H.vptr(a), H.vptr(raw), w, h, 1.0 / 1000.0, 0.0)
+        R.ref_view_convert_affine(H.vptr(b), H.vptr(raw), w, h, 1.0 / 1000.0, 0.0)
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+        assert (a == -1.0).any() and (a > 0).any()
+        # Kinect disparity trafo (Objects/ITMDisparityCalib.h:25-26) with the calib-file style parameters
+        disp = (raw // 4).astype(np.int16)
+        disp[0, :5] = 1135                                   # disparity_tmp == 0 -> depth 0 -> -1
+        L.oracle_convert_disparity_to_depth(H.vptr(a), H.vptr(disp), w, h, 1135.09, 0.0819141, 573.71)
+        R.ref_view_convert_disparity(H.vptr(b), H.vptr(disp), w, h, 1135.09, 0.0819141, 573.71)
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+
+
+def test_view_filter_and_update_view_bit_exact():
+    L, R = H.oracle(), H.ref()
+    for raw in _vb_inputs():
+        h, w = raw.shape
+        d0 = np.zeros((h, w), np.float32)
+        R.ref_view_convert_affine(H.vptr(d0), H.vptr(raw), w, h, 1.0 / 1000.0, 0.0)
+        # one pass: the target's 2-pixel border must stay what it was
+        a, b = np.full((h, w), 7.0, np.float32), np.full((h, w), 7.0, np.float32)
+        L.oracle_depth_filtering(H.vptr(a), H.vptr(d0), w, h)
+        R.ref_view_filter_pass(H.vptr(b), H.vptr(d0), w, h)
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+        assert (a[:2] == 7.0).all() and (a[:, -2:] == 7.0).all()
+        # UpdateView: the reference's own sequence (ITMViewBuilder_CUDA.cu:64-79) composed from its functions
+        depth_r, float_r = d0.copy(), np.zeros((h, w), np.float32)
+        for _ in range(2):
+            R.ref_view_filter_pass(H.vptr(float_r), H.vptr(depth_r), w, h)
+            R.ref_view_filter_pass(H.vptr(depth_r), H.vptr(float_r), w, h)
+        R.ref_view_filter_pass(H.vptr(float_r), H.vptr(depth_r), w, h)
+        calib = abi.ViewCalib()
+        calib.trafoType, calib.useBilateralFilter, calib.modelSensorNoise = 1, 1, 1
+        calib.params = (C.c_float * 2)(1.0 / 1000.0, 0.0)
+        calib.intrinsics_d = (C.c_float * 4)(707.0912, 707.0912, w / 2.0, h / 2.0)
+        depth_o, float_o = np.zeros((h, w), np.float32), np.zeros((h, w), np.float32)
+        nrm_o, sig_o = np.zeros((h, w, 4), np.float32), np.zeros((h, w), np.float32)
+        L.oracle_update_view(H.vptr(raw), w, h, C.byref(calib), H.vptr(depth_o), H.vptr(float_o), H.vptr(nrm_o), H.vptr(sig_o))
+        assert np.array_equal(depth_o.view(np.uint32), float_r.view(np.uint32))
+        assert (depth_o[:2] == 0).all() and (depth_o[-2:] == 0).all() and (depth_o[:, :2] == 0).all()   # floatImage's border
+        nrm_r, sig_r = np.zeros((h, w, 4), np.float32), np.zeros((h, w), np.float32)
+        R.ref_view_normal_weight(H.vptr(float_r), H.vptr(nrm_r), H.vptr(sig_r), w, h, calib.intrinsics_d)
+        assert np.array_equal(nrm_o.view(np.uint32), nrm_r.view(np.uint32))
+        assert np.array_equal(sig_o.view(np.uint32), sig_r.view(np.uint32))
+        assert (nrm_o[..., 3] == 1.0).sum() > 0.3 * w * h
