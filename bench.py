@@ -266,6 +266,29 @@ def run_hires(local_rank, frames_n):
     return out
 
 
+# --------------------------------------------------------------------------------------------------
+# view builder: ITMViewBuilder::UpdateView of one raw KITTI-shaped frame through the real
+# ITMLib classes — the reference's ITMViewBuilder_CUDA (7 launches) vs ITMViewBuilder_B200 (one fused kernel)
+# --------------------------------------------------------------------------------------------------
+def run_view_builder(frames, iters=60):
+    from tests import harnesslib as HL
+    if not HL.available():
+        return {"error": "oracle/_ref/libitmharness.so not built"}
+    raw = np.round(frames[0][0] * 1000.0).astype(np.int16)
+    out = {"what": "UpdateView(rgb, raw int16 depth, useBilateralFilter=true) at 1242x375: 'update_view_us' = the call as "
+                   "ITMMainEngine makes it (two blocking H2D copies from ITMLib's pinned host images + conversion + 5 filter passes "
+                   "+ copy), 'device_only_us' = the same stages on a device-resident raw image; wall clock, device synchronised",
+           "alg_bytes": raw.size * 6}
+    for name, impl in (("reference_cuda_build", HL.REFERENCE_CUDA), ("b200", HL.B200_SHIM)):
+        vb = HL.ViewBuilderHarness(impl, synth.KITTI_W, synth.KITTI_H, frames[0][3])
+        vb.update_view(raw, frames[0][1])
+        vb.time_update_view(5); vb.time_device_only(5)
+        out[name] = {"update_view_us": 1000.0 * vb.time_update_view(iters), "device_only_us": 1000.0 * vb.time_device_only(iters)}
+        vb.close()
+    out["speedup_device_only"] = out["reference_cuda_build"]["device_only_us"] / out["b200"]["device_only_us"]
+    return out
+
+
 def gen_frames_hires(seed, count):
     scene = synth.StreetScene(seed=seed, length_m=60.0)
     return [synth.kitti_frame(scene, f, zmax=8.0) for f in range(count)]
@@ -286,7 +309,8 @@ def run_own(args, rank, local_rank, world):
     W, H_ = synth.KITTI_W, synth.KITTI_H
     K, Wm = args.steps, args.warmup
     n_e2e = args.e2e_steps
-    total_frames = args.preroll + Wm + K + 3 + n_e2e
+    n_raw = args.e2e_raw_steps if world == 1 else 0
+    total_frames = args.preroll + Wm + K + 3 + n_e2e + n_raw
     length_m = total_frames * 0.8 + 60.0
     seed = 6 + rank
     t_gen = time.perf_counter()
@@ -408,6 +432,30 @@ def run_own(args, rank, local_rank, world):
         t_e2e = time.perf_counter() - t_e2e
         e2e_frames = n_e2e - e2e_warm
 
+        # ---- e2e from RAW sensor frames: int16 depth + RGB in, UpdateView (conversion + 5-pass bilateral filter) on the
+        # device, fused frame, grey image out (what DynSLAM does per frame from InfiniTamDriver::UpdateView onwards) ----
+        e2e_raw = None
+        if n_raw > 3:
+            calib = E.make_view_calib()
+            base = idx + n_e2e
+            h_raw = [torch.from_numpy(np.round(frames[base + i][0] * 1000.0).astype(np.int16)).pin_memory() for i in range(n_raw)]
+            h_rgb2 = [torch.from_numpy(frames[base + i][1]).pin_memory() for i in range(n_raw)]
+            t_raw = 0.0
+            for i in range(n_raw):
+                if i == 3:
+                    eng.host_frame_wait(0); eng.host_frame_wait(1)
+                    torch.cuda.synchronize(dev)
+                    t_raw = time.perf_counter()
+                slot = i & 1
+                eng.host_frame_wait(slot)
+                ev.set_pose(frames[base + i][2])
+                eng.host_frame_submit_raw(rs, ev, h_raw[i], h_rgb2[i], calib, points, normals, decay=DECAY, h_out=h_out[slot], slot=slot)
+            eng.host_frame_wait(0); eng.host_frame_wait(1)
+            torch.cuda.synchronize(dev)
+            t_raw = time.perf_counter() - t_raw
+            e2e_raw = {"value": (n_raw - 3) / t_raw, "unit": "frames/s", "h2d_bytes_per_step": W * H_ * 6, "d2h_bytes_per_step": W * H_ * 4,
+                       "steps": n_raw - 3, "what": "raw int16 depth + RGB in -> UpdateView with bilateral filter -> fused frame -> image out"}
+
     # ---- reduce over ranks (max time) ----
     ms = max(gpu_ms, 0.0)
     if world > 1:
@@ -455,6 +503,13 @@ def run_own(args, rank, local_rank, world):
         except Exception as ex:
             hires = {"error": str(ex)}
 
+    vbuild = None
+    if world == 1 and args.harness_frames > 0:
+        try:
+            vbuild = run_view_builder(frames)
+        except Exception as ex:
+            vbuild = {"error": str(ex)}
+
     line = {
         "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": Wm,
         "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
@@ -478,6 +533,8 @@ def run_own(args, rank, local_rank, world):
         "roofline_hires": hires,
         "cpu_baseline": cpu,
         "itmlib_harness": itm,
+        "view_builder": vbuild,
+        "e2e_raw": e2e_raw,
         "e2e": {"value": world * e2e_frames / t_e2e, "unit": "frames/s", "h2d_bytes_per_step": W * H_ * 8,
                 "d2h_bytes_per_step": W * H_ * 4, "steps": e2e_frames},
         "gpu_launches": int(launches_all),
@@ -496,6 +553,7 @@ def main():
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
     ap.add_argument("--preroll", type=int, default=230, help="untimed frames that build the map (> decay minAge)")
     ap.add_argument("--e2e-steps", type=int, default=103)
+    ap.add_argument("--e2e-raw-steps", type=int, default=53, help="frames of the raw-sensor-frame e2e variant (1 GPU only)")
     ap.add_argument("--flush-l2", dest="flush_l2", action="store_true", default=True)
     ap.add_argument("--no-flush-l2", dest="flush_l2", action="store_false")
     ap.add_argument("--cpu-steps", type=int, default=6)

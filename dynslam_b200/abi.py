@@ -85,6 +85,20 @@ class ViewCalib(C.Structure):
                 ("intrinsics_d", C.c_float * 4), ("useBilateralFilter", C.c_int32), ("modelSensorNoise", C.c_int32)]
 
 
+class Mask(C.Structure):
+    """b200_mask: inclusive bounding box + box-sized u8 mask (1 = inside)."""
+    _fields_ = [("x0", C.c_int32), ("y0", C.c_int32), ("x1", C.c_int32), ("y1", C.c_int32), ("d_data", C.c_void_p)]
+
+
+class SilhouetteOp(C.Structure):
+    _fields_ = [("action", C.c_int32), ("copy_mask", Mask), ("delete_mask", Mask), ("d_dest_rgb", C.c_void_p),
+                ("d_dest_depth", C.c_void_p)]
+
+
+class InstanceLayer(C.Structure):
+    _fields_ = [("d_color", C.c_void_p), ("d_depth", C.c_void_p), ("tint", C.c_int32 * 4)]
+
+
 class FrameStats(C.Structure):
     _fields_ = [("ms_allocate", C.c_float), ("ms_integrate", C.c_float), ("ms_expected", C.c_float),
                 ("ms_raycast", C.c_float), ("ms_decay", C.c_float), ("ms_total", C.c_float),
@@ -103,6 +117,8 @@ EXPORTS = [
     "b200_process_frame_host", "b200_set_timing", "b200_get_stats", "b200_host_frame_submit", "b200_host_frame_wait",
     "b200_convert_disparity_to_depth", "b200_convert_depth_affine_to_float", "b200_depth_filtering",
     "b200_compute_normal_and_weights", "b200_update_view", "b200_update_view_async", "b200_host_frame_submit_raw",
+    "b200_process_silhouettes", "b200_process_silhouettes_async", "b200_composite_depth", "b200_composite_color",
+    "b200_composite_instances",
 ]
 
 _lib = None
@@ -162,6 +178,11 @@ def load_library():
     lib.b200_update_view_async.argtypes = [vp, vp, C.c_int, C.c_int, P(ViewCalib), vp, vp, vp]
     lib.b200_host_frame_submit_raw.argtypes = [vp, P(Scene), P(RenderState), P(View), vp, vp, P(ViewCalib), vp, vp, P(FrameOpts),
                                                vp, C.c_int]
+    lib.b200_process_silhouettes.argtypes = [vp, vp, vp, C.c_int, C.c_int, P(SilhouetteOp), C.c_int]
+    lib.b200_process_silhouettes_async.argtypes = [vp, vp, vp, C.c_int, C.c_int, P(SilhouetteOp), C.c_int]
+    lib.b200_composite_depth.argtypes = [vp, vp, vp, C.c_int]
+    lib.b200_composite_color.argtypes = [vp, vp, vp, vp, vp, C.c_int, P(C.c_int32), C.c_float]
+    lib.b200_composite_instances.argtypes = [vp, vp, vp, C.c_int, P(InstanceLayer), C.c_int, C.c_float, C.c_float]
     lib.b200_set_timing.argtypes = [vp, C.c_int]
     lib.b200_set_timing.restype = None
     lib.b200_get_stats.argtypes = [vp, P(FrameStats)]

@@ -155,7 +155,7 @@ void b200_engine_destroy(b200_engine *e) {
   if (e->stream) cudaStreamSynchronize(e->stream);
   cudaFree(e->d_ctr); cudaFreeHost(e->h_ctr); cudaFree(e->d_reqKey); cudaFree(e->d_reqBits); cudaFree(e->d_scanDesc);
   cudaFree(e->d_ring); cudaFree(e->d_snapCount); cudaFree(e->d_snapStart); cudaFree(e->d_delTag); cudaFree(e->d_itemPtr); cudaFree(e->d_visiblePtr);
-  cudaFree(e->d_delList); cudaFree(e->d_isLeader); cudaFree(e->d_allocatedPos); cudaFree(e->d_tileCounts); cudaFree(e->d_blockRecs);
+  cudaFree(e->d_viewScratch); cudaFree(e->d_delList); cudaFree(e->d_isLeader); cudaFree(e->d_allocatedPos); cudaFree(e->d_tileCounts); cudaFree(e->d_blockRecs);
   for (int i = 0; i < 8; ++i) if (e->ev[i]) cudaEventDestroy(e->ev[i]);
   if (e->copyStream) {
     cudaStreamSynchronize(e->copyStream);
@@ -561,7 +561,14 @@ b200_status b200_update_view_async(b200_engine *e, const int16_t *d_rawDepth, in
   if (c->trafoType != 0 && c->trafoType != 1) { snprintf(e->err, sizeof(e->err), "unknown disparity calibration type %d", c->trafoType); return B200_ERR_INVALID; }
   if (c->modelSensorNoise && (!d_depthNormal || !d_depthUncertainty)) { snprintf(e->err, sizeof(e->err), "modelSensorNoise needs depthNormal and depthUncertainty"); return B200_ERR_INVALID; }
   CK(cudaSetDevice(e->device));
-  launch_update_view(e, d_rawDepth, nullptr, d_depth, w, h, c->trafoType, c->params[0], c->params[1], c->fx_depth, c->useBilateralFilter != 0);
+  if (c->useBilateralFilter && e->viewScratchPixels < (size_t)w * h) {
+    CK(cudaStreamSynchronize(e->stream));
+    cudaFree(e->d_viewScratch);
+    CK(cudaMalloc(&e->d_viewScratch, (size_t)w * h * sizeof(float)));
+    e->viewScratchPixels = (size_t)w * h;
+  }
+  launch_update_view(e, d_rawDepth, d_depth, e->d_viewScratch, w, h, c->trafoType, c->params[0], c->params[1], c->fx_depth,
+                     c->useBilateralFilter != 0);
   if (c->modelSensorNoise) launch_view_normals(e, d_depth, d_depthNormal, d_depthUncertainty, w, h, c->intrinsics_d);
   return B200_OK;
 }
@@ -571,6 +578,54 @@ b200_status b200_update_view(b200_engine *e, const int16_t *d_rawDepth, int w, i
   b200_status st = b200_update_view_async(e, d_rawDepth, w, h, c, d_depth, d_depthNormal, d_depthUncertainty); if (st) return st;
   CK(cudaStreamSynchronize(e->stream)); CK(cudaGetLastError());
   return B200_OK;
+}
+
+// ---- instance frame splitting and compositing (frames.cu) -------------------------------------------------
+b200_status b200_process_silhouettes_async(b200_engine *e, b200_vec4u *d_rgb, float *d_depth, int w, int h, const b200_silhouette_op *ops,
+                                           int n) {
+  if (!d_rgb || !d_depth || w <= 0 || h <= 0 || n < 0 || (n > 0 && !ops)) { snprintf(e->err, sizeof(e->err), "process_silhouettes: bad arguments"); return B200_ERR_INVALID; }
+  for (int k = 0; k < n; ++k) {
+    const b200_silhouette_op &o = ops[k];
+    if (o.action < 0 || o.action > 2) { snprintf(e->err, sizeof(e->err), "op %d: unknown action %d", k, o.action); return B200_ERR_INVALID; }
+    if (o.action == 2 && (!o.d_dest_rgb || !o.d_dest_depth || !o.copy_mask.d_data)) { snprintf(e->err, sizeof(e->err), "op %d: instance frame or copy mask missing", k); return B200_ERR_INVALID; }
+    if (o.action != 0 && !o.delete_mask.d_data) { snprintf(e->err, sizeof(e->err), "op %d: delete mask missing", k); return B200_ERR_INVALID; }
+  }
+  CK(cudaSetDevice(e->device));
+  if (n > 0) launch_process_silhouettes(e, d_rgb, d_depth, w, h, ops, n);
+  return B200_OK;
+}
+
+b200_status b200_process_silhouettes(b200_engine *e, b200_vec4u *d_rgb, float *d_depth, int w, int h, const b200_silhouette_op *ops, int n) {
+  b200_status st = b200_process_silhouettes_async(e, d_rgb, d_depth, w, h, ops, n); if (st) return st;
+  CK(cudaStreamSynchronize(e->stream)); CK(cudaGetLastError());
+  return B200_OK;
+}
+
+b200_status b200_composite_depth(b200_engine *e, float *d_target, const float *d_source, int n) {
+  if (!d_target || !d_source || n <= 0) { snprintf(e->err, sizeof(e->err), "composite_depth: bad arguments"); return B200_ERR_INVALID; }
+  CK(cudaSetDevice(e->device));
+  launch_composite_depth(e, d_target, d_source, n);
+  CK(cudaStreamSynchronize(e->stream)); CK(cudaGetLastError());
+  return B200_OK;
+}
+
+b200_status b200_composite_instances(b200_engine *e, b200_vec4u *d_out_color, float *d_out_depth, int n, const b200_instance_layer *layers,
+                                     int n_layers, float dim_factor, float tint_strength) {
+  if (!d_out_color || !d_out_depth || n <= 0 || n_layers < 0 || (n_layers > 0 && !layers)) { snprintf(e->err, sizeof(e->err), "composite_instances: bad arguments"); return B200_ERR_INVALID; }
+  for (int k = 0; k < n_layers; ++k)
+    if (!layers[k].d_color || !layers[k].d_depth) { snprintf(e->err, sizeof(e->err), "layer %d: image missing", k); return B200_ERR_INVALID; }
+  CK(cudaSetDevice(e->device));
+  launch_composite_layers(e, d_out_color, d_out_depth, n, layers, n_layers, dim_factor >= 0.0f, dim_factor, tint_strength);
+  CK(cudaStreamSynchronize(e->stream)); CK(cudaGetLastError());
+  return B200_OK;
+}
+
+b200_status b200_composite_color(b200_engine *e, b200_vec4u *d_target_color, float *d_target_depth, const b200_vec4u *d_instance_color,
+                                 const float *d_instance_depth, int n, const int32_t tint[4], float tint_strength) {
+  b200_instance_layer l{};
+  l.d_color = d_instance_color; l.d_depth = d_instance_depth;
+  for (int k = 0; k < 4; ++k) l.tint[k] = tint ? tint[k] : 0;
+  return b200_composite_instances(e, d_target_color, d_target_depth, n, &l, 1, -1.0f, tint_strength);
 }
 
 // ---- pipelined host frames ----------------------------------------------------------------------------

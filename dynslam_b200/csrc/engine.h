@@ -75,6 +75,7 @@ struct b200_engine {
   float *d_stageDepth[2]; b200_vec4u *d_stageRgb[2]; b200_vec4u *d_stageOut[2]; int16_t *d_stageRaw[2];
   cudaEvent_t evH2D[2], evCompute[2], evD2H[2];
   bool slotBusy[2]; size_t stagePixels;
+  float *d_viewScratch; size_t viewScratchPixels;   // plays view->depth inside UpdateView (view.cu)
   cudaEvent_t *evRing;                // timing mode 2: event pairs around every integrate launch
   int evRingCap, evRingCount, timingMode;
   long long launches;
@@ -116,9 +117,14 @@ void launch_swap_move_out(b200_engine *e, const SceneRef &s, b200_voxel *synced,
 
 void launch_view_convert(b200_engine *e, const int16_t *raw, float *out, int w, int h, int type, float p0, float p1, float fx);
 void launch_view_filter_pass(b200_engine *e, const float *in, float *out, int w, int h);
-void launch_update_view(b200_engine *e, const int16_t *raw, const float *depthIn, float *out, int w, int h, int type, float p0,
-                        float p1, float fx, bool filter);
+void launch_update_view(b200_engine *e, const int16_t *raw, float *out, float *scratch, int w, int h, int type, float p0, float p1,
+                        float fx, bool filter);
 void launch_view_normals(b200_engine *e, const float *depth, b200_vec4f *normal, float *sigmaZ, int w, int h, const float intr[4]);
+
+void launch_process_silhouettes(b200_engine *e, b200_vec4u *rgb, float *depth, int w, int h, const b200_silhouette_op *ops, int n);
+void launch_composite_depth(b200_engine *e, float *target, const float *source, int n);
+void launch_composite_layers(b200_engine *e, b200_vec4u *tcol, float *tdep, int n, const b200_instance_layer *layers, int nLayers,
+                             bool dim, float dimFactor, float tintStrength);
 
 static inline int persistent_grid(const b200_engine *e, int ctasPerSm, long long workItems) {
   long long g = (long long)e->smCount * ctasPerSm;

@@ -6,11 +6,13 @@
 // ping-ponging view->depth <-> floatImage, then a device-to-device copy back) and, for the weighted-ICP
 // tracker, ComputeNormalAndWeights (:59-114).
 //
-// B200 design: ONE kernel for convert + 5 passes + copy. A CTA owns a 64x32 output tile, converts the
-// (64+20)x(32+20) raw neighbourhood into shared memory once, and runs the passes between two shared
-// buffers; every pass shrinks the valid region by the filter radius, the fifth writes straight to global.
-// 2 B/pixel are read and 4 B/pixel written instead of 2 + 5*(4+4) + 8; the six launch gaps disappear.
-// The kernel is bound by the 25 exp() per pixel and pass, not by memory.
+// B200 design. The filter is bound by arithmetic (25 exp() per pixel and pass), not by memory: a first version that
+// fused all five passes over a shared-memory tile with a 10-pixel halo measured 2.4x SLOWER than five plain passes,
+// because the halo recomputation (+42 %) costs more than the L2 round trips it saves (1.9 MB images, L2-resident).
+// What is fused is everything that is not arithmetic: the raw->float conversion happens while pass 1 stages its tile,
+// the final device-to-device copy disappears by letting view->depth play the role of floatImage (passes 1, 3, 5 write
+// it) and an engine-owned scratch image the role of view->depth, so UpdateView is 5 launches instead of 7 and never
+// materialises the converted image. Each pass stages a (32+4)x(8+4) tile in shared memory once.
 //
 // Border semantics are the CUDA reference's, not the CPU twin's (which clears the target of every pass,
 // CPU/ITMViewBuilder_CPU.cpp:116-127): filterDepth_device leaves the two outermost rows/columns of its
@@ -76,69 +78,38 @@ __global__ void k_convert(const short *__restrict__ in, float *__restrict__ out,
   out[i] = type == 0 ? convert_disparity(in[i], p0, p1, fx) : convert_affine(in[i], p0, p1);
 }
 
-__global__ void k_filter_pass(const float *__restrict__ in, float *__restrict__ out, int w, int h) {
-  const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
-  if (x >= w || y >= h || on_border(x, y, w, h)) return;          // target border untouched
-  out[x + y * w] = filter_depth_at(in + x + y * w, w);
-}
-
-// ---- fused UpdateView ------------------------------------------------------------------------------
-constexpr int VB_TW = 64, VB_TH = 32, VB_HALO = 10, VB_THREADS = 256;
-constexpr int VB_SW = VB_TW + 2 * VB_HALO, VB_SH = VB_TH + 2 * VB_HALO;
+// One DepthFiltering pass. 32x8 output pixels per CTA, the (32+4)x(8+4) input neighbourhood staged in shared memory
+// (converted from the raw image on the fly when RAW). Border pixels of the target are left untouched (reference
+// semantics) unless zeroBorder, which writes the 0 that floatImage's border holds in the reference; borderCopy, if
+// given, receives the staged (converted) value of border pixels — the border view->depth keeps through all passes.
+constexpr int FP_TW = 32, FP_TH = 8, FP_SW = FP_TW + 4, FP_SH = FP_TH + 4;
 
 template <bool RAW>
-__global__ void __launch_bounds__(VB_THREADS) k_update_view(const short *__restrict__ raw, const float *__restrict__ depthIn,
-                                                            float *__restrict__ out, int w, int h, int type, float p0, float p1,
-                                                            float fx, int filter) {
-  __shared__ float bufA[VB_SH * VB_SW];   // plays view->depth
-  __shared__ float bufB[VB_SH * VB_SW];   // plays floatImage
-  const int x0 = blockIdx.x * VB_TW - VB_HALO, y0 = blockIdx.y * VB_TH - VB_HALO;   // image coords of smem cell (0,0)
-
-  if (!filter) {   // conversion only
-    for (int c = threadIdx.x; c < VB_TW * VB_TH; c += VB_THREADS) {
-      const int gx = x0 + VB_HALO + c % VB_TW, gy = y0 + VB_HALO + c / VB_TW;
-      if (gx < w && gy < h) {
-        const int g = gx + gy * w;
-        out[g] = RAW ? (type == 0 ? convert_disparity(raw[g], p0, p1, fx) : convert_affine(raw[g], p0, p1)) : depthIn[g];
-      }
-    }
-    return;
-  }
-
-  for (int c = threadIdx.x; c < VB_SW * VB_SH; c += VB_THREADS) {
-    const int gx = x0 + c % VB_SW, gy = y0 + c / VB_SW;
+__global__ void __launch_bounds__(FP_TW * FP_TH) k_filter_pass(const short *__restrict__ raw, const float *__restrict__ in,
+                                                                  float *__restrict__ out, float *__restrict__ borderCopy, int w, int h,
+                                                                  int type, float p0, float p1, float fx, int zeroBorder) {
+  __shared__ float tile[FP_SH * FP_SW];
+  const int x0 = blockIdx.x * FP_TW - 2, y0 = blockIdx.y * FP_TH - 2;
+  for (int c = threadIdx.x; c < FP_SW * FP_SH; c += FP_TW * FP_TH) {
+    const int gx = x0 + c % FP_SW, gy = y0 + c / FP_SW;
     float v = 0.0f;
     if (gx >= 0 && gx < w && gy >= 0 && gy < h) {
       const int g = gx + gy * w;
-      v = RAW ? (type == 0 ? convert_disparity(raw[g], p0, p1, fx) : convert_affine(raw[g], p0, p1)) : depthIn[g];
+      v = RAW ? (type == 0 ? convert_disparity(raw[g], p0, p1, fx) : convert_affine(raw[g], p0, p1)) : in[g];
     }
-    bufA[c] = v;
+    tile[c] = v;
   }
   __syncthreads();
-
-#pragma unroll 1
-  for (int pass = 1; pass <= 5; ++pass) {
-    const int halo = VB_HALO - 2 * pass;                 // valid region after this pass: tile + halo
-    const int rw = VB_TW + 2 * halo, rh = VB_TH + 2 * halo, off = VB_HALO - halo;
-    const float *src = (pass & 1) ? bufA : bufB;
-    float *dst = (pass & 1) ? bufB : bufA;
-    for (int c = threadIdx.x; c < rw * rh; c += VB_THREADS) {
-      const int sx = off + c % rw, sy = off + c / rw;
-      const int gx = x0 + sx, gy = y0 + sy;
-      if (gx < 0 || gx >= w || gy < 0 || gy >= h) continue;
-      const int s = sx + sy * VB_SW;
-      if (on_border(gx, gy, w, h)) {
-        // odd passes write floatImage, whose border is the constructor's 0; even passes write view->depth,
-        // whose border keeps the converted value (bufA still holds it)
-        if (pass == 5) out[gx + gy * w] = 0.0f;
-        else if (pass & 1) dst[s] = 0.0f;
-        continue;
-      }
-      const float r = filter_depth_at(src + s, VB_SW);
-      if (pass == 5) out[gx + gy * w] = r; else dst[s] = r;
-    }
-    __syncthreads();
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int x = x0 + 2 + tx, y = y0 + 2 + ty;
+  if (x >= w || y >= h) return;
+  const float *c = tile + (ty + 2) * FP_SW + tx + 2;
+  if (on_border(x, y, w, h)) {
+    if (zeroBorder) out[x + y * w] = 0.0f;
+    if (borderCopy) borderCopy[x + y * w] = c[0];
+    return;
   }
+  out[x + y * w] = filter_depth_at(c, FP_SW);
 }
 
 // ---- ComputeNormalAndWeights (ITMViewBuilder_CUDA.cu:211-227, DA/ITMViewBuilder.h:59-114) -----------
@@ -184,17 +155,24 @@ void launch_view_convert(b200_engine *e, const int16_t *raw, float *out, int w, 
 }
 
 void launch_view_filter_pass(b200_engine *e, const float *in, float *out, int w, int h) {
-  dim3 grid((w + 31) / 32, (h + 7) / 8);
-  k_filter_pass<<<grid, 256, 0, e->stream>>>(in, out, w, h);
+  dim3 grid((w + FP_TW - 1) / FP_TW, (h + FP_TH - 1) / FP_TH);
+  k_filter_pass<false><<<grid, FP_TW * FP_TH, 0, e->stream>>>(nullptr, in, out, nullptr, w, h, 1, 0.0f, 0.0f, 0.0f, 0);
   e->launches++;
 }
 
-void launch_update_view(b200_engine *e, const int16_t *raw, const float *depthIn, float *out, int w, int h, int type, float p0,
-                        float p1, float fx, bool filter) {
-  dim3 grid((w + VB_TW - 1) / VB_TW, (h + VB_TH - 1) / VB_TH);
-  if (raw) k_update_view<true><<<grid, VB_THREADS, 0, e->stream>>>((const short *)raw, nullptr, out, w, h, type, p0, p1, fx, filter ? 1 : 0);
-  else k_update_view<false><<<grid, VB_THREADS, 0, e->stream>>>(nullptr, depthIn, out, w, h, type, p0, p1, fx, filter ? 1 : 0);
-  e->launches++;
+// UpdateView's device part. `scratch` (w*h floats, engine-owned) plays view->depth, `out` plays floatImage:
+//   pass 1: raw -> out (+ converted border -> scratch), 2: out -> scratch, 3: scratch -> out, 4: out -> scratch, 5: scratch -> out
+void launch_update_view(b200_engine *e, const int16_t *raw, float *out, float *scratch, int w, int h, int type, float p0, float p1,
+                        float fx, bool filter) {
+  if (!filter) { launch_view_convert(e, raw, out, w, h, type, p0, p1, fx); return; }
+  dim3 grid((w + FP_TW - 1) / FP_TW, (h + FP_TH - 1) / FP_TH);
+  const int T = FP_TW * FP_TH;
+  k_filter_pass<true><<<grid, T, 0, e->stream>>>((const short *)raw, nullptr, out, scratch, w, h, type, p0, p1, fx, 1);
+  k_filter_pass<false><<<grid, T, 0, e->stream>>>(nullptr, out, scratch, nullptr, w, h, 1, 0.0f, 0.0f, 0.0f, 0);
+  k_filter_pass<false><<<grid, T, 0, e->stream>>>(nullptr, scratch, out, nullptr, w, h, 1, 0.0f, 0.0f, 0.0f, 1);
+  k_filter_pass<false><<<grid, T, 0, e->stream>>>(nullptr, out, scratch, nullptr, w, h, 1, 0.0f, 0.0f, 0.0f, 0);
+  k_filter_pass<false><<<grid, T, 0, e->stream>>>(nullptr, scratch, out, nullptr, w, h, 1, 0.0f, 0.0f, 0.0f, 1);
+  e->launches += 5;
 }
 
 void launch_view_normals(b200_engine *e, const float *depth, b200_vec4f *normal, float *sigmaZ, int w, int h, const float intr[4]) {

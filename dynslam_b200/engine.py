@@ -309,6 +309,67 @@ class ViewBuilder:
         self.e.check(f(self.e.h, _ptr(rawDepth), w, h, C.byref(self.calib), _ptr(depth_out), _ptr(depthNormal), _ptr(depthUncertainty)))
 
 
+# kMatplotlib2Palette (DS/InstRecLib/InstanceReconstructor.cpp:43-55)
+MATPLOTLIB2_PALETTE = [(0x1f, 0x77, 0xb4, 255), (0xff, 0x7f, 0x0e, 255), (0x2c, 0xa0, 0x2c, 255), (0xd6, 0x27, 0x28, 255),
+                       (0x94, 0x67, 0xbd, 255), (0x8c, 0x56, 0x4b, 255), (0xe3, 0x77, 0xc2, 255), (0x71, 0x71, 0x71, 255),
+                       (0xbc, 0xbd, 0x22, 255), (0x17, 0xbe, 0xcf, 255)]
+
+KEEP, REMOVE, EXTRACT = 0, 1, 2   # b200_silhouette_op.action
+
+
+def make_mask(bbox, data):
+    """b200_mask from an inclusive (x0, y0, x1, y1) box and a box-sized uint8 CUDA tensor (1 = inside)."""
+    x0, y0, x1, y1 = [int(v) for v in bbox]
+    assert data.dtype == torch.uint8 and tuple(data.shape) == (y1 - y0 + 1, x1 - x0 + 1) and data.is_contiguous()
+    m = abi.Mask()
+    m.x0, m.y0, m.x1, m.y1, m.d_data = x0, y0, x1, y1, data.data_ptr()
+    m._keep = data
+    return m
+
+
+class InstanceFrames:
+    """The image work of InstanceReconstructor (DS/InstRecLib/InstanceReconstructor.cpp) that touches full frames:
+    cutting detections out of the main frame into per-instance frames, and compositing the per-volume renders."""
+
+    def __init__(self, engine):
+        self.e = engine
+
+    def ProcessSilhouettes(self, rgb, depth, ops, sync=True):
+        """ops: list of (action, copy_mask, delete_mask, dest_rgb, dest_depth) in the order of the active tracks."""
+        torch.cuda.current_stream().synchronize()
+        h, w = depth.shape
+        arr = (abi.SilhouetteOp * max(len(ops), 1))()
+        for k, (action, cm, dm, drgb, ddepth) in enumerate(ops):
+            arr[k].action = int(action)
+            if cm is not None:
+                arr[k].copy_mask = cm
+            if dm is not None:
+                arr[k].delete_mask = dm
+            arr[k].d_dest_rgb, arr[k].d_dest_depth = _ptr(drgb), _ptr(ddepth)
+        f = self.e.lib.b200_process_silhouettes if sync else self.e.lib.b200_process_silhouettes_async
+        self.e.check(f(self.e.h, _ptr(rgb), _ptr(depth), w, h, arr, len(ops)))
+
+    def CompositeDepth(self, target, source):
+        torch.cuda.current_stream().synchronize()
+        self.e.check(self.e.lib.b200_composite_depth(self.e.h, _ptr(target), _ptr(source), target.numel()))
+
+    def CompositeColor(self, target_color, target_depth, instance_color, instance_depth, tint, tint_strength):
+        torch.cuda.current_stream().synchronize()
+        self.e.check(self.e.lib.b200_composite_color(self.e.h, _ptr(target_color), _ptr(target_depth), _ptr(instance_color),
+                                                      _ptr(instance_depth), target_depth.numel(),
+                                                      (C.c_int32 * 4)(*[int(t) for t in tint]), float(tint_strength)))
+
+    def CompositeInstances(self, out_color, out_depth, layers, dim_factor=0.10, tint_strength=1.0):
+        """layers: list of (color, depth, tint) in the order of the active tracks; dim_factor < 0 skips the dimming."""
+        torch.cuda.current_stream().synchronize()
+        arr = (abi.InstanceLayer * max(len(layers), 1))()
+        for k, (col, dep, tint) in enumerate(layers):
+            arr[k].d_color, arr[k].d_depth = _ptr(col), _ptr(dep)
+            arr[k].tint = (C.c_int32 * 4)(*[int(t) for t in tint])
+        self.e.check(self.e.lib.b200_composite_instances(self.e.h, _ptr(out_color), _ptr(out_depth), out_depth.numel(), arr, len(layers),
+                                                          float(dim_factor), float(tint_strength)))
+
+
 class SceneReconstructionEngine:
     """ITMSceneReconstructionEngine<ITMVoxel, ITMVoxelBlockHash> (B200 back-end)."""
 

@@ -35,30 +35,26 @@ def gather_renders(color, depth, dst=0, group=None):
     return cols, deps
 
 
-def composite_depth(target, source):
-    """CompositeDepth — InstanceReconstructor.cpp:851-869 (0 = no measurement)."""
-    both = (target != 0) & (source != 0)
-    out = torch.where(target == 0, source, target)
-    return torch.where(both, torch.minimum(target, source), out)
+def _need_cuda(*tensors):
+    for t in tensors:
+        if not t.is_cuda:
+            raise RuntimeError("dynslam_b200.multi composites on the GPU only (libb200fusion, frames.cu); there is no CPU fallback")
 
 
-def composite_color(t_color, t_depth, s_color, s_depth, tint=(0, 0, 0, 0), tint_strength=0.0, color_boost=0.5):
-    """CompositeColor — InstanceReconstructor.cpp:873-908: the instance wins a pixel when it has depth
-    and the target has none or is farther. Returns (color, depth)."""
-    on_top = (s_depth != 0) & ((t_depth == 0) | (t_depth > s_depth))
-    strength = 1.0 + color_boost - tint_strength
-    tint_t = torch.tensor(tint[:3], dtype=torch.float64, device=s_color.device)
-    boosted = torch.clamp(s_color[..., :3].to(torch.float64) * strength + tint_t * tint_strength, max=255.0).to(torch.uint8)
-    color = t_color.clone()
-    color[..., :3] = torch.where(on_top[..., None], boosted, t_color[..., :3])
-    depth = torch.where(on_top, s_depth, t_depth)
-    return color, depth
+def composite_depth(engine, target, source):
+    """CompositeDepth — InstanceReconstructor.cpp:850-869, in place on `target` (0 = no measurement)."""
+    from . import engine as E
+    _need_cuda(target, source)
+    E.InstanceFrames(engine).CompositeDepth(target, source)
+    return target
 
 
-def composite_all(colors, depths, tints=None, tint_strength=0.0):
-    """Background = volume 0; every further volume is composited on top in rank order."""
+def composite_all(engine, colors, depths, tints=None, tint_strength=0.0, dim_factor=-1.0):
+    """CompositeInstances — InstanceReconstructor.cpp:932-987 on the gathered renders: background = volume 0, every
+    further volume z-composited on top in rank order, one kernel (b200_composite_instances). Returns (color, depth)."""
+    from . import engine as E
+    _need_cuda(*colors, *depths)
     color, depth = colors[0].clone(), depths[0].clone()
-    for i in range(1, len(colors)):
-        tint = tints[i] if tints is not None else (0, 0, 0, 0)
-        color, depth = composite_color(color, depth, colors[i], depths[i], tint, tint_strength)
+    layers = [(colors[i], depths[i], tints[i] if tints is not None else (0, 0, 0, 0)) for i in range(1, len(colors))]
+    E.InstanceFrames(engine).CompositeInstances(color, depth, layers, dim_factor=dim_factor, tint_strength=tint_strength)
     return color, depth

@@ -299,6 +299,53 @@ b200_status b200_host_frame_submit_raw(b200_engine *e, b200_scene *scene, b200_r
                                        b200_vec4f *d_points, b200_vec4f *d_normals, const b200_frame_opts *opts,
                                        b200_vec4u *h_outImage, int slot);
 
+/* ---- instance frame splitting ---------------------------------------------------
+   Replaces the download / CPU masking / upload round trip of InstanceReconstructor::ProcessFrame
+   (DS/InstRecLib/InstanceReconstructor.cpp:180-197) around ProcessSilhouette_CPU / RemoveSilhouette_CPU
+   (:59-170). The frame (view->rgb, view->depth) and the instance frames stay on the device. */
+
+typedef struct {
+  int32_t x0, y0, x1, y1;      /* instreclib::utils::BoundingBox::r, inclusive (Utils/BoundingBox.h:35-37) */
+  const uint8_t *d_data;       /* Mask::mask_data_ (cv::Mat1b, box-sized, row-major; 1 = inside) on the DEVICE */
+} b200_mask;
+
+typedef struct {
+  int32_t action;              /* what InstanceReconstructor::ProcessSilhouette (:226-285) decides for the track:
+                                  0 = keep in the main map (static / static class),
+                                  1 = RemoveSilhouette_CPU(delete_mask) only (uncertain or unreconstructable),
+                                  2 = ProcessSilhouette_CPU(copy_mask -> instance frame) then RemoveSilhouette_CPU(delete_mask) */
+  b200_mask copy_mask, delete_mask;
+  b200_vec4u *d_dest_rgb;      /* instance_view->rgb, full frame size (action 2) */
+  float *d_dest_depth;         /* instance_view->depth */
+} b200_silhouette_op;
+
+/* Applies ops[0..n) in order to the frame, exactly like the reference's loop over the active tracks
+   (InstanceReconstructor::UpdateTracks, :210-224): a later op sees the pixels an earlier one blanked. */
+b200_status b200_process_silhouettes(b200_engine *e, b200_vec4u *d_rgb, float *d_depth, int w, int h,
+                                     const b200_silhouette_op *ops, int n);
+b200_status b200_process_silhouettes_async(b200_engine *e, b200_vec4u *d_rgb, float *d_depth, int w, int h,
+                                           const b200_silhouette_op *ops, int n);
+
+/* ---- compositing of per-volume renders (the consumer of the multi-GPU gather) ------ */
+
+typedef struct {
+  const b200_vec4u *d_color;   /* the instance's render (GetImage) */
+  const float *d_depth;        /* its depth render (GetFloatImage kDepth); 0 = nothing */
+  int32_t tint[4];             /* kMatplotlib2Palette[track id % size] (InstanceReconstructor.cpp:43-55) */
+} b200_instance_layer;
+
+/* CompositeDepth (InstanceReconstructor.cpp:850-869) */
+b200_status b200_composite_depth(b200_engine *e, float *d_target, const float *d_source, int n);
+/* CompositeColor (InstanceReconstructor.cpp:873-905) */
+b200_status b200_composite_color(b200_engine *e, b200_vec4u *d_target_color, float *d_target_depth,
+                                 const b200_vec4u *d_instance_color, const float *d_instance_depth, int n,
+                                 const int32_t tint[4], float tint_strength);
+/* CompositeInstances (InstanceReconstructor.cpp:932-987) without the renders: dims the background by
+   dim_factor (< 0: no dimming) and composites layers[0..n_layers) in order, all in one pass over the image. */
+b200_status b200_composite_instances(b200_engine *e, b200_vec4u *d_out_color, float *d_out_depth, int n,
+                                     const b200_instance_layer *layers, int n_layers, float dim_factor,
+                                     float tint_strength);
+
 /* ---- introspection used by bench.py / tests -------------------------------------------------- */
 
 typedef struct {

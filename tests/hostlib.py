@@ -26,7 +26,7 @@ def oracle():
     global _oracle
     if _oracle is not None:
         return _oracle
-    srcs = [os.path.join(ROOT, "oracle", f) for f in ("tsdf_oracle.c", "view_oracle.c")]
+    srcs = [os.path.join(ROOT, "oracle", f) for f in ("tsdf_oracle.c", "view_oracle.c", "frames_oracle.c")]
     if not os.path.exists(ORACLE_SO) or os.path.getmtime(ORACLE_SO) < max(os.path.getmtime(s) for s in srcs):
         build_oracle()
     L = C.CDLL(ORACLE_SO)
@@ -77,6 +77,14 @@ def oracle():
     L.oracle_compute_normal_and_weights.restype = None
     L.oracle_update_view.argtypes = [vp, C.c_int, C.c_int, P(abi.ViewCalib), vp, vp, vp, vp]
     L.oracle_update_view.restype = None
+    L.oracle_process_silhouettes.argtypes = [vp, vp, C.c_int, C.c_int, P(abi.SilhouetteOp), C.c_int]
+    L.oracle_process_silhouettes.restype = None
+    L.oracle_composite_depth.argtypes = [vp, vp, C.c_int]
+    L.oracle_composite_depth.restype = None
+    L.oracle_composite_color.argtypes = [vp, vp, vp, vp, C.c_int, P(C.c_int32), C.c_float]
+    L.oracle_composite_color.restype = None
+    L.oracle_composite_instances.argtypes = [vp, vp, C.c_int, P(abi.InstanceLayer), C.c_int, C.c_float, C.c_float]
+    L.oracle_composite_instances.restype = None
     L.oracle_num_threads.restype = C.c_int
     L.oracle_set_threads.argtypes = [C.c_int]
     L.oracle_set_threads.restype = None

@@ -1,6 +1,7 @@
-"""N>1 host logic on CPU: two gloo ranks each "render" a volume, the renders are gathered on rank 0
-and z-composited; the result must equal the serial CompositeColor/CompositeDepth semantics
-(DS/InstRecLib/InstanceReconstructor.cpp:851-908)."""
+"""N>1 host logic on CPU: two gloo ranks each "render" a volume and the renders are gathered on rank 0
+(dynslam_b200.multi: ownership + gather). The z-composite itself is a CUDA kernel (b200_composite_instances, checked
+against the oracle in tests/test_gpu_frames.py); here the gathered images are composited by the ORACLE and compared
+with a literal Python transcription of CompositeColor (DS/InstRecLib/InstanceReconstructor.cpp:873-905)."""
 import os
 import socket
 
@@ -41,8 +42,7 @@ def _worker(rank, world, port, q):
     color, depth = _render(rank)
     cols, deps = multi.gather_renders(torch.from_numpy(color), torch.from_numpy(depth), dst=0)
     if rank == 0:
-        out_c, out_d = multi.composite_all(cols, deps)
-        q.put((out_c.numpy(), out_d.numpy()))
+        q.put(([c.numpy() for c in cols], [d.numpy() for d in deps]))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -57,18 +57,32 @@ def test_two_rank_gather_and_composite():
     procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
-    got_c, got_d = q.get(timeout=120)
+    cols, deps = q.get(timeout=120)
     for p in procs:
         p.join(timeout=120)
         assert p.exitcode == 0
     renders = [_render(r) for r in range(2)]
+    for r in range(2):                                       # the gather delivered every rank's render, in rank order
+        assert np.array_equal(cols[r], renders[r][0]) and np.array_equal(deps[r], renders[r][1])
+    import ctypes as C
+    from dynslam_b200 import abi
+    from tests import hostlib
+    got_c, got_d = np.ascontiguousarray(cols[0]).copy(), np.ascontiguousarray(deps[0]).copy()
+    layers = (abi.InstanceLayer * 1)()
+    s_c, s_d = np.ascontiguousarray(cols[1]), np.ascontiguousarray(deps[1])
+    layers[0].d_color, layers[0].d_depth = s_c.ctypes.data, s_d.ctypes.data
+    hostlib.oracle().oracle_composite_instances(hostlib.vptr(got_c), hostlib.vptr(got_d), H * W, layers, 1, -1.0, 0.0)
     want_c, want_d = _reference_composite([r[0] for r in renders], [r[1] for r in renders])
     assert np.array_equal(got_d, want_d)
     assert np.array_equal(got_c[..., :3], want_c[..., :3])
 
 
-def test_composite_depth_rule():
-    t = torch.tensor([[0.0, 2.0, 3.0, 0.0]])
-    s = torch.tensor([[1.0, 0.0, 2.5, 0.0]])
-    assert multi.composite_depth(t, s).tolist() == [[1.0, 2.0, 2.5, 0.0]]
+def test_ownership_and_no_cpu_fallback():
     assert multi.volume_owner(0, 8) == 0 and multi.volume_owner(9, 8) == 1
+    t = torch.tensor([[0.0, 2.0, 3.0, 0.0]])
+    try:
+        multi.composite_depth(None, t, t.clone())
+    except RuntimeError as ex:
+        assert "no CPU fallback" in str(ex)
+    else:
+        raise AssertionError("compositing CPU tensors must fail loudly")
