@@ -289,6 +289,74 @@ def run_view_builder(frames, iters=60):
     return out
 
 
+# --------------------------------------------------------------------------------------------------
+# instance frame splitting + compositing: HBM-bound byte work, so each gets a roofline line.
+# 7 cars (configs[2]) at 1242x375; L2 flushed before every timed launch; CUDA events on the engine's stream.
+# --------------------------------------------------------------------------------------------------
+def run_frames_ops(local_rank, iters=30, ncars=7):
+    import torch
+    from dynslam_b200 import engine as E
+    dev = torch.device("cuda", local_rank)
+    W, H_ = synth.KITTI_W, synth.KITTI_H
+    stream = torch.cuda.Stream(device=dev)
+    peak, _ = peaks()
+    with torch.cuda.stream(stream):
+        eng = E.Engine(E.Scene(E.SceneParams(), 2048, 0x800, 0x400, device=f"cuda:{local_rank}"), (W, H_), stream=stream.cuda_stream)
+        fr = E.InstanceFrames(eng)
+        rng = np.random.default_rng(7)
+        rgb0 = torch.from_numpy(rng.integers(0, 256, (H_, W, 4), dtype=np.uint8)).to(dev)
+        depth0 = torch.from_numpy(rng.uniform(0.5, 20.0, (H_, W)).astype(np.float32)).to(dev)
+        ops, keep = [], []
+        for i in range(ncars):           # car-sized boxes (~150x90 px) spread over the frame, elliptical silhouettes
+            bw, bh = 150 + 10 * i, 90 + 4 * i
+            x0, y0 = 40 + i * 160, 120 + (i % 3) * 40
+            yy, xx = np.mgrid[0:bh, 0:bw]
+            m = ((((xx - bw / 2) / (bw / 2)) ** 2 + ((yy - bh / 2) / (bh / 2)) ** 2) <= 1.0).astype(np.uint8)
+            t = torch.from_numpy(m).to(dev)
+            mask = E.make_mask((x0, y0, x0 + bw - 1, y0 + bh - 1), t)
+            drgb = torch.zeros((H_, W, 4), dtype=torch.uint8, device=dev)
+            ddep = torch.zeros((H_, W), dtype=torch.float32, device=dev)
+            keep.append((t, mask, drgb, ddep))
+            ops.append((E.EXTRACT, mask, mask, drgb, ddep))
+        flush = torch.zeros(256 * 1024 * 1024 // 4, dtype=torch.int32, device=dev)
+        rgb, depth = rgb0.clone(), depth0.clone()
+
+        def timed(fn, reset):
+            tot = 0.0
+            for it in range(iters + 3):
+                reset()
+                flush.add_(1)
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(stream); fn(); b.record(stream)
+                stream.synchronize()
+                if it >= 3:
+                    tot += a.elapsed_time(b)
+            return 1000.0 * tot / iters
+
+        def reset_split():
+            rgb.copy_(rgb0); depth.copy_(depth0)
+        us_split = timed(lambda: fr.ProcessSilhouettes(rgb, depth, ops, sync=False), reset_split)
+        # algorithmic bytes: the frame is read once (8 B/px); every instance frame is written in full (8 B/px each, the
+        # reference's two memsets + copies); the blanked pixels of the main frame are written back
+        blanked = int((depth == 0).sum().item())
+        bytes_split = W * H_ * 8 + ncars * W * H_ * 8 + blanked * 8
+        layers = [(k[2], k[3], E.MATPLOTLIB2_PALETTE[i % 10]) for i, k in enumerate(keep)]
+        out_c, out_d = rgb0.clone(), depth0.clone()
+
+        def reset_cmp():
+            out_c.copy_(rgb0); out_d.copy_(depth0)
+        us_cmp = timed(lambda: fr.CompositeInstances(out_c, out_d, layers, dim_factor=0.10, tint_strength=1.0), reset_cmp)
+        # every layer's depth is read (4 B/px); its colour only where it wins; background read + written (16 B/px)
+        bytes_cmp = W * H_ * 16 + ncars * W * H_ * 4
+        eng.close()
+    return {"instance_split": {"us": us_split, "ops": ncars, "alg_bytes": bytes_split, "achieved": bytes_split / us_split / 1e3,
+                               "peak": peak, "unit": "GB/s", "frac": bytes_split / us_split / 1e3 / peak,
+                               "what": "b200_process_silhouettes_async: 7 detections cut out of a 1242x375 frame into 7 instance frames, one launch"},
+            "composite": {"us": us_cmp, "layers": ncars, "alg_bytes": bytes_cmp, "achieved": bytes_cmp / us_cmp / 1e3, "peak": peak,
+                          "unit": "GB/s", "frac": bytes_cmp / us_cmp / 1e3 / peak,
+                          "what": "b200_composite_instances (synchronous call): background dim + 7 layers z-composited, one launch"}}
+
+
 def gen_frames_hires(seed, count):
     scene = synth.StreetScene(seed=seed, length_m=60.0)
     return [synth.kitti_frame(scene, f, zmax=8.0) for f in range(count)]
@@ -510,6 +578,13 @@ def run_own(args, rank, local_rank, world):
         except Exception as ex:
             vbuild = {"error": str(ex)}
 
+    frames_ops = None
+    if world == 1 and args.harness_frames > 0:
+        try:
+            frames_ops = run_frames_ops(local_rank)
+        except Exception as ex:
+            frames_ops = {"error": str(ex)}
+
     line = {
         "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": Wm,
         "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
@@ -534,6 +609,7 @@ def run_own(args, rank, local_rank, world):
         "cpu_baseline": cpu,
         "itmlib_harness": itm,
         "view_builder": vbuild,
+        "frames_ops": frames_ops,
         "e2e_raw": e2e_raw,
         "e2e": {"value": world * e2e_frames / t_e2e, "unit": "frames/s", "h2d_bytes_per_step": W * H_ * 8,
                 "d2h_bytes_per_step": W * H_ * 4, "steps": e2e_frames},

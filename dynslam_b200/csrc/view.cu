@@ -7,7 +7,7 @@
 // tracker, ComputeNormalAndWeights (:59-114).
 //
 // B200 design. The filter is bound by arithmetic (25 exp() per pixel and pass), not by memory: a first version that
-// fused all five passes over a shared-memory tile with a 10-pixel halo measured 2.4x SLOWER than five plain passes,
+// fused all five passes over a shared-memory tile with a 10-pixel halo measured 2x SLOWER (123 us) than five plain passes (62 us),
 // because the halo recomputation (+42 %) costs more than the L2 round trips it saves (1.9 MB images, L2-resident).
 // What is fused is everything that is not arithmetic: the raw->float conversion happens while pass 1 stages its tile,
 // the final device-to-device copy disappears by letting view->depth play the role of floatImage (passes 1, 3, 5 write
@@ -23,7 +23,7 @@
 //   * those border values ARE read as taps by the neighbouring inner pixels (0 is not < 0).
 //
 // Arithmetic: the expressions keep the reference's operation order; the library is compiled without
-// contraction, division and sqrt are IEEE. exp()/acos() are the CUDA math library's (<= 2 ulp) where the
+// contraction, division and sqrt are IEEE. exp() is the CUDA math library's algorithm (<= 2 ulp), acos() its acosf, where the
 // oracle uses the host libm, so this file is compared within a stated tolerance (tests/test_gpu_view.py),
 // not bit for bit; the reference's own CUDA build uses --use_fast_math here.
 #include "engine.h"
@@ -46,7 +46,24 @@ __device__ __forceinline__ float convert_disparity(short disparity, float p0, fl
   return (depth > 0) ? depth : -1.0f;
 }
 
-// filterDepth (DA/ITMViewBuilder.h:31-56) for the pixel at *c; rows are `stride` floats apart.
+// exp(x) for x <= 0, the algorithm of the CUDA math library's expf (magic-number rounding of x*log2(e), two-term
+// Cody-Waite reduction in ln 2, ex2.approx, exponent splice; <= 2 ulp) without its overflow/underflow special cases:
+// the argument is clamped at -86 instead. A bilateral weight below e^-86 = 4e-38 can never change the sums it is added
+// to (the centre tap contributes weight 1 and depth >= 1e-3), so the filter output is the same bits either way.
+__device__ __forceinline__ float exp_nonpositive(float x) {
+  x = fmaxf(x, -86.0f);
+  const float t = __fmaf_rn(x, 1.44269504088896341f, 12582912.0f);
+  const float j = t - 12582912.0f;
+  float r = __fmaf_rn(j, -0.693145751953125f, x);
+  r = __fmaf_rn(j, -1.42860682030941723e-06f, r);
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(r * 1.44269504088896341f));
+  return __int_as_float(__float_as_int(e) + (__float_as_int(t) << 23));
+}
+
+// filterDepth (DA/ITMViewBuilder.h:31-56) for the pixel at *c; rows are `stride` floats apart. Branch-free form of the
+// reference's `if (tmpz < 0) continue;`: an invalid tap gets weight +0, and x + 0 and x + (0 * tmpz) leave every partial
+// sum bit-identical (the sums are >= 0; +0 + -0 = +0 in round-to-nearest).
 __device__ __forceinline__ float filter_depth_at(const float *c, int stride) {
   const float z = c[0];
   if (z < 0.0f) return -1.0f;
@@ -57,10 +74,10 @@ __device__ __forceinline__ float filter_depth_at(const float *c, int stride) {
 #pragma unroll
     for (int j = -2; j <= 2; j++) {
       const float tmpz = c[i * stride + j];
-      if (tmpz < 0.0f) continue;
       float dz = (tmpz - z); dz *= dz;
       const int a = (i < 0 ? -i : i) + (j < 0 ? -j : j);
-      const float w = expf(-0.5f * ((float)a * MEAN_SIGMA_L * MEAN_SIGMA_L + dz * sigma_z * sigma_z));
+      float w = exp_nonpositive(-0.5f * ((float)a * MEAN_SIGMA_L * MEAN_SIGMA_L + dz * sigma_z * sigma_z));
+      w = tmpz < 0.0f ? 0.0f : w;
       w_sum += w;
       final_depth += w * tmpz;
     }
