@@ -80,11 +80,12 @@ __device__ bool block_visible(int bx, int by, int bz, const Mat4 &M, const float
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 k_prepare(const b200_hash_entry *__restrict__ table, int numBuckets, const b200_vec3i *__restrict__ visiblePos, uint8_t *visType,
-          const DevCounters *ctr, unsigned *reqBits, unsigned *req2Bits, int noWords, Mat4 M, float p0, float p1, float p2, float p3,
+          DevCounters *ctr, unsigned *reqBits, unsigned *req2Bits, int noWords, Mat4 M, float p0, float p1, float p2, float p3,
           float voxelSize, int w, int h, int capacity, float2 *minmaxDead, int mw, int mh) {
   const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
   for (int i = tid; i < noWords; i += nth) { reqBits[i] = 0u; req2Bits[i] = 0u; }
-  if (minmaxDead) {   // fused frame: initialise the cells of the expected-depth image outside its live 1/8-res corner here
+  if (minmaxDead) {
+    if (tid == 0) ctr->noRenderingBlocks = 0;   // k_visible_list of this frame sums the rendering-tile counts into it   // fused frame: initialise the cells of the expected-depth image outside its live 1/8-res corner here
     const int liveX = (mw - 1) / B200_MINMAX_SUBSAMPLE, liveY = (mh - 1) / B200_MINMAX_SUBSAMPLE;
     const float2 v = make_float2(B200_FAR_AWAY, B200_VERY_CLOSE);
     for (int i = tid; i < mw * mh; i += nth) { const int y = i / mw, x = i - y * mw; if (x > liveX || y > liveY) minmaxDead[i] = v; }
@@ -292,10 +293,11 @@ __global__ void __launch_bounds__(256, 4)
 k_visible_list(const b200_hash_entry *__restrict__ table, int numBuckets, int noTotal, uint8_t *visType, b200_vec3i *visiblePos,
                int *visiblePtr, int capacity, DevCounters *ctr, unsigned long long *scanDesc, unsigned gen, Mat4 M, float p0, float p1,
                float p2, float p3, float voxelSize, int w, int h, b200_vec3i *ring, long long ringCap, long long *snapStart,
-               int *snapCount, int slot, int oldestSlot) {
+               int *snapCount, int slot, int oldestSlot, BlockRec *recs, int rw, int rh) {
   __shared__ unsigned sm[33];
   __shared__ unsigned tileBase;
   __shared__ int hits[VIS_TILE];
+  unsigned myTiles = 0;   // rendering tiles of the blocks this thread projected (fused frame only)
   const float proj[4] = {p0, p1, p2, p3};
   const long long ringStart = ctr->ringHead;   // advanced by the last tile only, at its very end
   const int noTiles = (noTotal + VIS_TILE - 1) / VIS_TILE;
@@ -350,6 +352,18 @@ k_visible_list(const b200_hash_entry *__restrict__ table, int numBuckets, int no
         int ptr = en.ptr;
         if (ptr < 0) { if (find_block<false>(table, numBuckets, en.x, en.y, en.z, &ptr) < 0) ptr = -1; }   // stale entry: what findBlock(pos) would hit
         visiblePtr[out] = ptr;
+        if (recs) {
+          // fused frame: CreateExpectedDepths renders from this very pose, so the block's 1/8-resolution box is produced here
+          // (ProjectSingleBlock) and the expected-depth pass only rasterises. All blocks are assumed drawn; k_project_blocks
+          // re-does the job with the ordered MAX_RENDERING_BLOCKS rule if the tile total exceeds the cap (never at KITTI sizes).
+          BlockRec r; r.ulx = 1; r.uly = 1; r.lrx = 0; r.lry = 0; r.zmin = 0; r.zmax = 0;
+          int ulx, uly, lrx, lry; float zmin, zmax;
+          if (ptr >= 0 && project_single_block(en.x, en.y, en.z, M, proj, rw, rh, voxelSize, ulx, uly, lrx, lry, zmin, zmax)) {
+            r.ulx = (short)ulx; r.uly = (short)uly; r.lrx = (short)lrx; r.lry = (short)lry; r.zmin = zmin; r.zmax = zmax;
+            myTiles += rendering_tiles(ulx, uly, lrx, lry);
+          }
+          recs[out] = r;
+        }
       }
     }
     __syncthreads();
@@ -364,6 +378,10 @@ k_visible_list(const b200_hash_entry *__restrict__ table, int numBuckets, int no
       snapCount[slot] = kept;
       ctr->ringHead = ringStart + kept;
     }
+  }
+  if (recs) {
+    for (int o = 16; o > 0; o >>= 1) myTiles += __shfl_xor_sync(0xffffffffu, myTiles, o);
+    if ((threadIdx.x & 31) == 0 && myTiles) atomicAdd(&ctr->noRenderingBlocks, myTiles);
   }
 }
 
@@ -420,27 +438,36 @@ void launch_allocate(b200_engine *e, const SceneRef &s, const FrameGeom &g, cons
   const int noWords = e->noWords;
   const unsigned frameTag = (unsigned)(frameIdx + 1) & 0xffffffu;
   if (frameTag == 0) cudaMemsetAsync(e->d_reqKey, 0, sizeof(unsigned long long) * (size_t)s.noTotal, st);
+  trace_begin(e, st, "k_prepare");
   k_prepare<<<e->smCount * 4, 256, 0, st>>>(s.hash, s.numBuckets, s.visiblePos, s.visType, e->d_ctr, e->d_reqBits, e->d_req2Bits, noWords,
                                            g.M_d, g.proj_d[0], g.proj_d[1], g.proj_d[2], g.proj_d[3], g.voxelSize, g.w, g.h, s.numBlocks,
                                            (float2 *)minmaxDead, mw, mh);
+  trace_end(e, st);
   const int tiles = ((g.w + 7) / 8) * ((g.h + 3) / 4);
+  trace_begin(e, st, "k_mark");
   k_mark<<<(tiles + 7) / 8, 256, 0, st>>>(depth, s.hash, s.numBuckets, s.visType, e->d_reqKey, e->d_reqBits, e->d_req2Bits, g,
                                          frameTag);
+  trace_end(e, st);
   e->launches += 2;
   if (!onlyVisible) {
     const int bmpTiles = (noWords + BMP_TILE - 1) / BMP_TILE;
     const unsigned gen = ++e->scanGen;
+    trace_begin(e, st, "k_serve_requests");
     k_serve_requests<<<persistent_grid(e, 2, bmpTiles), 256, 0, st>>>(depth, s.hash, s.numBuckets, s.visType, e->d_reqKey, e->d_reqBits,
                                                                      e->d_req2Bits, noWords, s.allocationList, s.excessList, e->d_ctr,
                                                                      g, frameIdx, e->d_scanDesc, e->d_scanDesc + e->scanDescCap / 2, gen);
+    trace_end(e, st);
     e->launches += 1;
   }
   const int noTiles = (s.noTotal + VIS_TILE - 1) / VIS_TILE;
   const int oldest = e->qSize > 0 ? (e->qHead % SNAP_SLOTS) : -1;
+  trace_begin(e, st, "k_visible_list");
   k_visible_list<<<persistent_grid(e, 2, noTiles), 256, 0, st>>>(s.hash, s.numBuckets, s.noTotal, s.visType, s.visiblePos, e->d_visiblePtr,
                                                                 s.numBlocks, e->d_ctr, e->d_scanDesc, ++e->scanGen, g.M_d, g.proj_d[0],
                                                                 g.proj_d[1], g.proj_d[2], g.proj_d[3], g.voxelSize, g.w, g.h, e->d_ring,
-                                                                e->ringCap, e->d_snapStart, e->d_snapCount, snapSlot, oldest);
+                                                                e->ringCap, e->d_snapStart, e->d_snapCount, snapSlot, oldest,
+                                                                minmaxDead ? (BlockRec *)e->d_blockRecs : nullptr, mw, mh);
+  trace_end(e, st);
   e->launches += 1;
 }
 

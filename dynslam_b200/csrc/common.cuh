@@ -93,6 +93,7 @@ struct DevCounters {
   int decayItems;          // number of list items of the decay pass in flight
   int decayDeleted;        // unique blocks deleted by the pass
   int freedLastDecay;
+  int decayCand;           // partial decay: items that found their block empty this pass (candidates, unordered)
   int errorFlags;          // bit0: decay ring overflow
   unsigned noRenderingBlocks;
   int noNeededEntries;     // swapping
@@ -183,3 +184,46 @@ DEV void st_stream(uint4 *p, uint4 v) {
 // positive-float atomic min/max through the order-preserving int view (all values here are > 0)
 DEV void atomic_min_posf(float *a, float v) { atomicMin(reinterpret_cast<int *>(a), __float_as_int(v)); }
 DEV void atomic_max_posf(float *a, float v) { atomicMax(reinterpret_cast<int *>(a), __float_as_int(v)); }
+
+// ------------------------------------------------------------------------------------------------
+// expected depths: block projection shared by vis.cu (k_project_blocks) and alloc.cu (k_visible_list)
+// ------------------------------------------------------------------------------------------------
+// ProjectSingleBlock — DA/ITMVisualisationEngine.h:29-71
+DEV bool project_single_block(int bx, int by, int bz, const Mat4 &pose, const float *intr, int w, int h, float voxelSize,
+                              int &ulx, int &uly, int &lrx, int &lry, float &zmin, float &zmax) {
+  ulx = w / B200_MINMAX_SUBSAMPLE; uly = h / B200_MINMAX_SUBSAMPLE;
+  lrx = -1; lry = -1;
+  zmin = B200_FAR_AWAY; zmax = B200_VERY_CLOSE;
+#pragma unroll
+  for (int corner = 0; corner < 8; ++corner) {
+    const short tx = (short)(bx + ((corner & 1) ? 1 : 0)), ty = (short)(by + ((corner & 2) ? 1 : 0)), tz = (short)(bz + ((corner & 4) ? 1 : 0));
+    Vec4 q = m4v4(pose, (float)tx * (float)BS * voxelSize, (float)ty * (float)BS * voxelSize, (float)tz * (float)BS * voxelSize, 1.0f);
+    if (q.z < 1e-6) continue;
+    const float px = (intr[0] * q.x / q.z + intr[2]) / B200_MINMAX_SUBSAMPLE;
+    const float py = (intr[1] * q.y / q.z + intr[3]) / B200_MINMAX_SUBSAMPLE;
+    if (ulx > floorf(px)) ulx = (int)floorf(px);
+    if (lrx < ceilf(px)) lrx = (int)ceilf(px);
+    if (uly > floorf(py)) uly = (int)floorf(py);
+    if (lry < ceilf(py)) lry = (int)ceilf(py);
+    if (zmin > q.z) zmin = q.z;
+    if (zmax < q.z) zmax = q.z;
+  }
+  if (ulx < 0) ulx = 0;
+  if (uly < 0) uly = 0;
+  if (lrx >= w) lrx = w - 1;
+  if (lry >= h) lry = h - 1;
+  if (ulx > lrx) return false;
+  if (uly > lry) return false;
+  if (zmin < B200_VERY_CLOSE) zmin = B200_VERY_CLOSE;
+  if (zmax < B200_VERY_CLOSE) return false;
+  return true;
+}
+
+
+// one visible block's 1/8-resolution bounding box + depth range (an undrawn block has ulx > lrx)
+struct __align__(16) BlockRec { short ulx, uly, lrx, lry; float zmin, zmax; };
+
+DEV unsigned rendering_tiles(int ulx, int uly, int lrx, int lry) {   // CreateRenderingBlocks' count, DA/ITMVisualisationEngine.h:73-91
+  const int rx = (int)ceilf((float)(lrx - ulx + 1) / 16), ry = (int)ceilf((float)(lry - uly + 1) / 16);
+  return (unsigned)(rx * ry);
+}

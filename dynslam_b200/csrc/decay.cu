@@ -25,7 +25,7 @@ __global__ void __launch_bounds__(256)
 k_decay_blocks(b200_voxel *voxels, const b200_hash_entry *__restrict__ table, int numBuckets, const b200_vec3i *ring,
                long long ringCap, const long long *snapStart, const int *snapCount, int slot, const short4 *allocatedPos,
                int numBlocks, int minAge, int maxWeight, int currentFrame, unsigned gen, unsigned long long *delTag,
-               int *itemPtr, DevCounters *ctr) {
+               int *itemPtr, DevCounters *ctr, int *candList) {
   __shared__ int sEmpty[8];
   const int n = (MODE == 0) ? snapCount[slot] : numBlocks;
   const long long s0 = (MODE == 0) ? snapStart[slot] : 0;
@@ -75,7 +75,13 @@ k_decay_blocks(b200_voxel *voxels, const b200_hash_entry *__restrict__ table, in
     }
     if (threadIdx.x == 0) {
       itemPtr[item] = claim ? ptr : -1;
-      if (claim) atomicMax(&delTag[ptr], del_tag(gen, (unsigned)item));
+      if (claim) {
+        atomicMax(&delTag[ptr], del_tag(gen, (unsigned)item));
+        if (MODE == 0) {   // remember the candidate: k_decay_commit ranks the few of them instead of scanning the whole list
+          const int c = atomicAdd(&ctr->decayCand, 1);
+          if (c < DECAY_CAND_CAP) candList[c] = item;
+        }
+      }
     }
   }
 }
@@ -224,12 +230,32 @@ __global__ void k_decay_unlink(b200_hash_entry *table, int numBuckets, uint8_t *
 __global__ void __launch_bounds__(1024)
 k_decay_commit(b200_hash_entry *table, int numBuckets, uint8_t *visType, const b200_vec3i *ring, long long ringCap,
                const long long *snapStart, int slot, const int *itemPtr, const unsigned long long *delTag, unsigned gen, int *allocList,
-               int *delList, uint8_t *isLeader, DevCounters *ctr) {
+               int *delList, uint8_t *isLeader, DevCounters *ctr, const int *candList) {
   __shared__ unsigned sm[33];
+  __shared__ int cand[DECAY_CAND_CAP];
   const int n = ctr->decayItems;
   const int lastFree = ctr->lastFreeBlockId;
   const long long s0 = snapStart[slot];
+  const int nc = ctr->decayCand;
   unsigned running = 0;
+  if (nc <= DECAY_CAND_CAP) {
+    // Few candidates (a few dozen per frame): keep the winners of the block claims and rank them by list position by
+    // counting — the same order the scan over the whole list produces, without walking the list.
+    int v = 0x7fffffff, ptr = -1;
+    if ((int)threadIdx.x < nc) {
+      const int item = candList[threadIdx.x];
+      ptr = itemPtr[item];
+      if (ptr >= 0 && delTag[ptr] == del_tag(gen, (unsigned)item)) v = item;
+    }
+    if (threadIdx.x < DECAY_CAND_CAP) cand[threadIdx.x] = v;
+    running = (unsigned)__syncthreads_count(v != 0x7fffffff);
+    if (v != 0x7fffffff) {
+      int r = 0;
+      for (int j = 0; j < nc; ++j) r += (cand[j] < v);
+      allocList[lastFree + 1 + r] = ptr;      // free-list push by list position (:1072-1073)
+      delList[r] = v;
+    }
+  } else
   for (int base = 0; base < n; base += blockDim.x) {
     const int item = base + threadIdx.x;
     int ptr = -1;
@@ -260,6 +286,7 @@ k_decay_commit(b200_hash_entry *table, int numBuckets, uint8_t *visType, const b
     ctr->totalDecayed += nDel;
     ctr->decayDeleted = 0;
     ctr->decayItems = 0;
+    ctr->decayCand = 0;
   }
 }
 
@@ -285,17 +312,24 @@ static void decay_common(b200_engine *e, const SceneRef &s, int mode, int slot, 
   cudaStream_t st = e->stream;
   const unsigned gen = ++e->decayGen;
   const int grid1 = persistent_grid(e, 6, items);
-  if (mode == 0)
+  if (mode == 0) {
+    trace_begin(e, st, "k_decay_blocks<0>");
     k_decay_blocks<0><<<grid1, 256, 0, st>>>(s.voxels, s.hash, s.numBuckets, e->d_ring, e->ringCap, e->d_snapStart, e->d_snapCount,
                                             slot, e->d_allocatedPos, s.numBlocks, minAge, maxWeight, frameIdx, gen, e->d_delTag,
-                                            e->d_itemPtr, e->d_ctr);
-  else
+                                            e->d_itemPtr, e->d_ctr, e->d_candList);
+    trace_end(e, st);
+  } else {
+    trace_begin(e, st, "k_decay_blocks<1>");
     k_decay_blocks<1><<<grid1, 256, 0, st>>>(s.voxels, s.hash, s.numBuckets, e->d_ring, e->ringCap, e->d_snapStart, e->d_snapCount,
                                             slot, e->d_allocatedPos, s.numBlocks, minAge, maxWeight, frameIdx, gen, e->d_delTag,
-                                            e->d_itemPtr, e->d_ctr);
+                                            e->d_itemPtr, e->d_ctr, e->d_candList);
+    trace_end(e, st);
+  }
   if (mode == 0) {
+    trace_begin(e, st, "k_decay_commit");
     k_decay_commit<<<1, 1024, 0, st>>>(s.hash, s.numBuckets, s.visType, e->d_ring, e->ringCap, e->d_snapStart, slot, e->d_itemPtr, e->d_delTag,
-                                       gen, s.allocationList, e->d_delList, e->d_isLeader, e->d_ctr);
+                                       gen, s.allocationList, e->d_delList, e->d_isLeader, e->d_ctr, e->d_candList);
+    trace_end(e, st);
     e->launches += 2;
     return;
   }

@@ -87,6 +87,7 @@ extern "C" {
 b200_status b200_engine_create(const b200_engine_config *cfg, b200_engine **out) {
   if (!cfg || !out) return B200_ERR_INVALID;
   b200_engine *e = new b200_engine();
+  e->useGraph = -1;
   memset(e, 0, sizeof(*e));
   *out = e;
   e->device = cfg->device;
@@ -133,6 +134,7 @@ b200_status b200_engine_create(const b200_engine_config *cfg, b200_engine **out)
   CK(cudaMalloc(&e->d_visiblePtr, sizeof(int) * (size_t)e->numBlocks));
   CK(cudaMalloc(&e->d_itemPtr, sizeof(int) * (size_t)e->numBlocks));
   CK(cudaMalloc(&e->d_delList, sizeof(int) * (size_t)e->numBlocks));
+  CK(cudaMalloc(&e->d_candList, sizeof(int) * DECAY_CAND_CAP));
   CK(cudaMalloc(&e->d_isLeader, (size_t)e->numBlocks));
   CK(cudaMalloc(&e->d_allocatedPos, sizeof(short4) * (size_t)e->numBlocks));
   CK(cudaMalloc(&e->d_blockRecs, 16 * (size_t)e->numBlocks));
@@ -155,7 +157,7 @@ void b200_engine_destroy(b200_engine *e) {
   if (e->stream) cudaStreamSynchronize(e->stream);
   cudaFree(e->d_ctr); cudaFreeHost(e->h_ctr); cudaFree(e->d_reqKey); cudaFree(e->d_reqBits); cudaFree(e->d_scanDesc);
   cudaFree(e->d_ring); cudaFree(e->d_snapCount); cudaFree(e->d_snapStart); cudaFree(e->d_delTag); cudaFree(e->d_itemPtr); cudaFree(e->d_visiblePtr);
-  cudaFree(e->d_viewScratch); cudaFree(e->d_delList); cudaFree(e->d_isLeader); cudaFree(e->d_allocatedPos); cudaFree(e->d_tileCounts); cudaFree(e->d_blockRecs);
+  cudaFree(e->d_viewScratch); cudaFree(e->d_delList); cudaFree(e->d_candList); cudaFree(e->d_isLeader); cudaFree(e->d_allocatedPos); cudaFree(e->d_tileCounts); cudaFree(e->d_blockRecs);
   for (int i = 0; i < 8; ++i) if (e->ev[i]) cudaEventDestroy(e->ev[i]);
   if (e->copyStream) {
     cudaStreamSynchronize(e->copyStream);
@@ -164,6 +166,7 @@ void b200_engine_destroy(b200_engine *e) {
     cudaStreamDestroy(e->copyStream);
     if (e->d2hStream) { cudaStreamSynchronize(e->d2hStream); cudaStreamDestroy(e->d2hStream); }
   }
+  if (e->frameGraph) cudaGraphExecDestroy(e->frameGraph);
   if (e->sideStream) { cudaStreamSynchronize(e->sideStream); cudaEventDestroy(e->evFork); cudaEventDestroy(e->evJoin); cudaStreamDestroy(e->sideStream); }
   if (e->ownStream && e->stream) cudaStreamDestroy(e->stream);
   delete e;
@@ -182,6 +185,32 @@ void b200_set_timing(b200_engine *e, int mode) {
     for (int i = 0; i < e->evRingCap * 2; ++i) cudaEventCreate(&e->evRing[i]);
   }
   e->timingMode = mode;
+  e->traceOn = mode == 3;
+  e->traceCount = 0;
+  if (mode == 3 && !e->traceEv) {
+    e->traceCap = 4096;
+    e->traceEv = (cudaEvent_t *)calloc((size_t)e->traceCap * 2, sizeof(cudaEvent_t));
+    e->traceName = (const char **)calloc((size_t)e->traceCap, sizeof(char *));
+    for (int i = 0; i < e->traceCap * 2; ++i) cudaEventCreate(&e->traceEv[i]);
+  }
+}
+
+// Text dump of the launch trace: one line per launch, "name start_us end_us" relative to the first launch's begin event.
+int b200_get_trace(b200_engine *e, char *out, int cap) {
+  if (!e->traceEv || e->traceCount == 0 || cap <= 0) { if (cap > 0) out[0] = 0; return 0; }
+  cudaSetDevice(e->device);
+  cudaDeviceSynchronize();
+  int n = 0;
+  for (int i = 0; i < e->traceCount; ++i) {
+    float a = 0, b = 0;
+    cudaEventElapsedTime(&a, e->traceEv[0], e->traceEv[2 * i]);
+    cudaEventElapsedTime(&b, e->traceEv[0], e->traceEv[2 * i + 1]);
+    int w = snprintf(out + n, (size_t)(cap - n), "%s %.2f %.2f\n", e->traceName[i], a * 1000.0f, b * 1000.0f);
+    if (w < 0 || w >= cap - n) break;
+    n += w;
+  }
+  e->traceCount = 0;
+  return n;
 }
 
 // Matrix4::inv — OR/Matrix.h:162-224
@@ -418,11 +447,40 @@ b200_status b200_swap_out(b200_engine *e, b200_scene *s, b200_render_state *rs, 
 
 // ---- fused fast path -----------------------------------------------------------------------------
 
+static b200_status frame_enqueue(b200_engine *e, b200_scene *s, b200_render_state *rs, const b200_view *v, b200_vec4f *d_points,
+                                 b200_vec4f *d_normals, const b200_frame_opts *opts);
+
 b200_status b200_process_frame_async(b200_engine *e, b200_scene *s, b200_render_state *rs, const b200_view *v, b200_vec4f *d_points,
                                      b200_vec4f *d_normals, const b200_frame_opts *opts) {
   b200_status st = check_scene(e, s); if (st) return st;
   CK(cudaSetDevice(e->device));
   if (e->hostAuthoritative) { st = upload(e, s, rs); if (st) return st; e->hostAuthoritative = false; }
+  if (e->useGraph < 0) { const char *g = getenv("B200_GRAPH"); e->useGraph = (g && atoi(g) != 0) ? 1 : 0; }
+  if (!e->useGraph || e->timing || e->traceOn || !e->graphWarm) {   // the first frame also runs one-time initialisation: never captured
+    e->graphWarm = true;
+    return frame_enqueue(e, s, rs, v, d_points, d_normals, opts);
+  }
+  // Graph mode: the frame's ~11 launches (two streams, two fork/joins) are captured and replayed as ONE graph launch; the
+  // executable graph is updated in place every frame (same topology, new kernel arguments), re-instantiated if that fails.
+  cudaGraph_t graph = nullptr;
+  CK(cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
+  st = frame_enqueue(e, s, rs, v, d_points, d_normals, opts);
+  cudaError_t ce = cudaStreamEndCapture(e->stream, &graph);
+  if (st) { if (graph) cudaGraphDestroy(graph); return st; }
+  CK(ce);
+  if (e->frameGraph) {
+    cudaGraphExecUpdateResultInfo info;
+    if (cudaGraphExecUpdate(e->frameGraph, graph, &info) != cudaSuccess) { cudaGetLastError(); cudaGraphExecDestroy(e->frameGraph); e->frameGraph = nullptr; }
+  }
+  if (!e->frameGraph) CK(cudaGraphInstantiate(&e->frameGraph, graph, 0));
+  CK(cudaGraphDestroy(graph));
+  CK(cudaGraphLaunch(e->frameGraph, e->stream));
+  return B200_OK;
+}
+
+static b200_status frame_enqueue(b200_engine *e, b200_scene *s, b200_render_state *rs, const b200_view *v, b200_vec4f *d_points,
+                                 b200_vec4f *d_normals, const b200_frame_opts *opts) {
+  b200_status st;
   if (e->timing) CK(cudaEventRecord(e->ev[0], e->stream));
   const bool doRay = (!opts || opts->doRaycast);
   st = enqueue_allocate(e, s, rs, v, 0, doRay); if (st) return st;
@@ -439,7 +497,7 @@ b200_status b200_process_frame_async(b200_engine *e, b200_scene *s, b200_render_
     CK(cudaEventRecord(e->evFork, mainStream));
     CK(cudaStreamWaitEvent(e->sideStream, e->evFork, 0));
     e->stream = e->sideStream;
-    launch_expected_depths(e, r, g.M_d, g.proj_d, rs->img_w, rs->img_h, s->voxelSize, rs->d_minmax, true);
+    launch_expected_depths(e, r, g.M_d, g.proj_d, rs->img_w, rs->img_h, s->voxelSize, rs->d_minmax, true, true);
     e->stream = mainStream;
     CK(cudaEventRecord(e->evJoin, e->sideStream));
   }
@@ -448,7 +506,7 @@ b200_status b200_process_frame_async(b200_engine *e, b200_scene *s, b200_render_
   if (e->timing) CK(cudaEventRecord(e->ev[2], e->stream));
   if (doRay) {
     if (overlap) CK(cudaStreamWaitEvent(mainStream, e->evJoin, 0));
-    else launch_expected_depths(e, r, g.M_d, g.proj_d, rs->img_w, rs->img_h, s->voxelSize, rs->d_minmax, true);
+    else launch_expected_depths(e, r, g.M_d, g.proj_d, rs->img_w, rs->img_h, s->voxelSize, rs->d_minmax, true, true);
     if (e->timing) CK(cudaEventRecord(e->ev[3], e->stream));
     launch_raycast(e, r, g.invM_d, g.proj_d, rs->img_w, rs->img_h, s->voxelSize, s->mu, rs->d_minmax, rs->d_raycastResult);
     if (overlap) {   // the ICP-map pass (image space) runs beside the decay sweep (voxel space)

@@ -56,6 +56,7 @@ struct b200_engine {
   int *d_itemPtr;                     // per decay item: VBA ptr (or -1)
   unsigned *d_itemFlag;               // per decay item: 1 = deletes its block
   int *d_delList;                     // compacted deleting items (list order)
+  int *d_candList;                    // DECAY_CAND_CAP unordered candidates of the partial pass (decay.cu)
   uint8_t *d_isLeader;
   short4 *d_allocatedPos;             // full decay: pos per VBA slot (w = valid)
   unsigned decayGen;
@@ -75,9 +76,12 @@ struct b200_engine {
   float *d_stageDepth[2]; b200_vec4u *d_stageRgb[2]; b200_vec4u *d_stageOut[2]; int16_t *d_stageRaw[2];
   cudaEvent_t evH2D[2], evCompute[2], evD2H[2];
   bool slotBusy[2]; size_t stagePixels;
+  int useGraph; bool graphWarm; cudaGraphExec_t frameGraph;         // B200_GRAPH=1: the fused frame is captured and replayed as a CUDA graph
   float *d_viewScratch; size_t viewScratchPixels;   // plays view->depth inside UpdateView (view.cu)
   cudaEvent_t *evRing;                // timing mode 2: event pairs around every integrate launch
   int evRingCap, evRingCount, timingMode;
+  // timing mode 3: an event pair around every kernel launch (launch trace, b200_get_trace)
+  bool traceOn; int traceCount, traceCap; cudaEvent_t *traceEv; const char **traceName;
   long long launches;
   int lastNoIntegrated;
   int integrateImpl;                  // 0 = LDG variant, 1 = TMA bulk-copy variant (env B200_INTEGRATE_IMPL=ldg|tma)
@@ -99,7 +103,7 @@ void launch_decay_partial(b200_engine *e, const SceneRef &s, int snapSlot, int m
 void launch_decay_full(b200_engine *e, const SceneRef &s, int minAge, int maxWeight, int frameIdx);
 void launch_find_visible(b200_engine *e, const SceneRef &s, const Mat4 &M, const float proj[4], int w, int h, float voxelSize);
 void launch_expected_depths(b200_engine *e, const SceneRef &s, const Mat4 &M, const float proj[4], int w, int h,
-                            float voxelSize, b200_vec2f *minmax, bool deadInitDone = false);
+                            float voxelSize, b200_vec2f *minmax, bool deadInitDone = false, bool recsReady = false);
 void launch_raycast(b200_engine *e, const SceneRef &s, const Mat4 &invM, const float proj[4], int w, int h, float voxelSize,
                     float mu, const b200_vec2f *minmax, b200_vec4f *out);
 void launch_shade(b200_engine *e, const SceneRef &s, const Mat4 &M, const Mat4 &invM, int w, int h, float voxelSize, int maxW,
@@ -125,6 +129,21 @@ void launch_process_silhouettes(b200_engine *e, b200_vec4u *rgb, float *depth, i
 void launch_composite_depth(b200_engine *e, float *target, const float *source, int n);
 void launch_composite_layers(b200_engine *e, b200_vec4u *tcol, float *tdep, int n, const b200_instance_layer *layers, int nLayers,
                              bool dim, float dimFactor, float tintStrength);
+
+// Launch trace (timing mode 3): TRACED(e, stream, "kernel", launch-statement) brackets the launch with two events.
+static inline void trace_begin(b200_engine *e, cudaStream_t st, const char *name) {
+  if (!e->traceOn || e->traceCount >= e->traceCap) return;
+  e->traceName[e->traceCount] = name;
+  cudaEventRecord(e->traceEv[2 * e->traceCount], st);
+}
+static inline void trace_end(b200_engine *e, cudaStream_t st) {
+  if (!e->traceOn || e->traceCount >= e->traceCap) return;
+  cudaEventRecord(e->traceEv[2 * e->traceCount + 1], st);
+  e->traceCount++;
+}
+#define TRACED(e, st, name, ...) do { trace_begin(e, st, name); __VA_ARGS__; trace_end(e, st); } while (0)
+
+#define DECAY_CAND_CAP 1024
 
 static inline int persistent_grid(const b200_engine *e, int ctasPerSm, long long workItems) {
   long long g = (long long)e->smCount * ctasPerSm;

@@ -100,7 +100,9 @@ void launch_process_silhouettes(b200_engine *e, b200_vec4u *rgb, float *depth, i
     SilOps so;
     so.n = n - base < SIL_MAX_OPS ? n - base : SIL_MAX_OPS;
     for (int k = 0; k < so.n; ++k) so.op[k] = ops[base + k];
+    trace_begin(e, e->stream, "k_process_silhouettes");
     k_process_silhouettes<<<grid, 256, 0, e->stream>>>((uchar4 *)rgb, depth, w, h, so);
+    trace_end(e, e->stream);
     e->launches++;
   }
 }
@@ -117,7 +119,9 @@ void launch_composite_layers(b200_engine *e, b200_vec4u *tcol, float *tdep, int 
     Layers L;
     L.n = nLayers - base < CMP_MAX_LAYERS ? nLayers - base : CMP_MAX_LAYERS;
     for (int k = 0; k < L.n; ++k) L.l[k] = layers[base + k];
+    trace_begin(e, e->stream, "k_composite_layers");
     k_composite_layers<<<(n + 255) / 256, 256, 0, e->stream>>>((uchar4 *)tcol, tdep, n, L, (dim && base == 0) ? 1 : 0, dimFactor, tintStrength);
+    trace_end(e, e->stream);
     e->launches++;
     base += CMP_MAX_LAYERS;
   } while (base < nLayers);

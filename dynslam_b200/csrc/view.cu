@@ -173,7 +173,9 @@ void launch_view_convert(b200_engine *e, const int16_t *raw, float *out, int w, 
 
 void launch_view_filter_pass(b200_engine *e, const float *in, float *out, int w, int h) {
   dim3 grid((w + FP_TW - 1) / FP_TW, (h + FP_TH - 1) / FP_TH);
+  trace_begin(e, e->stream, "k_filter_pass<false>");
   k_filter_pass<false><<<grid, FP_TW * FP_TH, 0, e->stream>>>(nullptr, in, out, nullptr, w, h, 1, 0.0f, 0.0f, 0.0f, 0);
+  trace_end(e, e->stream);
   e->launches++;
 }
 
@@ -184,11 +186,21 @@ void launch_update_view(b200_engine *e, const int16_t *raw, float *out, float *s
   if (!filter) { launch_view_convert(e, raw, out, w, h, type, p0, p1, fx); return; }
   dim3 grid((w + FP_TW - 1) / FP_TW, (h + FP_TH - 1) / FP_TH);
   const int T = FP_TW * FP_TH;
+  trace_begin(e, e->stream, "k_filter_pass<true>");
   k_filter_pass<true><<<grid, T, 0, e->stream>>>((const short *)raw, nullptr, out, scratch, w, h, type, p0, p1, fx, 1);
+  trace_end(e, e->stream);
+  trace_begin(e, e->stream, "k_filter_pass<false>");
   k_filter_pass<false><<<grid, T, 0, e->stream>>>(nullptr, out, scratch, nullptr, w, h, 1, 0.0f, 0.0f, 0.0f, 0);
+  trace_end(e, e->stream);
+  trace_begin(e, e->stream, "k_filter_pass<false>");
   k_filter_pass<false><<<grid, T, 0, e->stream>>>(nullptr, scratch, out, nullptr, w, h, 1, 0.0f, 0.0f, 0.0f, 1);
+  trace_end(e, e->stream);
+  trace_begin(e, e->stream, "k_filter_pass<false>");
   k_filter_pass<false><<<grid, T, 0, e->stream>>>(nullptr, out, scratch, nullptr, w, h, 1, 0.0f, 0.0f, 0.0f, 0);
+  trace_end(e, e->stream);
+  trace_begin(e, e->stream, "k_filter_pass<false>");
   k_filter_pass<false><<<grid, T, 0, e->stream>>>(nullptr, scratch, out, nullptr, w, h, 1, 0.0f, 0.0f, 0.0f, 1);
+  trace_end(e, e->stream);
   e->launches += 5;
 }
 

@@ -18,37 +18,8 @@
 // ------------------------------------------------------------------------------------------------
 // expected depths
 // ------------------------------------------------------------------------------------------------
-// ProjectSingleBlock — DA/ITMVisualisationEngine.h:29-71
-DEV bool project_single_block(int bx, int by, int bz, const Mat4 &pose, const float *intr, int w, int h, float voxelSize,
-                              int &ulx, int &uly, int &lrx, int &lry, float &zmin, float &zmax) {
-  ulx = w / B200_MINMAX_SUBSAMPLE; uly = h / B200_MINMAX_SUBSAMPLE;
-  lrx = -1; lry = -1;
-  zmin = B200_FAR_AWAY; zmax = B200_VERY_CLOSE;
-#pragma unroll
-  for (int corner = 0; corner < 8; ++corner) {
-    const short tx = (short)(bx + ((corner & 1) ? 1 : 0)), ty = (short)(by + ((corner & 2) ? 1 : 0)), tz = (short)(bz + ((corner & 4) ? 1 : 0));
-    Vec4 q = m4v4(pose, (float)tx * (float)BS * voxelSize, (float)ty * (float)BS * voxelSize, (float)tz * (float)BS * voxelSize, 1.0f);
-    if (q.z < 1e-6) continue;
-    const float px = (intr[0] * q.x / q.z + intr[2]) / B200_MINMAX_SUBSAMPLE;
-    const float py = (intr[1] * q.y / q.z + intr[3]) / B200_MINMAX_SUBSAMPLE;
-    if (ulx > floorf(px)) ulx = (int)floorf(px);
-    if (lrx < ceilf(px)) lrx = (int)ceilf(px);
-    if (uly > floorf(py)) uly = (int)floorf(py);
-    if (lry < ceilf(py)) lry = (int)ceilf(py);
-    if (zmin > q.z) zmin = q.z;
-    if (zmax < q.z) zmax = q.z;
-  }
-  if (ulx < 0) ulx = 0;
-  if (uly < 0) uly = 0;
-  if (lrx >= w) lrx = w - 1;
-  if (lry >= h) lry = h - 1;
-  if (ulx > lrx) return false;
-  if (uly > lry) return false;
-  if (zmin < B200_VERY_CLOSE) zmin = B200_VERY_CLOSE;
-  if (zmax < B200_VERY_CLOSE) return false;
-  return true;
-}
-
+// ProjectSingleBlock (DA/ITMVisualisationEngine.h:29-71) and the 16-byte block record live in common.cuh: the visible-list
+// pass of the fused frame (alloc.cu) produces the records too.
 // Stage 1: project every visible block (one thread each, small CTAs so that a few thousand blocks spread over
 // many SMs), apply the MAX_RENDERING_BLOCKS rule from the list-order prefix of the tile counts (Vis_CUDA.cu:609)
 // and emit a 16-byte record {bbox, z-range}. Cells of a bounding box that lie outside the live 1/8-resolution
@@ -58,13 +29,12 @@ DEV bool project_single_block(int bx, int by, int bz, const Mat4 &pose, const fl
 // records, rasterises the boxes that overlap its tile into shared memory with shared-memory atomics and
 // writes the tile out with plain stores — no global atomics on the hot cells that hundreds of far blocks
 // cover, and no separate initialisation of the live corner.
-struct __align__(16) BlockRec { short ulx, uly, lrx, lry; float zmin, zmax; };
 
-#define PRJ_THREADS 256
+#define PRJ_THREADS 128   // small CTAs: they must fit beside the integrate kernel's CTAs (register file)
 __global__ void __launch_bounds__(PRJ_THREADS)
 k_project_blocks(const b200_hash_entry *__restrict__ table, int numBuckets, const b200_vec3i *__restrict__ visiblePos,
                  const int *__restrict__ visiblePtr, int capacity, DevCounters *ctr, Mat4 M, float p0, float p1, float p2, float p3, int w,
-                 int h, float voxelSize, float2 *minmax, BlockRec *recs, unsigned long long *scanDesc, unsigned gen) {
+                 int h, float voxelSize, float2 *minmax, BlockRec *recs, unsigned long long *scanDesc, unsigned gen, int recsReady) {
   __shared__ unsigned sm[33];
   __shared__ unsigned tileBase;
   const float intr[4] = {p0, p1, p2, p3};
@@ -73,17 +43,28 @@ k_project_blocks(const b200_hash_entry *__restrict__ table, int numBuckets, cons
   const int noTiles = (n + PRJ_THREADS - 1) / PRJ_THREADS;
   const int liveX = (w - 1) / B200_MINMAX_SUBSAMPLE, liveY = (h - 1) / B200_MINMAX_SUBSAMPLE;   // last live cell
   const int lane = threadIdx.x & 31;
+  // Fused frame: k_visible_list already wrote the records (every block drawn) and the tile total. Unless that total breaks
+  // the MAX_RENDERING_BLOCKS cap, only the dead-cell part of the boxes is left to do here — no scan, no look-back.
+  const bool fast = recsReady && ctr->noRenderingBlocks <= (unsigned)B200_MAX_RENDERING_BLOCKS;
   for (int tile = blockIdx.x; tile < noTiles; tile += gridDim.x) {
     const int item = tile * PRJ_THREADS + threadIdx.x;
     int ulx = 0, uly = 0, lrx = -1, lry = -1; float zmin = 0, zmax = 0;
     unsigned required = 0;
+    bool draw;
+    if (fast) {
+      if (item < n) {
+        const uint4 q = __ldg(reinterpret_cast<const uint4 *>(recs) + item);
+        ulx = (short)(q.x & 0xffff); uly = (short)(q.x >> 16); lrx = (short)(q.y & 0xffff); lry = (short)(q.y >> 16);
+        zmin = __uint_as_float(q.z); zmax = __uint_as_float(q.w);
+      }
+      draw = ulx <= lrx;
+    } else {
     if (item < n) {
       const b200_vec3i p = visiblePos[item];
       const bool allocated = visiblePtr ? (visiblePtr[item] >= 0) : (find_block<false>(table, numBuckets, p.x, p.y, p.z) >= 0);
       if (allocated) {
         if (project_single_block(p.x, p.y, p.z, M, intr, w, h, voxelSize, ulx, uly, lrx, lry, zmin, zmax)) {
-          const int rx = (int)ceilf((float)(lrx - ulx + 1) / 16), ry = (int)ceilf((float)(lry - uly + 1) / 16);
-          required = (unsigned)(rx * ry);
+          required = rendering_tiles(ulx, uly, lrx, lry);
         }
       }
     }
@@ -95,12 +76,13 @@ k_project_blocks(const b200_hash_entry *__restrict__ table, int numBuckets, cons
     }
     __syncthreads();
     const unsigned out_offset = tileBase + local;
-    const bool draw = required > 0 && (out_offset + required <= (unsigned)B200_MAX_RENDERING_BLOCKS);   // :609
+    draw = required > 0 && (out_offset + required <= (unsigned)B200_MAX_RENDERING_BLOCKS);   // :609
     if (item < n) {
       BlockRec r;
       if (draw) { r.ulx = (short)ulx; r.uly = (short)uly; r.lrx = (short)lrx; r.lry = (short)lry; r.zmin = zmin; r.zmax = zmax; }
       else { r.ulx = 1; r.uly = 1; r.lrx = 0; r.lry = 0; r.zmin = 0; r.zmax = 0; }
       recs[item] = r;
+    }
     }
     // the part of a box outside the live corner (dead cells): warp-cooperative, one box at a time
     unsigned todo = __ballot_sync(0xffffffffu, item < n && draw && (lrx > liveX || lry > liveY));
@@ -118,7 +100,7 @@ k_project_blocks(const b200_hash_entry *__restrict__ table, int numBuckets, cons
     }
     __syncthreads();
   }
-  if (noTiles == 0 && blockIdx.x == 0 && threadIdx.x == 0) ctr->noRenderingBlocks = 0;
+  if (!fast && noTiles == 0 && blockIdx.x == 0 && threadIdx.x == 0) ctr->noRenderingBlocks = 0;
 }
 
 #define FILL_T 8          // tile edge in 1/8-resolution cells
@@ -172,15 +154,19 @@ __global__ void k_minmax_init_dead(float2 *minmax, int w, int h) {
 }
 
 void launch_expected_depths(b200_engine *e, const SceneRef &s, const Mat4 &M, const float proj[4], int w, int h, float voxelSize,
-                            b200_vec2f *minmax, bool deadInitDone) {
+                            b200_vec2f *minmax, bool deadInitDone, bool recsReady) {
   if (!deadInitDone) { k_minmax_init_dead<<<e->smCount * 4, 256, 0, e->stream>>>((float2 *)minmax, w, h); e->launches++; }
   const int noTiles = (s.numBlocks + PRJ_THREADS - 1) / PRJ_THREADS;
+  trace_begin(e, e->stream, "k_project_blocks");
   k_project_blocks<<<persistent_grid(e, 2, noTiles), PRJ_THREADS, 0, e->stream>>>(s.hash, s.numBuckets, s.visiblePos, fresh_ptr_list(e, s),
                                                                                  s.numBlocks, e->d_ctr, M, proj[0], proj[1], proj[2], proj[3],
                                                                                  w, h, voxelSize, (float2 *)minmax, (BlockRec *)e->d_blockRecs,
-                                                                                 e->d_scanDesc, ++e->scanGen);
+                                                                                 e->d_scanDesc, ++e->scanGen, recsReady ? 1 : 0);
+  trace_end(e, e->stream);
   dim3 grid(((w - 1) / B200_MINMAX_SUBSAMPLE) / FILL_T + 1, ((h - 1) / B200_MINMAX_SUBSAMPLE) / FILL_T + 1);
+  trace_begin(e, e->stream, "k_fill_minmax");
   k_fill_minmax<<<grid, FILL_THREADS, 0, e->stream>>>((const BlockRec *)e->d_blockRecs, e->d_ctr, s.numBlocks, w, h, (float2 *)minmax);
+  trace_end(e, e->stream);
   e->launches += 2;
 }
 
@@ -371,9 +357,11 @@ void launch_raycast(b200_engine *e, const SceneRef &s, const Mat4 &invM, const f
   const int tw = 1 << twLog2, th = 32 >> twLog2;
   const int tiles = ((w + tw - 1) / tw) * ((h + th - 1) / th);
   const int warpsPerCta = RC_THREADS / 32;
+  trace_begin(e, e->stream, "k_raycast");
   k_raycast<<<(tiles + warpsPerCta - 1) / warpsPerCta, RC_THREADS, 0, e->stream>>>((float4 *)out, s.voxels, s.hash, s.numBuckets, w, h, invM,
                                                                                   proj[0], proj[1], proj[2], proj[3], voxelSize, mu,
                                                                                   (const float2 *)minmax, twLog2);
+  trace_end(e, e->stream);
   e->launches++;
 }
 
@@ -597,8 +585,10 @@ k_icp(const float4 *__restrict__ rays, int w, int h, float voxelSize, float lx, 
 void launch_icp(b200_engine *e, const Mat4 &invM, int w, int h, float voxelSize, const b200_vec4f *rays, b200_vec4u *outImg,
                 b200_vec4f *points, b200_vec4f *normals) {
   dim3 grid((w + 31) / 32, (h + 7) / 8);
+  trace_begin(e, e->stream, "k_icp");
   k_icp<<<grid, 256, 0, e->stream>>>((const float4 *)rays, w, h, voxelSize, -invM.m[8], -invM.m[9], -invM.m[10], (uchar4 *)outImg,
                                      (float4 *)points, (float4 *)normals);
+  trace_end(e, e->stream);
   e->launches++;
 }
 
@@ -687,8 +677,10 @@ void launch_forward_render(b200_engine *e, const SceneRef &s, const FrameGeom &g
                                                        g.proj_d[0], g.proj_d[1], g.proj_d[2], g.proj_d[3], g.voxelSize, g.mu,
                                                        (const float2 *)minmax);
   dim3 grid((g.w + 31) / 32, (g.h + 7) / 8);
+  trace_begin(e, st, "k_icp");
   k_icp<<<grid, 256, 0, st>>>((const float4 *)fwd, g.w, g.h, g.voxelSize, -g.invM_d.m[8], -g.invM_d.m[9], -g.invM_d.m[10], (uchar4 *)outImg,
                               nullptr, nullptr);
+  trace_end(e, st);
   e->launches += 4;
 }
 

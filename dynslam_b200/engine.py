@@ -252,6 +252,16 @@ class Engine:
                                                         _ptr(h_raw), _ptr(h_rgb), C.byref(calib), _ptr(points), _ptr(normals),
                                                         C.byref(o), _ptr(h_out), slot))
 
+    def trace(self):
+        """Launch trace collected since set_timing(3): list of (kernel, start_us, end_us)."""
+        buf = C.create_string_buffer(1 << 20)
+        n = self.lib.b200_get_trace(self.h, buf, len(buf))
+        out = []
+        for ln in buf.raw[:n].decode().splitlines():
+            name, a, b = ln.split()
+            out.append((name, float(a), float(b)))
+        return out
+
     def host_frame_wait(self, slot):
         self.check(self.lib.b200_host_frame_wait(self.h, slot))
 
@@ -334,9 +344,11 @@ class InstanceFrames:
     def __init__(self, engine):
         self.e = engine
 
-    def ProcessSilhouettes(self, rgb, depth, ops, sync=True):
-        """ops: list of (action, copy_mask, delete_mask, dest_rgb, dest_depth) in the order of the active tracks."""
-        torch.cuda.current_stream().synchronize()
+    def ProcessSilhouettes(self, rgb, depth, ops, sync=True, wait_inputs=True):
+        """ops: list of (action, copy_mask, delete_mask, dest_rgb, dest_depth) in the order of the active tracks.
+        wait_inputs=False: the caller already orders the tensors on the engine's stream."""
+        if wait_inputs:
+            torch.cuda.current_stream().synchronize()
         h, w = depth.shape
         arr = (abi.SilhouetteOp * max(len(ops), 1))()
         for k, (action, cm, dm, drgb, ddepth) in enumerate(ops):
@@ -359,9 +371,10 @@ class InstanceFrames:
                                                       _ptr(instance_depth), target_depth.numel(),
                                                       (C.c_int32 * 4)(*[int(t) for t in tint]), float(tint_strength)))
 
-    def CompositeInstances(self, out_color, out_depth, layers, dim_factor=0.10, tint_strength=1.0):
+    def CompositeInstances(self, out_color, out_depth, layers, dim_factor=0.10, tint_strength=1.0, wait_inputs=True):
         """layers: list of (color, depth, tint) in the order of the active tracks; dim_factor < 0 skips the dimming."""
-        torch.cuda.current_stream().synchronize()
+        if wait_inputs:
+            torch.cuda.current_stream().synchronize()
         arr = (abi.InstanceLayer * max(len(layers), 1))()
         for k, (col, dep, tint) in enumerate(layers):
             arr[k].d_color, arr[k].d_depth = _ptr(col), _ptr(dep)

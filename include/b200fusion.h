@@ -359,8 +359,11 @@ typedef struct {
 } b200_frame_stats;
 
 /* 0 = off; 1 = per-stage CUDA events of the last fused frame; 2 = 1 + an event pair around every
-   integrate launch (ring of 8192 frames), reset whenever the mode is set */
+   integrate launch (ring of 8192 frames), reset whenever the mode is set; 3 = an event pair around EVERY
+   kernel launch of the frame path (launch trace, read and cleared by b200_get_trace; perturbs the timing) */
 void b200_set_timing(b200_engine *e, int enabled);
+/* "kernel start_us end_us" lines (relative to the first traced launch); returns the number of bytes written */
+int b200_get_trace(b200_engine *e, char *out, int cap);
 b200_status b200_get_stats(b200_engine *e, b200_frame_stats *out);
 
 #ifdef __cplusplus

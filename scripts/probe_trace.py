@@ -1,0 +1,58 @@
+"""GPU probe: launch trace (b200_set_timing(3)) of fused frames — where the frame's time goes, gaps included."""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+from dynslam_b200 import engine as E, synth
+
+W, H = synth.KITTI_W, synth.KITTI_H
+street = synth.StreetScene(seed=6, length_m=200.0)
+N0, N1 = 60, 6
+DECAY = (1, 30)
+frames = [synth.kitti_frame(street, f) for f in range(N0 + N1)]
+dev = torch.device("cuda:0")
+scene = E.Scene(E.SceneParams(), 0x60000, 0x100000, 0x80000, device="cuda:0")
+eng = E.Engine(scene, (W, H))
+reco = E.SceneReconstructionEngine(eng)
+rs = E.VisualisationEngine(eng, scene).CreateRenderState((W, H))
+reco.ResetScene(scene)
+points = torch.zeros((H, W, 4), dtype=torch.float32, device=dev)
+normals = torch.zeros((H, W, 4), dtype=torch.float32, device=dev)
+views = [E.View(torch.from_numpy(f[0]).to(dev), torch.from_numpy(f[1]).to(dev), f[2], f[3]) for f in frames]
+flush = torch.zeros(256 * 1024 * 1024 // 4, dtype=torch.int32, device=dev)
+torch.cuda.synchronize()
+for v in views[:N0]:
+    eng.process_frame_async(rs, v, points, normals, decay=DECAY, raycast=True)
+eng.sync(rs)
+print("visible", rs.noVisibleBlocks)
+for i, v in enumerate(views[N0:]):
+    flush.add_(1); torch.cuda.synchronize()
+    eng.set_timing(3)
+    eng.process_frame_async(rs, v, points, normals, decay=DECAY, raycast=True)
+    eng.sync(rs)
+    tr = eng.trace()
+    eng.set_timing(0)
+    if i >= 2:
+        print("--- frame", i)
+        prev_end = 0.0
+        for name, a, b in tr:
+            print("%-22s start %7.1f  end %7.1f  dur %6.1f" % (name, a, b, b - a))
+
+# UpdateView (five passes) under the trace
+calib = E.make_view_calib()
+vb = E.ViewBuilder(eng, calib)
+raw = torch.from_numpy(np.round(frames[N0][0] * 1000.0).astype(np.int16)).to(dev)
+dep = torch.zeros((H, W), dtype=torch.float32, device=dev)
+vb.UpdateView(dep, raw)
+for i in range(3):
+    flush.add_(1); torch.cuda.synchronize()
+    eng.set_timing(3)
+    vb.UpdateView(dep, raw, sync=False)
+    eng.sync(rs)
+    tr = eng.trace()
+    eng.set_timing(0)
+print("--- UpdateView")
+for name, a, b in tr:
+    print("%-22s start %7.1f  end %7.1f  dur %6.1f" % (name, a, b, b - a))
+
+import bench
+print(bench.run_frames_ops(0))

@@ -36,6 +36,14 @@ def test_decay_partial_with_chains():
     assert pair.reco.GetDecayedBlockCount() > 200
 
 
+def test_decay_partial_mass_deletion():
+    """maxWeight >= maxW with minAge 1: every block seen one frame ago is emptied and deleted, thousands per call — more
+    candidates than k_decay_commit's ranked fast path holds (1024), so the scan-the-whole-list path runs."""
+    cfg = P.Cfg(frames=5, scale=0.5, numBlocks=32768, numBuckets=0x2000, excessSize=0x4000, decay=(50, 1), raycast=False)
+    pair, _ = P.run_sequence(cfg)
+    assert pair.reco.GetDecayedBlockCount() > 3 * 1024
+
+
 def test_decay_default_parameters():
     cfg = P.Cfg(frames=8, decay=(1, 3), raycast=False)
     pair, _ = P.run_sequence(cfg)
