@@ -451,11 +451,8 @@ def run_own(args, rank, local_rank, world):
         eng.sync(rs)
         st = eng.stats()
         time.sleep(0.05)
-        sampler.stop()
-        clk_all = len(sampler.rows)
-        sampler.rows = sampler.rows[max(clk_first - 1, 0):] or sampler.rows   # samples taken during the timed region
-        clocks = sampler.summary()
-        clocks["samples_since_start"] = clk_all
+        clk_timed_end = len(sampler.rows)      # the sampler keeps running through the e2e phases: terminating nvidia-smi stalls
+                                               # the driver for tens of milliseconds, which used to land in the e2e timing
         launches = st.launches - launches0
         blocks = st.totalIntegratedBlocks - blocks0
         int_ms, int_n = st.ring_ms_integrate, st.ring_count
@@ -525,6 +522,12 @@ def run_own(args, rank, local_rank, world):
             t_raw = time.perf_counter() - t_raw
             e2e_raw = {"value": (n_raw - 3) / t_raw, "unit": "frames/s", "h2d_bytes_per_step": W * H_ * 6, "d2h_bytes_per_step": W * H_ * 4,
                        "steps": n_raw - 3, "what": "raw int16 depth + RGB in -> UpdateView with bilateral filter -> fused frame -> image out"}
+
+    sampler.stop()
+    clk_all = len(sampler.rows)
+    sampler.rows = sampler.rows[max(clk_first - 1, 0):clk_timed_end] or sampler.rows   # samples taken during the timed region
+    clocks = sampler.summary()
+    clocks["samples_since_start"] = clk_all
 
     # ---- reduce over ranks (max time) ----
     ms = max(gpu_ms, 0.0)

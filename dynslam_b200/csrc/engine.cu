@@ -165,6 +165,7 @@ void b200_engine_destroy(b200_engine *e) {
       cudaEventDestroy(e->evH2D[i]); cudaEventDestroy(e->evCompute[i]); cudaEventDestroy(e->evD2H[i]); }
     cudaStreamDestroy(e->copyStream);
     if (e->d2hStream) { cudaStreamSynchronize(e->d2hStream); cudaStreamDestroy(e->d2hStream); }
+    if (e->evMid) cudaEventDestroy(e->evMid);
   }
   if (e->frameGraph) cudaGraphExecDestroy(e->frameGraph);
   if (e->sideStream) { cudaStreamSynchronize(e->sideStream); cudaEventDestroy(e->evFork); cudaEventDestroy(e->evJoin); cudaStreamDestroy(e->sideStream); }
@@ -498,15 +499,20 @@ static b200_status frame_enqueue(b200_engine *e, b200_scene *s, b200_render_stat
     CK(cudaStreamWaitEvent(e->sideStream, e->evFork, 0));
     e->stream = e->sideStream;
     launch_expected_depths(e, r, g.M_d, g.proj_d, rs->img_w, rs->img_h, s->voxelSize, rs->d_minmax, true, true);
+    CK(cudaEventRecord(e->evJoin, e->sideStream));      // the raycast waits for the fill only ...
+    launch_expected_depths_dead(e, r, g.M_d, g.proj_d, rs->img_w, rs->img_h, s->voxelSize, rs->d_minmax);   // ... not for the dead cells
     e->stream = mainStream;
-    CK(cudaEventRecord(e->evJoin, e->sideStream));
   }
   launch_integrate(e, r, g, v->d_depth, v->d_rgb);
+  if (e->evMid && !e->useGraph) { CK(cudaEventRecord(e->evMid, e->stream)); e->midValid = true; }
   if (ring) { CK(cudaEventRecord(e->evRing[2 * e->evRingCount + 1], e->stream)); e->evRingCount++; }
   if (e->timing) CK(cudaEventRecord(e->ev[2], e->stream));
   if (doRay) {
     if (overlap) CK(cudaStreamWaitEvent(mainStream, e->evJoin, 0));
-    else launch_expected_depths(e, r, g.M_d, g.proj_d, rs->img_w, rs->img_h, s->voxelSize, rs->d_minmax, true, true);
+    else {
+      launch_expected_depths(e, r, g.M_d, g.proj_d, rs->img_w, rs->img_h, s->voxelSize, rs->d_minmax, true, true);
+      launch_expected_depths_dead(e, r, g.M_d, g.proj_d, rs->img_w, rs->img_h, s->voxelSize, rs->d_minmax);
+    }
     if (e->timing) CK(cudaEventRecord(e->ev[3], e->stream));
     launch_raycast(e, r, g.invM_d, g.proj_d, rs->img_w, rs->img_h, s->voxelSize, s->mu, rs->d_minmax, rs->d_raycastResult);
     if (overlap) {   // the ICP-map pass (image space) runs beside the decay sweep (voxel space)
@@ -553,6 +559,7 @@ static b200_status ensure_pipeline(b200_engine *e, size_t pixels) {
   if (!e->copyStream) {
     CK(cudaStreamCreateWithFlags(&e->copyStream, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&e->d2hStream, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&e->evMid, cudaEventDisableTiming));
     for (int i = 0; i < 2; ++i) {
       CK(cudaEventCreateWithFlags(&e->evH2D[i], cudaEventDisableTiming));
       CK(cudaEventCreateWithFlags(&e->evCompute[i], cudaEventDisableTiming));
@@ -697,9 +704,14 @@ static b200_status host_frame_submit(b200_engine *e, b200_scene *s, b200_render_
   b200_status st = ensure_pipeline(e, px); if (st) return st;
   if (e->slotBusy[slot]) { snprintf(e->err, sizeof(e->err), "slot %d resubmitted before b200_host_frame_wait", slot); return B200_ERR_INVALID; }
   // H2D on the copy stream (the slot's previous frame was waited for, so its staging buffers are free)
+  // The upload of frame f+1 is held back until frame f's allocation chain and integration are through: its DMA traffic slows
+  // the latency-bound scan kernels of the allocation stage down by 2x when they overlap; under the raycast it is free.
+  if (e->midValid) CK(cudaStreamWaitEvent(e->copyStream, e->evMid, 0));
+  trace_begin(e, e->copyStream, "h2d_frame");
   if (h_raw) CK(cudaMemcpyAsync(e->d_stageRaw[slot], h_raw, nd * sizeof(int16_t), cudaMemcpyHostToDevice, e->copyStream));
   else CK(cudaMemcpyAsync(e->d_stageDepth[slot], h_depth, nd * sizeof(float), cudaMemcpyHostToDevice, e->copyStream));
   CK(cudaMemcpyAsync(e->d_stageRgb[slot], h_rgb, nc * sizeof(b200_vec4u), cudaMemcpyHostToDevice, e->copyStream));
+  trace_end(e, e->copyStream);
   CK(cudaEventRecord(e->evH2D[slot], e->copyStream));
   // the frame on the compute stream
   CK(cudaStreamWaitEvent(e->stream, e->evH2D[slot], 0));
@@ -710,10 +722,14 @@ static b200_status host_frame_submit(b200_engine *e, b200_scene *s, b200_render_
   v->d_depth = e->d_stageDepth[slot]; v->d_rgb = e->d_stageRgb[slot];
   st = b200_process_frame_async(e, s, rs, v, d_points, d_normals, opts); if (st) return st;
   if (h_outImage) {
+    trace_begin(e, e->stream, "d2d_image");
     CK(cudaMemcpyAsync(e->d_stageOut[slot], rs->d_raycastImage, no * sizeof(b200_vec4u), cudaMemcpyDeviceToDevice, e->stream));
+    trace_end(e, e->stream);
     CK(cudaEventRecord(e->evCompute[slot], e->stream));
     CK(cudaStreamWaitEvent(e->d2hStream, e->evCompute[slot], 0));
+    trace_begin(e, e->d2hStream, "d2h_image");
     CK(cudaMemcpyAsync(h_outImage, e->d_stageOut[slot], no * sizeof(b200_vec4u), cudaMemcpyDeviceToHost, e->d2hStream));
+    trace_end(e, e->d2hStream);
     CK(cudaEventRecord(e->evD2H[slot], e->d2hStream));
   } else {
     CK(cudaEventRecord(e->evD2H[slot], e->stream));

@@ -76,7 +76,8 @@ struct b200_engine {
   float *d_stageDepth[2]; b200_vec4u *d_stageRgb[2]; b200_vec4u *d_stageOut[2]; int16_t *d_stageRaw[2];
   cudaEvent_t evH2D[2], evCompute[2], evD2H[2];
   bool slotBusy[2]; size_t stagePixels;
-  int useGraph; bool graphWarm; cudaGraphExec_t frameGraph;         // B200_GRAPH=1: the fused frame is captured and replayed as a CUDA graph
+  int useGraph; bool graphWarm; cudaGraphExec_t frameGraph;
+  cudaEvent_t evMid; bool midValid;                 // "allocation + integration of the last frame are done" (pipelined uploads wait for it)         // B200_GRAPH=1: the fused frame is captured and replayed as a CUDA graph
   float *d_viewScratch; size_t viewScratchPixels;   // plays view->depth inside UpdateView (view.cu)
   cudaEvent_t *evRing;                // timing mode 2: event pairs around every integrate launch
   int evRingCap, evRingCount, timingMode;
@@ -104,6 +105,8 @@ void launch_decay_full(b200_engine *e, const SceneRef &s, int minAge, int maxWei
 void launch_find_visible(b200_engine *e, const SceneRef &s, const Mat4 &M, const float proj[4], int w, int h, float voxelSize);
 void launch_expected_depths(b200_engine *e, const SceneRef &s, const Mat4 &M, const float proj[4], int w, int h,
                             float voxelSize, b200_vec2f *minmax, bool deadInitDone = false, bool recsReady = false);
+void launch_expected_depths_dead(b200_engine *e, const SceneRef &s, const Mat4 &M, const float proj[4], int w, int h, float voxelSize,
+                                 b200_vec2f *minmax);
 void launch_raycast(b200_engine *e, const SceneRef &s, const Mat4 &invM, const float proj[4], int w, int h, float voxelSize,
                     float mu, const b200_vec2f *minmax, b200_vec4f *out);
 void launch_shade(b200_engine *e, const SceneRef &s, const Mat4 &M, const Mat4 &invM, int w, int h, float voxelSize, int maxW,

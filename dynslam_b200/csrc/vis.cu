@@ -44,8 +44,16 @@ k_project_blocks(const b200_hash_entry *__restrict__ table, int numBuckets, cons
   const int liveX = (w - 1) / B200_MINMAX_SUBSAMPLE, liveY = (h - 1) / B200_MINMAX_SUBSAMPLE;   // last live cell
   const int lane = threadIdx.x & 31;
   // Fused frame: k_visible_list already wrote the records (every block drawn) and the tile total. Unless that total breaks
-  // the MAX_RENDERING_BLOCKS cap, only the dead-cell part of the boxes is left to do here — no scan, no look-back.
-  const bool fast = recsReady && ctr->noRenderingBlocks <= (unsigned)B200_MAX_RENDERING_BLOCKS;
+  // the MAX_RENDERING_BLOCKS cap, only the dead-cell part of the boxes is left to do — no scan, no look-back. The work is
+  // split over two launches so that k_fill_minmax (which the raycast waits for) does not queue behind the dead cells
+  // (which nothing in the frame reads; a block next to the camera can cover 10^5 of them):
+  //   recsReady 1 ("fix"):  before the fill — acts only if the cap is broken (full projection + ordered cap rule), no dead cells
+  //   recsReady 2 ("dead"): after the fill  — dead-cell rasterisation from the (possibly fixed) records
+  //   recsReady 0:          stand-alone CreateExpectedDepths — everything in one launch
+  const bool overflow = recsReady && ctr->noRenderingBlocks > (unsigned)B200_MAX_RENDERING_BLOCKS;
+  if (recsReady == 1 && !overflow) return;
+  const bool fast = recsReady == 2 || (recsReady == 1 && !overflow);
+  const bool doDead = recsReady != 1;
   for (int tile = blockIdx.x; tile < noTiles; tile += gridDim.x) {
     const int item = tile * PRJ_THREADS + threadIdx.x;
     int ulx = 0, uly = 0, lrx = -1, lry = -1; float zmin = 0, zmax = 0;
@@ -85,7 +93,7 @@ k_project_blocks(const b200_hash_entry *__restrict__ table, int numBuckets, cons
     }
     }
     // the part of a box outside the live corner (dead cells): warp-cooperative, one box at a time
-    unsigned todo = __ballot_sync(0xffffffffu, item < n && draw && (lrx > liveX || lry > liveY));
+    unsigned todo = __ballot_sync(0xffffffffu, doDead && item < n && draw && (lrx > liveX || lry > liveY));
     while (todo) {
       const int src = __ffs(todo) - 1;
       todo &= todo - 1;
@@ -157,17 +165,32 @@ void launch_expected_depths(b200_engine *e, const SceneRef &s, const Mat4 &M, co
                             b200_vec2f *minmax, bool deadInitDone, bool recsReady) {
   if (!deadInitDone) { k_minmax_init_dead<<<e->smCount * 4, 256, 0, e->stream>>>((float2 *)minmax, w, h); e->launches++; }
   const int noTiles = (s.numBlocks + PRJ_THREADS - 1) / PRJ_THREADS;
-  trace_begin(e, e->stream, "k_project_blocks");
-  k_project_blocks<<<persistent_grid(e, 2, noTiles), PRJ_THREADS, 0, e->stream>>>(s.hash, s.numBuckets, s.visiblePos, fresh_ptr_list(e, s),
-                                                                                 s.numBlocks, e->d_ctr, M, proj[0], proj[1], proj[2], proj[3],
-                                                                                 w, h, voxelSize, (float2 *)minmax, (BlockRec *)e->d_blockRecs,
-                                                                                 e->d_scanDesc, ++e->scanGen, recsReady ? 1 : 0);
+  const int prjGrid = persistent_grid(e, 2, noTiles);
+  // recsReady: the records come from k_visible_list of this frame (see k_project_blocks): fix (no-op unless the cap is broken),
+  // fill, dead cells; otherwise one full projection pass, then the fill
+  trace_begin(e, e->stream, recsReady ? "k_project_blocks/fix" : "k_project_blocks");
+  k_project_blocks<<<prjGrid, PRJ_THREADS, 0, e->stream>>>(s.hash, s.numBuckets, s.visiblePos, fresh_ptr_list(e, s), s.numBlocks, e->d_ctr, M,
+                                                         proj[0], proj[1], proj[2], proj[3], w, h, voxelSize, (float2 *)minmax,
+                                                         (BlockRec *)e->d_blockRecs, e->d_scanDesc, ++e->scanGen, recsReady ? 1 : 0);
   trace_end(e, e->stream);
   dim3 grid(((w - 1) / B200_MINMAX_SUBSAMPLE) / FILL_T + 1, ((h - 1) / B200_MINMAX_SUBSAMPLE) / FILL_T + 1);
   trace_begin(e, e->stream, "k_fill_minmax");
   k_fill_minmax<<<grid, FILL_THREADS, 0, e->stream>>>((const BlockRec *)e->d_blockRecs, e->d_ctr, s.numBlocks, w, h, (float2 *)minmax);
   trace_end(e, e->stream);
   e->launches += 2;
+}
+
+// second half of the fused frame's expected-depth work: the dead cells (after launch_expected_depths(..., recsReady = true))
+void launch_expected_depths_dead(b200_engine *e, const SceneRef &s, const Mat4 &M, const float proj[4], int w, int h, float voxelSize,
+                                 b200_vec2f *minmax) {
+  const int noTiles = (s.numBlocks + PRJ_THREADS - 1) / PRJ_THREADS;
+  trace_begin(e, e->stream, "k_project_blocks/dead");
+  k_project_blocks<<<persistent_grid(e, 2, noTiles), PRJ_THREADS, 0, e->stream>>>(s.hash, s.numBuckets, s.visiblePos, fresh_ptr_list(e, s),
+                                                                                 s.numBlocks, e->d_ctr, M, proj[0], proj[1], proj[2], proj[3],
+                                                                                 w, h, voxelSize, (float2 *)minmax, (BlockRec *)e->d_blockRecs,
+                                                                                 e->d_scanDesc, ++e->scanGen, 2);
+  trace_end(e, e->stream);
+  e->launches++;
 }
 
 // ------------------------------------------------------------------------------------------------
