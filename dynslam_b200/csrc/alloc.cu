@@ -293,7 +293,7 @@ __global__ void __launch_bounds__(256, 4)
 k_visible_list(const b200_hash_entry *__restrict__ table, int numBuckets, int noTotal, uint8_t *visType, b200_vec3i *visiblePos,
                int *visiblePtr, int capacity, DevCounters *ctr, unsigned long long *scanDesc, unsigned gen, Mat4 M, float p0, float p1,
                float p2, float p3, float voxelSize, int w, int h, b200_vec3i *ring, long long ringCap, long long *snapStart,
-               int *snapCount, int slot, int oldestSlot, BlockRec *recs, int rw, int rh) {
+               int *snapCount, int slot, int oldestSlot, BlockRec *recs, int rw, int rh, unsigned maxRB) {
   __shared__ unsigned sm[33];
   __shared__ unsigned tileBase;
   __shared__ int hits[VIS_TILE];
@@ -382,6 +382,33 @@ k_visible_list(const b200_hash_entry *__restrict__ table, int numBuckets, int no
   if (recs) {
     for (int o = 16; o > 0; o >>= 1) myTiles += __shfl_xor_sync(0xffffffffu, myTiles, o);
     if ((threadIdx.x & 31) == 0 && myTiles) atomicAdd(&ctr->noRenderingBlocks, myTiles);
+    // The CTA that finishes last knows the tile total. In the (pathological) case that it breaks MAX_RENDERING_BLOCKS it
+    // re-applies the reference's ordered rule (Vis_CUDA.cu:609: a block is dropped when the running tile count would pass the
+    // cap) on its own, serially over the list — so that no extra launch sits between this kernel and the expected-depth fill.
+    __shared__ bool lastCta;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) lastCta = (atomicAdd(&ctr->visCtasDone, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (!lastCta) return;
+    if (threadIdx.x == 0) ctr->visCtasDone = 0;
+    __threadfence();
+    if (ctr->noRenderingBlocks <= maxRB) return;
+    int n = ctr->noVisibleBlocks; if (n > capacity) n = capacity;
+    unsigned running = 0;
+    for (int base = 0; base < n; base += blockDim.x) {
+      const int item = base + threadIdx.x;
+      unsigned required = 0;
+      BlockRec r; r.ulx = 1; r.uly = 1; r.lrx = 0; r.lry = 0; r.zmin = 0; r.zmax = 0;
+      if (item < n) { r = recs[item]; if (r.ulx <= r.lrx) required = rendering_tiles(r.ulx, r.uly, r.lrx, r.lry); }
+      unsigned total;
+      const unsigned local = running + block_exclusive_scan(required, sm, &total);
+      if (item < n && required > 0 && local + required > maxRB) {
+        r.ulx = 1; r.uly = 1; r.lrx = 0; r.lry = 0; r.zmin = 0; r.zmax = 0;
+        recs[item] = r;
+      }
+      running += total;
+    }
   }
 }
 
@@ -466,7 +493,8 @@ void launch_allocate(b200_engine *e, const SceneRef &s, const FrameGeom &g, cons
                                                                 s.numBlocks, e->d_ctr, e->d_scanDesc, ++e->scanGen, g.M_d, g.proj_d[0],
                                                                 g.proj_d[1], g.proj_d[2], g.proj_d[3], g.voxelSize, g.w, g.h, e->d_ring,
                                                                 e->ringCap, e->d_snapStart, e->d_snapCount, snapSlot, oldest,
-                                                                minmaxDead ? (BlockRec *)e->d_blockRecs : nullptr, mw, mh);
+                                                                minmaxDead ? (BlockRec *)e->d_blockRecs : nullptr, mw, mh,
+                                                                (unsigned)e->maxRenderingBlocks);
   trace_end(e, st);
   e->launches += 1;
 }

@@ -96,6 +96,7 @@ struct DevCounters {
   int decayCand;           // partial decay: items that found their block empty this pass (candidates, unordered)
   int errorFlags;          // bit0: decay ring overflow
   unsigned noRenderingBlocks;
+  unsigned visCtasDone;    // k_visible_list: CTAs that have finished (the last one applies the rendering-block cap if needed)
   int noNeededEntries;     // swapping
   unsigned noTotalPoints;
   int noFwdMissing;

@@ -88,6 +88,7 @@ b200_status b200_engine_create(const b200_engine_config *cfg, b200_engine **out)
   if (!cfg || !out) return B200_ERR_INVALID;
   b200_engine *e = new b200_engine();
   e->useGraph = -1;
+  { const char *m = getenv("B200_TEST_MAX_RENDERING_BLOCKS"); e->maxRenderingBlocks = (m && atoi(m) > 0) ? atoi(m) : B200_MAX_RENDERING_BLOCKS; }
   memset(e, 0, sizeof(*e));
   *out = e;
   e->device = cfg->device;

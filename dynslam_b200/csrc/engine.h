@@ -76,6 +76,7 @@ struct b200_engine {
   float *d_stageDepth[2]; b200_vec4u *d_stageRgb[2]; b200_vec4u *d_stageOut[2]; int16_t *d_stageRaw[2];
   cudaEvent_t evH2D[2], evCompute[2], evD2H[2];
   bool slotBusy[2]; size_t stagePixels;
+  int maxRenderingBlocks;                           // MAX_RENDERING_BLOCKS; B200_TEST_MAX_RENDERING_BLOCKS lowers it (tests)
   int useGraph; bool graphWarm; cudaGraphExec_t frameGraph;
   cudaEvent_t evMid; bool midValid;                 // "allocation + integration of the last frame are done" (pipelined uploads wait for it)         // B200_GRAPH=1: the fused frame is captured and replayed as a CUDA graph
   float *d_viewScratch; size_t viewScratchPixels;   // plays view->depth inside UpdateView (view.cu)

@@ -34,7 +34,7 @@
 __global__ void __launch_bounds__(PRJ_THREADS)
 k_project_blocks(const b200_hash_entry *__restrict__ table, int numBuckets, const b200_vec3i *__restrict__ visiblePos,
                  const int *__restrict__ visiblePtr, int capacity, DevCounters *ctr, Mat4 M, float p0, float p1, float p2, float p3, int w,
-                 int h, float voxelSize, float2 *minmax, BlockRec *recs, unsigned long long *scanDesc, unsigned gen, int recsReady) {
+                 int h, float voxelSize, float2 *minmax, BlockRec *recs, unsigned long long *scanDesc, unsigned gen, int recsReady, unsigned maxRB) {
   __shared__ unsigned sm[33];
   __shared__ unsigned tileBase;
   const float intr[4] = {p0, p1, p2, p3};
@@ -43,17 +43,11 @@ k_project_blocks(const b200_hash_entry *__restrict__ table, int numBuckets, cons
   const int noTiles = (n + PRJ_THREADS - 1) / PRJ_THREADS;
   const int liveX = (w - 1) / B200_MINMAX_SUBSAMPLE, liveY = (h - 1) / B200_MINMAX_SUBSAMPLE;   // last live cell
   const int lane = threadIdx.x & 31;
-  // Fused frame: k_visible_list already wrote the records (every block drawn) and the tile total. Unless that total breaks
-  // the MAX_RENDERING_BLOCKS cap, only the dead-cell part of the boxes is left to do — no scan, no look-back. The work is
-  // split over two launches so that k_fill_minmax (which the raycast waits for) does not queue behind the dead cells
-  // (which nothing in the frame reads; a block next to the camera can cover 10^5 of them):
-  //   recsReady 1 ("fix"):  before the fill — acts only if the cap is broken (full projection + ordered cap rule), no dead cells
-  //   recsReady 2 ("dead"): after the fill  — dead-cell rasterisation from the (possibly fixed) records
-  //   recsReady 0:          stand-alone CreateExpectedDepths — everything in one launch
-  const bool overflow = recsReady && ctr->noRenderingBlocks > (unsigned)B200_MAX_RENDERING_BLOCKS;
-  if (recsReady == 1 && !overflow) return;
-  const bool fast = recsReady == 2 || (recsReady == 1 && !overflow);
-  const bool doDead = recsReady != 1;
+  // Fused frame (recsReady): k_visible_list already wrote the records, tile total and cap rule included; what is left is
+  // the dead-cell part of the boxes, which nothing in the frame reads (a block next to the camera can cover 10^5 of them), so
+  // it runs AFTER the fill the raycast waits for. Stand-alone CreateExpectedDepths (recsReady 0) does everything here.
+  const bool fast = recsReady != 0;
+  const bool doDead = true;
   for (int tile = blockIdx.x; tile < noTiles; tile += gridDim.x) {
     const int item = tile * PRJ_THREADS + threadIdx.x;
     int ulx = 0, uly = 0, lrx = -1, lry = -1; float zmin = 0, zmax = 0;
@@ -84,7 +78,7 @@ k_project_blocks(const b200_hash_entry *__restrict__ table, int numBuckets, cons
     }
     __syncthreads();
     const unsigned out_offset = tileBase + local;
-    draw = required > 0 && (out_offset + required <= (unsigned)B200_MAX_RENDERING_BLOCKS);   // :609
+    draw = required > 0 && (out_offset + required <= maxRB);   // :609
     if (item < n) {
       BlockRec r;
       if (draw) { r.ulx = (short)ulx; r.uly = (short)uly; r.lrx = (short)lrx; r.lry = (short)lry; r.zmin = zmin; r.zmax = zmax; }
@@ -165,19 +159,20 @@ void launch_expected_depths(b200_engine *e, const SceneRef &s, const Mat4 &M, co
                             b200_vec2f *minmax, bool deadInitDone, bool recsReady) {
   if (!deadInitDone) { k_minmax_init_dead<<<e->smCount * 4, 256, 0, e->stream>>>((float2 *)minmax, w, h); e->launches++; }
   const int noTiles = (s.numBlocks + PRJ_THREADS - 1) / PRJ_THREADS;
-  const int prjGrid = persistent_grid(e, 2, noTiles);
-  // recsReady: the records come from k_visible_list of this frame (see k_project_blocks): fix (no-op unless the cap is broken),
-  // fill, dead cells; otherwise one full projection pass, then the fill
-  trace_begin(e, e->stream, recsReady ? "k_project_blocks/fix" : "k_project_blocks");
-  k_project_blocks<<<prjGrid, PRJ_THREADS, 0, e->stream>>>(s.hash, s.numBuckets, s.visiblePos, fresh_ptr_list(e, s), s.numBlocks, e->d_ctr, M,
-                                                         proj[0], proj[1], proj[2], proj[3], w, h, voxelSize, (float2 *)minmax,
-                                                         (BlockRec *)e->d_blockRecs, e->d_scanDesc, ++e->scanGen, recsReady ? 1 : 0);
-  trace_end(e, e->stream);
+  if (!recsReady) {   // otherwise the records come from k_visible_list of this frame; the dead cells follow in launch_expected_depths_dead
+    trace_begin(e, e->stream, "k_project_blocks");
+    k_project_blocks<<<persistent_grid(e, 2, noTiles), PRJ_THREADS, 0, e->stream>>>(s.hash, s.numBuckets, s.visiblePos, fresh_ptr_list(e, s),
+                                                                                   s.numBlocks, e->d_ctr, M, proj[0], proj[1], proj[2], proj[3],
+                                                                                   w, h, voxelSize, (float2 *)minmax, (BlockRec *)e->d_blockRecs,
+                                                                                   e->d_scanDesc, ++e->scanGen, 0, (unsigned)e->maxRenderingBlocks);
+    trace_end(e, e->stream);
+    e->launches++;
+  }
   dim3 grid(((w - 1) / B200_MINMAX_SUBSAMPLE) / FILL_T + 1, ((h - 1) / B200_MINMAX_SUBSAMPLE) / FILL_T + 1);
   trace_begin(e, e->stream, "k_fill_minmax");
   k_fill_minmax<<<grid, FILL_THREADS, 0, e->stream>>>((const BlockRec *)e->d_blockRecs, e->d_ctr, s.numBlocks, w, h, (float2 *)minmax);
   trace_end(e, e->stream);
-  e->launches += 2;
+  e->launches += 1;
 }
 
 // second half of the fused frame's expected-depth work: the dead cells (after launch_expected_depths(..., recsReady = true))
@@ -188,7 +183,7 @@ void launch_expected_depths_dead(b200_engine *e, const SceneRef &s, const Mat4 &
   k_project_blocks<<<persistent_grid(e, 2, noTiles), PRJ_THREADS, 0, e->stream>>>(s.hash, s.numBuckets, s.visiblePos, fresh_ptr_list(e, s),
                                                                                  s.numBlocks, e->d_ctr, M, proj[0], proj[1], proj[2], proj[3],
                                                                                  w, h, voxelSize, (float2 *)minmax, (BlockRec *)e->d_blockRecs,
-                                                                                 e->d_scanDesc, ++e->scanGen, 2);
+                                                                                 e->d_scanDesc, ++e->scanGen, 2, (unsigned)e->maxRenderingBlocks);
   trace_end(e, e->stream);
   e->launches++;
 }

@@ -667,6 +667,11 @@ static int project_single_block(const int16_t pos[3], const float *pose, const f
 /* sit in the dropped range; the canonical result treats them as absent (documented deviation,   */
 /* only reachable with > 262144 tiles).                                                          */
 /* ------------------------------------------------------------------------------------------- */
+/* MAX_RENDERING_BLOCKS (DA/ITMVisualisationEngine.h:25); a test hook lowers it so that the overflow rule (Vis_CUDA.cu:609)
+ * can be exercised with a few hundred blocks */
+static int g_max_rendering_blocks = B200_MAX_RENDERING_BLOCKS;
+void oracle_set_max_rendering_blocks(int n) { g_max_rendering_blocks = n > 0 ? n : B200_MAX_RENDERING_BLOCKS; }
+
 void oracle_expected_depths(const b200_scene *s, b200_render_state *rs, const b200_camera *cam) {
   const int w = rs->img_w, h = rs->img_h;
   for (int i = 0; i < w * h; ++i) { rs->d_minmax[i].x = B200_FAR_AWAY; rs->d_minmax[i].y = B200_VERY_CLOSE; }
@@ -682,7 +687,7 @@ void oracle_expected_depths(const b200_scene *s, b200_render_state *rs, const b2
     unsigned out_offset = offset;
     offset += required;
     if (required == 0) continue;
-    if (out_offset + required > (unsigned)B200_MAX_RENDERING_BLOCKS) continue;
+    if (out_offset + required > (unsigned)g_max_rendering_blocks) continue;
     for (int y = ul[1]; y <= lr[1]; ++y) for (int x = ul[0]; x <= lr[0]; ++x) {
       b200_vec2f *px = &rs->d_minmax[x + y * w];
       if (zr[0] < px->x) px->x = zr[0];

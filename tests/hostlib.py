@@ -85,6 +85,8 @@ def oracle():
     L.oracle_composite_color.restype = None
     L.oracle_composite_instances.argtypes = [vp, vp, C.c_int, P(abi.InstanceLayer), C.c_int, C.c_float, C.c_float]
     L.oracle_composite_instances.restype = None
+    L.oracle_set_max_rendering_blocks.argtypes = [C.c_int]
+    L.oracle_set_max_rendering_blocks.restype = None
     L.oracle_num_threads.restype = C.c_int
     L.oracle_set_threads.argtypes = [C.c_int]
     L.oracle_set_threads.restype = None

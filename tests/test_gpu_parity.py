@@ -174,7 +174,38 @@ def test_fused_async_path_equals_stepwise():
     P._cmp("fused visType", ra["visType"], rb["visType"])
     P._cmp("fused visible", ra["visiblePos"], rb["visiblePos"])
     P._cmp("fused image", pair.rs.raycastImage.cpu().numpy(), stepwise.rs.raycastImage.cpu().numpy())
+    P._cmp("fused minmax", pair.rs.renderingRangeImage.cpu().numpy(), stepwise.rs.renderingRangeImage.cpu().numpy())
     assert pair.reco.GetDecayedBlockCount() == stepwise.reco.GetDecayedBlockCount()
+
+
+def test_rendering_block_cap_rule():
+    """MAX_RENDERING_BLOCKS overflow (Vis_CUDA.cu:609): blocks whose tiles would pass the cap are dropped in list order.
+    The cap is lowered to 300 tiles (test hook) so that a ~1000-block frame overflows it; both the stand-alone
+    CreateExpectedDepths and the fused frame (cap applied by the last CTA of the visible-list pass) must match the oracle."""
+    os.environ["B200_TEST_MAX_RENDERING_BLOCKS"] = "300"
+    H.oracle().oracle_set_max_rendering_blocks(300)
+    try:
+        cfg = P.Cfg(frames=4)
+        stepwise, _ = P.run_sequence(cfg)            # every step is compared with the oracle, min/max image included
+        mm = stepwise.rs.renderingRangeImage.cpu().numpy().reshape(-1, 2)
+        live = mm[:, 0] < 999999.0
+        assert 0 < live.sum()
+        pair = P.Pair(cfg)
+        for depth, rgb, M, proj in P.frames_of(cfg):
+            gv, _ = pair.views(depth, rgb, M, proj)
+            pair.eng.process_frame_async(pair.rs, gv, pair.points, pair.normals)
+        pair.eng.sync(pair.rs)
+        P._cmp("capped fused minmax", pair.rs.renderingRangeImage.cpu().numpy(), stepwise.rs.renderingRangeImage.cpu().numpy())
+        P._cmp("capped fused rays", pair.rs.raycastResult.cpu().numpy(), stepwise.rs.raycastResult.cpu().numpy())
+        # and the cap really bit: without it more of the image is covered
+        os.environ.pop("B200_TEST_MAX_RENDERING_BLOCKS")
+        H.oracle().oracle_set_max_rendering_blocks(0)
+        free, _ = P.run_sequence(cfg)
+        mm2 = free.rs.renderingRangeImage.cpu().numpy().reshape(-1, 2)
+        assert (mm2[:, 0] < 999999.0).sum() > live.sum()
+    finally:
+        os.environ.pop("B200_TEST_MAX_RENDERING_BLOCKS", None)
+        H.oracle().oracle_set_max_rendering_blocks(0)
 
 
 def test_pipelined_host_frames_equal_stepwise():
