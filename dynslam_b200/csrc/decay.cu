@@ -26,19 +26,23 @@ k_decay_blocks(b200_voxel *voxels, const b200_hash_entry *__restrict__ table, in
                long long ringCap, const long long *snapStart, const int *snapCount, int slot, const short4 *allocatedPos,
                int numBlocks, int minAge, int maxWeight, int currentFrame, unsigned gen, unsigned long long *delTag,
                int *itemPtr, DevCounters *ctr, int *candList) {
-  __shared__ int sEmpty[8];
+  // One WARP per list item (a block = 256 uint4 = 8 per lane, all 8 loads in flight), 8 items per CTA: the per-item chain of
+  // dependent loads (ring position -> hash chain -> voxels) overlaps across warps, so the few thousand items of a frame are
+  // one wave of warps instead of ~5 sequential items per CTA.
+  const int lane = threadIdx.x & 31;
+  const int warpsTotal = gridDim.x * (blockDim.x >> 5), warpId = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int n = (MODE == 0) ? snapCount[slot] : numBlocks;
   const long long s0 = (MODE == 0) ? snapStart[slot] : 0;
   if (blockIdx.x == 0 && threadIdx.x == 0) ctr->decayItems = n;
-  for (int item = blockIdx.x; item < n; item += gridDim.x) {
+  for (int item = warpId; item < n; item += warpsTotal) {
     int x, y, z;
     if (MODE == 0) { b200_vec3i p = ring[(s0 + item) % ringCap]; x = p.x; y = p.y; z = p.z; }
     else {
       short4 p = allocatedPos[item];
-      if (p.w == 0) { if (threadIdx.x == 0) itemPtr[item] = -1; continue; }
+      if (p.w == 0) { if (lane == 0) itemPtr[item] = -1; continue; }
       x = p.x; y = p.y; z = p.z;
     }
-    // findBlock / findVoxel (:1214, :1138): uniform across the CTA
+    // findBlock / findVoxel (:1214, :1138): uniform across the warp
     int idx = hash_index(x, y, z, numBuckets - 1), ptr = -1, allocatedTime = 0;
     for (;;) {
       const int *w = reinterpret_cast<const int *>(table) + (size_t)idx * 5;
@@ -51,29 +55,27 @@ k_decay_blocks(b200_voxel *voxels, const b200_hash_entry *__restrict__ table, in
     }
     bool claim = false;
     if (ptr >= 0 && (currentFrame - allocatedTime) >= minAge) {   // safeToClear (:1151-1157)
-      uint4 *blk = reinterpret_cast<uint4 *>(voxels + (size_t)ptr * BS3) + threadIdx.x;
-      uint4 raw = ld_stream(blk);
-      bool ch = false; int empty = 0;
-      {
-        int wd = (raw.x >> 16) & 0xff;
-        if (wd <= maxWeight && wd > 0) { raw.x = 0x00007fffu; raw.y &= 0xff000000u; ch = true; wd = 0; }
+      uint4 *blk = reinterpret_cast<uint4 *>(voxels + (size_t)ptr * BS3) + lane;
+      uint4 raw[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) raw[k] = ld_stream(blk + 32 * k);
+      int empty = 0;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        bool ch = false;
+        int wd = (raw[k].x >> 16) & 0xff;
+        if (wd <= maxWeight && wd > 0) { raw[k].x = 0x00007fffu; raw[k].y &= 0xff000000u; ch = true; wd = 0; }
         empty += (wd == 0);
-        wd = (raw.z >> 16) & 0xff;
-        if (wd <= maxWeight && wd > 0) { raw.z = 0x00007fffu; raw.w &= 0xff000000u; ch = true; wd = 0; }
+        wd = (raw[k].z >> 16) & 0xff;
+        if (wd <= maxWeight && wd > 0) { raw[k].z = 0x00007fffu; raw[k].w &= 0xff000000u; ch = true; wd = 0; }
         empty += (wd == 0);
+        if (ch) st_stream(blk + 32 * k, raw[k]);
       }
-      if (ch) st_stream(blk, raw);
       // block-wide count of empty voxels (replaces the 512-int shared-memory tree, ITMCUDAUtils.h:145-160)
       for (int o = 16; o > 0; o >>= 1) empty += __shfl_xor_sync(0xffffffffu, empty, o);
-      if ((threadIdx.x & 31) == 0) sEmpty[threadIdx.x >> 5] = empty;
-      __syncthreads();
-      int tot = 0;
-#pragma unroll
-      for (int k = 0; k < 8; ++k) tot += sEmpty[k];
-      claim = (tot == BS3);
-      __syncthreads();
+      claim = (empty == BS3);
     }
-    if (threadIdx.x == 0) {
+    if (lane == 0) {
       itemPtr[item] = claim ? ptr : -1;
       if (claim) {
         atomicMax(&delTag[ptr], del_tag(gen, (unsigned)item));
@@ -311,7 +313,7 @@ static void decay_common(b200_engine *e, const SceneRef &s, int mode, int slot, 
                          long long items) {
   cudaStream_t st = e->stream;
   const unsigned gen = ++e->decayGen;
-  const int grid1 = persistent_grid(e, 6, items);
+  const int grid1 = persistent_grid(e, 6, (items + 7) / 8);   // 8 items (warps) per CTA
   if (mode == 0) {
     trace_begin(e, st, "k_decay_blocks<0>");
     k_decay_blocks<0><<<grid1, 256, 0, st>>>(s.voxels, s.hash, s.numBuckets, e->d_ring, e->ringCap, e->d_snapStart, e->d_snapCount,

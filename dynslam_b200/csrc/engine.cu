@@ -87,9 +87,9 @@ extern "C" {
 b200_status b200_engine_create(const b200_engine_config *cfg, b200_engine **out) {
   if (!cfg || !out) return B200_ERR_INVALID;
   b200_engine *e = new b200_engine();
+  memset(e, 0, sizeof(*e));
   e->useGraph = -1;
   { const char *m = getenv("B200_TEST_MAX_RENDERING_BLOCKS"); e->maxRenderingBlocks = (m && atoi(m) > 0) ? atoi(m) : B200_MAX_RENDERING_BLOCKS; }
-  memset(e, 0, sizeof(*e));
   *out = e;
   e->device = cfg->device;
   e->numBlocks = cfg->numBlocks; e->numBuckets = cfg->numBuckets; e->excessSize = cfg->excessSize;
