@@ -63,9 +63,20 @@ class ClockSampler(threading.Thread):
         except Exception:
             pass
 
+    def pause(self, on):
+        """SIGSTOP / SIGCONT nvidia-smi: its 20 ms polling was measured to stall the driver for 50-70 ms now and then, which a
+        host-synchronous loop (the e2e phases) sees in full; the clocks are only needed for the device-timed region."""
+        import signal
+        if self.proc and self.proc.poll() is None:
+            try:
+                self.proc.send_signal(signal.SIGSTOP if on else signal.SIGCONT)
+            except Exception:
+                pass
+
     def stop(self):
         self.stop_flag = True
         if self.proc:
+            self.pause(False)
             self.proc.terminate()
 
     def summary(self):
@@ -82,6 +93,14 @@ class ClockSampler(threading.Thread):
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def frame_gaps(marks):
+    """Host-side spacing of consecutive pipelined submissions (ms): median / max / index of the max — exposes one-off stalls."""
+    if len(marks) < 3:
+        return None
+    d = np.diff(np.asarray(marks)) * 1000.0
+    return {"median": float(np.median(d)), "max": float(d.max()), "argmax": int(d.argmax()), "n": int(d.size)}
 
 
 def gen_frames(seed, first, count, length_m):
@@ -387,6 +406,16 @@ def run_own(args, rank, local_rank, world):
     frames = gen_frames_parallel(seed, 0, total_frames, length_m, max(1, min(16, (os.cpu_count() or 2) // max(world, 1))))
     log(f"[rank {rank}] generated {len(frames)} frames in {time.perf_counter() - t_gen:.1f}s")
 
+    # Host buffers of the e2e phases are pinned NOW, long before they are used: pinning several hundred MB was followed, some
+    # milliseconds later, by a one-off 50-70 ms host stall (seen as a single gap between two pipelined submissions, with the
+    # clock sampler paused and the GC off), which a 50 ms e2e phase cannot absorb.
+    e2e_first = args.preroll + Wm + K + 3
+    h_depth = [torch.from_numpy(frames[e2e_first + i][0]).pin_memory() for i in range(n_e2e)]
+    h_rgb = [torch.from_numpy(frames[e2e_first + i][1]).pin_memory() for i in range(n_e2e)]
+    h_raw = [torch.from_numpy(np.round(frames[e2e_first + n_e2e + i][0] * 1000.0).astype(np.int16)).pin_memory() for i in range(n_raw)]
+    h_rgb2 = [torch.from_numpy(frames[e2e_first + n_e2e + i][1]).pin_memory() for i in range(n_raw)]
+    h_out = [torch.zeros(H_ * W * 4, dtype=torch.uint8).pin_memory() for _ in range(2)]
+
     stream = torch.cuda.Stream(device=dev)
     with torch.cuda.stream(stream):
         scene = E.Scene(E.SceneParams(), NUM_BLOCKS, NUM_BUCKETS, EXCESS, device=f"cuda:{local_rank}")
@@ -411,8 +440,13 @@ def run_own(args, rank, local_rank, world):
             if world > 1:
                 dist.gather(rs.raycastImage, gather_buf, dst=0)
 
+        diag = os.environ.get("B200_BENCH_DIAG", "")
         sampler = ClockSampler(local_rank)
-        sampler.start()
+        if "nosampler" not in diag:
+            sampler.start()
+        if "nogc" in diag:
+            import gc
+            gc.disable()
         # ---- pre-roll: build the map to steady state (untimed set-up) ----
         idx = 0
         for _ in range(args.preroll):
@@ -451,12 +485,18 @@ def run_own(args, rank, local_rank, world):
         eng.sync(rs)
         st = eng.stats()
         time.sleep(0.05)
-        clk_timed_end = len(sampler.rows)      # the sampler keeps running through the e2e phases: terminating nvidia-smi stalls
+        sampler.pause(True)
+        clk_timed_end = len(sampler.rows)      # the sampler process stays alive (paused) through the e2e phases: terminating nvidia-smi stalls
                                                # the driver for tens of milliseconds, which used to land in the e2e timing
         launches = st.launches - launches0
         blocks = st.totalIntegratedBlocks - blocks0
         int_ms, int_n = st.ring_ms_integrate, st.ring_count
         n_vis = rs.noVisibleBlocks
+        # sanity of the timed work: the last timed frame's raycast must have hit the surface on a large part of the image
+        # (a broken expected-depth image makes every ray exit at once and the frame look fast)
+        rays_hit = int((rs.raycastResult.view(-1, 4)[:, 3] > 0).sum().item())
+        if rays_hit < 0.3 * W * H_ or n_vis < 1000:
+            raise RuntimeError(f"bench sanity check failed: {rays_hit} of {W * H_} rays hit the surface, {n_vis} visible blocks")
         used_blocks = NUM_BLOCKS - 1 - scene.lastFreeBlockId
         decayed = reco.GetDecayedBlockCount()
         # per-stage breakdown of a few extra frames (per-frame sync; not part of the timed region)
@@ -471,12 +511,11 @@ def run_own(args, rank, local_rank, world):
         eng.set_timing(0)
 
         # ---- e2e: host buffers -> H2D -> frame -> D2H image, every step ----
-        h_depth = [torch.from_numpy(frames[idx + i][0]).pin_memory() for i in range(n_e2e)]
-        h_rgb = [torch.from_numpy(frames[idx + i][1]).pin_memory() for i in range(n_e2e)]
-        h_out = [torch.zeros(H_ * W * 4, dtype=torch.uint8).pin_memory() for _ in range(2)]
+        assert idx == e2e_first, (idx, e2e_first)
         ev = E.View(torch.zeros((H_, W), dtype=torch.float32, device=dev), torch.zeros((H_, W, 4), dtype=torch.uint8, device=dev),
                     frames[idx][2], frames[idx][3])
         e2e_warm = min(3, n_e2e // 2)
+        e2e_marks = []
         t_e2e = 0.0
         for i in range(n_e2e):
             if i == e2e_warm:
@@ -487,6 +526,7 @@ def run_own(args, rank, local_rank, world):
                 t_e2e = time.perf_counter()
             slot = i & 1
             eng.host_frame_wait(slot)          # frame i-2 (same staging slot) has delivered its image
+            e2e_marks.append(time.perf_counter())
             ev.set_pose(frames[idx + i][2])
             # public API: host depth+RGB in, grey raycast image out; copies of neighbouring frames overlap the kernels
             eng.host_frame_submit(rs, ev, h_depth[i], h_rgb[i], points, normals, decay=DECAY, h_out=h_out[slot], slot=slot)
@@ -505,9 +545,8 @@ def run_own(args, rank, local_rank, world):
         if n_raw > 3:
             calib = E.make_view_calib()
             base = idx + n_e2e
-            h_raw = [torch.from_numpy(np.round(frames[base + i][0] * 1000.0).astype(np.int16)).pin_memory() for i in range(n_raw)]
-            h_rgb2 = [torch.from_numpy(frames[base + i][1]).pin_memory() for i in range(n_raw)]
             t_raw = 0.0
+            raw_marks = []
             for i in range(n_raw):
                 if i == 3:
                     eng.host_frame_wait(0); eng.host_frame_wait(1)
@@ -515,12 +554,13 @@ def run_own(args, rank, local_rank, world):
                     t_raw = time.perf_counter()
                 slot = i & 1
                 eng.host_frame_wait(slot)
+                raw_marks.append(time.perf_counter())
                 ev.set_pose(frames[base + i][2])
                 eng.host_frame_submit_raw(rs, ev, h_raw[i], h_rgb2[i], calib, points, normals, decay=DECAY, h_out=h_out[slot], slot=slot)
             eng.host_frame_wait(0); eng.host_frame_wait(1)
             torch.cuda.synchronize(dev)
             t_raw = time.perf_counter() - t_raw
-            e2e_raw = {"value": (n_raw - 3) / t_raw, "unit": "frames/s", "h2d_bytes_per_step": W * H_ * 6, "d2h_bytes_per_step": W * H_ * 4,
+            e2e_raw = {"frame_ms": frame_gaps(raw_marks[3:]), "value": (n_raw - 3) / t_raw, "unit": "frames/s", "h2d_bytes_per_step": W * H_ * 6, "d2h_bytes_per_step": W * H_ * 4,
                        "steps": n_raw - 3, "what": "raw int16 depth + RGB in -> UpdateView with bilateral filter -> fused frame -> image out"}
 
     sampler.stop()
@@ -602,7 +642,7 @@ def run_own(args, rank, local_rank, world):
                          f"no flush (--no-flush-l2): per-step footprint ~{footprint_mb:.0f} MB, consecutive frames reuse L2",
                    "integrate_impl": os.environ.get("B200_INTEGRATE_IMPL", "tma"),
                    "parallelism": f"{world} independent volume(s), NCCL gather of raycast images to rank 0" if world > 1 else "1 volume"},
-        "mvoxels_per_s": mvox, "visible_blocks": n_vis, "allocated_blocks": used_blocks, "decayed_blocks": int(decayed),
+        "mvoxels_per_s": mvox, "rays_hit": rays_hit, "visible_blocks": n_vis, "allocated_blocks": used_blocks, "decayed_blocks": int(decayed),
         "wall_ms_per_step": wall_ms / K,
         "stage_ms": {"allocate": stage[0], "integrate": stage[1], "expected_depths": stage[2], "raycast_icp": stage[3],
                      "decay": stage[4], "total": stage[5]},
@@ -617,7 +657,7 @@ def run_own(args, rank, local_rank, world):
         "frames_ops": frames_ops,
         "e2e_raw": e2e_raw,
         "e2e": {"value": world * e2e_frames / t_e2e, "unit": "frames/s", "h2d_bytes_per_step": W * H_ * 8,
-                "d2h_bytes_per_step": W * H_ * 4, "steps": e2e_frames},
+                "d2h_bytes_per_step": W * H_ * 4, "steps": e2e_frames, "frame_ms": frame_gaps(e2e_marks[e2e_warm:])},
         "gpu_launches": int(launches_all),
         "clocks": clocks,
     }
@@ -633,8 +673,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
     ap.add_argument("--preroll", type=int, default=230, help="untimed frames that build the map (> decay minAge)")
-    ap.add_argument("--e2e-steps", type=int, default=103)
-    ap.add_argument("--e2e-raw-steps", type=int, default=53, help="frames of the raw-sensor-frame e2e variant (1 GPU only)")
+    ap.add_argument("--e2e-steps", type=int, default=203)
+    ap.add_argument("--e2e-raw-steps", type=int, default=103, help="frames of the raw-sensor-frame e2e variant (1 GPU only)")
     ap.add_argument("--flush-l2", dest="flush_l2", action="store_true", default=True)
     ap.add_argument("--no-flush-l2", dest="flush_l2", action="store_false")
     ap.add_argument("--cpu-steps", type=int, default=6)

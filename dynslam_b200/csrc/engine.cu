@@ -458,7 +458,7 @@ b200_status b200_process_frame_async(b200_engine *e, b200_scene *s, b200_render_
   CK(cudaSetDevice(e->device));
   if (e->hostAuthoritative) { st = upload(e, s, rs); if (st) return st; e->hostAuthoritative = false; }
   if (e->useGraph < 0) { const char *g = getenv("B200_GRAPH"); e->useGraph = (g && atoi(g) != 0) ? 1 : 0; }
-  if (!e->useGraph || e->timing || e->traceOn || !e->graphWarm) {   // the first frame also runs one-time initialisation: never captured
+  if (!e->useGraph || e->timing || e->traceOn || !e->graphWarm) {   // (events recorded inside a capture cannot be synchronised on)   // the first frame also runs one-time initialisation: never captured
     e->graphWarm = true;
     return frame_enqueue(e, s, rs, v, d_points, d_normals, opts);
   }
