@@ -118,7 +118,7 @@ EXPORTS = [
     "b200_convert_disparity_to_depth", "b200_convert_depth_affine_to_float", "b200_depth_filtering",
     "b200_compute_normal_and_weights", "b200_update_view", "b200_update_view_async", "b200_host_frame_submit_raw",
     "b200_process_silhouettes", "b200_process_silhouettes_async", "b200_composite_depth", "b200_composite_color",
-    "b200_composite_instances", "b200_get_trace",
+    "b200_composite_instances", "b200_get_trace", "b200_selftest_divide",
 ]
 
 _lib = None
@@ -187,6 +187,7 @@ def load_library():
     lib.b200_set_timing.restype = None
     lib.b200_get_stats.argtypes = [vp, P(FrameStats)]
     lib.b200_get_trace.argtypes = [vp, C.c_char_p, C.c_int]
+    lib.b200_selftest_divide.argtypes = [vp, C.c_uint64, C.c_uint64, C.c_float, P(C.c_uint64)]
     _lib = lib
     return lib
 

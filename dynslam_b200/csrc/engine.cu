@@ -147,8 +147,8 @@ b200_status b200_engine_create(const b200_engine_config *cfg, b200_engine **out)
     CK(cudaEventCreateWithFlags(&e->evJoin, cudaEventDisableTiming));
   }
   e->hostAuthoritative = true;
-  // default: TMA variant (measured faster); B200_INTEGRATE_IMPL=ldg selects the simple one
-  { const char *v = getenv("B200_INTEGRATE_IMPL"); e->integrateImpl = (v && v[0] == 'l') ? 0 : 1; }
+  // default: V3 (warp-decoupled TMA ring, integrate.cu); B200_INTEGRATE_IMPL=tma|ldg select the earlier variants
+  { const char *v = getenv("B200_INTEGRATE_IMPL"); e->integrateImpl = (v && v[0] == 'l') ? 0 : ((v && v[0] == 't') ? 1 : 2); }
   return B200_OK;
 }
 

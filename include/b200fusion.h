@@ -366,6 +366,14 @@ void b200_set_timing(b200_engine *e, int enabled);
 int b200_get_trace(b200_engine *e, char *out, int cap);
 b200_status b200_get_stats(b200_engine *e, b200_frame_stats *out);
 
+/* Self-test of the division sequences of the default IntegrateIntoScene kernel (integrate.cu, variant V3): on the
+   engine's device, `pairs` pseudo-random operand pairs (a, b) drawn from the ranges the kernel's fast path accepts
+   (|a| in {0} U [2^-40, 2^40], b in [2^-20, 2^20], plus the constant divisors mu, 255, 32767 and the integer weights
+   1..271) are divided with the kernel's sequence and with the IEEE operator `/` (what DA/ITMSceneReconstructionEngine.h
+   :14-128 evaluates on the host); *mismatches receives the number of quotients whose bits differ (signed zeros
+   compare equal). Test infrastructure only. */
+b200_status b200_selftest_divide(b200_engine *e, uint64_t pairs, uint64_t seed, float mu, uint64_t *mismatches);
+
 #ifdef __cplusplus
 }
 #endif

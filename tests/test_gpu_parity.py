@@ -71,6 +71,50 @@ def test_integrate_ldg_variant_matches():
     assert pair.rs.noVisibleBlocks > 1000
 
 
+def test_integrate_tma_variant_matches():
+    os.environ["B200_INTEGRATE_IMPL"] = "tma"
+    try:
+        pair, _ = P.run_sequence(P.Cfg(frames=5, raycast=False, decay=(1, 2)))
+    finally:
+        os.environ.pop("B200_INTEGRATE_IMPL", None)
+    assert pair.rs.noVisibleBlocks > 1000
+
+
+def test_integrate_wide_band_colour_on_rejected_voxels():
+    """mu >= 4 m: computeUpdatedVoxelDepthInfo's -1 for a rejected voxel passes the |eta / mu| <= 0.25 colour gate
+    (SURVEY 8a'), so voxels outside the depth image or on depth holes still get a colour update. The default
+    kernel sends those voxels to its generic per-voxel path."""
+    pair, _ = P.run_sequence(P.Cfg(frames=3, mu=4.0, raycast=False, numBlocks=65536, numBuckets=0x10000, excessSize=0x4000))
+    assert pair.rs.noVisibleBlocks > 1000
+
+
+def test_integrate_four_resident_ctas_build():
+    os.environ["B200_V3_CTAS"] = "4"
+    try:
+        # the register-budget switch is read once per process: run in a child
+        import subprocess, sys
+        code = ("from tests import parity as P; pair,_=P.run_sequence(P.Cfg(frames=4, raycast=False, decay=(1, 2))); "
+                "assert pair.rs.noVisibleBlocks > 1000; print('ok')")
+        out = subprocess.run([sys.executable, "-c", code], cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+                             capture_output=True, text=True, timeout=600)
+        assert out.returncode == 0 and "ok" in out.stdout, out.stdout + out.stderr
+    finally:
+        os.environ.pop("B200_V3_CTAS", None)
+
+
+def test_division_sequences_equal_ieee_division():
+    """The default integrate kernel divides with the hardware's own IEEE sequence (shared reciprocals, no per-division
+    slow-path call); 2^28 operand pairs x 5 divisor kinds against `/`, bit for bit."""
+    p = E.SceneParams(0.05, 0.75, 50, 0.1, 300.0, False)
+    scene = E.Scene(p, 1024, 0x400, 0x100, device="cuda:0")
+    eng = E.Engine(scene, (64, 64))
+    lib = abi.load_library()
+    for mu in (0.75, 1.0, 0.016, 0.032, 4.0, 0.3333):
+        bad = C.c_uint64(12345)
+        assert lib.b200_selftest_divide(eng.h, 1 << 28, 7 + int(mu * 1000), C.c_float(mu), C.byref(bad)) == 0
+        assert bad.value == 0, (mu, bad.value)
+
+
 def _oracle_camera(M, proj):
     return H.make_camera(M, proj)
 
