@@ -473,7 +473,13 @@ def run_own(args, rank, local_rank, world):
                 flush_ev[i][0].record(stream)
                 flush_buf.add_(1)
                 flush_ev[i][1].record(stream)
+            if args.profile_step == i:   # ncu --profile-from-start off: exactly this frame's kernels are captured
+                torch.cuda.synchronize(dev)
+                torch.cuda.cudart().cudaProfilerStart()
             step(views[Wm + i])
+            if args.profile_step == i:
+                torch.cuda.synchronize(dev)
+                torch.cuda.cudart().cudaProfilerStop()
         ev1.record(stream)
         torch.cuda.synchronize(dev)
         if world > 1:
@@ -677,6 +683,8 @@ def main():
     ap.add_argument("--e2e-raw-steps", type=int, default=103, help="frames of the raw-sensor-frame e2e variant (1 GPU only)")
     ap.add_argument("--flush-l2", dest="flush_l2", action="store_true", default=True)
     ap.add_argument("--no-flush-l2", dest="flush_l2", action="store_false")
+    ap.add_argument("--profile-step", type=int, default=-1,
+                    help="bracket this timed step with cudaProfilerStart/Stop (for ncu --profile-from-start off; not a bench run)")
     ap.add_argument("--cpu-steps", type=int, default=6)
     ap.add_argument("--harness-frames", type=int, default=100, help="frames timed through the real ITMLib objects (0 = skip)")
     ap.add_argument("--harness-preroll", type=int, default=60)

@@ -103,6 +103,8 @@ struct DevCounters {
   long long ringHead;      // device-side bump cursor of the decay ring (items)
   long long totalDecayed;  // GetDecayedBlockCount, Reco_CUDA.cu:563-566
   long long totalIntegrated; // cumulative blocks integrated (never reset; bench reads deltas)
+  int integCursor;         // k_integrate_v3: next visible-list item to hand out (dynamic distribution over the persistent grid)
+  int integDone;           // k_integrate_v3: CTAs that have stopped claiming; the last one zeroes both for the next launch
 };
 
 // ---- chained-scan (decoupled look-back) for ordered compaction --------------------------------

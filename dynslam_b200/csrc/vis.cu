@@ -353,14 +353,23 @@ __device__ bool cast_ray(float4 &out, int x, int y, const b200_voxel *__restrict
 #define RC_THREADS 64
 __global__ void __launch_bounds__(RC_THREADS)
 k_raycast(float4 *out, const b200_voxel *__restrict__ voxels, const b200_hash_entry *__restrict__ table, int nb, int w, int h, Mat4 invM,
-          float fx, float fy, float cxp, float cyp, float voxelSize, float mu, const float2 *__restrict__ minmax, int twLog2) {
+          float fx, float fy, float cxp, float cyp, float voxelSize, float mu, const float2 *__restrict__ minmax, int twLog2, int centreRow) {
   // warp tile: (1 << twLog2) x (32 >> twLog2) pixels
   const int tw = 1 << twLog2, th = 32 >> twLog2;
   const int tilesX = (w + tw - 1) >> twLog2, tilesY = (h + th - 1) / th;
   const int warpGlobal = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (warpGlobal >= tilesX * tilesY) return;
   const int lane = threadIdx.x & 31;
-  const int x = (warpGlobal % tilesX) * tw + (lane & (tw - 1)), y = (warpGlobal / tilesX) * th + (lane >> twLog2);
+  int tileRow = warpGlobal / tilesX;
+  if (centreRow >= 0) {
+    // dispatch order = tile rows sorted by distance from `centreRow` (c, c+1, c-1, c+2, ...): the rows around the horizon
+    // hold the rays that skim the ground inside its truncation band for hundreds of steps; started first, they overlap
+    // the rest of the image instead of forming the kernel's tail. Every pixel is still written exactly once.
+    const int c = centreRow, up = tilesY - 1 - c, down = c, m = up < down ? up : down, k = tileRow;
+    if (k <= 2 * m) { const int off = (k + 1) >> 1; tileRow = (k & 1) ? c + off : c - off; }
+    else { const int rest = k - 2 * m; tileRow = (up > down) ? c + m + rest : c - m - rest; }
+  }
+  const int x = (warpGlobal % tilesX) * tw + (lane & (tw - 1)), y = tileRow * th + (lane >> twLog2);
   if (x >= w || y >= h) return;
   const int locId2 = (int)floorf((float)x / B200_MINMAX_SUBSAMPLE) + (int)floorf((float)y / B200_MINMAX_SUBSAMPLE) * w;
   float4 o;
@@ -375,10 +384,19 @@ void launch_raycast(b200_engine *e, const SceneRef &s, const Mat4 &invM, const f
   const int tw = 1 << twLog2, th = 32 >> twLog2;
   const int tiles = ((w + tw - 1) / tw) * ((h + th - 1) / th);
   const int warpsPerCta = RC_THREADS / 32;
+  static int order = -1;
+  if (order < 0) { const char *v = getenv("B200_RC_ORDER"); order = v ? atoi(v) : 1; }   // default: principal-point row first; 0 = plain row-major
+  int centreRow = -1;
+  if (order == 1) {   // principal-point row first (level camera: the horizon)
+    const int tilesY = (h + th - 1) / th;
+    centreRow = (int)(proj[3] / (float)th);
+    if (centreRow < 0) centreRow = 0;
+    if (centreRow > tilesY - 1) centreRow = tilesY - 1;
+  }
   trace_begin(e, e->stream, "k_raycast");
   k_raycast<<<(tiles + warpsPerCta - 1) / warpsPerCta, RC_THREADS, 0, e->stream>>>((float4 *)out, s.voxels, s.hash, s.numBuckets, w, h, invM,
                                                                                   proj[0], proj[1], proj[2], proj[3], voxelSize, mu,
-                                                                                  (const float2 *)minmax, twLog2);
+                                                                                  (const float2 *)minmax, twLog2, centreRow);
   trace_end(e, e->stream);
   e->launches++;
 }
