@@ -191,9 +191,9 @@ HD V3A v3_stage_a(const float4 X, const float4 Y, const float4 Z, float m12x, fl
   const float yz = rcp_nr(a.pcz);
   a.ix = div_nr(ax, a.pcz, yz) + g.proj_d[2];
   a.iy = div_nr(ay, a.pcz, yz) + g.proj_d[3];
-  a.inb = !((a.ix < 1) || (a.ix > k.wm2) || (a.iy < 1) || (a.iy > k.hm2));
+  a.inb = !((a.ix < 1) | (a.ix > k.wm2) | (a.iy < 1) | (a.iy > k.hm2));   // (non-short-circuit: no branches)
   const int px = (int)(a.ix + 0.5f), py = (int)(a.iy + 0.5f);
-  a.idx = (a.ok && a.inb) ? (unsigned)(px + py * g.w) : 0u;
+  a.idx = (unsigned)(px + py * g.w) & (0u - (unsigned)(a.ok & a.inb));    // 0 when the voxel will not sample the image
   return a;
 }
 
