@@ -15,6 +15,27 @@ mkdir -p "$HERE/_ref"
     -o "$HERE/_ref/libitmref.so" "$HERE/ref_driver.cpp"
 echo "built $HERE/_ref/libitmref.so"
 
+# ---- instance frame splitting / compositing: the reference's own free functions (oracle/_ref/libinstrecref.so) ---------
+# InstanceReconstructor.cpp needs OpenCV/Eigen/Pangolin as a translation unit, but ProcessSilhouette_CPU, RemoveSilhouette_CPU,
+# CompositeDepth and CompositeColor only need ORUtils images, the reference's Mask/BoundingBox headers, a byte matrix and two
+# integer vectors (oracle/stubs, oracle/ref_frames_driver.cpp). They are cut out of the reference file here, at build time,
+# into oracle/_ref/ (git-ignored) and compiled unmodified.
+DS=${DS:-/root/reference/src/DynSLAM}
+IRC="$DS/InstRecLib/InstanceReconstructor.cpp"
+if [ -f "$IRC" ]; then
+  awk '/^template <typename DEPTH_T>/ {on=1} /^void InstanceReconstructor::ProcessFrame\(/ {on=0} on' "$IRC" > "$HERE/_ref/instrec_extract.inc"
+  awk '/^void CompositeDepth\(/ {on=1} /^void InstanceReconstructor::CompositeInstanceDepthMaps\(/ {on=0} on' "$IRC" >> "$HERE/_ref/instrec_extract.inc"
+  if grep -q "ProcessSilhouette_CPU" "$HERE/_ref/instrec_extract.inc" && grep -q "void CompositeColor" "$HERE/_ref/instrec_extract.inc"; then
+    /usr/bin/g++ -std=c++14 -O2 -ffp-contract=off -fno-fast-math -shared -fPIC -w -DCOMPILE_WITHOUT_CUDA -D__device__= \
+        -I"$HERE/stubs" -I"$REF" -I"$DS/InstRecLib/Utils" -I"$HERE" \
+        -o "$HERE/_ref/libinstrecref.so" "$HERE/ref_frames_driver.cpp"
+    echo "built $HERE/_ref/libinstrecref.so"
+    rm -f "$HERE/_ref/instrec_extract.inc"   # the cut-out text is a build intermediate only
+  else
+    echo "could not locate the silhouette / compositing functions in $IRC" >&2; rm -f "$HERE/_ref/instrec_extract.inc"
+  fi
+fi
+
 # ---- reference CUDA build + ITMLib harness (oracle/_ref/libitmharness.so) -------------------------
 # The reference's own CUDA engines, unmodified, compiled per-TU for sm_100a with the reference's
 # flags (--use_fast_math, ITMLib/CMakeLists.txt:226-230) directly from /root/reference, plus the few

@@ -6,10 +6,13 @@
  *   CompositeDepth / CompositeColor                    DS/InstRecLib/InstanceReconstructor.cpp:850-905
  *   background dimming + loop of CompositeInstances    DS/InstRecLib/InstanceReconstructor.cpp:932-987
  *
- * PARITY UNPINNED: these functions live in a translation unit that needs OpenCV, Eigen and Pangolin
- * (none installed here), the reference ships no tests or golden vectors for them, and there is no other
- * implementation of them in the reference to run. The restatement below follows the reference statement by
- * statement (loops, operand types and conversion order kept: uchar*double, int*float, double->uchar cast).
+ * PINNED (tests/test_frames_oracle.py): process_silhouette, remove_silhouette, oracle_composite_depth and
+ * oracle_composite_color are compared byte for byte with ProcessSilhouette_CPU<float>, RemoveSilhouette_CPU<float>,
+ * CompositeDepth and CompositeColor compiled from the reference file itself (oracle/build_ref.sh cuts the four free functions
+ * out of InstanceReconstructor.cpp at build time and compiles them against the reference's Mask / BoundingBox / ORUtils headers;
+ * oracle/_ref/libinstrecref.so). NOT pinned, because they are member functions entangled with the tracker, Pangolin and the
+ * renderers: the three-statement background dimming loop of CompositeInstances (:944-952) and the per-track dispatch
+ * (:210-285); they are restated statement by statement and fixed by hand-computed known answers.
  */
 #include <stdint.h>
 #include <string.h>

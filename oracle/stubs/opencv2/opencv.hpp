@@ -1,0 +1,27 @@
+// Minimal stand-in for <opencv2/opencv.hpp> — TEST INFRASTRUCTURE ONLY (oracle/build_ref.sh).
+// OpenCV is not installed here; the reference's InstRecLib/Utils/Mask.h only needs a byte matrix with at<T>(row, col), and the
+// silhouette functions of InstanceReconstructor.cpp only read it. Nothing of OpenCV's implementation is reproduced.
+#pragma once
+#include <cassert>
+#include <cstddef>
+#include <vector>
+typedef unsigned char uchar;
+namespace cv {
+struct Size { int width, height; Size(int w = 0, int h = 0) : width(w), height(h) {} };
+class Mat {
+ public:
+  int rows, cols;
+  std::vector<unsigned char> bytes;
+  Mat() : rows(0), cols(0) {}
+  Mat(int r, int c) : rows(r), cols(c), bytes((size_t)r * c) {}
+  template <typename T> T &at(int r, int c) { return reinterpret_cast<T *>(bytes.data())[(size_t)r * cols + c]; }
+  template <typename T> const T &at(int r, int c) const { return reinterpret_cast<const T *>(bytes.data())[(size_t)r * cols + c]; }
+  Size size() const { return Size(cols, rows); }
+};
+class Mat1b : public Mat {
+ public:
+  Mat1b() {}
+  Mat1b(int r, int c) : Mat(r, c) {}
+  explicit Mat1b(Size s) : Mat(s.height, s.width) {}
+};
+}   // namespace cv
