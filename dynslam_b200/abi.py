@@ -12,6 +12,7 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "csrc", "libb200fusion.so")
+HOST_LIB_PATH = os.path.join(HERE, "csrc", "libb200host.so")   # host-side helpers of this mirror (csrc/hostmath.c), not the C-ABI
 
 SDF_BLOCK_SIZE = 8
 SDF_BLOCK_SIZE3 = 512
@@ -103,23 +104,26 @@ class FrameStats(C.Structure):
     _fields_ = [("ms_allocate", C.c_float), ("ms_integrate", C.c_float), ("ms_expected", C.c_float),
                 ("ms_raycast", C.c_float), ("ms_decay", C.c_float), ("ms_total", C.c_float),
                 ("launches", C.c_int64), ("noVisibleBlocks", C.c_int32), ("noIntegratedBlocks", C.c_int32),
-                ("ring_ms_integrate", C.c_float), ("ring_count", C.c_int32), ("totalIntegratedBlocks", C.c_int64)]
+                ("ring_ms_integrate", C.c_float), ("ring_count", C.c_int32), ("totalIntegratedBlocks", C.c_int64),
+                ("droppedSnapshots", C.c_int64)]
 
 
 # every symbol include/b200fusion.h declares; tests assert the .so exports all of them
 EXPORTS = [
     "b200_engine_create", "b200_engine_destroy", "b200_last_error", "b200_engine_stream",
-    "b200_frame_index", "b200_mat4_inv", "b200_mat4_mul", "b200_reset_scene",
+    "b200_frame_index", "b200_reset_scene",
     "b200_allocate_from_depth", "b200_integrate", "b200_decay", "b200_decayed_block_count",
     "b200_find_visible_blocks", "b200_expected_depths", "b200_find_surface", "b200_render_image",
     "b200_icp_maps", "b200_forward_render", "b200_point_cloud", "b200_swap_list_in",
     "b200_swap_integrate_in", "b200_swap_out", "b200_process_frame_async", "b200_sync",
-    "b200_process_frame_host", "b200_set_timing", "b200_get_stats", "b200_host_frame_submit", "b200_host_frame_wait",
+    "b200_process_frame_host", "b200_host_frame_submit", "b200_host_frame_wait",
     "b200_convert_disparity_to_depth", "b200_convert_depth_affine_to_float", "b200_depth_filtering",
     "b200_compute_normal_and_weights", "b200_update_view", "b200_update_view_async", "b200_host_frame_submit_raw",
     "b200_process_silhouettes", "b200_process_silhouettes_async", "b200_composite_depth", "b200_composite_color",
-    "b200_composite_instances", "b200_get_trace", "b200_selftest_divide",
+    "b200_composite_instances",
 ]
+# measurement / test hooks (include/b200fusion_diag.h): exported by the same library, not part of the drop-in boundary
+DIAG_EXPORTS = ["b200_set_timing", "b200_get_trace", "b200_get_stats", "b200_selftest_divide", "b200_diag_set_max_rendering_blocks"]
 
 _lib = None
 
@@ -144,9 +148,6 @@ def load_library():
     lib.b200_engine_stream.argtypes = [vp]
     lib.b200_engine_stream.restype = vp
     lib.b200_frame_index.argtypes = [vp]
-    lib.b200_mat4_inv.argtypes = [P(C.c_float), P(C.c_float)]
-    lib.b200_mat4_mul.argtypes = [P(C.c_float), P(C.c_float), P(C.c_float)]
-    lib.b200_mat4_mul.restype = None
     lib.b200_reset_scene.argtypes = [vp, P(Scene)]
     lib.b200_allocate_from_depth.argtypes = [vp, P(Scene), P(RenderState), P(View), C.c_int]
     lib.b200_integrate.argtypes = [vp, P(Scene), P(RenderState), P(View)]
@@ -188,8 +189,28 @@ def load_library():
     lib.b200_get_stats.argtypes = [vp, P(FrameStats)]
     lib.b200_get_trace.argtypes = [vp, C.c_char_p, C.c_int]
     lib.b200_selftest_divide.argtypes = [vp, C.c_uint64, C.c_uint64, C.c_float, P(C.c_uint64)]
+    lib.b200_diag_set_max_rendering_blocks.argtypes = [vp, C.c_int]
+    lib.b200_diag_set_max_rendering_blocks.restype = None
     _lib = lib
     return lib
+
+
+_host = None
+
+
+def host_library():
+    """libb200host.so: Matrix4f::inv / operator* in the reference's operation order for hosts without ORUtils."""
+    global _host
+    if _host is None:
+        if not os.path.exists(HOST_LIB_PATH):
+            raise RuntimeError(f"{HOST_LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'`")
+        h = C.CDLL(HOST_LIB_PATH)
+        P = C.POINTER
+        h.b200h_mat4_inv.argtypes = [P(C.c_float), P(C.c_float)]
+        h.b200h_mat4_mul.argtypes = [P(C.c_float), P(C.c_float), P(C.c_float)]
+        h.b200h_mat4_mul.restype = None
+        _host = h
+    return _host
 
 
 def mat_to_c(m):

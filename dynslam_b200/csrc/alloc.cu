@@ -372,8 +372,8 @@ k_visible_list(const b200_hash_entry *__restrict__ table, int numBuckets, int no
       ctr->noVisibleBlocks = n;
       ctr->noIntegrated = 0;            // IntegrateIntoScene of this frame counts from zero (no separate memset)
       const int kept = n < capacity ? n : capacity;
-      if (oldestSlot >= 0) { if (ringStart + kept - snapStart[oldestSlot] > ringCap) ctr->errorFlags |= 1; }
-      else if (kept > ringCap) ctr->errorFlags |= 1;
+      // (a snapshot that wraps onto older live ones simply overwrites them: decay.cu recognises an overwritten snapshot by
+      // ringHead - snapStart > ringCap when its turn comes and sweeps nothing — the oldest snapshots are dropped, never an error)
       snapStart[slot] = ringStart;
       snapCount[slot] = kept;
       ctr->ringHead = ringStart + kept;

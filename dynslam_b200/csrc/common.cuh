@@ -94,7 +94,7 @@ struct DevCounters {
   int decayDeleted;        // unique blocks deleted by the pass
   int freedLastDecay;
   int decayCand;           // partial decay: items that found their block empty this pass (candidates, unordered)
-  int errorFlags;          // bit0: decay ring overflow
+  int droppedSnapshots;    // decay: snapshots found overwritten in the ring when their turn came (swept as empty)
   unsigned noRenderingBlocks;
   unsigned visCtasDone;    // k_visible_list: CTAs that have finished (the last one applies the rendering-block cap if needed)
   int noNeededEntries;     // swapping

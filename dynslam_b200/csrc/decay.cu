@@ -31,9 +31,12 @@ k_decay_blocks(b200_voxel *voxels, const b200_hash_entry *__restrict__ table, in
   // one wave of warps instead of ~5 sequential items per CTA.
   const int lane = threadIdx.x & 31;
   const int warpsTotal = gridDim.x * (blockDim.x >> 5), warpId = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const int n = (MODE == 0) ? snapCount[slot] : numBlocks;
+  int n = (MODE == 0) ? snapCount[slot] : numBlocks;
   const long long s0 = (MODE == 0) ? snapStart[slot] : 0;
-  if (blockIdx.x == 0 && threadIdx.x == 0) ctr->decayItems = n;
+  // a snapshot the ring has wrapped over since it was taken is gone (b200_engine_config.decayRingItems): sweep nothing
+  const bool overwritten = (MODE == 0) && (ctr->ringHead - s0 > ringCap);
+  if (overwritten) n = 0;
+  if (blockIdx.x == 0 && threadIdx.x == 0) { ctr->decayItems = n; if (overwritten) ctr->droppedSnapshots++; }
   for (int item = warpId; item < n; item += warpsTotal) {
     int x, y, z;
     if (MODE == 0) { b200_vec3i p = ring[(s0 + item) % ringCap]; x = p.x; y = p.y; z = p.z; }

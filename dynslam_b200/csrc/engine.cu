@@ -10,6 +10,7 @@
 // upload, the launches, one asynchronous download and one stream synchronise; the fused
 // b200_process_frame_async path does none of that until b200_sync().
 #include "engine.h"
+#include "../../include/b200fusion_diag.h"
 
 #include <cstdio>
 #include <cstdlib>
@@ -25,6 +26,18 @@
   } while (0)
 
 static Mat4 to_mat(const float *m) { Mat4 r; memcpy(r.m, m, sizeof(r.m)); return r; }
+
+// lhs * rhs for column-major 4x4 (m[col*4+row]), accumulated over k in ascending order from 0.0f like the reference's
+// operator* (OR/Matrix.h:102-108) so that CreatePointCloud's invM * calib keeps its bits
+static void mat_mul(const float *lhs, const float *rhs, float *out) {
+  float r[16];
+  for (int c = 0; c < 4; ++c) for (int row = 0; row < 4; ++row) {
+    float acc = 0.0f;
+    for (int k = 0; k < 4; ++k) acc += lhs[k * 4 + row] * rhs[c * 4 + k];
+    r[c * 4 + row] = acc;
+  }
+  memcpy(out, r, sizeof(r));
+}
 
 static SceneRef scene_ref(const b200_scene *s, const b200_render_state *rs) {
   SceneRef r;
@@ -60,6 +73,9 @@ static b200_status check_scene(b200_engine *e, const b200_scene *s) {
 
 // host -> device counters (only the three the host owns); device -> host (everything)
 static b200_status upload(b200_engine *e, const b200_scene *s, const b200_render_state *rs) {
+  // Frames enqueued by the asynchronous entry points since the last b200_sync() have moved the device counters on: the
+  // host copies are stale then and must not be written over them (the call's own download refreshes the host fields).
+  if (!e->hostAuthoritative) return B200_OK;
   int *in = reinterpret_cast<int *>(e->h_ctr + 1);   // second pinned struct = upload staging
   in[0] = s->lastFreeBlockId; in[1] = s->lastFreeExcessListId; in[2] = rs ? rs->noVisibleBlocks : 0;
   CK(cudaMemcpyAsync(e->d_ctr, in, rs ? 3 * sizeof(int) : 2 * sizeof(int), cudaMemcpyHostToDevice, e->stream));
@@ -75,22 +91,33 @@ static b200_status download_sync(b200_engine *e, b200_scene *s, b200_render_stat
   e->totalDecayed = e->h_ctr->totalDecayed;
   e->lastNoIntegrated = e->h_ctr->noIntegrated;
   e->hostAuthoritative = true;
-  if (e->h_ctr->errorFlags & 1) {
-    snprintf(e->err, sizeof(e->err), "decay snapshot ring overflow (raise b200_engine_config.decayRingItems)");
-    return B200_ERR_DECAY_RING_FULL;
-  }
   return B200_OK;
 }
 
 extern "C" {
 
+static b200_status engine_create_body(const b200_engine_config *cfg, b200_engine *e);
+
+static thread_local char g_createErr[512] = "";
+
 b200_status b200_engine_create(const b200_engine_config *cfg, b200_engine **out) {
-  if (!cfg || !out) return B200_ERR_INVALID;
+  if (out) *out = nullptr;
+  if (!cfg || !out) { snprintf(g_createErr, sizeof(g_createErr), "null configuration or output pointer"); return B200_ERR_INVALID; }
   b200_engine *e = new b200_engine();
   memset(e, 0, sizeof(*e));
-  e->useGraph = -1;
-  { const char *m = getenv("B200_TEST_MAX_RENDERING_BLOCKS"); e->maxRenderingBlocks = (m && atoi(m) > 0) ? atoi(m) : B200_MAX_RENDERING_BLOCKS; }
+  const b200_status st = engine_create_body(cfg, e);
+  if (st != B200_OK) {          // nothing stays allocated after a failed create; the reason survives in b200_last_error(NULL)
+    snprintf(g_createErr, sizeof(g_createErr), "%s", e->err);
+    b200_engine_destroy(e);
+    return st;
+  }
   *out = e;
+  return B200_OK;
+}
+
+static b200_status engine_create_body(const b200_engine_config *cfg, b200_engine *e) {
+  e->useGraph = -1;
+  e->maxRenderingBlocks = B200_MAX_RENDERING_BLOCKS;
   e->device = cfg->device;
   e->numBlocks = cfg->numBlocks; e->numBuckets = cfg->numBuckets; e->excessSize = cfg->excessSize;
   e->noTotal = cfg->numBuckets + cfg->excessSize; e->img_w = cfg->img_w; e->img_h = cfg->img_h;
@@ -147,6 +174,8 @@ b200_status b200_engine_create(const b200_engine_config *cfg, b200_engine **out)
     CK(cudaEventCreateWithFlags(&e->evJoin, cudaEventDisableTiming));
   }
   e->hostAuthoritative = true;
+  integrate_init_device(e);     // per-device tables and function attributes of integrate.cu (one engine per GPU is the multi-GPU unit)
+  CK(cudaGetLastError());
   // default: V3 (warp-decoupled TMA ring, integrate.cu); B200_INTEGRATE_IMPL=tma|ldg select the earlier variants
   { const char *v = getenv("B200_INTEGRATE_IMPL"); e->integrateImpl = (v && v[0] == 'l') ? 0 : ((v && v[0] == 't') ? 1 : 2); }
   return B200_OK;
@@ -163,18 +192,21 @@ void b200_engine_destroy(b200_engine *e) {
   if (e->copyStream) {
     cudaStreamSynchronize(e->copyStream);
     for (int i = 0; i < 2; ++i) { cudaFree(e->d_stageDepth[i]); cudaFree(e->d_stageRgb[i]); cudaFree(e->d_stageOut[i]); cudaFree(e->d_stageRaw[i]);
-      cudaEventDestroy(e->evH2D[i]); cudaEventDestroy(e->evCompute[i]); cudaEventDestroy(e->evD2H[i]); }
+      if (e->evH2D[i]) cudaEventDestroy(e->evH2D[i]); if (e->evCompute[i]) cudaEventDestroy(e->evCompute[i]); if (e->evD2H[i]) cudaEventDestroy(e->evD2H[i]); }
     cudaStreamDestroy(e->copyStream);
     if (e->d2hStream) { cudaStreamSynchronize(e->d2hStream); cudaStreamDestroy(e->d2hStream); }
     if (e->evMid) cudaEventDestroy(e->evMid);
   }
   if (e->frameGraph) cudaGraphExecDestroy(e->frameGraph);
-  if (e->sideStream) { cudaStreamSynchronize(e->sideStream); cudaEventDestroy(e->evFork); cudaEventDestroy(e->evJoin); cudaStreamDestroy(e->sideStream); }
+  if (e->sideStream) { cudaStreamSynchronize(e->sideStream); if (e->evFork) cudaEventDestroy(e->evFork); if (e->evJoin) cudaEventDestroy(e->evJoin); cudaStreamDestroy(e->sideStream); }
+  if (e->evRing) { for (int i = 0; i < e->evRingCap * 2; ++i) cudaEventDestroy(e->evRing[i]); free(e->evRing); }
+  if (e->traceEv) { for (int i = 0; i < e->traceCap * 2; ++i) cudaEventDestroy(e->traceEv[i]); free(e->traceEv); free(e->traceName); }
+  cudaGetLastError();
   if (e->ownStream && e->stream) cudaStreamDestroy(e->stream);
   delete e;
 }
 
-const char *b200_last_error(const b200_engine *e) { return e ? e->err : "null engine"; }
+const char *b200_last_error(const b200_engine *e) { return e ? e->err : g_createErr; }
 void *b200_engine_stream(b200_engine *e) { return (void *)e->stream; }
 int32_t b200_frame_index(const b200_engine *e) { return e->frameIdx; }
 size_t b200_decayed_block_count(const b200_engine *e) { return (size_t)e->totalDecayed; }
@@ -215,46 +247,7 @@ int b200_get_trace(b200_engine *e, char *out, int cap) {
   return n;
 }
 
-// Matrix4::inv — OR/Matrix.h:162-224
-int b200_mat4_inv(const float *m, float *dst) {
-  float tmp[12], src[16], det;
-  for (int i = 0; i < 4; i++) { src[i] = m[i * 4]; src[i + 4] = m[i * 4 + 1]; src[i + 8] = m[i * 4 + 2]; src[i + 12] = m[i * 4 + 3]; }
-  tmp[0] = src[10] * src[15]; tmp[1] = src[11] * src[14]; tmp[2] = src[9] * src[15]; tmp[3] = src[11] * src[13];
-  tmp[4] = src[9] * src[14]; tmp[5] = src[10] * src[13]; tmp[6] = src[8] * src[15]; tmp[7] = src[11] * src[12];
-  tmp[8] = src[8] * src[14]; tmp[9] = src[10] * src[12]; tmp[10] = src[8] * src[13]; tmp[11] = src[9] * src[12];
-  dst[0] = (tmp[0] * src[5] + tmp[3] * src[6] + tmp[4] * src[7]) - (tmp[1] * src[5] + tmp[2] * src[6] + tmp[5] * src[7]);
-  dst[1] = (tmp[1] * src[4] + tmp[6] * src[6] + tmp[9] * src[7]) - (tmp[0] * src[4] + tmp[7] * src[6] + tmp[8] * src[7]);
-  dst[2] = (tmp[2] * src[4] + tmp[7] * src[5] + tmp[10] * src[7]) - (tmp[3] * src[4] + tmp[6] * src[5] + tmp[11] * src[7]);
-  dst[3] = (tmp[5] * src[4] + tmp[8] * src[5] + tmp[11] * src[6]) - (tmp[4] * src[4] + tmp[9] * src[5] + tmp[10] * src[6]);
-  det = src[0] * dst[0] + src[1] * dst[1] + src[2] * dst[2] + src[3] * dst[3];
-  if (det == 0.0f) return 0;
-  dst[4] = (tmp[1] * src[1] + tmp[2] * src[2] + tmp[5] * src[3]) - (tmp[0] * src[1] + tmp[3] * src[2] + tmp[4] * src[3]);
-  dst[5] = (tmp[0] * src[0] + tmp[7] * src[2] + tmp[8] * src[3]) - (tmp[1] * src[0] + tmp[6] * src[2] + tmp[9] * src[3]);
-  dst[6] = (tmp[3] * src[0] + tmp[6] * src[1] + tmp[11] * src[3]) - (tmp[2] * src[0] + tmp[7] * src[1] + tmp[10] * src[3]);
-  dst[7] = (tmp[4] * src[0] + tmp[9] * src[1] + tmp[10] * src[2]) - (tmp[5] * src[0] + tmp[8] * src[1] + tmp[11] * src[2]);
-  tmp[0] = src[2] * src[7]; tmp[1] = src[3] * src[6]; tmp[2] = src[1] * src[7]; tmp[3] = src[3] * src[5];
-  tmp[4] = src[1] * src[6]; tmp[5] = src[2] * src[5]; tmp[6] = src[0] * src[7]; tmp[7] = src[3] * src[4];
-  tmp[8] = src[0] * src[6]; tmp[9] = src[2] * src[4]; tmp[10] = src[0] * src[5]; tmp[11] = src[1] * src[4];
-  dst[8] = (tmp[0] * src[13] + tmp[3] * src[14] + tmp[4] * src[15]) - (tmp[1] * src[13] + tmp[2] * src[14] + tmp[5] * src[15]);
-  dst[9] = (tmp[1] * src[12] + tmp[6] * src[14] + tmp[9] * src[15]) - (tmp[0] * src[12] + tmp[7] * src[14] + tmp[8] * src[15]);
-  dst[10] = (tmp[2] * src[12] + tmp[7] * src[13] + tmp[10] * src[15]) - (tmp[3] * src[12] + tmp[6] * src[13] + tmp[11] * src[15]);
-  dst[11] = (tmp[5] * src[12] + tmp[8] * src[13] + tmp[11] * src[14]) - (tmp[4] * src[12] + tmp[9] * src[13] + tmp[10] * src[14]);
-  dst[12] = (tmp[2] * src[10] + tmp[5] * src[11] + tmp[1] * src[9]) - (tmp[4] * src[11] + tmp[0] * src[9] + tmp[3] * src[10]);
-  dst[13] = (tmp[8] * src[11] + tmp[0] * src[8] + tmp[7] * src[10]) - (tmp[6] * src[10] + tmp[9] * src[11] + tmp[1] * src[8]);
-  dst[14] = (tmp[6] * src[9] + tmp[11] * src[11] + tmp[3] * src[8]) - (tmp[10] * src[11] + tmp[2] * src[8] + tmp[7] * src[9]);
-  dst[15] = (tmp[10] * src[10] + tmp[4] * src[8] + tmp[9] * src[9]) - (tmp[8] * src[9] + tmp[11] * src[10] + tmp[5] * src[8]);
-  const float s = 1 / det;
-  for (int i = 0; i < 16; ++i) dst[i] *= s;
-  return 1;
-}
-
-// Matrix4 operator* — OR/Matrix.h:102-108
-void b200_mat4_mul(const float *lhs, const float *rhs, float *out) {
-  float r[16];
-  for (int i = 0; i < 16; ++i) r[i] = 0.0f;
-  for (int x = 0; x < 4; x++) for (int y = 0; y < 4; y++) for (int k = 0; k < 4; k++) r[x * 4 + y] += lhs[k * 4 + y] * rhs[x * 4 + k];
-  memcpy(out, r, sizeof(r));
-}
+void b200_diag_set_max_rendering_blocks(b200_engine *e, int n) { e->maxRenderingBlocks = n > 0 ? n : B200_MAX_RENDERING_BLOCKS; }
 
 // ---- ITMSceneReconstructionEngine ---------------------------------------------------------------
 
@@ -270,10 +263,11 @@ b200_status b200_reset_scene(b200_engine *e, b200_scene *s) {
 
 static b200_status enqueue_allocate(b200_engine *e, b200_scene *s, b200_render_state *rs, const b200_view *v, int onlyVisible,
                                     bool fuseDeadInit = false) {
-  if (e->qSize >= SNAP_SLOTS - 1) {
-    snprintf(e->err, sizeof(e->err), "decay queue deeper than %d frames", SNAP_SLOTS);
-    return B200_ERR_DECAY_RING_FULL;
-  }
+  // The reference's queue of visible-list copies is unbounded (Reco_CUDA.cu:302-317); this one has SNAP_SLOTS frame slots and
+  // a ring of list items. When Decay() is never called (--voxel_decay=false) or min_decay_age is very large, the OLDEST
+  // snapshot is dropped to make room — never an error (the ring's item overflow is handled the same way on the device:
+  // decay.cu recognises an overwritten snapshot by its start position and sweeps nothing).
+  if (e->qSize >= SNAP_SLOTS - 1) { e->qHead++; e->qSize--; e->droppedSnapshots++; }
   if (v->depth_w != e->img_w || v->depth_h != e->img_h) {
     snprintf(e->err, sizeof(e->err), "view size %dx%d differs from engine %dx%d", v->depth_w, v->depth_h, e->img_w, e->img_h);
     return B200_ERR_INVALID;
@@ -353,6 +347,7 @@ b200_status b200_find_surface(b200_engine *e, const b200_scene *s, b200_render_s
   launch_raycast(e, scene_ref(s, rs), to_mat(cam->invM), cam->proj, rs->img_w, rs->img_h, s->voxelSize, s->mu, rs->d_minmax,
                  rs->d_raycastResult);
   CK(cudaStreamSynchronize(e->stream));
+  CK(cudaGetLastError());
   return B200_OK;
 }
 
@@ -397,7 +392,7 @@ b200_status b200_point_cloud(b200_engine *e, const b200_scene *s, b200_render_st
   b200_status st = check_scene(e, s); if (st) return st;
   CK(cudaSetDevice(e->device));
   float invMf[16];
-  b200_mat4_mul(v->invM_d, calib, invMf);
+  mat_mul(v->invM_d, calib, invMf);
   Mat4 invM = to_mat(invMf);
   SceneRef r = scene_ref(s, rs);
   launch_raycast(e, r, invM, v->proj_rgb, rs->img_w, rs->img_h, s->voxelSize, s->mu, rs->d_minmax, rs->d_raycastResult);
@@ -767,6 +762,7 @@ b200_status b200_get_stats(b200_engine *e, b200_frame_stats *out) {
   out->noVisibleBlocks = e->h_ctr->noVisibleBlocks;
   out->noIntegratedBlocks = e->h_ctr->noIntegrated;
   out->totalIntegratedBlocks = e->h_ctr->totalIntegrated;
+  out->droppedSnapshots = e->droppedSnapshots + e->h_ctr->droppedSnapshots;
   if (e->timingMode >= 2 && e->evRingCount > 0) {
     CK(cudaEventSynchronize(e->evRing[2 * e->evRingCount - 1]));
     float sum = 0;

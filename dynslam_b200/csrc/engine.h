@@ -49,6 +49,7 @@ struct b200_engine {
   int *d_snapCount;                   // device-side count per ring slot (slot = frame % SNAP_SLOTS)
   long long *d_snapStart;
   int qHead, qSize;                   // host view of the queue (slots qHead .. qHead+qSize-1)
+  long long droppedSnapshots;         // snapshots dropped on the host side because the queue was SNAP_SLOTS deep
   unsigned long long *d_delTag;       // per VBA block: gen | ~itemIndex of the deleting item
   int *d_visiblePtr;                  // VBA ptr of every item of the list built by the last allocate (or -1)
   const void *ptrListFor;             // the visible list buffer d_visiblePtr describes
@@ -76,7 +77,7 @@ struct b200_engine {
   float *d_stageDepth[2]; b200_vec4u *d_stageRgb[2]; b200_vec4u *d_stageOut[2]; int16_t *d_stageRaw[2];
   cudaEvent_t evH2D[2], evCompute[2], evD2H[2];
   bool slotBusy[2]; size_t stagePixels;
-  int maxRenderingBlocks;                           // MAX_RENDERING_BLOCKS; B200_TEST_MAX_RENDERING_BLOCKS lowers it (tests)
+  int maxRenderingBlocks;                           // MAX_RENDERING_BLOCKS; b200_diag_set_max_rendering_blocks lowers it (tests)
   int useGraph; bool graphWarm; cudaGraphExec_t frameGraph;
   cudaEvent_t evMid; bool midValid;                 // "allocation + integration of the last frame are done" (pipelined uploads wait for it)         // B200_GRAPH=1: the fused frame is captured and replayed as a CUDA graph
   float *d_viewScratch; size_t viewScratchPixels;   // plays view->depth inside UpdateView (view.cu)
@@ -98,6 +99,7 @@ void launch_reset(b200_engine *e, const SceneRef &s);
 void launch_allocate(b200_engine *e, const SceneRef &s, const FrameGeom &g, const float *depth, bool onlyVisible,
                      int frameIdx, int snapSlot, b200_vec2f *minmaxDead, int mw, int mh);
 void launch_integrate(b200_engine *e, const SceneRef &s, const FrameGeom &g, const float *depth, const b200_vec4u *rgb);
+void integrate_init_device(b200_engine *e);   // per-device: division table upload, dynamic shared-memory attributes
 static inline const int *fresh_ptr_list(const b200_engine *e, const SceneRef &s) {
   return (e->ptrListFor == (const void *)s.visiblePos && e->ptrListVersion == e->tableVersion) ? e->d_visiblePtr : nullptr;
 }

@@ -129,21 +129,21 @@ class View:
         self.set_pose(M_d, M_rgb)
 
     def set_pose(self, M_d, M_rgb=None):
-        lib = abi.load_library()
+        lib = abi.host_library()
         self.c.M_d = abi.mat_to_c(M_d)
         inv = abi.f16()
-        if not lib.b200_mat4_inv(self.c.M_d, inv):
+        if not lib.b200h_mat4_inv(self.c.M_d, inv):
             raise ValueError("singular pose")
         self.c.invM_d = inv
         self.c.M_rgb = abi.mat_to_c(M_rgb if M_rgb is not None else M_d)
 
 
 def make_camera(M, proj):
-    lib = abi.load_library()
+    lib = abi.host_library()
     c = abi.Camera()
     c.M = abi.mat_to_c(M)
     inv = abi.f16()
-    if not lib.b200_mat4_inv(c.M, inv):
+    if not lib.b200h_mat4_inv(c.M, inv):
         raise ValueError("singular pose")
     c.invM = inv
     c.proj = abi.f4(*[float(x) for x in proj])
@@ -165,11 +165,18 @@ class Engine:
         cfg.stream = stream
         h = C.c_void_p()
         rc = self.lib.b200_engine_create(C.byref(cfg), C.byref(h))
-        self.h = h
-        if rc:
-            msg = self.lib.b200_last_error(h).decode() if h else "engine create failed"
-            raise CudaError(msg)
+        self.h = h if rc == abi.OK else None
+        if rc:      # a failed create leaves nothing allocated; the reason is in b200_last_error(NULL)
+            msg = self.lib.b200_last_error(None).decode()
+            raise (CudaError if rc == abi.ERR_CUDA else ValueError)(msg)
         self.scene = scene
+        self._ext = torch.cuda.ExternalStream(self.lib.b200_engine_stream(self.h), device=scene.device)
+
+    def after_torch(self):
+        """Order the engine's stream behind the work already enqueued on torch's current stream (tensor fills, uploads,
+        torch kernels that produced depth / rgb): the engine runs on its own non-blocking stream and would otherwise race
+        with them. One event record + one stream wait, no host synchronisation; a no-op when both are the same stream."""
+        self._ext.wait_stream(torch.cuda.current_stream(self.scene.device))
 
     def close(self):
         if getattr(self, "h", None):
@@ -208,12 +215,17 @@ class Engine:
     def set_timing(self, on):
         self.lib.b200_set_timing(self.h, int(on))
 
+    def set_max_rendering_blocks(self, n):
+        """test hook (include/b200fusion_diag.h): lower MAX_RENDERING_BLOCKS to reach the cap rule with small scenes"""
+        self.lib.b200_diag_set_max_rendering_blocks(self.h, int(n))
+
     # ---- fused fast path --------------------------------------------------------------------
     def process_frame_async(self, renderState, view, points=None, normals=None, decay=None, raycast=True):
         o = abi.FrameOpts()
         o.doRaycast = int(raycast)
         if decay is not None:
             o.doDecay, o.decayMaxWeight, o.decayMinAge = 1, decay[0], decay[1]
+        self.after_torch()
         self.check(self.lib.b200_process_frame_async(self.h, C.byref(self.scene.c), C.byref(renderState.c), C.byref(view.c),
                                                       _ptr(points), _ptr(normals), C.byref(o)))
 
@@ -394,17 +406,21 @@ class SceneReconstructionEngine:
         self.fusionWeightParams["depthWeighting"] = bool(depthWeighting)
 
     def ResetScene(self, scene):
+        self.e.after_torch()
         self.e.check(self.e.lib.b200_reset_scene(self.e.h, C.byref(scene.c)))
 
     def AllocateSceneFromDepth(self, scene, view, renderState, onlyUpdateVisibleList=False):
+        self.e.after_torch()
         self.e.check(self.e.lib.b200_allocate_from_depth(self.e.h, C.byref(scene.c), C.byref(renderState.c), C.byref(view.c),
                                                           int(onlyUpdateVisibleList)))
 
     def IntegrateIntoScene(self, scene, view, renderState):
         view.c.depthWeighting = int(self.fusionWeightParams["depthWeighting"])
+        self.e.after_torch()
         self.e.check(self.e.lib.b200_integrate(self.e.h, C.byref(scene.c), C.byref(renderState.c), C.byref(view.c)))
 
     def Decay(self, scene, renderState, maxWeight, minAge, forceAllVoxels=False):
+        self.e.after_torch()
         self.e.check(self.e.lib.b200_decay(self.e.h, C.byref(scene.c), C.byref(renderState.c), maxWeight, minAge,
                                            int(forceAllVoxels)))
 
@@ -422,29 +438,36 @@ class VisualisationEngine:
         return RenderStateVH(self.scene, imgSize, forward=forward)
 
     def FindVisibleBlocks(self, camera, renderState):
+        self.e.after_torch()
         self.e.check(self.e.lib.b200_find_visible_blocks(self.e.h, C.byref(self.scene.c), C.byref(renderState.c), C.byref(camera)))
 
     def CreateExpectedDepths(self, camera, renderState):
+        self.e.after_torch()
         self.e.check(self.e.lib.b200_expected_depths(self.e.h, C.byref(self.scene.c), C.byref(renderState.c), C.byref(camera)))
 
     def FindSurface(self, camera, renderState):
+        self.e.after_torch()
         self.e.check(self.e.lib.b200_find_surface(self.e.h, C.byref(self.scene.c), C.byref(renderState.c), C.byref(camera)))
 
     def RenderImage(self, camera, renderState, outputCharImage, outputFloatImage, type=abi.RENDER_SHADED_GREYSCALE):
+        self.e.after_torch()
         self.e.check(self.e.lib.b200_render_image(self.e.h, C.byref(self.scene.c), C.byref(renderState.c), C.byref(camera),
                                                    _ptr(outputCharImage), _ptr(outputFloatImage), renderState.w, renderState.h, type))
 
     def CreateICPMaps(self, view, renderState, points, normals):
+        self.e.after_torch()
         self.e.check(self.e.lib.b200_icp_maps(self.e.h, C.byref(self.scene.c), C.byref(renderState.c), C.byref(view.c),
                                                _ptr(points), _ptr(normals)))
 
     def ForwardRender(self, view, renderState):
+        self.e.after_torch()
         self.e.check(self.e.lib.b200_forward_render(self.e.h, C.byref(self.scene.c), C.byref(renderState.c), C.byref(view.c)))
         return renderState.c.noFwdProjMissingPoints
 
     def CreatePointCloud(self, view, renderState, locations, colours, skipPoints=False, calib_rgb_to_depth=None):
         calib = abi.mat_to_c(calib_rgb_to_depth if calib_rgb_to_depth is not None else np.eye(4, dtype=np.float32))
         n = C.c_uint32()
+        self.e.after_torch()
         self.e.check(self.e.lib.b200_point_cloud(self.e.h, C.byref(self.scene.c), C.byref(renderState.c), C.byref(view.c), calib,
                                                   int(skipPoints), _ptr(locations), _ptr(colours), C.byref(n)))
         return n.value

@@ -36,14 +36,19 @@ static_assert(sizeof(Vector3i) == sizeof(b200_vec3i) && sizeof(Vector4f) == size
 class B200EngineHandle {
  public:
   b200_engine *e = nullptr;
-  B200EngineHandle(int device, long sdfLocalBlockNum, Vector2i imgSize) {
+  /// decayRingItems: capacity of the engine's decay-snapshot ring in visible-list items (0 = 24 x sdfLocalBlockNum); size it as
+  /// min_decay_age x visible blocks per frame with headroom. When it (or the 4095-frame queue) is full, the oldest snapshots
+  /// are dropped instead of growing without bound like the reference's std::queue (Reco_CUDA.cu:302-317).
+  B200EngineHandle(int device, long sdfLocalBlockNum, Vector2i imgSize, long long decayRingItems = 0) {
     b200_engine_config cfg{};
+    cfg.decayRingItems = decayRingItems;
     cfg.device = device;
     cfg.numBlocks = (int)sdfLocalBlockNum;
     cfg.numBuckets = (int)SDF_BUCKET_NUM;
     cfg.excessSize = (int)SDF_EXCESS_LIST_SIZE;
     cfg.img_w = imgSize.x; cfg.img_h = imgSize.y;
-    check(b200_engine_create(&cfg, &e));
+    const b200_status st = b200_engine_create(&cfg, &e);
+    if (st != B200_OK) { fprintf(stderr, "b200fusion: engine create failed (%d): %s\n", (int)st, b200_last_error(nullptr)); exit(-1); }
   }
   ~B200EngineHandle() { b200_engine_destroy(e); }
   void check(b200_status st) const {
@@ -54,7 +59,6 @@ class B200EngineHandle {
     case B200_ERR_EXCESS_FULL:
       throw std::runtime_error("Invalid free excess list slot ID. InfiniTAM has run out of slots in the hash table excess list. "
                                "Consider increasing the size of the excess list or the number of buckets.");
-    case B200_ERR_DECAY_RING_FULL: throw std::runtime_error(b200_last_error(e));
     default:
       fprintf(stderr, "b200fusion error %d: %s\n", (int)st, b200_last_error(e));
       exit(-1);

@@ -44,7 +44,7 @@ typedef enum {
   B200_ERR_VBA_FULL = 2,      /* reference: throw runtime_error, Reco_CUDA.cu:348-351 */
   B200_ERR_EXCESS_FULL = 3,   /* reference: throw runtime_error, Reco_CUDA.cu:353-357 */
   B200_ERR_INVALID = 4,
-  B200_ERR_DECAY_RING_FULL = 5,
+  B200_ERR_DECAY_RING_FULL = 5, /* no longer returned: a full decay queue drops its oldest snapshots (see b200_engine_config) */
   B200_ERR_UNSUPPORTED = 6
 } b200_status;
 
@@ -147,20 +147,21 @@ typedef struct {
   int32_t numBuckets;
   int32_t excessSize;
   int32_t img_w, img_h;
-  int64_t decayRingItems;      /* capacity (visible-list items) of the decay snapshot ring;
-                                  0 = default 24*numBlocks */
+  int64_t decayRingItems;      /* capacity (visible-list items) of the decay snapshot ring; 0 = default 24*numBlocks.
+                                  The reference keeps one copy of the visible list per frame in an unbounded std::queue
+                                  (Reco_CUDA.cu:302-317); here the queue holds at most 4095 frames and decayRingItems list
+                                  items. Beyond either bound the OLDEST snapshots are dropped (a Decay() that would have
+                                  swept a dropped snapshot sweeps nothing; b200_frame_stats.droppedSnapshots counts them) —
+                                  size it as min_decay_age x (visible blocks per frame) with headroom. Never an error. */
   void *stream;                /* optional caller cudaStream_t; NULL = engine-owned stream */
 } b200_engine_config;
 
+/* On failure nothing is left allocated, *out is NULL and b200_last_error(NULL) gives the reason (thread-local). */
 b200_status b200_engine_create(const b200_engine_config *cfg, b200_engine **out);
 void b200_engine_destroy(b200_engine *e);
 const char *b200_last_error(const b200_engine *e);
 void *b200_engine_stream(b200_engine *e);
 int32_t b200_frame_index(const b200_engine *e);      /* frameIdx, Reco_CUDA.h:37-45 */
-
-/* Matrix4f::inv restated for hosts without ORUtils (ORUtils/Matrix.h:162-224) */
-int b200_mat4_inv(const float *m, float *out);
-void b200_mat4_mul(const float *lhs, const float *rhs, float *out);
 
 /* ---- ITMSceneReconstructionEngine ------------------------------------------------------- */
 
@@ -345,34 +346,6 @@ b200_status b200_composite_color(b200_engine *e, b200_vec4u *d_target_color, flo
 b200_status b200_composite_instances(b200_engine *e, b200_vec4u *d_out_color, float *d_out_depth, int n,
                                      const b200_instance_layer *layers, int n_layers, float dim_factor,
                                      float tint_strength);
-
-/* ---- introspection used by bench.py / tests -------------------------------------------------- */
-
-typedef struct {
-  float ms_allocate, ms_integrate, ms_expected, ms_raycast, ms_decay, ms_total;
-  int64_t launches;            /* kernels launched by this engine since creation */
-  int32_t noVisibleBlocks, noIntegratedBlocks;
-  /* timing mode 2: CUDA-event pairs around EVERY IntegrateIntoScene launch since the mode was set */
-  float ring_ms_integrate;     /* sum of the launch durations */
-  int32_t ring_count;          /* number of launches measured */
-  int64_t totalIntegratedBlocks; /* cumulative blocks integrated since engine creation */
-} b200_frame_stats;
-
-/* 0 = off; 1 = per-stage CUDA events of the last fused frame; 2 = 1 + an event pair around every
-   integrate launch (ring of 8192 frames), reset whenever the mode is set; 3 = an event pair around EVERY
-   kernel launch of the frame path (launch trace, read and cleared by b200_get_trace; perturbs the timing) */
-void b200_set_timing(b200_engine *e, int enabled);
-/* "kernel start_us end_us" lines (relative to the first traced launch); returns the number of bytes written */
-int b200_get_trace(b200_engine *e, char *out, int cap);
-b200_status b200_get_stats(b200_engine *e, b200_frame_stats *out);
-
-/* Self-test of the division sequences of the default IntegrateIntoScene kernel (integrate.cu, variant V3): on the
-   engine's device, `pairs` pseudo-random operand pairs (a, b) drawn from the ranges the kernel's fast path accepts
-   (|a| in {0} U [2^-40, 2^40], b in [2^-20, 2^20], plus the constant divisors mu, 255, 32767 and the integer weights
-   1..271) are divided with the kernel's sequence and with the IEEE operator `/` (what DA/ITMSceneReconstructionEngine.h
-   :14-128 evaluates on the host); *mismatches receives the number of quotients whose bits differ (signed zeros
-   compare equal). Test infrastructure only. */
-b200_status b200_selftest_divide(b200_engine *e, uint64_t pairs, uint64_t seed, float mu, uint64_t *mismatches);
 
 #ifdef __cplusplus
 }

@@ -132,6 +132,53 @@ int harness_process_frame(Harness *H, const float *depth, const unsigned char *r
 }
 
 void harness_sync(Harness *H) { ORcudaSafeCall(cudaDeviceSynchronize()); }
+// The same frame with a device synchronise + wall clock after every call: where the synchronous ITMLib loop spends its time
+// (bench.py `itmlib_harness.stages_us`). stage_us[6] += {H2D of the frame, AllocateSceneFromDepth, IntegrateIntoScene,
+// CreateExpectedDepths, CreateICPMaps, Decay} in microseconds.
+int harness_process_frame_timed(Harness *H, const float *depth, const unsigned char *rgba, const float *M_d, int decayMaxWeight,
+                                int decayMinAge, int doDecay, double *stage_us) {
+  const size_t n = (size_t)H->imgSize.x * H->imgSize.y;
+  auto now = [] { return std::chrono::steady_clock::now(); };
+  auto us = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+    return std::chrono::duration<double, std::micro>(b - a).count();
+  };
+  ORcudaSafeCall(cudaDeviceSynchronize());
+  auto t0 = now();
+  ORcudaSafeCall(cudaMemcpy(H->view->depth->GetData(MEMORYDEVICE_CUDA), depth, n * sizeof(float), cudaMemcpyHostToDevice));
+  ORcudaSafeCall(cudaMemcpy(H->view->rgb->GetData(MEMORYDEVICE_CUDA), rgba, n * 4, cudaMemcpyHostToDevice));
+  Matrix4f M; for (int i = 0; i < 16; ++i) M.m[i] = M_d[i];
+  H->trackingState->pose_d->SetM(M);
+  H->trackingState->requiresFullRendering = true;
+  ORcudaSafeCall(cudaDeviceSynchronize());
+  auto t1 = now(); stage_us[0] += us(t0, t1);
+  try {
+    H->reco->AllocateSceneFromDepth(H->scene, H->view, H->trackingState, H->renderState);
+    ORcudaSafeCall(cudaDeviceSynchronize());
+    auto t2 = now(); stage_us[1] += us(t1, t2);
+    H->reco->IntegrateIntoScene(H->scene, H->view, H->trackingState, H->renderState);
+    ORcudaSafeCall(cudaDeviceSynchronize());
+    auto t3 = now(); stage_us[2] += us(t2, t3);
+    H->vis->CreateExpectedDepths(H->trackingState->pose_d, &(H->view->calib->intrinsics_d), H->renderState);
+    ORcudaSafeCall(cudaDeviceSynchronize());
+    auto t4 = now(); stage_us[3] += us(t3, t4);
+    H->vis->CreateICPMaps(H->view, H->trackingState, H->renderState);
+    H->trackingState->pose_pointCloud->SetFrom(H->trackingState->pose_d);
+    ORcudaSafeCall(cudaDeviceSynchronize());
+    auto t5 = now(); stage_us[4] += us(t4, t5);
+    if (doDecay) H->reco->Decay(H->scene, H->renderState, decayMaxWeight, decayMinAge, false);
+    ORcudaSafeCall(cudaDeviceSynchronize());
+    stage_us[5] += us(t5, now());
+  } catch (std::runtime_error &e) {
+    snprintf(H->err, sizeof(H->err), "%s", e.what());
+    return 2;
+  }
+  return 0;
+}
+
+// page-lock a caller buffer (frames held in numpy arrays) so that the per-frame cudaMemcpy is a DMA from pinned memory
+int harness_pin(void *p, size_t bytes) { return (int)cudaHostRegister(p, bytes, cudaHostRegisterDefault); }
+int harness_unpin(void *p) { return (int)cudaHostUnregister(p); }
+
 
 void harness_counters(Harness *H, int *lastFreeBlockId, int *lastFreeExcess, int *noVisible, long *decayed) {
   *lastFreeBlockId = H->scene->localVBA.lastFreeBlockId;

@@ -36,6 +36,9 @@ def lib():
         L.harness_mute_stdout.argtypes = [vp, C.c_int]
         L.harness_mute_stdout.restype = None
         L.harness_process_frame.argtypes = [vp, vp, vp, C.POINTER(C.c_float), C.c_int, C.c_int, C.c_int, C.c_int]
+        L.harness_process_frame_timed.argtypes = [vp, vp, vp, C.POINTER(C.c_float), C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double)]
+        L.harness_pin.argtypes = [vp, C.c_size_t]
+        L.harness_unpin.argtypes = [vp]
         L.harness_sync.argtypes = [vp]
         L.harness_sync.restype = None
         L.harness_counters.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_long)]
@@ -102,6 +105,14 @@ class Harness:
         m = abi.mat_to_c(M)
         rc = self.L.harness_process_frame(self.h_, depth.ctypes.data, rgb.ctypes.data, m, decay[0] if decay else 0,
                                           decay[1] if decay else 0, int(decay is not None), int(raycast))
+        if rc:
+            raise RuntimeError(self.L.harness_error(self.h_).decode())
+
+    def process_frame_timed(self, depth, rgb, M, stage_us, decay=None):
+        """Same frame with a device synchronise + wall clock after every ITMLib call; stage_us (6 doubles) accumulates."""
+        m = abi.mat_to_c(M)
+        rc = self.L.harness_process_frame_timed(self.h_, depth.ctypes.data, rgb.ctypes.data, m, decay[0] if decay else 0,
+                                                decay[1] if decay else 0, int(decay is not None), stage_us)
         if rc:
             raise RuntimeError(self.L.harness_error(self.h_).decode())
 

@@ -26,6 +26,8 @@ class Cfg:
         self.depthWeighting = False
         self.stopMaxW = False
         self.zmax = 20.0
+        self.maxRenderingBlocks = 0   # > 0: lower MAX_RENDERING_BLOCKS on the engine (diag hook) to reach the cap rule
+        self.decayRingItems = 0
         self.scene_seed = 6
         self.raycast = True
         self.workload = "kitti"
@@ -53,7 +55,9 @@ class Pair:
             self.w, self.h = int(round(synth.KITTI_W * cfg.scale)), int(round(synth.KITTI_H * cfg.scale))
         p = E.SceneParams(cfg.voxelSize, cfg.mu, cfg.maxW, cfg.vf_min, cfg.vf_max, cfg.stopMaxW)
         self.scene = E.Scene(p, cfg.numBlocks, cfg.numBuckets, cfg.excessSize, device=device)
-        self.eng = E.Engine(self.scene, (self.w, self.h))
+        self.eng = E.Engine(self.scene, (self.w, self.h), decayRingItems=cfg.decayRingItems)
+        if cfg.maxRenderingBlocks > 0:
+            self.eng.set_max_rendering_blocks(cfg.maxRenderingBlocks)
         self.reco = E.SceneReconstructionEngine(self.eng)
         self.reco.SetFusionWeightParams(cfg.depthWeighting)
         self.vis = E.VisualisationEngine(self.eng, self.scene)

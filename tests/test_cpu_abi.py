@@ -19,6 +19,13 @@ def test_library_exports_every_declared_symbol():
     assert declared == set(abi.EXPORTS), declared ^ set(abi.EXPORTS)
     for name in declared:
         assert hasattr(lib, name), name
+    # the measurement / test hooks live in their own header, outside the drop-in boundary
+    diag = open(os.path.join(ROOT, "include", "b200fusion_diag.h")).read()
+    declared_diag = set(re.findall(r"\b(b200_[a-z0-9_]+)\s*\(", diag))
+    assert declared_diag == set(abi.DIAG_EXPORTS), declared_diag ^ set(abi.DIAG_EXPORTS)
+    for name in declared_diag:
+        assert hasattr(lib, name), name
+    assert not (declared & declared_diag)
 
 
 def test_pod_layouts_match_header():
@@ -29,16 +36,21 @@ def test_pod_layouts_match_header():
 
 
 def test_host_matrix_helpers_equal_oracle():
-    lib, L = abi.load_library(), H.oracle()
-    for i in range(20):
-        c = abi.mat_to_c(synth.kitti_pose(i * 11))
+    lib, L = abi.host_library(), H.oracle()
+    rng = np.random.default_rng(3)
+    mats = [synth.kitti_pose(i * 11) for i in range(20)]
+    mats += [(rng.standard_normal((4, 4)) * s).astype(np.float32) for s in (1e-3, 1.0, 50.0) for _ in range(200)]
+    for m in mats:
+        c = abi.mat_to_c(m)
         a, b = abi.f16(), abi.f16()
-        assert lib.b200_mat4_inv(c, a) == L.oracle_mat4_inv(c, b) == 1
+        assert lib.b200h_mat4_inv(c, a) == L.oracle_mat4_inv(c, b) == 1   # the oracle's is pinned to ORUtils' inv() (test_oracle_vs_ref)
         assert bytes(a) == bytes(b)
         m1, m2 = abi.f16(), abi.f16()
-        lib.b200_mat4_mul(c, a, m1)
+        lib.b200h_mat4_mul(c, a, m1)
         L.oracle_mat4_mul(c, a, m2)
         assert bytes(m1) == bytes(m2)
+    z = abi.f16(*([0.0] * 16))
+    assert lib.b200h_mat4_inv(z, abi.f16()) == L.oracle_mat4_inv(z, abi.f16()) == 0
 
 
 def test_engine_refuses_to_run_without_gpu():

@@ -226,10 +226,9 @@ def test_rendering_block_cap_rule():
     """MAX_RENDERING_BLOCKS overflow (Vis_CUDA.cu:609): blocks whose tiles would pass the cap are dropped in list order.
     The cap is lowered to 300 tiles (test hook) so that a ~1000-block frame overflows it; both the stand-alone
     CreateExpectedDepths and the fused frame (cap applied by the last CTA of the visible-list pass) must match the oracle."""
-    os.environ["B200_TEST_MAX_RENDERING_BLOCKS"] = "300"
     H.oracle().oracle_set_max_rendering_blocks(300)
     try:
-        cfg = P.Cfg(frames=4)
+        cfg = P.Cfg(frames=4, maxRenderingBlocks=300)
         stepwise, _ = P.run_sequence(cfg)            # every step is compared with the oracle, min/max image included
         mm = stepwise.rs.renderingRangeImage.cpu().numpy().reshape(-1, 2)
         live = mm[:, 0] < 999999.0
@@ -242,13 +241,12 @@ def test_rendering_block_cap_rule():
         P._cmp("capped fused minmax", pair.rs.renderingRangeImage.cpu().numpy(), stepwise.rs.renderingRangeImage.cpu().numpy())
         P._cmp("capped fused rays", pair.rs.raycastResult.cpu().numpy(), stepwise.rs.raycastResult.cpu().numpy())
         # and the cap really bit: without it more of the image is covered
-        os.environ.pop("B200_TEST_MAX_RENDERING_BLOCKS")
         H.oracle().oracle_set_max_rendering_blocks(0)
+        cfg.maxRenderingBlocks = 0
         free, _ = P.run_sequence(cfg)
         mm2 = free.rs.renderingRangeImage.cpu().numpy().reshape(-1, 2)
         assert (mm2[:, 0] < 999999.0).sum() > live.sum()
     finally:
-        os.environ.pop("B200_TEST_MAX_RENDERING_BLOCKS", None)
         H.oracle().oracle_set_max_rendering_blocks(0)
 
 
