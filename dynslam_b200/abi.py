@@ -77,7 +77,7 @@ class TransferBuffers(C.Structure):
 
 class FrameOpts(C.Structure):
     _fields_ = [("doDecay", C.c_int32), ("decayMaxWeight", C.c_int32), ("decayMinAge", C.c_int32),
-                ("doRaycast", C.c_int32)]
+                ("doRaycast", C.c_int32), ("d_colourRender", C.c_void_p), ("d_depthRender", C.c_void_p)]
 
 
 class ViewCalib(C.Structure):
@@ -121,6 +121,8 @@ EXPORTS = [
     "b200_compute_normal_and_weights", "b200_update_view", "b200_update_view_async", "b200_host_frame_submit_raw",
     "b200_process_silhouettes", "b200_process_silhouettes_async", "b200_composite_depth", "b200_composite_color",
     "b200_composite_instances",
+    "b200_comm_unique_id", "b200_comm_create", "b200_comm_destroy", "b200_comm_last_error", "b200_gather_composite_submit",
+    "b200_gather_composite_release", "b200_gather_composite_wait",
 ]
 # measurement / test hooks (include/b200fusion_diag.h): exported by the same library, not part of the drop-in boundary
 DIAG_EXPORTS = ["b200_set_timing", "b200_get_trace", "b200_get_stats", "b200_selftest_divide", "b200_diag_set_max_rendering_blocks"]
@@ -184,6 +186,15 @@ def load_library():
     lib.b200_composite_depth.argtypes = [vp, vp, vp, C.c_int]
     lib.b200_composite_color.argtypes = [vp, vp, vp, vp, vp, C.c_int, P(C.c_int32), C.c_float]
     lib.b200_composite_instances.argtypes = [vp, vp, vp, C.c_int, P(InstanceLayer), C.c_int, C.c_float, C.c_float]
+    lib.b200_comm_unique_id.argtypes = [C.c_char_p]
+    lib.b200_comm_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_int, C.c_int, P(vp)]
+    lib.b200_comm_destroy.argtypes = [vp]
+    lib.b200_comm_destroy.restype = None
+    lib.b200_comm_last_error.argtypes = [vp]
+    lib.b200_comm_last_error.restype = C.c_char_p
+    lib.b200_gather_composite_submit.argtypes = [vp, vp, vp, vp, vp, vp, P(C.c_int32), C.c_float, C.c_float, C.c_int]
+    lib.b200_gather_composite_release.argtypes = [vp, vp, C.c_int]
+    lib.b200_gather_composite_wait.argtypes = [vp, C.c_int]
     lib.b200_set_timing.argtypes = [vp, C.c_int]
     lib.b200_set_timing.restype = None
     lib.b200_get_stats.argtypes = [vp, P(FrameStats)]

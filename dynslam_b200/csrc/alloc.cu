@@ -14,9 +14,11 @@
 //    (pixel, step) when the request is served, so no 12 MB blockCoords array is written;
 //  * requested entries are recorded in a 1-bit-per-entry bitmap; one prefix over the bitmap words
 //    gives every request its rank in ascending entry order => slot = allocationList[lastFree - rank];
-//  * the visible list is an ordered compaction (decoupled look-back scan over 16-entry/thread tiles
+//  * the visible list is an ordered compaction (decoupled look-back scan over 32-entry/thread tiles
 //    of the visibility bytes, 128-bit loads), not an atomicAdd of per-CTA group offsets;
-//  * all counters stay on the device; nothing here synchronises with the host.
+//  * all counters stay on the device; nothing here synchronises with the host;
+//  * the whole call is TWO launches (k_mark_prepare, k_serve_list) whose latency chains were what the frame paid for:
+//    round 1 ran four (prepare, mark, serve, list: 11 + 19 + 15 + 26 us for ~50 new blocks and ~4.7 k listed ones).
 #include "engine.h"
 
 // ------------------------------------------------------------------------------------------------
@@ -68,37 +70,12 @@ __device__ bool block_visible(int bx, int by, int bz, const Mat4 &M, const float
   return false;
 }
 
-// Transient visibility codes, only alive between k_prepare and k_visible_list of ONE allocate call:
-// the reference marks every previously visible block 3 (setToType3) and re-tests the survivors'
-// frustum visibility inside the full-table sweep. Here the re-test is done eagerly, one previously
-// visible block per thread, and its verdict is parked in the byte; the sweep then only decodes it.
+// Transient visibility codes, only alive between the two kernels of ONE allocate call: the reference marks every
+// previously visible block 3 (setToType3) and re-tests the survivors' frustum visibility inside the full-table sweep.
+// Here the re-test is done eagerly, one previously visible block per thread, and its verdict is parked in the byte; the
+// sweep then only decodes it.
 #define VT_PREV_VISIBLE 5   // was 3, frustum test passed  -> ends as 3 unless re-observed (1)
 #define VT_PREV_HIDDEN 4    // was 3, frustum test failed  -> ends as 0 unless re-observed (1)
-
-// ------------------------------------------------------------------------------------------------
-// prepare: setToType3 over the previous visible list (+ eager frustum re-test) + clear the bitmaps
-// ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-k_prepare(const b200_hash_entry *__restrict__ table, int numBuckets, const b200_vec3i *__restrict__ visiblePos, uint8_t *visType,
-          DevCounters *ctr, unsigned *reqBits, unsigned *req2Bits, int noWords, Mat4 M, float p0, float p1, float p2, float p3,
-          float voxelSize, int w, int h, int capacity, float2 *minmaxDead, int mw, int mh) {
-  const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
-  for (int i = tid; i < noWords; i += nth) { reqBits[i] = 0u; req2Bits[i] = 0u; }
-  if (minmaxDead) {
-    if (tid == 0) ctr->noRenderingBlocks = 0;   // k_visible_list of this frame sums the rendering-tile counts into it   // fused frame: initialise the cells of the expected-depth image outside its live 1/8-res corner here
-    const int liveX = (mw - 1) / B200_MINMAX_SUBSAMPLE, liveY = (mh - 1) / B200_MINMAX_SUBSAMPLE;
-    const float2 v = make_float2(B200_FAR_AWAY, B200_VERY_CLOSE);
-    for (int i = tid; i < mw * mh; i += nth) { const int y = i / mw, x = i - y * mw; if (x > liveX || y > liveY) minmaxDead[i] = v; }
-  }
-  const float proj[4] = {p0, p1, p2, p3};
-  int n = ctr->noVisibleBlocks;
-  if (n > capacity) n = capacity;
-  for (int i = tid; i < n; i += nth) {
-    const b200_vec3i p = visiblePos[i];
-    const int idx = find_block<false>(table, numBuckets, p.x, p.y, p.z);
-    if (idx >= 0) visType[idx] = block_visible(p.x, p.y, p.z, M, proj, voxelSize, w, h) ? VT_PREV_VISIBLE : VT_PREV_HIDDEN;
-  }
-}
 
 // ------------------------------------------------------------------------------------------------
 // ray set-up shared by the marking kernel and by the request server (which replays one ray)
@@ -132,13 +109,67 @@ DEV unsigned long long make_key(unsigned frameTag, unsigned pixel, unsigned step
          ((unsigned long long)pixel << KEY_STEP_BITS) | step;
 }
 
-// One warp covers an 8x4 pixel tile (neighbouring rays probe the same buckets, so the 20-byte
-// entry loads of a warp collapse to a few L1/L2 transactions).
+// set a bit of a device-wide bitmap; the bit is read through L2 first (an L1 copy could stay stale for the whole launch
+// and make every warp of the SM repeat the atomic), so in the steady state — the bit already set by an earlier warp —
+// no atomic is issued at all
+DEV void bitmap_set(unsigned *bits, int idx) {
+  const unsigned bit = 1u << (idx & 31);
+  if (!(__ldcg(bits + (idx >> 5)) & bit)) atomicOr(bits + (idx >> 5), bit);
+}
+
+// ------------------------------------------------------------------------------------------------
+// kernel 1 of AllocateSceneFromDepth: marking (buildHashAllocAndVisibleTypePP) and, in the same launch on a few extra CTAs,
+// everything that only depends on the PREVIOUS frame's list: setToType3 by position lookup with the eager frustum re-test,
+// and the initialisation of the expected-depth image of the fused frame.
+//
+// The two parts do not touch the same state, so they need no ordering between them:
+//  * marking reads the table and records what it saw on the side — `markBytes` (entry observed this frame, i.e. the
+//    reference's entriesVisibleType = 1 / 2; plain idempotent byte stores: a bitmap would need an atomic per probe, measured
+//    3x slower) and the request bitmaps `reqBits` / `req2Bits` + the 64-bit request key (rare) — and never writes the
+//    visibility bytes;
+//  * the prepare part writes the transient codes VT_PREV_* into the bytes of the previously visible entries.
+// k_serve_list merges both (an entry observed this frame ends as 1 / 2 whatever its byte says) and clears the bitmaps it
+// consumed, so nothing has to be reset at the start of a frame.
+//
+// Marking: one warp covers an 8x4 pixel tile (neighbouring rays probe the same buckets, so the 20-byte entry loads of a
+// warp collapse to a few L1/L2 transactions). The ray's steps are independent probes: four bucket heads are fetched at a time
+// before any of them is looked at, so a pixel pays two dependent table latencies instead of eight.
+// ------------------------------------------------------------------------------------------------
+#define MARK_BATCH 4
 __global__ void __launch_bounds__(256)
-k_mark(const float *__restrict__ depth, const b200_hash_entry *__restrict__ table, int numBuckets, uint8_t *visType,
-       unsigned long long *reqKey, unsigned *reqBits, unsigned *req2Bits, FrameGeom g, unsigned frameTag) {
+k_mark_prepare(const float *__restrict__ depth, const b200_hash_entry *__restrict__ table, int numBuckets,
+               const b200_vec3i *__restrict__ prevList, uint8_t *visType, DevCounters *ctr, unsigned long long *reqKey, unsigned *reqBits,
+               unsigned *req2Bits, uint8_t *markBytes, const __grid_constant__ FrameGeom g, unsigned frameTag, int capacity, int prepCtas,
+               float2 *minmax, int mw, int mh) {
+  if ((int)blockIdx.x < prepCtas) {
+    // ---- prepare part ----
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = prepCtas * blockDim.x;
+    if (minmax) {
+      // fused frame: k_serve_list rasterises every listed block's box into the expected-depth image with atomic min / max,
+      // so the WHOLE image starts from (FAR_AWAY, VERY_CLOSE) here (Vis_CUDA.cu:204)
+      if (tid == 0) ctr->noRenderingBlocks = 0;
+      const int cells = mw * mh;
+      if ((reinterpret_cast<uintptr_t>(minmax) & 15) == 0) {
+        const float4 v2 = make_float4(B200_FAR_AWAY, B200_VERY_CLOSE, B200_FAR_AWAY, B200_VERY_CLOSE);
+        float4 *m4 = reinterpret_cast<float4 *>(minmax);
+        for (int i = tid; i < cells / 2; i += nth) m4[i] = v2;
+        if ((cells & 1) && tid == 0) minmax[cells - 1] = make_float2(B200_FAR_AWAY, B200_VERY_CLOSE);
+      } else {
+        for (int i = tid; i < cells; i += nth) minmax[i] = make_float2(B200_FAR_AWAY, B200_VERY_CLOSE);
+      }
+    }
+    int n = ctr->noVisibleBlocks;
+    if (n > capacity) n = capacity;
+    for (int i = tid; i < n; i += nth) {
+      const b200_vec3i p = prevList[i];
+      const int idx = find_block<false>(table, numBuckets, p.x, p.y, p.z);
+      if (idx >= 0) visType[idx] = block_visible(p.x, p.y, p.z, g.M_d, g.proj_d, g.voxelSize, g.w, g.h) ? VT_PREV_VISIBLE : VT_PREV_HIDDEN;
+    }
+    return;
+  }
+  // ---- marking part ----
   const int tilesX = (g.w + 7) >> 3, tilesY = (g.h + 3) >> 2;
-  const int warpGlobal = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int warpGlobal = (((int)blockIdx.x - prepCtas) * blockDim.x + threadIdx.x) >> 5;
   if (warpGlobal >= tilesX * tilesY) return;
   const int lane = threadIdx.x & 31;
   const int x = (warpGlobal % tilesX) * 8 + (lane & 7), y = (warpGlobal / tilesX) * 4 + (lane >> 3);
@@ -149,95 +180,214 @@ k_mark(const float *__restrict__ depth, const b200_hash_entry *__restrict__ tabl
   if (!make_ray(r, x, y, __ldg(depth + x + y * g.w), g, invfx, invfy, oneOverVoxelSize)) return;
   const unsigned pixel = (unsigned)(x + y * g.w);
   float px = r.px, py = r.py, pz = r.pz;
-  for (int i = 0; i < r.noSteps; i++) {
-    int bx = (short)(int)floorf(px), by = (short)(int)floorf(py), bz = (short)(int)floorf(pz);
-    int hashIdx = hash_index(bx, by, bz, numBuckets - 1);
-    Entry he = load_entry(table, hashIdx);
-    bool isFound = false;
-    if (he.x == bx && he.y == by && he.z == bz && he.ptr >= -1) {
-      visType[hashIdx] = (he.ptr == -1) ? 2 : 1;
-      isFound = true;
+  int lastX = 0x7fffffff, lastY = 0, lastZ = 0;   // block of the previous step
+  for (int i0 = 0; i0 < r.noSteps; i0 += MARK_BATCH) {
+    int bx[MARK_BATCH], by[MARK_BATCH], bz[MARK_BATCH], hidx[MARK_BATCH];
+    bool fresh[MARK_BATCH];
+    Entry head[MARK_BATCH];
+#pragma unroll
+    for (int j = 0; j < MARK_BATCH; ++j) {
+      bx[j] = (short)(int)floorf(px); by[j] = (short)(int)floorf(py); bz[j] = (short)(int)floorf(pz);
+      // A step is half a block long, so about every other step lands in the block of the step before: probing it again
+      // would find (or request) the same entry — same mark, same request up to the step number in its key, which only
+      // breaks ties between requests of the SAME pixel for the SAME block. Skipped.
+      fresh[j] = (i0 + j < r.noSteps) && !(bx[j] == lastX && by[j] == lastY && bz[j] == lastZ);
+      lastX = bx[j]; lastY = by[j]; lastZ = bz[j];
+      hidx[j] = hash_index(bx[j], by[j], bz[j], numBuckets - 1);
+      if (fresh[j]) head[j] = load_entry(table, hidx[j]);
+      px += r.dx; py += r.dy; pz += r.dz;     // the reference's own accumulation (DA/ITMSceneReconstructionEngine.h:311)
     }
-    if (!isFound) {
+#pragma unroll
+    for (int j = 0; j < MARK_BATCH; ++j) {
+      if (!fresh[j]) continue;
+      Entry he = head[j];
+      int hashIdx = hidx[j];
+      bool isFound = (he.x == bx[j] && he.y == by[j] && he.z == bz[j] && he.ptr >= -1);
       bool isExcess = false;
-      if (he.ptr >= -1) {
+      if (!isFound && he.ptr >= -1) {
         while (he.offset >= 1) {
           hashIdx = numBuckets + he.offset - 1;
           he = load_entry(table, hashIdx);
-          if (he.x == bx && he.y == by && he.z == bz && he.ptr >= -1) {
-            visType[hashIdx] = (he.ptr == -1) ? 2 : 1;
-            isFound = true;
-            break;
-          }
+          if (he.x == bx[j] && he.y == by[j] && he.z == bz[j] && he.ptr >= -1) { isFound = true; break; }
         }
         isExcess = true;
       }
-      if (!isFound) {
-        // Neighbouring rays miss the same block at the same step: the lanes of the warp that request the same
-        // entry elect the one with the largest key (lane order == raster order inside the 8x4 tile, the step
-        // is warp-uniform) and only that lane issues the atomics.
+      if (isFound) {
+        markBytes[hashIdx] = 1;               // entriesVisibleType = 1 (2 when swapped out: k_serve_list reads the entry's ptr)
+      } else {
+        // Neighbouring rays miss the same block at the same step: the lanes of the warp that request the same entry elect
+        // the one with the largest key (lane order == raster order inside the 8x4 tile, the step is warp-uniform) and only
+        // that lane issues the atomics.
         const unsigned peers = __match_any_sync(__activemask(), hashIdx);
         if (lane == 31 - __clz(peers)) {
-          atomicMax(&reqKey[hashIdx], make_key(frameTag, pixel, (unsigned)i));
-          const unsigned bit = 1u << (hashIdx & 31);
-          if (!(reqBits[hashIdx >> 5] & bit)) atomicOr(&reqBits[hashIdx >> 5], bit);
-          if (isExcess) { if (!(req2Bits[hashIdx >> 5] & bit)) atomicOr(&req2Bits[hashIdx >> 5], bit); }
-          else visType[hashIdx] = 1;
+          atomicMax(&reqKey[hashIdx], make_key(frameTag, pixel, (unsigned)(i0 + j)));
+          bitmap_set(reqBits, hashIdx);
+          if (isExcess) bitmap_set(req2Bits, hashIdx);
+          else markBytes[hashIdx] = 1;          // a requested ordered entry is visible (type 1) whether or not it gets a block
         }
       }
     }
-    px += r.dx; py += r.dy; pz += r.dz;
   }
 }
 
 // ------------------------------------------------------------------------------------------------
-// request server: ONE kernel ranks every request in ascending entry order (two chained scans over
-// the request bitmaps, 1024 words = 32768 entries per tile) and serves it:
-//   vbaIdx = lastFree - rank(all requests),  exlIdx = lastFreeExcess - rank(excess requests)
-// (every request decrements the counters, served or not — Reco_CUDA.cu:833, :857-858); the winning
-// pixel's ray is replayed up to its step to recover the block position.
+// Chained scans of kernel 2. Same descriptor format as scan_lookback (common.cuh), two differences in the walk:
+//  * the look-back window is 256 tiles — eight descriptors per lane, all eight loads in flight at once — so a table of up to
+//    2 M entries (256 tiles of 8192) is summed in ONE memory round trip instead of one per 32 tiles;
+//  * a tile that does not need its own prefix (no request of its own: the usual case, a frame adds a few dozen blocks) only
+//    publishes its aggregate and moves on; the tiles that do need one walk over plain aggregates, however far back.
+// NDESC descriptor arrays are walked together (the request ranks need the prefix of all requests AND of the excess ones).
 // ------------------------------------------------------------------------------------------------
-#define BMP_TILE 1024
-__global__ void __launch_bounds__(256)
-k_serve_requests(const float *__restrict__ depth, b200_hash_entry *table, int numBuckets, uint8_t *visType,
-                 const unsigned long long *__restrict__ reqKey, const unsigned *__restrict__ reqBits, const unsigned *__restrict__ req2Bits,
-                 int noWords, const int *__restrict__ allocList, const int *__restrict__ excessList, DevCounters *ctr, FrameGeom g,
-                 int currentFrame, unsigned long long *scanDesc, unsigned long long *scanDesc2, unsigned gen) {
+#define LB_WIN 8   // descriptors per lane and step
+template <int NDESC>
+DEV void lookback_wide(unsigned long long *const *desc, unsigned gen, int tile, const unsigned *agg, bool needPrefix, unsigned *ex) {
+  const int lane = threadIdx.x & 31;
+  const unsigned g30 = gen & 0x3fffffffu;
+#pragma unroll
+  for (int d = 0; d < NDESC; ++d) ex[d] = 0;
+  if (tile == 0) {
+    if (lane == 0) for (int d = 0; d < NDESC; ++d) ((volatile unsigned long long *)desc[d])[0] = scan_pack(gen, 2, agg[d]);
+    return;
+  }
+  if (lane == 0) for (int d = 0; d < NDESC; ++d) ((volatile unsigned long long *)desc[d])[tile] = scan_pack(gen, 1, agg[d]);
+  if (!needPrefix) return;
+  int look = tile - 1;          // nearest tile not yet accounted for
+  for (;;) {
+    // window: tiles look, look-1, ..., look-255; lane l holds look - (l + 32 j), j = 0..7
+    unsigned long long v[NDESC][LB_WIN];
+#pragma unroll
+    for (int j = 0; j < LB_WIN; ++j) {
+      const int t = look - (lane + 32 * j);
+#pragma unroll
+      for (int d = 0; d < NDESC; ++d) v[d][j] = (t >= 0) ? ((volatile unsigned long long *)desc[d])[t] : 0ull;
+    }
+    // status of a tile = the weaker of its descriptors' (they are published one after the other)
+    bool retry = false, done = false;
+    unsigned sum[NDESC];
+#pragma unroll
+    for (int d = 0; d < NDESC; ++d) sum[d] = 0;
+#pragma unroll
+    for (int j = 0; j < LB_WIN; ++j) {
+      const int t = look - (lane + 32 * j);
+      unsigned st = 3;              // beyond tile 0: nothing to add, ends the walk
+      bool mixed = false;
+      if (t >= 0) {
+        st = 2;
+#pragma unroll
+        for (int d = 0; d < NDESC; ++d) {
+          const unsigned sd = ((unsigned)(v[d][j] >> 34) == g30) ? ((unsigned)(v[d][j] >> 32) & 3u) : 0u;
+          if (d > 0 && sd != st && sd != 0 && st != 0) mixed = true;      // caught between its two publications
+          st = sd < st ? sd : st;
+        }
+        if (mixed) st = 0;          // re-read: an aggregate must not be mixed with a prefix
+      }
+      const unsigned validMask = __ballot_sync(0xffffffffu, st != 0);
+      const unsigned prefixMask = __ballot_sync(0xffffffffu, st >= 2);
+      const int firstPrefix = prefixMask ? (__ffs(prefixMask) - 1) : 32;
+      const unsigned need = (firstPrefix >= 32) ? 0xffffffffu : ((1u << firstPrefix) - 1u);
+      if (!done && !retry) {
+        if ((validMask & need) != need) retry = true;       // a tile in front of the nearest prefix has not published yet
+        else {
+          if (lane <= firstPrefix && t >= 0) {
+#pragma unroll
+            for (int d = 0; d < NDESC; ++d) sum[d] += (unsigned)(v[d][j] & 0xffffffffu);
+          }
+          if (prefixMask) done = true;
+        }
+      }
+    }
+    if (retry) continue;            // spin: re-read the window (volatile)
+#pragma unroll
+    for (int d = 0; d < NDESC; ++d) {
+      unsigned a = sum[d];
+      for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+      ex[d] += a;
+    }
+    if (done) break;
+    look -= 32 * LB_WIN;
+  }
+  if (lane == 0) {
+    __threadfence();
+    for (int d = 0; d < NDESC; ++d) ((volatile unsigned long long *)desc[d])[tile] = scan_pack(gen, 2, ex[d] + agg[d]);
+  }
+}
+
+// the frustum re-test of a type-3 byte the prepare pass did not produce (decay moved it, Reco_CUDA.cu:1109) — rare, kept out of line
+static __device__ __noinline__ bool stale_three_visible(const b200_hash_entry *table, int idx, const FrameGeom *g) {
+  const Entry en = load_entry(table, idx);
+  return block_visible(en.x, en.y, en.z, g->M_d, g->proj_d, g->voxelSize, g->w, g->h);
+}
+
+// 4-bit mask of the non-zero bytes of a word
+DEV unsigned nz_bytes(unsigned w) { return ((__vcmpne4(w, 0u) & 0x80808080u) * 0x00204081u) >> 28; }
+
+// ------------------------------------------------------------------------------------------------
+// kernel 2 of AllocateSceneFromDepth: request service (allocateVoxelBlocksList) + visible list (buildVisibleList) in one
+// persistent launch. A tile is 8192 consecutive entries: one word of each request bitmap and 32 mark / visibility bytes per
+// thread.
+//
+// Phase A, per tile: rank the requests in ascending entry order (block scan + chained look-back over both request bitmaps
+// at once) and serve them:  vbaIdx = lastFree - rank(all requests),  exlIdx = lastFreeExcess - rank(excess requests)
+// (every request decrements the counters, served or not — Reco_CUDA.cu:833, :857-858); the winning pixel's ray is replayed
+// up to its step to recover the block position. The bitmaps are cleared as they are read.
+// Phase B, per tile: final visibility byte of every entry (observed this frame -> 1 / 2, else the decoded previous state),
+// ordered compaction of the entries with type > 0 (block scan + look-back), and per listed entry: list item, decay-ring
+// snapshot (Reco_CUDA.cu:302-317 without the per-frame cudaMalloc), resolved VBA pointer, and — in the fused frame, where
+// CreateExpectedDepths renders from this very pose — ProjectSingleBlock and the rasterisation of the block's 1/8-resolution
+// box into the expected-depth image with atomic min / max on the (positive) float bit patterns. The listed entries of a
+// tile are dealt round-robin to its eight warps.
+// A new excess-list entry lies in another tile than the request that creates it: tiles of the excess part of the table
+// start phase B only when every tile has finished phase A (device-wide counter; the grid is persistent and co-resident, and
+// a CTA finishes phase A of ALL its tiles before it starts phase B of any).
+// ------------------------------------------------------------------------------------------------
+#define AL_EPT 32
+#define AL_TILE (256 * AL_EPT)   // 8192 entries = 256 bitmap words per tile
+__global__ void __launch_bounds__(256, 2)
+k_serve_list(const float *__restrict__ depth, b200_hash_entry *table, int numBuckets, int noTotal, uint8_t *visType,
+             const unsigned long long *__restrict__ reqKey, unsigned *reqBits, unsigned *req2Bits, uint8_t *markBytes,
+             const int *__restrict__ allocList, const int *__restrict__ excessList, DevCounters *ctr, const __grid_constant__ FrameGeom g,
+             int currentFrame, int onlyVisible, unsigned long long *descA, unsigned long long *descB, unsigned long long *descC,
+             unsigned gen, b200_vec3i *visiblePos, int *visiblePtr, int capacity, b200_vec3i *ring, long long ringCap, long long *snapStart,
+             int *snapCount, int slot, BlockRec *recs, float2 *minmax, int rw, int rh, unsigned maxRB) {
   __shared__ unsigned sm[33];
   __shared__ unsigned tileBase, tileBase2;
-  const int noTiles = (noWords + BMP_TILE - 1) / BMP_TILE;
-  const int baseVba = ctr->lastFreeBlockId, baseExl = ctr->lastFreeExcessListId;   // only the last tile updates them, at its very end
-  const float invfx = 1.0f / g.proj_d[0], invfy = 1.0f / g.proj_d[1];
-  const float oneOverVoxelSize = 1.0f / (g.voxelSize * BS);
-  for (int tile = blockIdx.x; tile < noTiles; tile += gridDim.x) {
-    const int first = tile * BMP_TILE + threadIdx.x * 4;
-    unsigned wv[4] = {0, 0, 0, 0}, wx[4] = {0, 0, 0, 0};
-    if (first + 4 <= noWords) {
-      const uint4 a = *reinterpret_cast<const uint4 *>(reqBits + first), b = *reinterpret_cast<const uint4 *>(req2Bits + first);
-      wv[0] = a.x; wv[1] = a.y; wv[2] = a.z; wv[3] = a.w; wx[0] = b.x; wx[1] = b.y; wx[2] = b.z; wx[3] = b.w;
-    } else for (int k = 0; k < 4; ++k) if (first + k < noWords) { wv[k] = reqBits[first + k]; wx[k] = req2Bits[first + k]; }
-    const unsigned c = __popc(wv[0]) + __popc(wv[1]) + __popc(wv[2]) + __popc(wv[3]);
-    const unsigned c2 = __popc(wx[0]) + __popc(wx[1]) + __popc(wx[2]) + __popc(wx[3]);
-    unsigned total, total2;
-    unsigned rank = block_exclusive_scan(c, sm, &total);
-    unsigned rank2 = block_exclusive_scan(c2, sm, &total2);
-    if (threadIdx.x < 32) {
-      const unsigned ex = scan_lookback(scanDesc, gen, tile, total);
-      const unsigned ex2 = scan_lookback(scanDesc2, gen, tile, total2);
-      if (threadIdx.x == 0) { tileBase = ex; tileBase2 = ex2; }
-    }
-    __syncthreads();
-    rank += tileBase; rank2 += tileBase2;
-    const bool last = (tile == noTiles - 1);
-    const unsigned grand = tileBase + total, grand2 = tileBase2 + total2;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      unsigned bits = wv[k];
-      while (bits) {
-        const int b = __ffs(bits) - 1;
-        bits &= bits - 1;
-        const int targetIdx = (first + k) * 32 + b;
-        const bool isExcess = (wx[k] >> b) & 1u;
+  __shared__ unsigned hits[AL_TILE];   // entry index | bit 31: observed this frame
+  const int noWords = noTotal >> 5;
+  const int noTiles = (noTotal + AL_TILE - 1) / AL_TILE;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // ---------------- phase A: requests ----------------
+  {
+    const int baseVba = ctr->lastFreeBlockId, baseExl = ctr->lastFreeExcessListId;   // only the last tile updates them, at its very end
+    const float invfx = 1.0f / g.proj_d[0], invfy = 1.0f / g.proj_d[1];
+    const float oneOverVoxelSize = 1.0f / (g.voxelSize * BS);
+    for (int tile = blockIdx.x; tile < noTiles; tile += gridDim.x) {
+      const int w = tile * 256 + threadIdx.x;
+      unsigned rq = 0, rq2 = 0;
+      if (w < noWords) {
+        rq = reqBits[w]; rq2 = req2Bits[w];
+        if (rq) reqBits[w] = 0u;                 // consumed: clean for the next frame
+        if (rq2) req2Bits[w] = 0u;
+      }
+      if (onlyVisible) { rq = 0u; rq2 = 0u; }     // onlyUpdateVisibleList: the marking ran, nothing is allocated (Reco_CUDA.cu:254-262)
+      unsigned totalPacked;
+      const unsigned localPacked = block_exclusive_scan(__popc(rq) | (__popc(rq2) << 16), sm, &totalPacked);   // <= 8192 each: no carry
+      const unsigned total = totalPacked & 0xffffu, total2 = totalPacked >> 16;
+      const bool last = (tile == noTiles - 1);
+      if (threadIdx.x < 32) {
+        unsigned long long *const d2[2] = {descA, descB};
+        const unsigned agg[2] = {total, total2};
+        unsigned ex[2];
+        lookback_wide<2>(d2, gen, tile, agg, total != 0 || last, ex);    // the last tile needs the grand totals for the counters
+        if (threadIdx.x == 0) { tileBase = ex[0]; tileBase2 = ex[1]; }
+      }
+      __syncthreads();
+      unsigned rank = tileBase + (localPacked & 0xffffu), rank2 = tileBase2 + (localPacked >> 16);
+      const unsigned grand = tileBase + total, grand2 = tileBase2 + total2;
+      while (rq) {
+        const int b = __ffs(rq) - 1;
+        rq &= rq - 1;
+        const int targetIdx = w * 32 + b;
+        const bool isExcess = (rq2 >> b) & 1u;
         const int vbaIdx = baseVba - (int)rank;
         const int exlIdx = baseExl - (int)rank2;
         rank++;
@@ -259,7 +409,7 @@ k_serve_requests(const float *__restrict__ depth, b200_hash_entry *table, int nu
           const int exlOffset = excessList[exlIdx];
           reinterpret_cast<int *>(table)[(size_t)targetIdx * 5 + 2] = exlOffset + 1;   // connect to child
           ew = reinterpret_cast<int *>(table) + (size_t)(numBuckets + exlOffset) * 5;
-          visType[numBuckets + exlOffset] = 1;                                         // child visible
+          markBytes[numBuckets + exlOffset] = 1;                                       // child visible (:875)
         }
         ew[0] = (int)(((unsigned)bx & 0xffffu) | ((unsigned)by << 16));
         ew[1] = (bz & 0xffff);
@@ -267,102 +417,133 @@ k_serve_requests(const float *__restrict__ depth, b200_hash_entry *table, int nu
         ew[3] = allocList[vbaIdx];
         ew[4] = currentFrame;
       }
-    }
-    __syncthreads();
-    if (last && threadIdx.x == 0) {
-      ctr->allocBaseVba = baseVba; ctr->allocBaseExl = baseExl;
-      ctr->noRequests = (int)grand; ctr->noRequestsExcess = (int)grand2;
-      ctr->lastFreeBlockId = baseVba - (int)grand;
-      ctr->lastFreeExcessListId = baseExl - (int)grand2;
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        if (last) {
+          ctr->allocBaseVba = baseVba; ctr->allocBaseExl = baseExl;
+          ctr->noRequests = (int)grand; ctr->noRequestsExcess = (int)grand2;
+          ctr->lastFreeBlockId = baseVba - (int)grand;
+          ctr->lastFreeExcessListId = baseExl - (int)grand2;
+        }
+        __threadfence();                          // this tile's new entries and child marks are visible device-wide ...
+        atomicAdd(&ctr->tilesServed, 1u);         // ... before it counts as served
+      }
     }
   }
-}
-
-// ------------------------------------------------------------------------------------------------
-// visible list (reconstruction engine): decode the visibility bytes and compact every entry with
-// type > 0 in ascending entry order — one pass over the 1.5 MB byte array with 128-bit accesses,
-// block scan + decoupled look-back for the global order, shared-memory compaction so that the
-// scattered 20-byte entry reads and the list writes are spread over all threads. The same pass
-// writes the snapshot for the decay queue into the ring (Reco_CUDA.cu:302-317 without the per-frame
-// cudaMalloc / blocking copies) and the resolved VBA pointer of every item (saves IntegrateIntoScene
-// and CreateExpectedDepths their hash lookups while the table is unchanged).
-// ------------------------------------------------------------------------------------------------
-#define VIS_EPT 32                 // entries per thread (2 x 128-bit loads)
-#define VIS_TILE (256 * VIS_EPT)   // 8192 entries per tile
-__global__ void __launch_bounds__(256, 4)
-k_visible_list(const b200_hash_entry *__restrict__ table, int numBuckets, int noTotal, uint8_t *visType, b200_vec3i *visiblePos,
-               int *visiblePtr, int capacity, DevCounters *ctr, unsigned long long *scanDesc, unsigned gen, Mat4 M, float p0, float p1,
-               float p2, float p3, float voxelSize, int w, int h, b200_vec3i *ring, long long ringCap, long long *snapStart,
-               int *snapCount, int slot, int oldestSlot, BlockRec *recs, int rw, int rh, unsigned maxRB) {
-  __shared__ unsigned sm[33];
-  __shared__ unsigned tileBase;
-  __shared__ int hits[VIS_TILE];
+  // ---------------- phase B: visibility bytes and the ordered list ----------------
   unsigned myTiles = 0;   // rendering tiles of the blocks this thread projected (fused frame only)
-  const float proj[4] = {p0, p1, p2, p3};
   const long long ringStart = ctr->ringHead;   // advanced by the last tile only, at its very end
-  const int noTiles = (noTotal + VIS_TILE - 1) / VIS_TILE;
+  const int liveX = (rw - 1) / B200_MINMAX_SUBSAMPLE, liveY = (rh - 1) / B200_MINMAX_SUBSAMPLE;   // last live cell of the expected-depth image
   for (int tile = blockIdx.x; tile < noTiles; tile += gridDim.x) {
-    const int first = tile * VIS_TILE + threadIdx.x * VIS_EPT;
+    const int first = tile * AL_TILE + threadIdx.x * AL_EPT;
+    const int w = tile * 256 + threadIdx.x;
+    if ((tile + 1) * AL_TILE > numBuckets) {
+      // the tile reaches into the excess part: entries created and child marks set by OTHER tiles' phase A must be in
+      if (threadIdx.x == 0) { while (*(volatile unsigned *)&ctr->tilesServed < (unsigned)noTiles) { } __threadfence(); }
+      __syncthreads();
+    }
     unsigned mask = 0;   // bit k: entry first+k goes to the list
+    unsigned mk = 0;     // bit k: entry first+k was observed this frame
+    if (w < noWords) {
+      uint4 raw[2], mb[2];
+      raw[0] = *reinterpret_cast<const uint4 *>(visType + first);          // noTotal is a multiple of 32
+      raw[1] = *reinterpret_cast<const uint4 *>(visType + first + 16);
+      mb[0] = __ldcg(reinterpret_cast<const uint4 *>(markBytes + first));  // written by the marking kernel and by other tiles' phase A: L2
+      mb[1] = __ldcg(reinterpret_cast<const uint4 *>(markBytes + first + 16));
 #pragma unroll
-    for (int q = 0; q < VIS_EPT / 16; ++q) {
-      const int f16 = first + q * 16;
-      if (f16 >= noTotal) break;
-      uint4 raw = *reinterpret_cast<const uint4 *>(visType + f16);   // noTotal is a multiple of 32
-      if (raw.x | raw.y | raw.z | raw.w) {
-        uint8_t *t = reinterpret_cast<uint8_t *>(&raw);
+      for (int q = 0; q < 2; ++q) {
+        const unsigned m16 = nz_bytes(mb[q].x) | (nz_bytes(mb[q].y) << 4) | (nz_bytes(mb[q].z) << 8) | (nz_bytes(mb[q].w) << 12);
+        if (m16) *reinterpret_cast<uint4 *>(markBytes + first + q * 16) = make_uint4(0u, 0u, 0u, 0u);   // consumed
+        mk |= m16 << (q * 16);
+        unsigned todo = m16 | nz_bytes(raw[q].x) | (nz_bytes(raw[q].y) << 4) | (nz_bytes(raw[q].z) << 8) | (nz_bytes(raw[q].w) << 12);
+        if (!todo) continue;
+        unsigned wv[4] = {raw[q].x, raw[q].y, raw[q].z, raw[q].w};
         bool dirty = false;
-#pragma unroll
-        for (int k = 0; k < 16; ++k) {
-          uint8_t v = t[k];
-          if (v == VT_PREV_VISIBLE) { v = 3; dirty = true; }
-          else if (v == VT_PREV_HIDDEN) { v = 0; dirty = true; }
-          else if (v == 3) {   // a 3 this frame's k_prepare did not produce (decay moved it, Reco_CUDA.cu:1109): test it now
-            Entry en = load_entry(table, f16 + k);
-            if (!block_visible(en.x, en.y, en.z, M, proj, voxelSize, w, h)) { v = 0; dirty = true; }
+        while (todo) {            // the few interesting bytes of the group (a thread lists ~0.1 entries on average)
+          const int k = __ffs(todo) - 1;
+          todo &= todo - 1;
+          const unsigned sh = (k & 3) * 8;
+          unsigned word = (k < 4) ? wv[0] : (k < 8) ? wv[1] : (k < 12) ? wv[2] : wv[3];
+          const unsigned old = (word >> sh) & 0xffu;
+          unsigned v = old;
+          if ((m16 >> k) & 1u) v = 1;                 // observed this frame (2 = swapped out is patched below, where the entry is read)
+          else if (v == VT_PREV_VISIBLE) v = 3;
+          else if (v == VT_PREV_HIDDEN) v = 0;
+          else if (v == 3) { if (!stale_three_visible(table, first + q * 16 + k, &g)) v = 0; }
+          if (v != old) {
+            dirty = true;
+            word = (word & ~(0xffu << sh)) | (v << sh);
+            if (k < 4) wv[0] = word; else if (k < 8) wv[1] = word; else if (k < 12) wv[2] = word; else wv[3] = word;
           }
-          t[k] = v;
           if (v > 0) mask |= 1u << (q * 16 + k);
         }
-        if (dirty) *reinterpret_cast<uint4 *>(visType + f16) = raw;
+        if (dirty) *reinterpret_cast<uint4 *>(visType + first + q * 16) = make_uint4(wv[0], wv[1], wv[2], wv[3]);
       }
     }
     unsigned total;
     const unsigned local = block_exclusive_scan(__popc(mask), sm, &total);
     if (threadIdx.x < 32) {
-      const unsigned ex = scan_lookback(scanDesc, gen, tile, total);
-      if (threadIdx.x == 0) tileBase = ex;
+      unsigned long long *const d1[1] = {descC};
+      const unsigned agg[1] = {total};
+      unsigned ex[1];
+      lookback_wide<1>(d1, gen, tile, agg, total != 0 || tile == noTiles - 1, ex);
+      if (threadIdx.x == 0) tileBase = ex[0];
     }
     unsigned o = local;
     while (mask) {
       const int k = __ffs(mask) - 1;
       mask &= mask - 1;
-      hits[o++] = first + k;
+      hits[o++] = (unsigned)(first + k) | (((mk >> k) & 1u) << 31);
     }
     __syncthreads();
     const unsigned base = tileBase;
-    for (unsigned t = threadIdx.x; t < total; t += blockDim.x) {
-      const int idx = hits[t];
-      const Entry en = load_entry(table, idx);
-      const long long out = (long long)base + t;
-      if (out < capacity) {
-        b200_vec3i p; p.x = en.x; p.y = en.y; p.z = en.z;
-        visiblePos[out] = p;
-        ring[(ringStart + out) % ringCap] = p;
-        int ptr = en.ptr;
-        if (ptr < 0) { if (find_block<false>(table, numBuckets, en.x, en.y, en.z, &ptr) < 0) ptr = -1; }   // stale entry: what findBlock(pos) would hit
-        visiblePtr[out] = ptr;
-        if (recs) {
-          // fused frame: CreateExpectedDepths renders from this very pose, so the block's 1/8-resolution box is produced here
-          // (ProjectSingleBlock) and the expected-depth pass only rasterises. All blocks are assumed drawn; k_project_blocks
-          // re-does the job with the ordered MAX_RENDERING_BLOCKS rule if the tile total exceeds the cap (never at KITTI sizes).
-          BlockRec r; r.ulx = 1; r.uly = 1; r.lrx = 0; r.lry = 0; r.zmin = 0; r.zmax = 0;
-          int ulx, uly, lrx, lry; float zmin, zmax;
-          if (ptr >= 0 && project_single_block(en.x, en.y, en.z, M, proj, rw, rh, voxelSize, ulx, uly, lrx, lry, zmin, zmax)) {
-            r.ulx = (short)ulx; r.uly = (short)uly; r.lrx = (short)lrx; r.lry = (short)lry; r.zmin = zmin; r.zmax = zmax;
-            myTiles += rendering_tiles(ulx, uly, lrx, lry);
+    // listed entry t of the tile is handled by lane (t / 8) % 32 of warp t % 8: the ~25 entries of a KITTI tile become ~3 per warp
+    for (unsigned t0 = 0; t0 < total; t0 += blockDim.x) {
+      const unsigned t = t0 + (unsigned)(lane * 8 + warp);
+      BlockRec r; r.ulx = 1; r.uly = 1; r.lrx = 0; r.lry = 0; r.zmin = 0; r.zmax = 0;
+      bool draw = false;
+      if (t < total) {
+        const int idx = (int)(hits[t] & 0x7fffffffu);
+        const Entry en = load_entry(table, idx);
+        if (en.ptr == -1 && (hits[t] >> 31)) visType[idx] = 2;   // observed while swapped out (DA/ITMSceneReconstructionEngine.h:261, :281)
+        const long long out = (long long)base + t;
+        if (out < capacity) {
+          b200_vec3i p; p.x = en.x; p.y = en.y; p.z = en.z;
+          visiblePos[out] = p;
+          ring[(ringStart + out) % ringCap] = p;
+          int ptr = en.ptr;
+          if (ptr < 0) { if (find_block<false>(table, numBuckets, en.x, en.y, en.z, &ptr) < 0) ptr = -1; }   // stale entry: what findBlock(pos) would hit
+          visiblePtr[out] = ptr;
+          if (recs) {
+            // fused frame: the block's 1/8-resolution box (ProjectSingleBlock). All blocks are assumed drawn; if the tile total
+            // breaks MAX_RENDERING_BLOCKS (never at KITTI sizes) the last CTA re-applies the ordered rule and rebuilds the image.
+            int ulx, uly, lrx, lry; float zmin, zmax;
+            if (ptr >= 0 && project_single_block(en.x, en.y, en.z, g.M_d, g.proj_d, rw, rh, g.voxelSize, ulx, uly, lrx, lry, zmin, zmax)) {
+              r.ulx = (short)ulx; r.uly = (short)uly; r.lrx = (short)lrx; r.lry = (short)lry; r.zmin = zmin; r.zmax = zmax;
+              myTiles += rendering_tiles(ulx, uly, lrx, lry);
+              draw = true;
+            }
+            recs[out] = r;
           }
-          recs[out] = r;
+        }
+      }
+      if (recs) {
+        // rasterise: warp-cooperative, one box at a time, the part of the box inside the live 1/8-resolution corner — the
+        // only cells the raycast reads. The reference clamps boxes to the FULL-resolution bounds
+        // (DA/ITMVisualisationEngine.h:57-60), so a block next to the camera can cover 10^5 cells outside the corner: those are
+        // rasterised from the records by k_project_blocks on the side stream, off the frame's critical path.
+        unsigned todo = __ballot_sync(0xffffffffu, draw && r.ulx <= liveX && r.uly <= liveY);
+        while (todo) {
+          const int src = __ffs(todo) - 1;
+          todo &= todo - 1;
+          const int ax = __shfl_sync(0xffffffffu, (int)r.ulx, src), ay = __shfl_sync(0xffffffffu, (int)r.uly, src);
+          const int bxx = min(__shfl_sync(0xffffffffu, (int)r.lrx, src), liveX), byy = min(__shfl_sync(0xffffffffu, (int)r.lry, src), liveY);
+          const float zn = __shfl_sync(0xffffffffu, r.zmin, src), zx = __shfl_sync(0xffffffffu, r.zmax, src);
+          const int bw = bxx - ax + 1, cnt = bw * (byy - ay + 1);
+          for (int k = lane; k < cnt; k += 32) {
+            float2 *px = &minmax[(ax + k % bw) + (ay + k / bw) * rw];
+            atomic_min_posf(&px->x, zn); atomic_max_posf(&px->y, zx);
+          }
         }
       }
     }
@@ -379,35 +560,61 @@ k_visible_list(const b200_hash_entry *__restrict__ table, int numBuckets, int no
       ctr->ringHead = ringStart + kept;
     }
   }
+  // ---------------- tail: the CTA that finishes last resets the per-launch counters and owns the cap rule ----------------
   if (recs) {
     for (int o = 16; o > 0; o >>= 1) myTiles += __shfl_xor_sync(0xffffffffu, myTiles, o);
-    if ((threadIdx.x & 31) == 0 && myTiles) atomicAdd(&ctr->noRenderingBlocks, myTiles);
-    // The CTA that finishes last knows the tile total. In the (pathological) case that it breaks MAX_RENDERING_BLOCKS it
-    // re-applies the reference's ordered rule (Vis_CUDA.cu:609: a block is dropped when the running tile count would pass the
-    // cap) on its own, serially over the list — so that no extra launch sits between this kernel and the expected-depth fill.
-    __shared__ bool lastCta;
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) lastCta = (atomicAdd(&ctr->visCtasDone, 1u) == gridDim.x - 1);
-    __syncthreads();
-    if (!lastCta) return;
-    if (threadIdx.x == 0) ctr->visCtasDone = 0;
-    __threadfence();
-    if (ctr->noRenderingBlocks <= maxRB) return;
-    int n = ctr->noVisibleBlocks; if (n > capacity) n = capacity;
-    unsigned running = 0;
-    for (int base = 0; base < n; base += blockDim.x) {
-      const int item = base + threadIdx.x;
-      unsigned required = 0;
-      BlockRec r; r.ulx = 1; r.uly = 1; r.lrx = 0; r.lry = 0; r.zmin = 0; r.zmax = 0;
-      if (item < n) { r = recs[item]; if (r.ulx <= r.lrx) required = rendering_tiles(r.ulx, r.uly, r.lrx, r.lry); }
-      unsigned total;
-      const unsigned local = running + block_exclusive_scan(required, sm, &total);
-      if (item < n && required > 0 && local + required > maxRB) {
-        r.ulx = 1; r.uly = 1; r.lrx = 0; r.lry = 0; r.zmin = 0; r.zmax = 0;
-        recs[item] = r;
+    if (lane == 0 && myTiles) atomicAdd(&ctr->noRenderingBlocks, myTiles);
+  }
+  __shared__ bool lastCta;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) lastCta = (atomicAdd(&ctr->visCtasDone, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (!lastCta) return;
+  if (threadIdx.x == 0) { ctr->visCtasDone = 0; ctr->tilesServed = 0; }
+  __threadfence();
+  if (!recs) return;
+  // The last CTA knows the tile total. In the (pathological) case that it breaks MAX_RENDERING_BLOCKS it re-applies the
+  // reference's ordered rule (Vis_CUDA.cu:609: a block is dropped when the running tile count would pass the cap), serially
+  // over the list, on the records, and REBUILDS the live corner from the surviving records — every other CTA has finished,
+  // so its atomics are all in.
+  if (*(volatile unsigned *)&ctr->noRenderingBlocks <= maxRB) return;
+  int n = *(volatile int *)&ctr->noVisibleBlocks; if (n > capacity) n = capacity;
+  for (int c = threadIdx.x; c < (liveX + 1) * (liveY + 1); c += blockDim.x)
+    minmax[(c % (liveX + 1)) + (c / (liveX + 1)) * rw] = make_float2(B200_FAR_AWAY, B200_VERY_CLOSE);
+  __syncthreads();
+  unsigned running = 0;
+  for (int base = 0; base < n; base += blockDim.x) {
+    const int item = base + threadIdx.x;
+    unsigned required = 0;
+    BlockRec r; r.ulx = 1; r.uly = 1; r.lrx = 0; r.lry = 0; r.zmin = 0; r.zmax = 0;
+    if (item < n) {
+      const uint4 q = __ldcg(reinterpret_cast<const uint4 *>(recs) + item);     // written by other CTAs: L2
+      r.ulx = (short)(q.x & 0xffff); r.uly = (short)(q.x >> 16); r.lrx = (short)(q.y & 0xffff); r.lry = (short)(q.y >> 16);
+      r.zmin = __uint_as_float(q.z); r.zmax = __uint_as_float(q.w);
+      if (r.ulx <= r.lrx) required = rendering_tiles(r.ulx, r.uly, r.lrx, r.lry);
+    }
+    unsigned total;
+    const unsigned local = running + block_exclusive_scan(required, sm, &total);
+    bool draw = required > 0;
+    if (item < n && required > 0 && local + required > maxRB) {
+      r.ulx = 1; r.uly = 1; r.lrx = 0; r.lry = 0; r.zmin = 0; r.zmax = 0;
+      recs[item] = r;
+      draw = false;
+    }
+    running += total;
+    unsigned todo = __ballot_sync(0xffffffffu, draw && r.ulx <= liveX && r.uly <= liveY);
+    while (todo) {
+      const int src = __ffs(todo) - 1;
+      todo &= todo - 1;
+      const int ax = __shfl_sync(0xffffffffu, (int)r.ulx, src), ay = __shfl_sync(0xffffffffu, (int)r.uly, src);
+      const int bxx = min(__shfl_sync(0xffffffffu, (int)r.lrx, src), liveX), byy = min(__shfl_sync(0xffffffffu, (int)r.lry, src), liveY);
+      const float zn = __shfl_sync(0xffffffffu, r.zmin, src), zx = __shfl_sync(0xffffffffu, r.zmax, src);
+      const int bw = bxx - ax + 1, cnt = bw * (byy - ay + 1);
+      for (int k = lane; k < cnt; k += 32) {
+        float2 *px = &minmax[(ax + k % bw) + (ay + k / bw) * rw];
+        atomic_min_posf(&px->x, zn); atomic_max_posf(&px->y, zx);
       }
-      running += total;
     }
   }
 }
@@ -460,43 +667,30 @@ k_freeview_list(const b200_hash_entry *__restrict__ table, int noTotal, b200_vec
 }
 
 void launch_allocate(b200_engine *e, const SceneRef &s, const FrameGeom &g, const float *depth, bool onlyVisible, int frameIdx,
-                     int snapSlot, b200_vec2f *minmaxDead, int mw, int mh) {
+                     int snapSlot, b200_vec2f *minmaxFused, int mw, int mh) {
   cudaStream_t st = e->stream;
-  const int noWords = e->noWords;
   const unsigned frameTag = (unsigned)(frameIdx + 1) & 0xffffffu;
   if (frameTag == 0) cudaMemsetAsync(e->d_reqKey, 0, sizeof(unsigned long long) * (size_t)s.noTotal, st);
-  trace_begin(e, st, "k_prepare");
-  k_prepare<<<e->smCount * 4, 256, 0, st>>>(s.hash, s.numBuckets, s.visiblePos, s.visType, e->d_ctr, e->d_reqBits, e->d_req2Bits, noWords,
-                                           g.M_d, g.proj_d[0], g.proj_d[1], g.proj_d[2], g.proj_d[3], g.voxelSize, g.w, g.h, s.numBlocks,
-                                           (float2 *)minmaxDead, mw, mh);
-  trace_end(e, st);
   const int tiles = ((g.w + 7) / 8) * ((g.h + 3) / 4);
-  trace_begin(e, st, "k_mark");
-  k_mark<<<(tiles + 7) / 8, 256, 0, st>>>(depth, s.hash, s.numBuckets, s.visType, e->d_reqKey, e->d_reqBits, e->d_req2Bits, g,
-                                         frameTag);
+  const int prepCtas = e->smCount;      // previous list (one block per thread) + expected-depth image initialisation
+  trace_begin(e, st, "k_mark_prepare");
+  k_mark_prepare<<<prepCtas + (tiles + 7) / 8, 256, 0, st>>>(depth, s.hash, s.numBuckets, s.visiblePos, s.visType, e->d_ctr, e->d_reqKey,
+                                                            e->d_reqBits, e->d_req2Bits, e->d_markBytes, g, frameTag, s.numBlocks, prepCtas,
+                                                            (float2 *)minmaxFused, mw, mh);
+  trace_end(e, st);
+  const int noTiles = (s.noTotal + AL_TILE - 1) / AL_TILE;
+  const unsigned gen = ++e->scanGen;
+  const int third = e->scanDescCap / 3;
+  trace_begin(e, st, "k_serve_list");
+  k_serve_list<<<persistent_grid(e, 2, noTiles), 256, 0, st>>>(depth, s.hash, s.numBuckets, s.noTotal, s.visType, e->d_reqKey, e->d_reqBits,
+                                                              e->d_req2Bits, e->d_markBytes, s.allocationList, s.excessList, e->d_ctr, g,
+                                                              frameIdx, onlyVisible ? 1 : 0, e->d_scanDesc, e->d_scanDesc + third,
+                                                              e->d_scanDesc + 2 * third, gen, s.visiblePos, e->d_visiblePtr, s.numBlocks,
+                                                              e->d_ring, e->ringCap, e->d_snapStart, e->d_snapCount, snapSlot,
+                                                              minmaxFused ? (BlockRec *)e->d_blockRecs : nullptr, (float2 *)minmaxFused, mw, mh,
+                                                              (unsigned)e->maxRenderingBlocks);
   trace_end(e, st);
   e->launches += 2;
-  if (!onlyVisible) {
-    const int bmpTiles = (noWords + BMP_TILE - 1) / BMP_TILE;
-    const unsigned gen = ++e->scanGen;
-    trace_begin(e, st, "k_serve_requests");
-    k_serve_requests<<<persistent_grid(e, 2, bmpTiles), 256, 0, st>>>(depth, s.hash, s.numBuckets, s.visType, e->d_reqKey, e->d_reqBits,
-                                                                     e->d_req2Bits, noWords, s.allocationList, s.excessList, e->d_ctr,
-                                                                     g, frameIdx, e->d_scanDesc, e->d_scanDesc + e->scanDescCap / 2, gen);
-    trace_end(e, st);
-    e->launches += 1;
-  }
-  const int noTiles = (s.noTotal + VIS_TILE - 1) / VIS_TILE;
-  const int oldest = e->qSize > 0 ? (e->qHead % SNAP_SLOTS) : -1;
-  trace_begin(e, st, "k_visible_list");
-  k_visible_list<<<persistent_grid(e, 2, noTiles), 256, 0, st>>>(s.hash, s.numBuckets, s.noTotal, s.visType, s.visiblePos, e->d_visiblePtr,
-                                                                s.numBlocks, e->d_ctr, e->d_scanDesc, ++e->scanGen, g.M_d, g.proj_d[0],
-                                                                g.proj_d[1], g.proj_d[2], g.proj_d[3], g.voxelSize, g.w, g.h, e->d_ring,
-                                                                e->ringCap, e->d_snapStart, e->d_snapCount, snapSlot, oldest,
-                                                                minmaxDead ? (BlockRec *)e->d_blockRecs : nullptr, mw, mh,
-                                                                (unsigned)e->maxRenderingBlocks);
-  trace_end(e, st);
-  e->launches += 1;
 }
 
 void launch_find_visible(b200_engine *e, const SceneRef &s, const Mat4 &M, const float proj[4], int w, int h, float voxelSize) {

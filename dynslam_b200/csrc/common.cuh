@@ -94,9 +94,11 @@ struct DevCounters {
   int decayDeleted;        // unique blocks deleted by the pass
   int freedLastDecay;
   int decayCand;           // partial decay: items that found their block empty this pass (candidates, unordered)
+  unsigned decayCtasDone;  // partial decay: CTAs of the sweep that have finished (the last one commits the pass)
   int droppedSnapshots;    // decay: snapshots found overwritten in the ring when their turn came (swept as empty)
   unsigned noRenderingBlocks;
-  unsigned visCtasDone;    // k_visible_list: CTAs that have finished (the last one applies the rendering-block cap if needed)
+  unsigned visCtasDone;    // k_serve_list: CTAs that have finished (the last one applies the rendering-block cap if needed)
+  unsigned tilesServed;    // k_serve_list: tiles whose requests have been served (excess-part tiles list only after all have)
   int noNeededEntries;     // swapping
   unsigned noTotalPoints;
   int noFwdMissing;

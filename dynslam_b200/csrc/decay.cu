@@ -19,13 +19,20 @@
 
 DEV unsigned long long del_tag(unsigned gen, unsigned item) { return ((unsigned long long)gen << 32) | (0xffffffffu - item); }
 
+DEV void item_pos(int mode, const b200_vec3i *ring, long long ringCap, long long s0, const short4 *allocatedPos, int item, int &x, int &y, int &z);
+DEV bool chain_leader(const b200_hash_entry *table, int numBuckets, int x, int y, int z, int item, const unsigned long long *delTag, unsigned gen);
+DEV void unlink_chain(b200_hash_entry *table, int numBuckets, uint8_t *visType, int head, const unsigned long long *delTag, unsigned gen);
+__device__ void decay_commit_body(b200_hash_entry *table, int numBuckets, uint8_t *visType, const b200_vec3i *ring, long long ringCap, long long s0,
+                                  const int *itemPtr, const unsigned long long *delTag, unsigned gen, int *allocList, int *delList,
+                                  uint8_t *isLeader, DevCounters *ctr, const int *candList, unsigned *sm, int *cand);
+
 // phase 1. MODE 0: items = ring snapshot; MODE 1: items = VBA slots with allocatedPos.w != 0
 template <int MODE>
 __global__ void __launch_bounds__(256)
-k_decay_blocks(b200_voxel *voxels, const b200_hash_entry *__restrict__ table, int numBuckets, const b200_vec3i *ring,
+k_decay_blocks(b200_voxel *voxels, const b200_hash_entry *table, int numBuckets, const b200_vec3i *ring,
                long long ringCap, const long long *snapStart, const int *snapCount, int slot, const short4 *allocatedPos,
                int numBlocks, int minAge, int maxWeight, int currentFrame, unsigned gen, unsigned long long *delTag,
-               int *itemPtr, DevCounters *ctr, int *candList) {
+               int *itemPtr, DevCounters *ctr, int *candList, uint8_t *visType, int *allocList, int *delList, uint8_t *isLeader) {
   // One WARP per list item (a block = 256 uint4 = 8 per lane, all 8 loads in flight), 8 items per CTA: the per-item chain of
   // dependent loads (ring position -> hash chain -> voxels) overlaps across warps, so the few thousand items of a frame are
   // one wave of warps instead of ~5 sequential items per CTA.
@@ -49,9 +56,9 @@ k_decay_blocks(b200_voxel *voxels, const b200_hash_entry *__restrict__ table, in
     int idx = hash_index(x, y, z, numBuckets - 1), ptr = -1, allocatedTime = 0;
     for (;;) {
       const int *w = reinterpret_cast<const int *>(table) + (size_t)idx * 5;
-      int w0 = __ldg(w), w1 = __ldg(w + 1), off = __ldg(w + 2), p = __ldg(w + 3);
+      int w0 = w[0], w1 = w[1], off = w[2], p = w[3];     // plain loads: the last CTA of a partial sweep rewrites the table (commit)
       if ((short)(w0 & 0xffff) == x && (short)(w0 >> 16) == y && (short)(w1 & 0xffff) == z && p >= 0) {
-        ptr = p; allocatedTime = __ldg(w + 4); break;
+        ptr = p; allocatedTime = w[4]; break;
       }
       if (off < 1) break;
       idx = numBuckets + off - 1;
@@ -82,12 +89,26 @@ k_decay_blocks(b200_voxel *voxels, const b200_hash_entry *__restrict__ table, in
       itemPtr[item] = claim ? ptr : -1;
       if (claim) {
         atomicMax(&delTag[ptr], del_tag(gen, (unsigned)item));
-        if (MODE == 0) {   // remember the candidate: k_decay_commit ranks the few of them instead of scanning the whole list
+        if (MODE == 0) {   // remember the candidate: the commit ranks the few of them instead of scanning the whole list
           const int c = atomicAdd(&ctr->decayCand, 1);
           if (c < DECAY_CAND_CAP) candList[c] = item;
         }
       }
     }
+  }
+  if (MODE == 0) {
+    // partial decay: the CTA that finishes last commits the pass (rank, elect, unlink, counters) — no second launch
+    __shared__ bool lastCta;
+    __shared__ unsigned smScan[33];
+    __shared__ int smCand[DECAY_CAND_CAP];
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) lastCta = (atomicAdd(&ctr->decayCtasDone, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (!lastCta) return;
+    __threadfence();
+    decay_commit_body(const_cast<b200_hash_entry *>(table), numBuckets, visType, ring, ringCap, s0, itemPtr, delTag, gen, allocList, delList,
+                      isLeader, ctr, candList, smScan, smCand);
   }
 }
 
@@ -229,42 +250,48 @@ __global__ void k_decay_unlink(b200_hash_entry *table, int numBuckets, uint8_t *
   }
 }
 
-// phases 2 + 3 + counters of a PARTIAL decay in one single-CTA launch (a frame's list is a few thousand
-// items; four tiny dependent launches cost more than the work). Ordered compaction of the claims,
-// leader election, chain unlinking, counter update.
-__global__ void __launch_bounds__(1024)
-k_decay_commit(b200_hash_entry *table, int numBuckets, uint8_t *visType, const b200_vec3i *ring, long long ringCap,
-               const long long *snapStart, int slot, const int *itemPtr, const unsigned long long *delTag, unsigned gen, int *allocList,
-               int *delList, uint8_t *isLeader, DevCounters *ctr, const int *candList) {
-  __shared__ unsigned sm[33];
-  __shared__ int cand[DECAY_CAND_CAP];
-  const int n = ctr->decayItems;
-  const int lastFree = ctr->lastFreeBlockId;
-  const long long s0 = snapStart[slot];
-  const int nc = ctr->decayCand;
+// phases 2 + 3 + counters of a PARTIAL decay, run by the LAST CTA of the sweep (k_decay_blocks<0>) — a frame's list is a few
+// thousand items and the few dozen blocks it empties are known as unordered candidates by then; a second launch for this cost
+// 13 us of the frame. Ordered compaction of the claims, leader election, chain unlinking, counter update. All threads of the
+// calling CTA take part; reads of what other CTAs produced go to L2 (__ldcg).
+__device__ void decay_commit_body(b200_hash_entry *table, int numBuckets, uint8_t *visType, const b200_vec3i *ring, long long ringCap, long long s0,
+                                  const int *itemPtr, const unsigned long long *delTag, unsigned gen, int *allocList, int *delList,
+                                  uint8_t *isLeader, DevCounters *ctr, const int *candList, unsigned *sm, int *cand) {
+  const int n = *(volatile int *)&ctr->decayItems;
+  const int lastFree = *(volatile int *)&ctr->lastFreeBlockId;
+  const int nc = *(volatile int *)&ctr->decayCand;
   unsigned running = 0;
   if (nc <= DECAY_CAND_CAP) {
     // Few candidates (a few dozen per frame): keep the winners of the block claims and rank them by list position by
     // counting — the same order the scan over the whole list produces, without walking the list.
-    int v = 0x7fffffff, ptr = -1;
-    if ((int)threadIdx.x < nc) {
-      const int item = candList[threadIdx.x];
-      ptr = itemPtr[item];
-      if (ptr >= 0 && delTag[ptr] == del_tag(gen, (unsigned)item)) v = item;
+    for (int c = threadIdx.x; c < DECAY_CAND_CAP; c += blockDim.x) {
+      int v = 0x7fffffff;
+      if (c < nc) {
+        const int item = __ldcg(candList + c);
+        const int ptr = __ldcg(itemPtr + item);
+        if (ptr >= 0 && __ldcg(delTag + ptr) == del_tag(gen, (unsigned)item)) v = item;
+      }
+      cand[c] = v;
     }
-    if (threadIdx.x < DECAY_CAND_CAP) cand[threadIdx.x] = v;
-    running = (unsigned)__syncthreads_count(v != 0x7fffffff);
-    if (v != 0x7fffffff) {
+    __syncthreads();
+    for (int c = threadIdx.x; c < nc; c += blockDim.x) {
+      const int v = cand[c];
+      if (v == 0x7fffffff) continue;
       int r = 0;
       for (int j = 0; j < nc; ++j) r += (cand[j] < v);
-      allocList[lastFree + 1 + r] = ptr;      // free-list push by list position (:1072-1073)
+      allocList[lastFree + 1 + r] = __ldcg(itemPtr + v);      // free-list push by list position (:1072-1073)
       delList[r] = v;
     }
+    int mine = 0;
+    for (int c = threadIdx.x; c < nc; c += blockDim.x) mine += (cand[c] != 0x7fffffff);
+    unsigned tot;
+    block_exclusive_scan((unsigned)mine, sm, &tot);   // (its barriers also order the writes above before the election below)
+    running = tot;
   } else
   for (int base = 0; base < n; base += blockDim.x) {
     const int item = base + threadIdx.x;
     int ptr = -1;
-    if (item < n) { ptr = itemPtr[item]; if (ptr >= 0 && delTag[ptr] != del_tag(gen, (unsigned)item)) ptr = -1; }
+    if (item < n) { ptr = __ldcg(itemPtr + item); if (ptr >= 0 && __ldcg(delTag + ptr) != del_tag(gen, (unsigned)item)) ptr = -1; }
     unsigned total;
     const unsigned r = running + block_exclusive_scan(ptr >= 0 ? 1u : 0u, sm, &total);
     if (ptr >= 0) { allocList[lastFree + 1 + (int)r] = ptr; delList[r] = item; }   // free-list push by list position (:1072-1073)
@@ -292,6 +319,7 @@ k_decay_commit(b200_hash_entry *table, int numBuckets, uint8_t *visType, const b
     ctr->decayDeleted = 0;
     ctr->decayItems = 0;
     ctr->decayCand = 0;
+    ctr->decayCtasDone = 0;
   }
 }
 
@@ -321,23 +349,16 @@ static void decay_common(b200_engine *e, const SceneRef &s, int mode, int slot, 
     trace_begin(e, st, "k_decay_blocks<0>");
     k_decay_blocks<0><<<grid1, 256, 0, st>>>(s.voxels, s.hash, s.numBuckets, e->d_ring, e->ringCap, e->d_snapStart, e->d_snapCount,
                                             slot, e->d_allocatedPos, s.numBlocks, minAge, maxWeight, frameIdx, gen, e->d_delTag,
-                                            e->d_itemPtr, e->d_ctr, e->d_candList);
+                                            e->d_itemPtr, e->d_ctr, e->d_candList, s.visType, s.allocationList, e->d_delList, e->d_isLeader);
     trace_end(e, st);
   } else {
     trace_begin(e, st, "k_decay_blocks<1>");
     k_decay_blocks<1><<<grid1, 256, 0, st>>>(s.voxels, s.hash, s.numBuckets, e->d_ring, e->ringCap, e->d_snapStart, e->d_snapCount,
                                             slot, e->d_allocatedPos, s.numBlocks, minAge, maxWeight, frameIdx, gen, e->d_delTag,
-                                            e->d_itemPtr, e->d_ctr, e->d_candList);
+                                            e->d_itemPtr, e->d_ctr, e->d_candList, s.visType, s.allocationList, e->d_delList, e->d_isLeader);
     trace_end(e, st);
   }
-  if (mode == 0) {
-    trace_begin(e, st, "k_decay_commit");
-    k_decay_commit<<<1, 1024, 0, st>>>(s.hash, s.numBuckets, s.visType, e->d_ring, e->ringCap, e->d_snapStart, slot, e->d_itemPtr, e->d_delTag,
-                                       gen, s.allocationList, e->d_delList, e->d_isLeader, e->d_ctr, e->d_candList);
-    trace_end(e, st);
-    e->launches += 2;
-    return;
-  }
+  if (mode == 0) { e->launches += 1; return; }   // the sweep's last CTA has committed the pass
   const int noTiles = (int)((items + DEC_TILE - 1) / DEC_TILE);
   k_decay_rank<<<persistent_grid(e, 4, noTiles), 256, 0, st>>>(e->d_itemPtr, e->d_delTag, gen, s.allocationList, e->d_delList,
                                                                e->d_ctr, e->d_scanDesc, ++e->scanGen);

@@ -143,9 +143,11 @@ static b200_status engine_create_body(const b200_engine_config *cfg, b200_engine
   e->noWords = e->noTotal / 32;
   CK(cudaMalloc(&e->d_reqKey, sizeof(unsigned long long) * (size_t)e->noTotal));
   CK(cudaMemset(e->d_reqKey, 0, sizeof(unsigned long long) * (size_t)e->noTotal));
-  CK(cudaMalloc(&e->d_reqBits, sizeof(unsigned) * (size_t)e->noWords * 4));
-  e->d_req2Bits = e->d_reqBits + e->noWords; e->d_reqPrefix = e->d_req2Bits + e->noWords; e->d_req2Prefix = e->d_reqPrefix + e->noWords;
-  CK(cudaMemset(e->d_reqBits, 0, sizeof(unsigned) * (size_t)e->noWords * 4));
+  CK(cudaMalloc(&e->d_reqBits, sizeof(unsigned) * (size_t)e->noWords * 2));
+  e->d_req2Bits = e->d_reqBits + e->noWords;
+  CK(cudaMemset(e->d_reqBits, 0, sizeof(unsigned) * (size_t)e->noWords * 2));   // kept clean by k_serve_list from here on
+  CK(cudaMalloc(&e->d_markBytes, (size_t)e->noTotal));
+  CK(cudaMemset(e->d_markBytes, 0, (size_t)e->noTotal));
   long long px = (long long)e->img_w * e->img_h;
   long long maxTiles = (e->noTotal + 255) / 256 + (px + 255) / 256 + e->numBlocks / 256 + 1024;
   e->scanDescCap = (int)maxTiles;
@@ -185,7 +187,7 @@ void b200_engine_destroy(b200_engine *e) {
   if (!e) return;
   cudaSetDevice(e->device);
   if (e->stream) cudaStreamSynchronize(e->stream);
-  cudaFree(e->d_ctr); cudaFreeHost(e->h_ctr); cudaFree(e->d_reqKey); cudaFree(e->d_reqBits); cudaFree(e->d_scanDesc);
+  cudaFree(e->d_ctr); cudaFreeHost(e->h_ctr); cudaFree(e->d_reqKey); cudaFree(e->d_reqBits); cudaFree(e->d_markBytes); cudaFree(e->d_scanDesc);
   cudaFree(e->d_ring); cudaFree(e->d_snapCount); cudaFree(e->d_snapStart); cudaFree(e->d_delTag); cudaFree(e->d_itemPtr); cudaFree(e->d_visiblePtr);
   cudaFree(e->d_viewScratch); cudaFree(e->d_delList); cudaFree(e->d_candList); cudaFree(e->d_isLeader); cudaFree(e->d_allocatedPos); cudaFree(e->d_tileCounts); cudaFree(e->d_blockRecs);
   for (int i = 0; i < 8; ++i) if (e->ev[i]) cudaEventDestroy(e->ev[i]);
@@ -486,17 +488,16 @@ static b200_status frame_enqueue(b200_engine *e, b200_scene *s, b200_render_stat
   FrameGeom g = frame_geom(s, v);
   const bool ring = e->timingMode >= 2 && e->evRingCount < e->evRingCap;
   if (ring) CK(cudaEventRecord(e->evRing[2 * e->evRingCount], e->stream));
-  // Fork: the expected-depth kernels only need the visible list (+ its ptr list), not the voxels IntegrateIntoScene is
-  // about to rewrite; they are small latency-bound launches, so they run on the side stream underneath the integrate kernel.
+  // The expected-depth image of the live 1/8-resolution corner was rasterised by the allocation's list pass (alloc.cu),
+  // MAX_RENDERING_BLOCKS rule included. Fork: what is left — the cells outside the corner, which nothing in the frame reads —
+  // runs on the side stream underneath the integrate kernel.
   cudaStream_t mainStream = e->stream;
   const bool overlap = doRay && e->sideStream != nullptr;
   if (overlap) {
     CK(cudaEventRecord(e->evFork, mainStream));
     CK(cudaStreamWaitEvent(e->sideStream, e->evFork, 0));
     e->stream = e->sideStream;
-    launch_expected_depths(e, r, g.M_d, g.proj_d, rs->img_w, rs->img_h, s->voxelSize, rs->d_minmax, true, true);
-    CK(cudaEventRecord(e->evJoin, e->sideStream));      // the raycast waits for the fill only ...
-    launch_expected_depths_dead(e, r, g.M_d, g.proj_d, rs->img_w, rs->img_h, s->voxelSize, rs->d_minmax);   // ... not for the dead cells
+    launch_expected_depths_dead(e, r, g.M_d, g.proj_d, rs->img_w, rs->img_h, s->voxelSize, rs->d_minmax);   // nothing in the frame waits for it
     e->stream = mainStream;
   }
   launch_integrate(e, r, g, v->d_depth, v->d_rgb);
@@ -504,22 +505,28 @@ static b200_status frame_enqueue(b200_engine *e, b200_scene *s, b200_render_stat
   if (ring) { CK(cudaEventRecord(e->evRing[2 * e->evRingCount + 1], e->stream)); e->evRingCount++; }
   if (e->timing) CK(cudaEventRecord(e->ev[2], e->stream));
   if (doRay) {
-    if (overlap) CK(cudaStreamWaitEvent(mainStream, e->evJoin, 0));
-    else {
-      launch_expected_depths(e, r, g.M_d, g.proj_d, rs->img_w, rs->img_h, s->voxelSize, rs->d_minmax, true, true);
-      launch_expected_depths_dead(e, r, g.M_d, g.proj_d, rs->img_w, rs->img_h, s->voxelSize, rs->d_minmax);
-    }
+    if (!overlap) launch_expected_depths_dead(e, r, g.M_d, g.proj_d, rs->img_w, rs->img_h, s->voxelSize, rs->d_minmax);
     if (e->timing) CK(cudaEventRecord(e->ev[3], e->stream));
     launch_raycast(e, r, g.invM_d, g.proj_d, rs->img_w, rs->img_h, s->voxelSize, s->mu, rs->d_minmax, rs->d_raycastResult);
+    // optional colour render for compositing: reads voxel colours, so it has to run before this frame's decay resets any
+    if (opts && opts->d_colourRender)
+      launch_shade(e, r, g.M_d, g.invM_d, rs->img_w, rs->img_h, s->voxelSize, s->maxW, rs->d_raycastResult, opts->d_colourRender, nullptr,
+                   B200_RENDER_COLOUR_FROM_VOLUME);
     if (overlap) {   // the ICP-map pass (image space) runs beside the decay sweep (voxel space)
       CK(cudaEventRecord(e->evFork, mainStream));
       CK(cudaStreamWaitEvent(e->sideStream, e->evFork, 0));
       e->stream = e->sideStream;
       launch_icp(e, g.invM_d, rs->img_w, rs->img_h, s->voxelSize, rs->d_raycastResult, rs->d_raycastImage, d_points, d_normals);
+      if (opts && opts->d_depthRender)   // depth render: ray points and the pose only, nothing of the volume — also beside the decay
+        launch_shade(e, r, g.M_d, g.invM_d, rs->img_w, rs->img_h, s->voxelSize, s->maxW, rs->d_raycastResult, nullptr, opts->d_depthRender,
+                     B200_RENDER_DEPTH_MAP);
       e->stream = mainStream;
       CK(cudaEventRecord(e->evJoin, e->sideStream));
     } else {
       launch_icp(e, g.invM_d, rs->img_w, rs->img_h, s->voxelSize, rs->d_raycastResult, rs->d_raycastImage, d_points, d_normals);
+      if (opts && opts->d_depthRender)
+        launch_shade(e, r, g.M_d, g.invM_d, rs->img_w, rs->img_h, s->voxelSize, s->maxW, rs->d_raycastResult, nullptr, opts->d_depthRender,
+                     B200_RENDER_DEPTH_MAP);
     }
   } else if (e->timing) CK(cudaEventRecord(e->ev[3], e->stream));
   if (e->timing) CK(cudaEventRecord(e->ev[4], e->stream));

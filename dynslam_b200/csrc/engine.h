@@ -38,7 +38,7 @@ struct b200_engine {
   DevCounters *h_ctr;                 // pinned mirror
   unsigned long long *d_reqKey;       // per entry: frameTag | pixel | step of the winning request
   unsigned *d_reqBits, *d_req2Bits;   // request bitmaps (all / excess-type), noTotal/32 words
-  unsigned *d_reqPrefix, *d_req2Prefix;
+  uint8_t *d_markBytes;               // per entry: observed by this frame's marking (entriesVisibleType 1 / 2), consumed and cleared by k_serve_list
   int noWords;
   unsigned long long *d_scanDesc;     // chained-scan tile descriptors
   int scanDescCap;

@@ -44,7 +44,7 @@ k_project_blocks(const b200_hash_entry *__restrict__ table, int numBuckets, cons
   const int noTiles = (n + PRJ_THREADS - 1) / PRJ_THREADS;
   const int liveX = (w - 1) / B200_MINMAX_SUBSAMPLE, liveY = (h - 1) / B200_MINMAX_SUBSAMPLE;   // last live cell
   const int lane = threadIdx.x & 31;
-  // Fused frame (recsReady): k_visible_list already wrote the records, tile total and cap rule included; what is left is
+  // Fused frame (recsReady): k_serve_list (alloc.cu) already wrote the records, cap rule included, and rasterised the live corner; what is left is
   // the dead-cell part of the boxes, which nothing in the frame reads (a block next to the camera can cover 10^5 of them), so
   // it runs AFTER the fill the raycast waits for. Stand-alone CreateExpectedDepths (recsReady 0) does everything here.
   const bool fast = recsReady != 0;
@@ -160,7 +160,7 @@ void launch_expected_depths(b200_engine *e, const SceneRef &s, const Mat4 &M, co
                             b200_vec2f *minmax, bool deadInitDone, bool recsReady) {
   if (!deadInitDone) { k_minmax_init_dead<<<e->smCount * 4, 256, 0, e->stream>>>((float2 *)minmax, w, h); e->launches++; }
   const int noTiles = (s.numBlocks + PRJ_THREADS - 1) / PRJ_THREADS;
-  if (!recsReady) {   // otherwise the records come from k_visible_list of this frame; the dead cells follow in launch_expected_depths_dead
+  if (!recsReady) {   // otherwise the records come from k_serve_list of this frame; the dead cells follow in launch_expected_depths_dead
     trace_begin(e, e->stream, "k_project_blocks");
     k_project_blocks<<<persistent_grid(e, 2, noTiles), PRJ_THREADS, 0, e->stream>>>(s.hash, s.numBuckets, s.visiblePos, fresh_ptr_list(e, s),
                                                                                    s.numBlocks, e->d_ctr, M, proj[0], proj[1], proj[2], proj[3],

@@ -220,9 +220,13 @@ class Engine:
         self.lib.b200_diag_set_max_rendering_blocks(self.h, int(n))
 
     # ---- fused fast path --------------------------------------------------------------------
-    def process_frame_async(self, renderState, view, points=None, normals=None, decay=None, raycast=True):
+    def process_frame_async(self, renderState, view, points=None, normals=None, decay=None, raycast=True, colour_out=None,
+                            depth_out=None):
+        """colour_out / depth_out: optional renders (RENDER_COLOUR_FROM_VOLUME / RENDER_DEPTH_MAP) shaded from this frame's ray
+        points, for compositing (multi-volume configuration)."""
         o = abi.FrameOpts()
         o.doRaycast = int(raycast)
+        o.d_colourRender, o.d_depthRender = _ptr(colour_out), _ptr(depth_out)
         if decay is not None:
             o.doDecay, o.decayMaxWeight, o.decayMinAge = 1, decay[0], decay[1]
         self.after_torch()
@@ -244,10 +248,11 @@ class Engine:
 
 
     def host_frame_submit(self, renderState, view, h_depth, h_rgb, points=None, normals=None, decay=None, raycast=True, h_out=None,
-                          slot=0):
+                          slot=0, colour_out=None, depth_out=None):
         """Pipelined host frames: H2D, fused frame and D2H of the grey image are enqueued without blocking."""
         o = abi.FrameOpts()
         o.doRaycast = int(raycast)
+        o.d_colourRender, o.d_depthRender = _ptr(colour_out), _ptr(depth_out)
         if decay is not None:
             o.doDecay, o.decayMaxWeight, o.decayMinAge = 1, decay[0], decay[1]
         self.check(self.lib.b200_host_frame_submit(self.h, C.byref(self.scene.c), C.byref(renderState.c), C.byref(view.c),

@@ -16,8 +16,11 @@
 
 #include <cstdio>
 #include <cstdlib>
+#include <map>
 #include <memory>
 #include <stdexcept>
+
+#include "ITMLib/Utils/ITMLibSettings.h"
 
 #include "ITMLib/Engine/ITMSceneReconstructionEngine.h"
 #include "ITMLib/Engine/ITMSwappingEngine.h"
@@ -65,6 +68,23 @@ class B200EngineHandle {
     }
   }
 };
+
+/// The engine handle of the volume configured by `settings` (one ITMLibSettings object per ITMMainEngine / InfiniTamDriver,
+/// i.e. per volume, in DynSLAM: DS/InfiniTamDriver.h, DS/InstRecLib/InstanceReconstructor.cpp:363-389). ITMMainEngine's
+/// constructor calls it first, with the image size (integration/itmlib_b200.patch); ITMDenseMapper's constructor, which only
+/// receives the settings, then picks the same handle up. Entries die with their last engine (weak references).
+inline std::shared_ptr<B200EngineHandle> B200HandleFor(const ITMLibSettings *settings, Vector2i imgSize = Vector2i(0, 0)) {
+  static std::map<const ITMLibSettings *, std::weak_ptr<B200EngineHandle>> registry;
+  std::shared_ptr<B200EngineHandle> h = registry[settings].lock();
+  if (!h) {
+    if (imgSize.x <= 0 || imgSize.y <= 0) throw std::runtime_error("B200HandleFor: no engine yet for these settings and no image size given");
+    int device = 0;
+    cudaGetDevice(&device);
+    h = std::make_shared<B200EngineHandle>(device, settings->sdfLocalBlockNum, imgSize);
+    registry[settings] = h;
+  }
+  return h;
+}
 
 namespace b200_detail {
 

@@ -179,3 +179,83 @@ def instance_frame(depth, rgb, ident, car_index):
     d = np.where(m, depth, np.float32(0.0)).astype(np.float32)
     c = np.where(m[..., None], rgb, np.uint8(255)).astype(np.uint8)
     return d, c
+
+
+def hash_index(pos, mask):
+    """hashIndex of DA/ITMRepresentationAccess.h:10-12 on (n,3) int block positions (uint32 wrap-around arithmetic)."""
+    p = np.asarray(pos).astype(np.int64) & 0xffffffff
+    h = ((p[:, 0] * 73856093) & 0xffffffff) ^ ((p[:, 1] * 19349669) & 0xffffffff) ^ ((p[:, 2] * 83492791) & 0xffffffff)
+    return (h & mask).astype(np.int64)
+
+
+def prefilled_hash(n_blocks, num_buckets, excess_size, seed=4, allocated_time=0):
+    """configs[3]: a valid ITMVoxelBlockHash state with `n_blocks` allocated blocks, built directly
+    instead of through thousands of frames: block i (seeded random distinct positions) owns VBA slot i;
+    the first block of every bucket sits in the ordered part, the others are chained through the excess list in order of
+    arrival, exactly as serial allocation would leave them. Returns (entries[num_buckets+excess_size] with the HASH_ENTRY
+    dtype, allocationList, excessList, lastFreeBlockId, lastFreeExcessListId) for a scene with numBlocks == n_blocks."""
+    from . import abi
+    rng = np.random.RandomState(seed)
+    # distinct positions scattered over a (2 * half)^3 box of blocks, about 2% occupancy (surfaces are sparse in block space)
+    half = max(8, int(np.ceil((n_blocks / 0.02) ** (1.0 / 3.0) / 2.0)))
+    codes = np.unique(rng.randint(0, (2 * half) ** 3, size=int(n_blocks * 1.1) + 64, dtype=np.int64))
+    while codes.size < n_blocks:
+        codes = np.unique(np.concatenate([codes, rng.randint(0, (2 * half) ** 3, size=n_blocks, dtype=np.int64)]))
+    codes = codes[rng.permutation(codes.size)[:n_blocks]]
+    pos = np.stack([codes % (2 * half), (codes // (2 * half)) % (2 * half), codes // (2 * half) ** 2], axis=-1).astype(np.int64) - half
+    pos = pos.astype(np.int16)
+    bucket = hash_index(pos, num_buckets - 1)
+    order = np.argsort(bucket, kind="stable")                  # arrival order inside a bucket = block id order
+    b_sorted = bucket[order]
+    first = np.ones(n_blocks, dtype=bool)
+    first[1:] = b_sorted[1:] != b_sorted[:-1]
+    ent = np.zeros(num_buckets + excess_size, dtype=abi.HASH_ENTRY_DTYPE)
+    ent["ptr"] = -2
+    heads = order[first]
+    ent["pos"][bucket[heads]] = pos[heads]
+    ent["ptr"][bucket[heads]] = heads
+    ent["allocatedTime"][bucket[heads]] = allocated_time
+    nf = np.nonzero(~first)[0]
+    rest = order[nf]
+    n_ex = rest.size
+    if n_ex > excess_size:
+        raise ValueError(f"{n_ex} chained blocks do not fit the excess list of {excess_size}")
+    # excess slots are popped from the top of the free stack (excessList[i] = i), in block-id order
+    slot_of = np.full(n_blocks, -1, dtype=np.int64)
+    slot_of[np.sort(rest)] = excess_size - 1 - np.arange(n_ex)
+    eidx = num_buckets + slot_of[rest]
+    ent["pos"][eidx] = pos[rest]
+    ent["ptr"][eidx] = rest
+    ent["allocatedTime"][eidx] = allocated_time
+    prev = order[nf - 1]                                       # predecessor in the same bucket's chain
+    prev_idx = np.where(first[nf - 1], bucket[prev], num_buckets + slot_of[prev])
+    ent["offset"][prev_idx] = slot_of[rest] + 1
+    alloc_list = np.arange(n_blocks, dtype=np.int32)
+    excess_list = np.arange(excess_size, dtype=np.int32)
+    return ent, alloc_list, excess_list, -1, excess_size - 1 - n_ex
+
+
+class FollowedCar(MovingCar):
+    """A car that stays in the ego camera's view for the whole stream (configs[2] bench): it drives at the ego speed with a
+    slow longitudinal oscillation, car `idx` further ahead than car `idx - 1`, alternating lanes."""
+
+    def __init__(self, idx, seed=3, step_m=0.8):
+        super().__init__(idx, seed)
+        self.step_m = step_m
+        self.z_rel = 5.5 + 1.7 * idx
+        self.phase = 0.9 * idx
+
+    def centre(self, frame, ground_y=1.65):
+        z = self.step_m * frame + self.z_rel + 1.2 * np.sin(frame / 23.0 + self.phase)
+        return np.array([self.lane_x, ground_y - self.half[1], z])
+
+
+def silhouette_mask(ident, car_index):
+    """(inclusive bbox, box-sized uint8 mask) of car `car_index` in an id map, or None when it is not visible — the form
+    DynSLAM's segmentation provider hands to InstanceReconstructor (Utils/Mask.h, Utils/BoundingBox.h)."""
+    m = ident == (1000 + car_index)
+    if not m.any():
+        return None
+    ys, xs = np.nonzero(m)
+    x0, x1, y0, y1 = int(xs.min()), int(xs.max()), int(ys.min()), int(ys.max())
+    return (x0, y0, x1, y1), np.ascontiguousarray(m[y0:y1 + 1, x0:x1 + 1]).astype(np.uint8)

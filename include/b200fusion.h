@@ -230,6 +230,11 @@ b200_status b200_swap_out(b200_engine *e, b200_scene *scene, b200_render_state *
 typedef struct {
   int32_t doDecay, decayMaxWeight, decayMinAge;
   int32_t doRaycast;           /* CreateExpectedDepths + CreateICPMaps */
+  /* Optional per-frame renders for compositing (the multi-volume configuration): shaded from the ray points of THIS frame's
+     raycast (same pose), i.e. RenderImage's shading pass without a second raycast, before Decay touches the volume.
+     NULL = not rendered. d_colourRender: RENDER_COLOUR_FROM_VOLUME (w*h RGBA8); d_depthRender: RENDER_DEPTH_MAP (w*h f32). */
+  b200_vec4u *d_colourRender;
+  float *d_depthRender;
 } b200_frame_opts;
 
 /* Enqueue allocate -> integrate -> expected depths -> ICP maps -> decay for one frame on the
@@ -346,6 +351,34 @@ b200_status b200_composite_color(b200_engine *e, b200_vec4u *d_target_color, flo
 b200_status b200_composite_instances(b200_engine *e, b200_vec4u *d_out_color, float *d_out_depth, int n,
                                      const b200_instance_layer *layers, int n_layers, float dim_factor,
                                      float tint_strength);
+
+/* ---- the exchange step of the multi-volume configuration -----------------------------------------------
+   One volume per GPU, one process per GPU: the static map on rank 0, one ITMScene per car on the other ranks
+   (DS/InstRecLib/InstanceReconstructor.cpp:363-389). Fusion, allocation and decay need no communication; per frame every
+   rank hands the colour (RGBA8) and depth (f32) renders of its volume to rank 0, which z-composites them over its own render
+   (CompositeInstances, InstanceReconstructor.cpp:932-987). NCCL send/recv over NVLink on the communicator's own stream,
+   double-buffered, so the next frame's kernels never wait for this frame's rendez-vous. libnccl.so.2 is loaded at run time. */
+
+#define B200_COMM_ID_BYTES 128
+typedef struct b200_comm b200_comm;
+
+/* rank 0 makes the rendez-vous id (ncclGetUniqueId); the host distributes it to the other ranks over any channel */
+b200_status b200_comm_unique_id(char id[B200_COMM_ID_BYTES]);
+b200_status b200_comm_create(int device, int nranks, int rank, const char id[B200_COMM_ID_BYTES], int img_w, int img_h,
+                             b200_comm **out);
+void b200_comm_destroy(b200_comm *c);
+const char *b200_comm_last_error(const b200_comm *c);   /* c == NULL: why the last create / unique_id failed on this thread */
+/* Per frame, every rank: d_color / d_depth (w*h each) are this volume's renders, produced by work already enqueued on e's
+   stream. Ranks > 0 send them to rank 0. Rank 0 receives the other ranks' layers, copies its own render to d_out_color /
+   d_out_depth and composites the layers over it in rank order (tints: 4 ints per layer, rank r at tints[4*(r-1)];
+   dim_factor < 0: no dimming). Only enqueues. slot in {0, 1} double-buffers the hand-over. */
+b200_status b200_gather_composite_submit(b200_comm *c, b200_engine *e, const b200_vec4u *d_color, const float *d_depth,
+                                         b200_vec4u *d_out_color, float *d_out_depth, const int32_t *tints, float dim_factor,
+                                         float tint_strength, int slot);
+/* e's stream waits on the device until slot's exchange has drained (call before overwriting the buffers handed over with it) */
+b200_status b200_gather_composite_release(b200_comm *c, b200_engine *e, int slot);
+/* the host waits until slot's exchange (on rank 0: and the composite) has finished */
+b200_status b200_gather_composite_wait(b200_comm *c, int slot);
 
 #ifdef __cplusplus
 }

@@ -143,3 +143,58 @@ class Harness:
             self.close()
         except Exception:
             pass
+
+
+PATCHED_SO = os.path.join(ROOT, "oracle", "_ref", "libitmpatched.so")
+
+
+def patched_available():
+    return os.path.exists(PATCHED_SO)
+
+
+class PatchedMainEngine:
+    """The reference's ITMMainEngine built from the PATCHED ITMLib (integration/itmlib_b200.patch, integration/build_patched.sh):
+    backend 0 = settings->engineBackend BACKEND_REFERENCE, 1 = BACKEND_B200. Frames go in as DynSLAM feeds them: raw int16
+    depth (mm) + RGBA through ITMMainEngine::ProcessFrame, pose set externally."""
+    _L = None
+
+    def __init__(self, backend, w, h, proj, voxelSize=0.05, mu=0.75, numBlocks=0x60000):
+        if PatchedMainEngine._L is None:
+            abi.load_library()
+            L = C.CDLL(PATCHED_SO)
+            vp = C.c_void_p
+            L.med_create.restype = vp
+            L.med_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_long]
+            L.med_error.argtypes = [vp]; L.med_error.restype = C.c_char_p
+            L.med_process_frame.argtypes = [vp, vp, vp, C.POINTER(C.c_float)]
+            L.med_get_raycast_image.argtypes = [vp, vp]; L.med_get_raycast_image.restype = None
+            L.med_counters.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]; L.med_counters.restype = None
+            L.med_destroy.argtypes = [vp]; L.med_destroy.restype = None
+            PatchedMainEngine._L = L
+        self.L, self.w, self.h = PatchedMainEngine._L, w, h
+        self.h_ = self.L.med_create(backend, w, h, float(proj[0]), float(proj[1]), float(proj[2]), float(proj[3]), voxelSize, mu, numBlocks)
+        err = self.L.med_error(self.h_).decode()
+        if err:
+            raise RuntimeError(err)
+
+    def process_frame(self, raw, rgb, M):
+        raw = np.ascontiguousarray(raw, dtype=np.int16)
+        rgb = np.ascontiguousarray(rgb, dtype=np.uint8)
+        rc = self.L.med_process_frame(self.h_, raw.ctypes.data, rgb.ctypes.data, abi.mat_to_c(M))
+        if rc:
+            raise RuntimeError(self.L.med_error(self.h_).decode())
+
+    def raycast_image(self):
+        out = np.zeros((self.h, self.w, 4), dtype=np.uint8)
+        self.L.med_get_raycast_image(self.h_, out.ctypes.data)
+        return out
+
+    def counters(self):
+        a, b, c = C.c_int(), C.c_int(), C.c_int()
+        self.L.med_counters(self.h_, C.byref(a), C.byref(b), C.byref(c))
+        return dict(lastFreeBlockId=a.value, allocatedEntries=c.value)
+
+    def close(self):
+        if self.h_:
+            self.L.med_destroy(self.h_)
+            self.h_ = None

@@ -15,8 +15,9 @@ pytestmark = pytest.mark.gpu
 
 def test_config3_instance_volumes_masked_frames():
     """configs[2]: per-car volumes (mu 1.0, voxel 0.035, 7142 blocks; InstanceReconstructor.cpp:365-389) fed the
-    frame masked to the car's silhouette (depth 0 / RGB 255 outside, :91-127) with the object pose."""
-    scale = 0.5
+    frame masked to the car's silhouette (depth 0 / RGB 255 outside, :91-127) with the object pose — at the full
+    1242x375 resolution and table size of the configuration."""
+    scale = 1.0
     cfg = P.Cfg(scale=scale, numBlocks=7142, numBuckets=0x100000, excessSize=0x80000, voxelSize=0.035, mu=1.0, maxW=50,
                 decay=(1, 2))
     scene = synth.StreetScene(seed=3, length_m=80.0)

@@ -127,3 +127,32 @@ def test_view_builder_through_itmlib_objects():
         err = np.abs(g.astype(np.float64) - want) / np.maximum(1.0, np.abs(want))
         assert err.max() <= tol, (impl, err.max())
         assert (g[:2] == 0).all() and (g[-2:] == 0).all() and (g[:, :2] == 0).all() and (g[:, -2:] == 0).all()
+
+
+@pytest.mark.skipif(not HL.patched_available(), reason="oracle/_ref/libitmpatched.so not built (integration/build_patched.sh)")
+def test_patched_main_engine_runs_both_backends():
+    """The binding a maintainer adds, compiled and RUN: integration/itmlib_b200.patch applied to the reference's ITMLib, the
+    whole library rebuilt, and the reference's own top-level object — ITMMainEngine, the base class of DynSLAM's
+    InfiniTamDriver — driven frame by frame with settings->engineBackend = BACKEND_B200 and BACKEND_REFERENCE. Everything
+    around the engines (view building, ITMDenseMapper::ProcessFrame, ITMTrackingController::Prepare, GetImage) is the
+    reference's host code. The two back-ends are compared on order-free invariants (the reference CUDA build is
+    nondeterministic and uses --use_fast_math)."""
+    scale = 0.5
+    w, h = int(round(synth.KITTI_W * scale)), int(round(synth.KITTI_H * scale))
+    street = synth.StreetScene(seed=6, length_m=60.0)
+    frames = [synth.kitti_frame(street, f, scale=scale) for f in range(6)]
+    res = {}
+    for backend in (0, 1):
+        eng = HL.PatchedMainEngine(backend, w, h, frames[0][3], numBlocks=65536)
+        for depth, rgb, M, proj in frames:
+            eng.process_frame(np.round(depth * 1000.0).astype(np.int16), rgb, M)
+        res[backend] = (eng.counters(), eng.raycast_image())
+        eng.close()
+    (c0, img0), (c1, img1) = res[0], res[1]
+    assert c1["allocatedEntries"] > 2000
+    assert abs(c1["allocatedEntries"] - c0["allocatedEntries"]) <= 0.01 * c0["allocatedEntries"]
+    assert c1["lastFreeBlockId"] == 65536 - 1 - c1["allocatedEntries"]
+    hit0, hit1 = img0[..., 0] > 0, img1[..., 0] > 0
+    assert hit1.mean() > 0.3 and abs(hit0.mean() - hit1.mean()) < 0.02
+    both = hit0 & hit1
+    assert np.abs(img0[..., 0].astype(np.int32) - img1[..., 0].astype(np.int32))[both].mean() < 3.0
