@@ -179,7 +179,10 @@ static b200_status engine_create_body(const b200_engine_config *cfg, b200_engine
   integrate_init_device(e);     // per-device tables and function attributes of integrate.cu (one engine per GPU is the multi-GPU unit)
   CK(cudaGetLastError());
   // default: V3 (warp-decoupled TMA ring, integrate.cu); B200_INTEGRATE_IMPL=tma|ldg select the earlier variants
-  { const char *v = getenv("B200_INTEGRATE_IMPL"); e->integrateImpl = (v && v[0] == 'l') ? 0 : ((v && v[0] == 't') ? 1 : 2); }
+  // default: V4 (packed-pair arithmetic, integrate.cu); B200_INTEGRATE_IMPL = v3 | tma | ldg select the earlier bit-exact variants,
+  // fast = V4 in tolerance mode (TSDF within 1 LSB of the 16-bit code, everything else bit-exact)
+  { const char *v = getenv("B200_INTEGRATE_IMPL");
+    e->integrateImpl = !v ? 3 : (v[0] == 'l' ? 0 : (v[0] == 't' ? 1 : (v[0] == 'f' ? 4 : ((v[0] == 'v' && v[1] == '3') ? 2 : 3)))); }
   return B200_OK;
 }
 

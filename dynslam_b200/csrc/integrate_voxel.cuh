@@ -263,3 +263,155 @@ HD bool v3_colour(unsigned &lo, unsigned &hi, float ix, float iy, const FrameGeo
   return ch;
 }
 
+
+// ================================================================================================================
+// V4: the same two stages on PAIRS of x-adjacent voxels with Blackwell's packed binary32 instructions
+// (add/mul/fma.rn.f32x2 -> FADD2 / FMUL2 / FFMA2: one issue slot for two IEEE-rounded results; measured on B200 at 1.97
+// warp-instructions per clock and SM against 2.81 for the scalar forms, i.e. 1.4x the arithmetic per issue slot). Every
+// element goes through exactly the operations of the scalar path above, in the same order, so the bits are the same:
+// tests/hostcheck runs v4 against the generic per-voxel code on the CPU like it does v3.
+// FAST = true is the tolerance-mode build (north_star's bar, not the reference's bits): in the TSDF update (stage B) quotients
+// become one multiplication by the tabulated reciprocal and sums are contracted into FMAs. The projection, the depth pixel it
+// selects, weights and colours stay bit-exact; a TSDF value may land on the neighbouring 16-bit code (1 LSB = 3.05e-5 after
+// SDF_valueToFloat) and the colour gate |eta / mu| <= 0.25 may flip on a tie — both counted by the tests.
+// ================================================================================================================
+#if defined(__CUDA_ARCH__)
+#define F2_DEV 1
+#else
+#define F2_DEV 0
+#endif
+HD float2 f2add(float2 a, float2 b) {
+#if F2_DEV
+  return __fadd2_rn(a, b);
+#else
+  return make_float2(a.x + b.x, a.y + b.y);
+#endif
+}
+HD float2 f2mul(float2 a, float2 b) {
+#if F2_DEV
+  return __fmul2_rn(a, b);
+#else
+  return make_float2(a.x * b.x, a.y * b.y);
+#endif
+}
+HD float2 f2fma(float2 a, float2 b, float2 c) {
+#if F2_DEV
+  return __ffma2_rn(a, b, c);
+#else
+  return make_float2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y));
+#endif
+}
+HD float2 f2dup(float v) { return make_float2(v, v); }
+HD float2 f2neg(float2 a) { return make_float2(-a.x, -a.y); }
+HD float rcp_approx(float b) {
+#ifdef __CUDA_ARCH__
+  float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(b)); return y;
+#else
+  return 1.0f / b;
+#endif
+}
+HD float2 rcp_nr2(float2 nb, float2 y0) {                 // nb = -b, y0 = MUFU.RCP(b): one Newton step, as rcp_nr
+  return f2fma(y0, f2fma(nb, y0, f2dup(1.0f)), y0);
+}
+HD float2 div_nr2(float2 a, float2 nb, float2 y) {        // nb = -b, y = rcp_nr(b): quotient + one residual correction, as div_nr
+  const float2 q = f2mul(a, y);
+  return f2fma(y, f2fma(nb, q, a), q);
+}
+
+struct V4C {            // constants of a launch, duplicated into both halves
+  float2 fx, fy, cx, cy, tx, ty, tz, nmu, rcpMu, n32767, rcp32767, c32767, half;
+};
+HD V4C v4_constants(const FrameGeom &g, const V3K &k) {
+  V4C c;
+  c.fx = f2dup(g.proj_d[0]); c.fy = f2dup(g.proj_d[1]); c.cx = f2dup(g.proj_d[2]); c.cy = f2dup(g.proj_d[3]);
+  c.tx = f2dup(g.M_d.m[12]); c.ty = f2dup(g.M_d.m[13]); c.tz = f2dup(g.M_d.m[14]);
+  c.nmu = f2dup(-g.mu); c.rcpMu = f2dup(k.rcpMu); c.n32767 = f2dup(-32767.0f); c.rcp32767 = f2dup(V3_RCP_32767); c.c32767 = f2dup(32767.0f);
+  c.half = f2dup(0.5f);
+  return c;
+}
+
+struct V4A { float2 pcz, ix, iy; unsigned idx0, idx1; bool ok0, ok1, inb0, inb1; };
+
+// XY* = X + Y of the pair (shared by the slabs a lane owns), Z* = the slab's products, both halves equal
+template <bool FAST>
+HD V4A v4_stage_a(float2 XYx, float2 XYy, float2 XYz, float2 Zx, float2 Zy, float2 Zz, const FrameGeom &g, const V3K &k, const V4C &c) {
+  V4A a;
+  const float2 pcx = f2add(f2add(XYx, Zx), c.tx), pcy = f2add(f2add(XYy, Zy), c.ty);
+  a.pcz = f2add(f2add(XYz, Zz), c.tz);
+  const float2 ax = f2mul(c.fx, pcx), ay = f2mul(c.fy, pcy);
+  {
+    const float lo0 = fminf(fminf(fabsf(ax.x), fabsf(ay.x)), a.pcz.x), hi0 = fmaxf(fmaxf(fabsf(ax.x), fabsf(ay.x)), a.pcz.x);
+    const float lo1 = fminf(fminf(fabsf(ax.y), fabsf(ay.y)), a.pcz.y), hi1 = fmaxf(fmaxf(fabsf(ax.y), fabsf(ay.y)), a.pcz.y);
+    a.ok0 = (lo0 >= V3_SAFE_LO) && (hi0 <= V3_SAFE_HI);
+    a.ok1 = (lo1 >= V3_SAFE_LO) && (hi1 <= V3_SAFE_HI);
+  }
+  // The projection stays exact in tolerance mode too: it picks the depth pixel ((int)(u + 0.5f)), decides the bounds test and
+  // is the colour sampling position — an approximate quotient would, on a tie, read a DIFFERENT pixel and change the voxel
+  // by far more than an LSB ("Defining parity").
+  const float2 y0 = make_float2(rcp_approx(a.pcz.x), rcp_approx(a.pcz.y));
+  const float2 npcz = f2neg(a.pcz);
+  const float2 yz = rcp_nr2(npcz, y0);
+  a.ix = f2add(div_nr2(ax, npcz, yz), c.cx);
+  a.iy = f2add(div_nr2(ay, npcz, yz), c.cy);
+  a.inb0 = !((a.ix.x < 1) | (a.ix.x > k.wm2) | (a.iy.x < 1) | (a.iy.x > k.hm2));
+  a.inb1 = !((a.ix.y < 1) | (a.ix.y > k.wm2) | (a.iy.y < 1) | (a.iy.y > k.hm2));
+  const float2 rx = f2add(a.ix, c.half), ry = f2add(a.iy, c.half);
+  a.idx0 = (unsigned)((int)rx.x + (int)ry.x * g.w) & (0u - (unsigned)(a.ok0 & a.inb0));
+  a.idx1 = (unsigned)((int)rx.y + (int)ry.y * g.w) & (0u - (unsigned)(a.ok1 & a.inb1));
+  return a;
+}
+
+// one element's bookkeeping of stage B (everything that is not binary32 arithmetic), shared by both halves
+struct V4E { bool valid, behind, etaOK; int oldW, newW; };
+
+template <bool DW, bool FAST>
+HD void v4_stage_b(unsigned &lo0, unsigned &lo1, const V4A &a, float2 dm, const FrameGeom &g, const V3K &k, const V4C &c, const float *rcpW,
+                    int &r0, int &r1) {
+  const float2 eta = f2add(dm, f2neg(a.pcz));          // dm - pc.z
+  const float2 eom = FAST ? f2mul(eta, c.rcpMu) : div_nr2(eta, c.nmu, c.rcpMu);
+  const float2 newFm = make_float2(minf_(1.0f, eom.x), minf_(1.0f, eom.y));
+  const int oldW0 = (lo0 >> 16) & 0xff, oldW1 = (lo1 >> 16) & 0xff;
+  const float2 sd = make_float2((float)(short)(lo0 & 0xffffu), (float)(short)(lo1 & 0xffffu));
+  const float2 oldF = FAST ? f2mul(sd, c.rcp32767) : div_nr2(sd, c.n32767, c.rcp32767);
+  const float2 oldWf = make_float2((float)oldW0, (float)oldW1);
+  int nw0 = 1, nw1 = 1;
+  float2 num;
+  if (DW) {
+    nw0 = (int)(100.0 / dm.x); nw0 = nw0 < 1 ? 1 : (nw0 > 10 ? 10 : nw0);
+    nw1 = (int)(100.0 / dm.y); nw1 = nw1 < 1 ? 1 : (nw1 > 10 ? 10 : nw1);
+    const float2 nwf = make_float2((float)nw0, (float)nw1);
+    num = FAST ? f2fma(oldWf, oldF, f2mul(nwf, newFm)) : f2add(f2mul(oldWf, oldF), f2mul(nwf, newFm));
+  } else {
+    num = FAST ? f2fma(oldWf, oldF, newFm) : f2add(f2mul(oldWf, oldF), newFm);     // newW == 1: 1 * newF is newF, exactly
+  }
+  int W0 = oldW0 + nw0, W1 = oldW1 + nw1;
+  const float2 Wf = make_float2((float)W0, (float)W1);
+  const float2 yw = make_float2(rcpW[W0], rcpW[W1]);
+  const float2 q = FAST ? f2mul(num, yw) : div_nr2(num, f2neg(Wf), yw);
+  W0 = mini_(W0, g.maxW); W1 = mini_(W1, g.maxW);
+  const float2 s = f2mul(q, c.c32767);
+  const unsigned nlo0 = (lo0 & 0xff000000u) | ((unsigned)(int)(short)(s.x) & 0xffffu) | ((unsigned)(W0 & 0xff) << 16);
+  const unsigned nlo1 = (lo1 & 0xff000000u) | ((unsigned)(int)(short)(s.y) & 0xffffu) | ((unsigned)(W1 & 0xff) << 16);
+  {
+    const bool rej = (dm.x <= 0.0f), valid = a.ok0 && a.inb0 && !rej, behind = eta.x < -g.mu;
+    const float ae = fabsf(eta.x);
+    const bool etaOK = ((ae >= V3_SAFE_LO) && (ae <= V3_SAFE_HI)) || (eta.x == 0.0f);
+    const bool upd = valid && !behind && etaOK;
+    lo0 = upd ? nlo0 : lo0;
+    const bool behindCamera = (a.pcz.x <= 0.0f) && (k.rejectColour == 0);
+    const bool slow = (!a.ok0 && !behindCamera) || ((!a.inb0 || rej) && (k.rejectColour != 0)) || (valid && !behind && !etaOK);
+    const bool col = upd && !(eta.x > g.mu) && !(fabsf(eom.x) > 0.25f);
+    r0 = slow ? 2 : (col ? 1 : 0);
+  }
+  {
+    const bool rej = (dm.y <= 0.0f), valid = a.ok1 && a.inb1 && !rej, behind = eta.y < -g.mu;
+    const float ae = fabsf(eta.y);
+    const bool etaOK = ((ae >= V3_SAFE_LO) && (ae <= V3_SAFE_HI)) || (eta.y == 0.0f);
+    const bool upd = valid && !behind && etaOK;
+    lo1 = upd ? nlo1 : lo1;
+    const bool behindCamera = (a.pcz.y <= 0.0f) && (k.rejectColour == 0);
+    const bool slow = (!a.ok1 && !behindCamera) || ((!a.inb1 || rej) && (k.rejectColour != 0)) || (valid && !behind && !etaOK);
+    const bool col = upd && !(eta.y > g.mu) && !(fabsf(eom.y) > 0.25f);
+    r1 = slow ? 2 : (col ? 1 : 0);
+  }
+}

@@ -20,6 +20,8 @@ def lib():
     L = C.CDLL(os.path.join(HERE, "libhostcheck.so"))
     L.hostcheck_integrate.restype = C.c_longlong
     L.hostcheck_integrate.argtypes = [C.c_longlong, C.c_uint, C.c_float, C.c_float, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_longlong)]
+    L.hostcheck_integrate_v4.restype = C.c_longlong
+    L.hostcheck_integrate_v4.argtypes = [C.c_longlong, C.c_uint, C.c_float, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_longlong)]
     return L
 
 
@@ -49,3 +51,32 @@ def test_fast_path_equals_generic_path(lib, mu, voxel, dw, maxw, ident):
         assert generic > 1000
     else:
         assert generic < voxels // 1000   # behind-the-camera voxels must not be sent to the generic path
+
+
+@pytest.mark.parametrize("mu,voxel,dw,maxw,ident", CASES)
+def test_v4_pair_path_equals_generic_path(lib, mu, voxel, dw, maxw, ident):
+    """The default kernel's arithmetic (V4: v4_stage_a / v4_stage_b on pairs of x-adjacent voxels — packed FADD2 / FMUL2 / FFMA2
+    on the device, the same operations element by element here) against the generic per-voxel code. Bit-exact."""
+    st = (C.c_longlong * 8)()
+    bad = 0
+    for seed in (2, 9):
+        bad += lib.hostcheck_integrate_v4(1200, seed, mu, voxel, dw, maxw, ident, 0, st)
+    voxels, fast, colour, generic, changed = list(st)[:5]
+    assert bad == 0
+    assert voxels == 2 * 1200 * 512 and fast + generic == voxels
+    assert changed > voxels // 20 and colour > 0
+
+
+@pytest.mark.parametrize("mu,voxel,dw,maxw,ident", [c for c in CASES if c[0] < 4.0])
+def test_v4_tolerance_mode_is_within_one_lsb(lib, mu, voxel, dw, maxw, ident):
+    """B200_INTEGRATE_IMPL=fast (MUFU reciprocals, quotients as products, contracted sums): weights and the update / skip
+    decision stay exact; a TSDF code moves by at most 1 LSB (3.05e-5 after SDF_valueToFloat), on a small share of the updated
+    voxels; the colour gate |eta / mu| <= 0.25 may flip on a tie. (On the host the reciprocal is IEEE's, so the device shows
+    slightly more flips: tests/test_gpu_parity.py::test_integrate_tolerance_mode counts them there.)"""
+    st = (C.c_longlong * 8)()
+    bad = 0
+    for seed in (3, 10):
+        bad += lib.hostcheck_integrate_v4(1200, seed, mu, voxel, dw, maxw, ident, 1, st)
+    voxels, changed, flips, gate = st[0], st[4], st[6], st[7]
+    assert bad == 0
+    assert flips < 0.02 * changed and gate < 0.002 * changed
