@@ -125,7 +125,8 @@ EXPORTS = [
     "b200_gather_composite_release", "b200_gather_composite_wait",
 ]
 # measurement / test hooks (include/b200fusion_diag.h): exported by the same library, not part of the drop-in boundary
-DIAG_EXPORTS = ["b200_set_timing", "b200_get_trace", "b200_get_stats", "b200_selftest_divide", "b200_diag_set_max_rendering_blocks"]
+DIAG_EXPORTS = ["b200_set_timing", "b200_get_trace", "b200_get_stats", "b200_selftest_divide", "b200_diag_set_max_rendering_blocks",
+                "b200_diag_read_debug"]
 
 _lib = None
 
@@ -202,6 +203,7 @@ def load_library():
     lib.b200_selftest_divide.argtypes = [vp, C.c_uint64, C.c_uint64, C.c_float, P(C.c_uint64)]
     lib.b200_diag_set_max_rendering_blocks.argtypes = [vp, C.c_int]
     lib.b200_diag_set_max_rendering_blocks.restype = None
+    lib.b200_diag_read_debug.argtypes = [vp, P(C.c_uint64), C.c_int]
     _lib = lib
     return lib
 

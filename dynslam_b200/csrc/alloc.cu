@@ -348,10 +348,14 @@ k_serve_list(const float *__restrict__ depth, b200_hash_entry *table, int numBuc
              const int *__restrict__ allocList, const int *__restrict__ excessList, DevCounters *ctr, const __grid_constant__ FrameGeom g,
              int currentFrame, int onlyVisible, unsigned long long *descA, unsigned long long *descB, unsigned long long *descC,
              unsigned gen, b200_vec3i *visiblePos, int *visiblePtr, int capacity, b200_vec3i *ring, long long ringCap, long long *snapStart,
-             int *snapCount, int slot, BlockRec *recs, float2 *minmax, int rw, int rh, unsigned maxRB) {
+             int *snapCount, int slot, BlockRec *recs, float2 *minmax, int rw, int rh, unsigned maxRB, unsigned long long *dbg) {
   __shared__ unsigned sm[33];
   __shared__ unsigned tileBase, tileBase2;
   __shared__ unsigned hits[AL_TILE];   // entry index | bit 31: observed this frame
+  // measurement hook (b200_diag_read_debug): CTAs 0, 1/3, 2/3 and the last one stamp %globaltimer at their phase boundaries
+  const int dbgSlot = !dbg ? -1 : (blockIdx.x == 0 ? 0 : (blockIdx.x == gridDim.x / 3 ? 1 : (blockIdx.x == 2 * gridDim.x / 3 ? 2 : (blockIdx.x == gridDim.x - 1 ? 3 : -1))));
+#define K2_STAMP(i) do { if (dbgSlot >= 0 && threadIdx.x == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); dbg[dbgSlot * 8 + (i)] = t_; } } while (0)
+  K2_STAMP(0);
   const int noWords = noTotal >> 5;
   const int noTiles = (noTotal + AL_TILE - 1) / AL_TILE;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -430,6 +434,7 @@ k_serve_list(const float *__restrict__ depth, b200_hash_entry *table, int numBuc
       }
     }
   }
+  K2_STAMP(1);
   // ---------------- phase B: visibility bytes and the ordered list ----------------
   unsigned myTiles = 0;   // rendering tiles of the blocks this thread projected (fused frame only)
   const long long ringStart = ctr->ringHead;   // advanced by the last tile only, at its very end
@@ -442,6 +447,7 @@ k_serve_list(const float *__restrict__ depth, b200_hash_entry *table, int numBuc
       if (threadIdx.x == 0) { while (*(volatile unsigned *)&ctr->tilesServed < (unsigned)noTiles) { } __threadfence(); }
       __syncthreads();
     }
+    K2_STAMP(2);
     unsigned mask = 0;   // bit k: entry first+k goes to the list
     unsigned mk = 0;     // bit k: entry first+k was observed this frame
     if (w < noWords) {
@@ -480,6 +486,7 @@ k_serve_list(const float *__restrict__ depth, b200_hash_entry *table, int numBuc
         if (dirty) *reinterpret_cast<uint4 *>(visType + first + q * 16) = make_uint4(wv[0], wv[1], wv[2], wv[3]);
       }
     }
+    K2_STAMP(3);
     unsigned total;
     const unsigned local = block_exclusive_scan(__popc(mask), sm, &total);
     if (threadIdx.x < 32) {
@@ -496,6 +503,7 @@ k_serve_list(const float *__restrict__ depth, b200_hash_entry *table, int numBuc
       hits[o++] = (unsigned)(first + k) | (((mk >> k) & 1u) << 31);
     }
     __syncthreads();
+    K2_STAMP(4);
     const unsigned base = tileBase;
     // listed entry t of the tile is handled by lane (t / 8) % 32 of warp t % 8: the ~25 entries of a KITTI tile become ~3 per warp
     for (unsigned t0 = 0; t0 < total; t0 += blockDim.x) {
@@ -548,6 +556,7 @@ k_serve_list(const float *__restrict__ depth, b200_hash_entry *table, int numBuc
       }
     }
     __syncthreads();
+    K2_STAMP(5);
     if (tile == noTiles - 1 && threadIdx.x == 0) {
       const int n = (int)(base + total);
       ctr->noVisibleBlocks = n;
@@ -568,6 +577,7 @@ k_serve_list(const float *__restrict__ depth, b200_hash_entry *table, int numBuc
   __shared__ bool lastCta;
   __threadfence();
   __syncthreads();
+  K2_STAMP(6);
   if (threadIdx.x == 0) lastCta = (atomicAdd(&ctr->visCtasDone, 1u) == gridDim.x - 1);
   __syncthreads();
   if (!lastCta) return;
@@ -688,7 +698,7 @@ void launch_allocate(b200_engine *e, const SceneRef &s, const FrameGeom &g, cons
                                                               e->d_scanDesc + 2 * third, gen, s.visiblePos, e->d_visiblePtr, s.numBlocks,
                                                               e->d_ring, e->ringCap, e->d_snapStart, e->d_snapCount, snapSlot,
                                                               minmaxFused ? (BlockRec *)e->d_blockRecs : nullptr, (float2 *)minmaxFused, mw, mh,
-                                                              (unsigned)e->maxRenderingBlocks);
+                                                              (unsigned)e->maxRenderingBlocks, e->traceOn ? e->d_dbg : nullptr);
   trace_end(e, st);
   e->launches += 2;
 }

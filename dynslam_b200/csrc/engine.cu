@@ -146,6 +146,8 @@ static b200_status engine_create_body(const b200_engine_config *cfg, b200_engine
   CK(cudaMalloc(&e->d_reqBits, sizeof(unsigned) * (size_t)e->noWords * 2));
   e->d_req2Bits = e->d_reqBits + e->noWords;
   CK(cudaMemset(e->d_reqBits, 0, sizeof(unsigned) * (size_t)e->noWords * 2));   // kept clean by k_serve_list from here on
+  CK(cudaMalloc(&e->d_dbg, 64 * sizeof(unsigned long long)));
+  CK(cudaMemset(e->d_dbg, 0, 64 * sizeof(unsigned long long)));
   CK(cudaMalloc(&e->d_markBytes, (size_t)e->noTotal));
   CK(cudaMemset(e->d_markBytes, 0, (size_t)e->noTotal));
   long long px = (long long)e->img_w * e->img_h;
@@ -190,7 +192,7 @@ void b200_engine_destroy(b200_engine *e) {
   if (!e) return;
   cudaSetDevice(e->device);
   if (e->stream) cudaStreamSynchronize(e->stream);
-  cudaFree(e->d_ctr); cudaFreeHost(e->h_ctr); cudaFree(e->d_reqKey); cudaFree(e->d_reqBits); cudaFree(e->d_markBytes); cudaFree(e->d_scanDesc);
+  cudaFree(e->d_ctr); cudaFreeHost(e->h_ctr); cudaFree(e->d_reqKey); cudaFree(e->d_reqBits); cudaFree(e->d_markBytes); cudaFree(e->d_dbg); cudaFree(e->d_scanDesc);
   cudaFree(e->d_ring); cudaFree(e->d_snapCount); cudaFree(e->d_snapStart); cudaFree(e->d_delTag); cudaFree(e->d_itemPtr); cudaFree(e->d_visiblePtr);
   cudaFree(e->d_viewScratch); cudaFree(e->d_delList); cudaFree(e->d_candList); cudaFree(e->d_isLeader); cudaFree(e->d_allocatedPos); cudaFree(e->d_tileCounts); cudaFree(e->d_blockRecs);
   for (int i = 0; i < 8; ++i) if (e->ev[i]) cudaEventDestroy(e->ev[i]);
@@ -254,6 +256,14 @@ int b200_get_trace(b200_engine *e, char *out, int cap) {
 
 void b200_diag_set_max_rendering_blocks(b200_engine *e, int n) { e->maxRenderingBlocks = n > 0 ? n : B200_MAX_RENDERING_BLOCKS; }
 
+int b200_diag_read_debug(b200_engine *e, unsigned long long *out, int n) {
+  if (!e || !out || n <= 0) return 0;
+  if (n > 64) n = 64;
+  cudaSetDevice(e->device);
+  cudaDeviceSynchronize();
+  return cudaMemcpy(out, e->d_dbg, sizeof(unsigned long long) * (size_t)n, cudaMemcpyDeviceToHost) == cudaSuccess ? n : 0;
+}
+
 // ---- ITMSceneReconstructionEngine ---------------------------------------------------------------
 
 b200_status b200_reset_scene(b200_engine *e, b200_scene *s) {
@@ -261,6 +271,7 @@ b200_status b200_reset_scene(b200_engine *e, b200_scene *s) {
   CK(cudaSetDevice(e->device));
   e->totalDecayed = 0;
   e->qHead += e->qSize; e->qSize = 0;          // clear the decay queue; frameIdx is NOT reset (Reco_CUDA.cu:150-155)
+  e->deadPending = false;
   e->tableVersion++;
   launch_reset(e, scene_ref(s, nullptr));
   return download_sync(e, s, nullptr);
@@ -342,6 +353,7 @@ b200_status b200_expected_depths(b200_engine *e, const b200_scene *s, b200_rende
   b200_status st = check_scene(e, s); if (st) return st;
   CK(cudaSetDevice(e->device));
   st = upload(e, s, rs); if (st) return st;
+  e->deadPending = false;      // the whole image is rebuilt here
   launch_expected_depths(e, scene_ref(s, rs), to_mat(cam->M), cam->proj, rs->img_w, rs->img_h, s->voxelSize, rs->d_minmax);
   return download_sync(e, nullptr, nullptr);
 }
@@ -496,19 +508,19 @@ static b200_status frame_enqueue(b200_engine *e, b200_scene *s, b200_render_stat
   // runs on the side stream underneath the integrate kernel.
   cudaStream_t mainStream = e->stream;
   const bool overlap = doRay && e->sideStream != nullptr;
-  if (overlap) {
-    CK(cudaEventRecord(e->evFork, mainStream));
-    CK(cudaStreamWaitEvent(e->sideStream, e->evFork, 0));
-    e->stream = e->sideStream;
-    launch_expected_depths_dead(e, r, g.M_d, g.proj_d, rs->img_w, rs->img_h, s->voxelSize, rs->d_minmax);   // nothing in the frame waits for it
-    e->stream = mainStream;
+  if (doRay) {
+    // The cells of the expected-depth image OUTSIDE the live corner (the reference clamps block boxes to the full-resolution
+    // bounds, so blocks along the right and bottom image borders smear over thousands of them: ~10^6 atomics, 38 us measured)
+    // are read by nothing on the device. They are brought up to date when the host can next look at the image — b200_sync() —
+    // from the block records of the latest frame, instead of every frame.
+    e->deadPending = true; e->deadScene = r; e->deadM = g.M_d; memcpy(e->deadProj, g.proj_d, sizeof(e->deadProj));
+    e->deadW = rs->img_w; e->deadH = rs->img_h; e->deadVoxelSize = s->voxelSize; e->deadMinmax = rs->d_minmax;
   }
   launch_integrate(e, r, g, v->d_depth, v->d_rgb);
   if (e->evMid && !e->useGraph) { CK(cudaEventRecord(e->evMid, e->stream)); e->midValid = true; }
   if (ring) { CK(cudaEventRecord(e->evRing[2 * e->evRingCount + 1], e->stream)); e->evRingCount++; }
   if (e->timing) CK(cudaEventRecord(e->ev[2], e->stream));
   if (doRay) {
-    if (!overlap) launch_expected_depths_dead(e, r, g.M_d, g.proj_d, rs->img_w, rs->img_h, s->voxelSize, rs->d_minmax);
     if (e->timing) CK(cudaEventRecord(e->ev[3], e->stream));
     launch_raycast(e, r, g.invM_d, g.proj_d, rs->img_w, rs->img_h, s->voxelSize, s->mu, rs->d_minmax, rs->d_raycastResult);
     // optional colour render for compositing: reads voxel colours, so it has to run before this frame's decay resets any
@@ -541,6 +553,10 @@ static b200_status frame_enqueue(b200_engine *e, b200_scene *s, b200_render_stat
 
 b200_status b200_sync(b200_engine *e, b200_scene *s, b200_render_state *rs) {
   CK(cudaSetDevice(e->device));
+  if (e->deadPending) {      // see frame_enqueue: the part of the expected-depth image nothing on the device reads
+    launch_expected_depths_dead(e, e->deadScene, e->deadM, e->deadProj, e->deadW, e->deadH, e->deadVoxelSize, e->deadMinmax);
+    e->deadPending = false;
+  }
   b200_status st = download_sync(e, s, rs); if (st) return st;
   if (s && s->lastFreeBlockId < 0) { snprintf(e->err, sizeof(e->err), "out of space in the voxel block array"); return B200_ERR_VBA_FULL; }
   if (s && s->lastFreeExcessListId < 0) { snprintf(e->err, sizeof(e->err), "out of slots in the hash table excess list"); return B200_ERR_EXCESS_FULL; }

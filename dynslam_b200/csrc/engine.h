@@ -85,6 +85,9 @@ struct b200_engine {
   int evRingCap, evRingCount, timingMode;
   // timing mode 3: an event pair around every kernel launch (launch trace, b200_get_trace)
   bool traceOn; int traceCount, traceCap; cudaEvent_t *traceEv; const char **traceName;
+  // expected-depth cells outside the live corner of the latest fused frame: rasterised lazily at b200_sync()
+  bool deadPending; SceneRef deadScene; Mat4 deadM; float deadProj[4]; int deadW, deadH; float deadVoxelSize; b200_vec2f *deadMinmax;
+  unsigned long long *d_dbg;          // 64 timestamps written by instrumented kernels while the launch trace is on (b200_diag_read_debug)
   long long launches;
   int lastNoIntegrated;
   int integrateImpl;                  // 0 = LDG variant, 1 = TMA bulk-copy variant (env B200_INTEGRATE_IMPL=ldg|tma)

@@ -302,6 +302,17 @@ HD float2 f2fma(float2 a, float2 b, float2 c) {
 #endif
 }
 HD float2 f2dup(float v) { return make_float2(v, v); }
+// A product that must NOT be contracted with the addition that consumes it: ptxas fuses mul.rn.f32x2 + add.rn.f32x2 into one
+// FFMA2 even though both carry an explicit rounding mode and the build passes -fmad=false (seen in the SASS of the first V4
+// build: 18 mul.rn.f32x2 in the PTX, 16 FMUL2 in the SASS, 1-LSB TSDF differences on a handful of voxels per frame). Two scalar
+// products (FMUL, which ptxas leaves alone under -fmad=false) cost one instruction more per pair.
+HD float2 f2mul_exact(float2 a, float2 b) {
+#if F2_DEV
+  return make_float2(__fmul_rn(a.x, b.x), __fmul_rn(a.y, b.y));
+#else
+  return make_float2(a.x * b.x, a.y * b.y);
+#endif
+}
 HD float2 f2neg(float2 a) { return make_float2(-a.x, -a.y); }
 HD float rcp_approx(float b) {
 #ifdef __CUDA_ARCH__
@@ -380,9 +391,9 @@ HD void v4_stage_b(unsigned &lo0, unsigned &lo1, const V4A &a, float2 dm, const 
     nw0 = (int)(100.0 / dm.x); nw0 = nw0 < 1 ? 1 : (nw0 > 10 ? 10 : nw0);
     nw1 = (int)(100.0 / dm.y); nw1 = nw1 < 1 ? 1 : (nw1 > 10 ? 10 : nw1);
     const float2 nwf = make_float2((float)nw0, (float)nw1);
-    num = FAST ? f2fma(oldWf, oldF, f2mul(nwf, newFm)) : f2add(f2mul(oldWf, oldF), f2mul(nwf, newFm));
+    num = FAST ? f2fma(oldWf, oldF, f2mul(nwf, newFm)) : f2add(f2mul_exact(oldWf, oldF), f2mul_exact(nwf, newFm));
   } else {
-    num = FAST ? f2fma(oldWf, oldF, newFm) : f2add(f2mul(oldWf, oldF), newFm);     // newW == 1: 1 * newF is newF, exactly
+    num = FAST ? f2fma(oldWf, oldF, newFm) : f2add(f2mul_exact(oldWf, oldF), newFm);     // newW == 1: 1 * newF is newF, exactly
   }
   int W0 = oldW0 + nw0, W1 = oldW1 + nw1;
   const float2 Wf = make_float2((float)W0, (float)W1);

@@ -12,7 +12,7 @@
 // What is fused is everything that is not arithmetic: the raw->float conversion happens while pass 1 stages its tile,
 // the final device-to-device copy disappears by letting view->depth play the role of floatImage (passes 1, 3, 5 write
 // it) and an engine-owned scratch image the role of view->depth, so UpdateView is 5 launches instead of 7 and never
-// materialises the converted image. Each pass stages a (32+4)x(8+4) tile in shared memory once.
+// materialises the converted image. Each pass stages a (32+4)x(16+4) tile in shared memory once, two pixels per thread.
 //
 // Border semantics are the CUDA reference's, not the CPU twin's (which clears the target of every pass,
 // CPU/ITMViewBuilder_CPU.cpp:116-127): filterDepth_device leaves the two outermost rows/columns of its
@@ -22,10 +22,10 @@
 //   * view->depth's border still holds the converted raw values when passes 3 and 5 read it,
 //   * those border values ARE read as taps by the neighbouring inner pixels (0 is not < 0).
 //
-// Arithmetic: the expressions keep the reference's operation order; the library is compiled without
-// contraction, division and sqrt are IEEE. exp() is the CUDA math library's algorithm (<= 2 ulp), acos() its acosf, where the
-// oracle uses the host libm, so this file is compared within a stated tolerance (tests/test_gpu_view.py),
-// not bit for bit; the reference's own CUDA build uses --use_fast_math here.
+// Arithmetic: conversions, masks and borders are bit-exact; the bilateral weights use MUFU.EX2 on pre-scaled arguments and
+// the final quotient a fast division (see filter_depth_two) — like the reference's own CUDA build, which compiles this file
+// with --use_fast_math — so the filtered depth is compared with the oracle (host libm) within a stated 2e-5 relative
+// tolerance (tests/test_gpu_view.py), not bit for bit. acos() in ComputeNormalAndWeights is CUDA's acosf.
 #include "engine.h"
 
 namespace {
@@ -46,43 +46,54 @@ __device__ __forceinline__ float convert_disparity(short disparity, float p0, fl
   return (depth > 0) ? depth : -1.0f;
 }
 
-// exp(x) for x <= 0, the algorithm of the CUDA math library's expf (magic-number rounding of x*log2(e), two-term
-// Cody-Waite reduction in ln 2, ex2.approx, exponent splice; <= 2 ulp) without its overflow/underflow special cases:
-// the argument is clamped at -86 instead. A bilateral weight below e^-86 = 4e-38 can never change the sums it is added
-// to (the centre tap contributes weight 1 and depth >= 1e-3), so the filter output is the same bits either way.
-__device__ __forceinline__ float exp_nonpositive(float x) {
-  x = fmaxf(x, -86.0f);
-  const float t = __fmaf_rn(x, 1.44269504088896341f, 12582912.0f);
-  const float j = t - 12582912.0f;
-  float r = __fmaf_rn(j, -0.693145751953125f, x);
-  r = __fmaf_rn(j, -1.42860682030941723e-06f, r);
+// The 25 bilateral weights exp(-0.5 (a sigma_L^2 + dz^2 sigma_z^2)) are evaluated as 2^(k_a + dz^2 * kz) with the constants
+// pre-scaled by log2(e): one FFMA and one MUFU.EX2 per tap (the reference's own CUDA build does the same through
+// --use_fast_math, ITMLib/CMakeLists.txt:230). Against the exactly rounded filter (host libm) the weights are off by a few
+// ulp, the filtered depth by <= 2e-5 relative (tests/test_gpu_view.py states and checks the bound); conversions, the
+// invalid mask and the border semantics stay bit-exact. Round 1 used an expf-grade exponential (<= 2 ulp, 16 instructions per
+// tap): 14.7 us per pass, slower than the reference's kernel; this form is 7 instructions per tap.
+__device__ __forceinline__ float ex2_approx(float x) {
   float e;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(r * 1.44269504088896341f));
-  return __int_as_float(__float_as_int(e) + (__float_as_int(t) << 23));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x));
+  return e;
 }
 
-// filterDepth (DA/ITMViewBuilder.h:31-56) for the pixel at *c; rows are `stride` floats apart. Branch-free form of the
-// reference's `if (tmpz < 0) continue;`: an invalid tap gets weight +0, and x + 0 and x + (0 * tmpz) leave every partial
-// sum bit-identical (the sums are >= 0; +0 + -0 = +0 in round-to-nearest).
-__device__ __forceinline__ float filter_depth_at(const float *c, int stride) {
-  const float z = c[0];
-  if (z < 0.0f) return -1.0f;
-  const float sigma_z = 1.0f / (0.0012f + 0.0019f * (z - 0.4f) * (z - 0.4f) + 0.0001f / sqrtf(z) * 0.25f);
-  float final_depth = 0.0f, w_sum = 0.0f;
+// filterDepth (DA/ITMViewBuilder.h:31-56) for TWO vertically adjacent pixels at c[0] and c[stride] (rows `stride` floats
+// apart): the 6 x 5 taps the two windows cover are read once. An invalid tap (tmpz < 0) gets weight 0, as the reference's
+// `continue`. Returns the filtered values (-1 where the centre is invalid).
+__device__ __forceinline__ void filter_depth_two(const float *c, int stride, float &out0, float &out1) {
+  constexpr float L2E = 1.44269504088896341f;
+  constexpr float KA = -0.5f * MEAN_SIGMA_L * MEAN_SIGMA_L * L2E;   // per unit of |i| + |j|
+  const float z0 = c[0], z1 = c[stride];
+  // sigma_z as the reference computes it (IEEE division and sqrt); only the exponential is approximated
+  const float sz0 = 1.0f / (0.0012f + 0.0019f * (z0 - 0.4f) * (z0 - 0.4f) + 0.0001f / sqrtf(fmaxf(z0, 1e-6f)) * 0.25f);
+  const float sz1 = 1.0f / (0.0012f + 0.0019f * (z1 - 0.4f) * (z1 - 0.4f) + 0.0001f / sqrtf(fmaxf(z1, 1e-6f)) * 0.25f);
+  const float kz0 = -0.5f * L2E * sz0 * sz0, kz1 = -0.5f * L2E * sz1 * sz1;
+  float f0 = 0.0f, w0 = 0.0f, f1 = 0.0f, w1 = 0.0f;
 #pragma unroll
-  for (int i = -2; i <= 2; i++) {
+  for (int r = -2; r <= 3; r++) {        // tap row relative to pixel 0; pixel 1 sees it as row r - 1
 #pragma unroll
     for (int j = -2; j <= 2; j++) {
-      const float tmpz = c[i * stride + j];
-      float dz = (tmpz - z); dz *= dz;
-      const int a = (i < 0 ? -i : i) + (j < 0 ? -j : j);
-      float w = exp_nonpositive(-0.5f * ((float)a * MEAN_SIGMA_L * MEAN_SIGMA_L + dz * sigma_z * sigma_z));
-      w = tmpz < 0.0f ? 0.0f : w;
-      w_sum += w;
-      final_depth += w * tmpz;
+      const float t = c[r * stride + j];
+      const bool ok = !(t < 0.0f);
+      if (r <= 2) {
+        const float d = t - z0;
+        const int a = (r < 0 ? -r : r) + (j < 0 ? -j : j);
+        float w = ex2_approx(__fmaf_rn(d * d, kz0, (float)a * KA));
+        w = ok ? w : 0.0f;
+        w0 += w; f0 = __fmaf_rn(w, t, f0);
+      }
+      if (r >= -1) {
+        const float d = t - z1;
+        const int a = (r - 1 < 0 ? 1 - r : r - 1) + (j < 0 ? -j : j);
+        float w = ex2_approx(__fmaf_rn(d * d, kz1, (float)a * KA));
+        w = ok ? w : 0.0f;
+        w1 += w; f1 = __fmaf_rn(w, t, f1);
+      }
     }
   }
-  return final_depth / w_sum;
+  out0 = (z0 < 0.0f) ? -1.0f : __fdividef(f0, w0);
+  out1 = (z1 < 0.0f) ? -1.0f : __fdividef(f1, w1);
 }
 
 __device__ __forceinline__ bool on_border(int x, int y, int w, int h) { return x < 2 || x >= w - 2 || y < 2 || y >= h - 2; }
@@ -95,19 +106,20 @@ __global__ void k_convert(const short *__restrict__ in, float *__restrict__ out,
   out[i] = type == 0 ? convert_disparity(in[i], p0, p1, fx) : convert_affine(in[i], p0, p1);
 }
 
-// One DepthFiltering pass. 32x8 output pixels per CTA, the (32+4)x(8+4) input neighbourhood staged in shared memory
-// (converted from the raw image on the fly when RAW). Border pixels of the target are left untouched (reference
-// semantics) unless zeroBorder, which writes the 0 that floatImage's border holds in the reference; borderCopy, if
-// given, receives the staged (converted) value of border pixels — the border view->depth keeps through all passes.
-constexpr int FP_TW = 32, FP_TH = 8, FP_SW = FP_TW + 4, FP_SH = FP_TH + 4;
+// One DepthFiltering pass. 32x16 output pixels per CTA of 256 threads (two vertically adjacent pixels per thread), the
+// (32+4)x(16+4) input neighbourhood staged in shared memory (converted from the raw image on the fly when RAW). Border pixels
+// of the target are left untouched (reference semantics) unless zeroBorder, which writes the 0 that floatImage's border
+// holds in the reference; borderCopy, if given, receives the staged (converted) value of border pixels — the border
+// view->depth keeps through all passes.
+constexpr int FP_TW = 32, FP_TH = 16, FP_SW = FP_TW + 4, FP_SH = FP_TH + 4, FP_THREADS = 256;
 
 template <bool RAW>
-__global__ void __launch_bounds__(FP_TW * FP_TH) k_filter_pass(const short *__restrict__ raw, const float *__restrict__ in,
-                                                                  float *__restrict__ out, float *__restrict__ borderCopy, int w, int h,
-                                                                  int type, float p0, float p1, float fx, int zeroBorder) {
+__global__ void __launch_bounds__(FP_THREADS) k_filter_pass(const short *__restrict__ raw, const float *__restrict__ in,
+                                                             float *__restrict__ out, float *__restrict__ borderCopy, int w, int h,
+                                                             int type, float p0, float p1, float fx, int zeroBorder) {
   __shared__ float tile[FP_SH * FP_SW];
   const int x0 = blockIdx.x * FP_TW - 2, y0 = blockIdx.y * FP_TH - 2;
-  for (int c = threadIdx.x; c < FP_SW * FP_SH; c += FP_TW * FP_TH) {
+  for (int c = threadIdx.x; c < FP_SW * FP_SH; c += FP_THREADS) {
     const int gx = x0 + c % FP_SW, gy = y0 + c / FP_SW;
     float v = 0.0f;
     if (gx >= 0 && gx < w && gy >= 0 && gy < h) {
@@ -117,16 +129,23 @@ __global__ void __launch_bounds__(FP_TW * FP_TH) k_filter_pass(const short *__re
     tile[c] = v;
   }
   __syncthreads();
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int tx = threadIdx.x & 31, ty = (threadIdx.x >> 5) * 2;
   const int x = x0 + 2 + tx, y = y0 + 2 + ty;
   if (x >= w || y >= h) return;
   const float *c = tile + (ty + 2) * FP_SW + tx + 2;
-  if (on_border(x, y, w, h)) {
-    if (zeroBorder) out[x + y * w] = 0.0f;
-    if (borderCopy) borderCopy[x + y * w] = c[0];
-    return;
+  float r0, r1;
+  filter_depth_two(c, FP_SW, r0, r1);
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const int yy = y + k;
+    if (yy >= h) break;
+    if (on_border(x, yy, w, h)) {
+      if (zeroBorder) out[x + yy * w] = 0.0f;
+      if (borderCopy) borderCopy[x + yy * w] = c[k * FP_SW];
+    } else {
+      out[x + yy * w] = k ? r1 : r0;
+    }
   }
-  out[x + y * w] = filter_depth_at(c, FP_SW);
 }
 
 // ---- ComputeNormalAndWeights (ITMViewBuilder_CUDA.cu:211-227, DA/ITMViewBuilder.h:59-114) -----------
@@ -174,7 +193,7 @@ void launch_view_convert(b200_engine *e, const int16_t *raw, float *out, int w, 
 void launch_view_filter_pass(b200_engine *e, const float *in, float *out, int w, int h) {
   dim3 grid((w + FP_TW - 1) / FP_TW, (h + FP_TH - 1) / FP_TH);
   trace_begin(e, e->stream, "k_filter_pass<false>");
-  k_filter_pass<false><<<grid, FP_TW * FP_TH, 0, e->stream>>>(nullptr, in, out, nullptr, w, h, 1, 0.0f, 0.0f, 0.0f, 0);
+  k_filter_pass<false><<<grid, FP_THREADS, 0, e->stream>>>(nullptr, in, out, nullptr, w, h, 1, 0.0f, 0.0f, 0.0f, 0);
   trace_end(e, e->stream);
   e->launches++;
 }
@@ -185,7 +204,7 @@ void launch_update_view(b200_engine *e, const int16_t *raw, float *out, float *s
                         float fx, bool filter) {
   if (!filter) { launch_view_convert(e, raw, out, w, h, type, p0, p1, fx); return; }
   dim3 grid((w + FP_TW - 1) / FP_TW, (h + FP_TH - 1) / FP_TH);
-  const int T = FP_TW * FP_TH;
+  const int T = FP_THREADS;
   trace_begin(e, e->stream, "k_filter_pass<true>");
   k_filter_pass<true><<<grid, T, 0, e->stream>>>((const short *)raw, nullptr, out, scratch, w, h, type, p0, p1, fx, 1);
   trace_end(e, e->stream);

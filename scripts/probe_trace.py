@@ -30,9 +30,15 @@ for i, v in enumerate(views[N0:]):
     eng.process_frame_async(rs, v, points, normals, decay=DECAY, raycast=True)
     eng.sync(rs)
     tr = eng.trace()
+    import ctypes as C
+    dbg = (C.c_uint64 * 32)()
+    eng.lib.b200_diag_read_debug(eng.h, dbg, 32)
     eng.set_timing(0)
     if i >= 2:
         print("--- frame", i)
+        t0 = min(dbg[s * 8] for s in range(4) if dbg[s * 8])
+        for s in range(4):
+            print("  k_serve_list CTA slot", s, "phase stamps (us):", ["%.1f" % ((dbg[s * 8 + k] - t0) / 1000.0) if dbg[s * 8 + k] else "-" for k in range(7)])
         prev_end = 0.0
         for name, a, b in tr:
             print("%-22s start %7.1f  end %7.1f  dur %6.1f" % (name, a, b, b - a))
