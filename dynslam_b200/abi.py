@@ -25,6 +25,8 @@ RENDER_SHADED_GREYSCALE, RENDER_COLOUR_FROM_VOLUME, RENDER_COLOUR_FROM_NORMAL, \
     RENDER_COLOUR_FROM_DEPTH_WEIGHT, RENDER_DEPTH_MAP = range(5)
 
 # numpy dtypes of the PODs (itemsize asserts below pin the layout)
+TRIANGLE_DTYPE = np.dtype([("p0", np.float32, 3), ("p1", np.float32, 3), ("p2", np.float32, 3),
+                           ("c0", np.float32, 3), ("c1", np.float32, 3), ("c2", np.float32, 3)])   # ITMMesh::Triangle, 72 bytes
 HASH_ENTRY_DTYPE = np.dtype([("pos", np.int16, 3), ("_pad", np.int16), ("offset", np.int32),
                              ("ptr", np.int32), ("allocatedTime", np.int32)])
 VOXEL_DTYPE = np.dtype([("sdf", np.int16), ("w_depth", np.uint8), ("clr", np.uint8, 3),
@@ -121,7 +123,7 @@ EXPORTS = [
     "b200_compute_normal_and_weights", "b200_update_view", "b200_update_view_async", "b200_host_frame_submit_raw",
     "b200_process_silhouettes", "b200_process_silhouettes_async", "b200_composite_depth", "b200_composite_color",
     "b200_composite_instances",
-    "b200_comm_unique_id", "b200_comm_create", "b200_comm_destroy", "b200_comm_last_error", "b200_gather_composite_submit",
+    "b200_mesh_scene", "b200_comm_unique_id", "b200_comm_create", "b200_comm_destroy", "b200_comm_last_error", "b200_gather_composite_submit",
     "b200_gather_composite_release", "b200_gather_composite_wait",
 ]
 # measurement / test hooks (include/b200fusion_diag.h): exported by the same library, not part of the drop-in boundary
@@ -187,6 +189,7 @@ def load_library():
     lib.b200_composite_depth.argtypes = [vp, vp, vp, C.c_int]
     lib.b200_composite_color.argtypes = [vp, vp, vp, vp, vp, C.c_int, P(C.c_int32), C.c_float]
     lib.b200_composite_instances.argtypes = [vp, vp, vp, C.c_int, P(InstanceLayer), C.c_int, C.c_float, C.c_float]
+    lib.b200_mesh_scene.argtypes = [vp, P(Scene), vp, C.c_uint32, P(C.c_uint32)]
     lib.b200_comm_unique_id.argtypes = [C.c_char_p]
     lib.b200_comm_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_int, C.c_int, P(vp)]
     lib.b200_comm_destroy.argtypes = [vp]

@@ -192,7 +192,7 @@ void b200_engine_destroy(b200_engine *e) {
   if (!e) return;
   cudaSetDevice(e->device);
   if (e->stream) cudaStreamSynchronize(e->stream);
-  cudaFree(e->d_ctr); cudaFreeHost(e->h_ctr); cudaFree(e->d_reqKey); cudaFree(e->d_reqBits); cudaFree(e->d_markBytes); cudaFree(e->d_dbg); cudaFree(e->d_scanDesc);
+  cudaFree(e->d_ctr); cudaFreeHost(e->h_ctr); cudaFree(e->d_reqKey); cudaFree(e->d_reqBits); cudaFree(e->d_markBytes); cudaFree(e->d_dbg); cudaFree(e->d_meshDesc); cudaFree(e->d_scanDesc);
   cudaFree(e->d_ring); cudaFree(e->d_snapCount); cudaFree(e->d_snapStart); cudaFree(e->d_delTag); cudaFree(e->d_itemPtr); cudaFree(e->d_visiblePtr);
   cudaFree(e->d_viewScratch); cudaFree(e->d_delList); cudaFree(e->d_candList); cudaFree(e->d_isLeader); cudaFree(e->d_allocatedPos); cudaFree(e->d_tileCounts); cudaFree(e->d_blockRecs);
   for (int i = 0; i < 8; ++i) if (e->ev[i]) cudaEventDestroy(e->ev[i]);
@@ -418,6 +418,18 @@ b200_status b200_point_cloud(b200_engine *e, const b200_scene *s, b200_render_st
   st = download_sync(e, nullptr, nullptr);
   if (noTotalPoints) *noTotalPoints = e->h_ctr->noTotalPoints;
   return st;
+}
+
+// ---- ITMMeshingEngine (mesh.cu) --------------------------------------------------------------------
+b200_status b200_mesh_scene(b200_engine *e, const b200_scene *s, b200_triangle *d_triangles, uint32_t noMaxTriangles, uint32_t *noTotalTriangles) {
+  b200_status st = check_scene(e, s); if (st) return st;
+  if (!d_triangles || noMaxTriangles < 2 || !noTotalTriangles) { snprintf(e->err, sizeof(e->err), "mesh_scene: bad arguments"); return B200_ERR_INVALID; }
+  CK(cudaSetDevice(e->device));
+  launch_mesh_scene(e, scene_ref(s, nullptr), s->voxelSize, d_triangles, noMaxTriangles);
+  CK(cudaGetLastError());
+  st = download_sync(e, nullptr, nullptr); if (st) return st;
+  *noTotalTriangles = e->h_ctr->noTotalPoints;
+  return B200_OK;
 }
 
 // ---- ITMSwappingEngine ---------------------------------------------------------------------------

@@ -87,6 +87,7 @@ struct b200_engine {
   bool traceOn; int traceCount, traceCap; cudaEvent_t *traceEv; const char **traceName;
   // expected-depth cells outside the live corner of the latest fused frame: rasterised lazily at b200_sync()
   bool deadPending; SceneRef deadScene; Mat4 deadM; float deadProj[4]; int deadW, deadH; float deadVoxelSize; b200_vec2f *deadMinmax;
+  unsigned long long *d_meshDesc;     // meshing: chained-scan descriptors, one per VBA block (allocated on first use)
   unsigned long long *d_dbg;          // 64 timestamps written by instrumented kernels while the launch trace is on (b200_diag_read_debug)
   long long launches;
   int lastNoIntegrated;
@@ -123,6 +124,7 @@ void launch_forward_render(b200_engine *e, const SceneRef &s, const FrameGeom &g
                            const b200_vec4f *rays, b200_vec4f *fwd, int *missing, b200_vec4u *outImg);
 void launch_point_cloud(b200_engine *e, const SceneRef &s, const Mat4 &invM, int w, int h, float voxelSize, int skipPoints,
                         const b200_vec4f *rays, b200_vec4u *outImg, b200_vec4f *locations, b200_vec4f *colours);
+void launch_mesh_scene(b200_engine *e, const SceneRef &s, float voxelSize, b200_triangle *triangles, unsigned noMaxTriangles);
 void launch_swap_list_in(b200_engine *e, const SceneRef &s, int *needed);
 void launch_swap_integrate_in(b200_engine *e, const SceneRef &s, const b200_voxel *synced, const int *needed, int n, int maxW);
 void launch_swap_list_out(b200_engine *e, const SceneRef &s, int *needed);

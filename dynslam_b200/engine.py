@@ -478,6 +478,45 @@ class VisualisationEngine:
         return n.value
 
 
+class Mesh:
+    """ITMMesh (Objects/ITMMesh.h:15-42): noMaxTriangles = sdfLocalBlockNum * 512 / 16 triangles of six Vector3f on the device."""
+
+    def __init__(self, scene, noMaxTriangles=None):
+        self.noMaxTriangles = int(noMaxTriangles if noMaxTriangles is not None else scene.numBlocks * abi.SDF_BLOCK_SIZE3 // 16)
+        self.triangles = torch.zeros(self.noMaxTriangles * 18, dtype=torch.float32, device=scene.device)
+        self.noTotalTriangles = 0
+
+    def to_host(self):
+        n = min(self.noTotalTriangles, self.noMaxTriangles - 1)
+        return self.triangles.cpu().numpy().view(abi.TRIANGLE_DTYPE)[:n].copy()
+
+    def WriteOBJ(self, fileName):
+        """ITMMesh::WriteOBJ (Objects/ITMMesh.h:46-122): `v x y z r g b` per vertex, then `f 3i+3 3i+2 3i+1`, printf's %f."""
+        if self.noTotalTriangles > self.noMaxTriangles:
+            raise RuntimeError(f"Unable to save mesh to file [{fileName}]. Too many triangles: {self.noTotalTriangles} while the maximum is {self.noMaxTriangles}.")
+        t = self.triangles.cpu().numpy().view(abi.TRIANGLE_DTYPE)[:self.noTotalTriangles]
+        with open(fileName, "w") as f:
+            for tr in t:
+                for p, c in ((tr["p0"], tr["c0"]), (tr["p1"], tr["c1"]), (tr["p2"], tr["c2"])):
+                    f.write("v %f %f %f %f %f %f\n" % (p[0], p[1], p[2], c[0], c[1], c[2]))
+            for i in range(len(t)):
+                f.write("f %d %d %d\n" % (i * 3 + 2 + 1, i * 3 + 1 + 1, i * 3 + 0 + 1))
+
+
+class MeshingEngine:
+    """ITMMeshingEngine<ITMVoxel, ITMVoxelBlockHash> (B200 back-end)."""
+
+    def __init__(self, engine):
+        self.e = engine
+
+    def MeshScene(self, mesh, scene):
+        n = C.c_uint32()
+        self.e.after_torch()
+        self.e.check(self.e.lib.b200_mesh_scene(self.e.h, C.byref(scene.c), _ptr(mesh.triangles), mesh.noMaxTriangles, C.byref(n)))
+        mesh.noTotalTriangles = n.value
+        return n.value
+
+
 class GlobalCache:
     """Host half of ITMGlobalCache (Objects/ITMGlobalCache.h:17-129): stored blocks per entry."""
 

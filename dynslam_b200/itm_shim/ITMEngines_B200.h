@@ -22,6 +22,7 @@
 
 #include "ITMLib/Utils/ITMLibSettings.h"
 
+#include "ITMLib/Engine/ITMMeshingEngine.h"
 #include "ITMLib/Engine/ITMSceneReconstructionEngine.h"
 #include "ITMLib/Engine/ITMSwappingEngine.h"
 #include "ITMLib/Engine/ITMVisualisationEngine.h"
@@ -353,6 +354,27 @@ class ITMSwappingEngine_B200<TVoxel, ITMVoxelBlockHash> : public ITMSwappingEngi
     ORcudaSafeCall(cudaMemcpy(has, gc->GetHasSyncedData(true), sizeof(bool) * n, cudaMemcpyDeviceToHost));
     ORcudaSafeCall(cudaMemcpy(blocks, gc->GetSyncedVoxelBlocks(true), sizeof(TVoxel) * SDF_BLOCK_SIZE3 * n, cudaMemcpyDeviceToHost));
     for (int i = 0; i < n; i++) if (has[i]) gc->SetStoredData(ids[i], blocks + (size_t)i * SDF_BLOCK_SIZE3);
+  }
+};
+
+// ---- ITMMeshingEngine (Engine/ITMMeshingEngine.h:18-27) ---------------------------------------------------------------
+template <class TVoxel, class TIndex> class ITMMeshingEngine_B200;
+
+template <class TVoxel>
+class ITMMeshingEngine_B200<TVoxel, ITMVoxelBlockHash> : public ITMMeshingEngine<TVoxel, ITMVoxelBlockHash> {
+  std::shared_ptr<B200EngineHandle> h;
+
+ public:
+  explicit ITMMeshingEngine_B200(std::shared_ptr<B200EngineHandle> handle) : h(handle) {}
+
+  // ITMMeshingEngine_CUDA.cu:37-81; the triangles arrive in the CPU engine's (deterministic) order
+  void MeshScene(ITMMesh *mesh, const ITMScene<TVoxel, ITMVoxelBlockHash> *scene) override {
+    static_assert(sizeof(ITMMesh::Triangle) == sizeof(b200_triangle), "ITMMesh::Triangle layout");
+    b200_scene s = b200_detail::PackScene(const_cast<ITMScene<TVoxel, ITMVoxelBlockHash> *>(scene));
+    uint32_t n = 0;
+    h->check(b200_mesh_scene(h->e, &s, (b200_triangle *)mesh->triangles->GetData(MEMORYDEVICE_CUDA), mesh->noMaxTriangles, &n));
+    mesh->noTotalTriangles = n;
+    printf("Meshing done: %d/%d triangles in mesh.\n", mesh->noTotalTriangles, mesh->noMaxTriangles);
   }
 };
 

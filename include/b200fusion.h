@@ -352,6 +352,17 @@ b200_status b200_composite_instances(b200_engine *e, b200_vec4u *d_out_color, fl
                                      const b200_instance_layer *layers, int n_layers, float dim_factor,
                                      float tint_strength);
 
+/* ---- meshing: ITMMeshingEngine<TVoxel, ITMVoxelBlockHash>::MeshScene --------------------------------
+   Engine/DeviceSpecific/CUDA/ITMMeshingEngine_CUDA.cu:37-81 with DeviceAgnostic/ITMMeshingEngine.h. d_triangles is
+   mesh->triangles->GetData(MEMORYDEVICE_CUDA) (ITMMesh::Triangle, Objects/ITMMesh.h:20-23: six Vector3f), noMaxTriangles
+   mesh->noMaxTriangles; *noTotalTriangles receives mesh->noTotalTriangles. Triangles come out in the order of the reference's
+   serial CPU engine (ascending hash entry, then z, y, x, then the case table), not in the CUDA engine's atomicAdd order. */
+
+typedef struct { float p0[3], p1[3], p2[3], c0[3], c1[3], c2[3]; } b200_triangle;
+
+b200_status b200_mesh_scene(b200_engine *e, const b200_scene *scene, b200_triangle *d_triangles, uint32_t noMaxTriangles,
+                            uint32_t *noTotalTriangles);
+
 /* ---- the exchange step of the multi-volume configuration -----------------------------------------------
    One volume per GPU, one process per GPU: the static map on rank 0, one ITMScene per car on the other ranks
    (DS/InstRecLib/InstanceReconstructor.cpp:363-389). Fusion, allocation and decay need no communication; per frame every

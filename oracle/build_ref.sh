@@ -12,7 +12,7 @@ if [ ! -d "$REF/ITMLib" ]; then echo "reference not present at $REF; keeping pre
 mkdir -p "$HERE/_ref"
 /usr/bin/g++ -std=c++14 -O2 -ffp-contract=off -fno-fast-math -shared -fPIC -w \
     -DCOMPILE_WITHOUT_CUDA -D__device__= -I"$REF" \
-    -o "$HERE/_ref/libitmref.so" "$HERE/ref_driver.cpp"
+    -o "$HERE/_ref/libitmref.so" "$HERE/ref_driver.cpp" "$REF/ITMLib/Engine/DeviceSpecific/CPU/ITMMeshingEngine_CPU.cpp"
 echo "built $HERE/_ref/libitmref.so"
 
 # ---- instance frame splitting / compositing: the reference's own free functions (oracle/_ref/libinstrecref.so) ---------

@@ -18,6 +18,9 @@
 #include "ITMLib/Engine/DeviceAgnostic/ITMSwappingEngine.h"
 #include "ITMLib/Engine/DeviceAgnostic/ITMRepresentationAccess.h"
 #include "ITMLib/Engine/DeviceAgnostic/ITMViewBuilder.h"
+#include "ITMLib/Engine/DeviceSpecific/CPU/ITMMeshingEngine_CPU.h"
+#include "ITMLib/Objects/ITMScene.h"
+#include "ITMLib/Objects/ITMMesh.h"
 
 #include "../include/b200fusion.h"
 
@@ -31,6 +34,7 @@ static_assert(sizeof(Vector3i) == sizeof(b200_vec3i), "vec3i layout");
 static_assert(sizeof(Vector4f) == sizeof(b200_vec4f), "vec4f layout");
 static_assert(sizeof(Vector2f) == sizeof(b200_vec2f), "vec2f layout");
 static_assert(sizeof(Vector4u) == sizeof(b200_vec4u), "vec4u layout");
+static_assert(sizeof(ITMMesh::Triangle) == sizeof(b200_triangle), "triangle layout");
 
 static Matrix4f M4(const float *m) { Matrix4f r; for (int i = 0; i < 16; ++i) r.m[i] = m[i]; return r; }
 static Vector4f V4(const float *v) { return Vector4f(v[0], v[1], v[2], v[3]); }
@@ -190,4 +194,22 @@ void ref_view_normal_weight(const float *depth, b200_vec4f *normal, float *sigma
   }
 }
 
+
+// ---- meshing: the reference's own serial engine, ITMMeshingEngine_CPU<ITMVoxel, ITMVoxelBlockHash>::MeshScene
+// (Engine/DeviceSpecific/CPU/ITMMeshingEngine_CPU.cpp:19-80), on a host ITMScene filled with the caller's table and voxels.
+// The table must have the reference's compile-time size (SDF_BUCKET_NUM + SDF_EXCESS_LIST_SIZE entries).
+unsigned ref_mesh_scene(const b200_hash_entry *hash, const b200_voxel *voxels, long numBlocks, float voxelSize, b200_triangle *out,
+                        unsigned noMaxTriangles) {
+  ITMSceneParams params(0.75f, 50, voxelSize, 0.1f, 300.0f, false);
+  ITMScene<ITMVoxel, ITMVoxelIndex> scene(&params, false, MEMORYDEVICE_CPU, numBlocks);
+  memcpy(scene.index.GetEntries(), hash, sizeof(ITMHashEntry) * (size_t)ITMVoxelBlockHash::noTotalEntries);
+  memcpy(scene.localVBA.GetVoxelBlocks(), voxels, sizeof(ITMVoxel) * (size_t)numBlocks * SDF_BLOCK_SIZE3);
+  ITMMesh mesh(MEMORYDEVICE_CPU, numBlocks);
+  ITMMeshingEngine_CPU<ITMVoxel, ITMVoxelIndex> engine;
+  engine.MeshScene(&mesh, &scene);
+  const unsigned n = mesh.noTotalTriangles < noMaxTriangles ? mesh.noTotalTriangles : noMaxTriangles;
+  memcpy(out, mesh.triangles->GetData(MEMORYDEVICE_CPU), sizeof(ITMMesh::Triangle) * (size_t)n);
+  return mesh.noTotalTriangles;
+}
+int ref_table_entries(void) { return ITMVoxelBlockHash::noTotalEntries; }
 } // extern "C"

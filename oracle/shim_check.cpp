@@ -8,6 +8,7 @@ using namespace ITMLib::Engine;
 template class ITMLib::Engine::ITMSceneReconstructionEngine_B200<ITMVoxel, ITMVoxelIndex>;
 template class ITMLib::Engine::ITMVisualisationEngine_B200<ITMVoxel, ITMVoxelIndex>;
 template class ITMLib::Engine::ITMSwappingEngine_B200<ITMVoxel, ITMVoxelIndex>;
+template class ITMLib::Engine::ITMMeshingEngine_B200<ITMVoxel, ITMVoxelIndex>;
 
 // what ITMDenseMapper's / ITMMainEngine's new `case ITMLibSettings::DEVICE_B200:` would do
 // (Engine/ITMDenseMapper.cpp:16-36, Engine/ITMMainEngine.cpp:24-54)

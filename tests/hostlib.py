@@ -26,7 +26,7 @@ def oracle():
     global _oracle
     if _oracle is not None:
         return _oracle
-    srcs = [os.path.join(ROOT, "oracle", f) for f in ("tsdf_oracle.c", "view_oracle.c", "frames_oracle.c")]
+    srcs = [os.path.join(ROOT, "oracle", f) for f in ("tsdf_oracle.c", "view_oracle.c", "frames_oracle.c", "mesh_oracle.c")]
     if not os.path.exists(ORACLE_SO) or os.path.getmtime(ORACLE_SO) < max(os.path.getmtime(s) for s in srcs):
         build_oracle()
     L = C.CDLL(ORACLE_SO)
@@ -40,6 +40,8 @@ def oracle():
     L.oracle_decayed_block_count.restype = C.c_long
     L.oracle_queue_size.argtypes = [vp]
     L.oracle_integrated_blocks.argtypes = [vp]
+    L.oracle_mesh_scene.argtypes = [P(abi.Scene), vp, C.c_uint32]
+    L.oracle_mesh_scene.restype = C.c_uint32
     L.oracle_mat4_inv.argtypes = [P(C.c_float), P(C.c_float)]
     L.oracle_mat4_mul.argtypes = [P(C.c_float), P(C.c_float), P(C.c_float)]
     L.oracle_mat4_mul.restype = None
@@ -105,6 +107,8 @@ def ref():
     L = C.CDLL(REF_SO)
     P, vp = C.POINTER, C.c_void_p
     L.ref_table_sizes.argtypes = [P(C.c_int), P(C.c_int)]
+    L.ref_mesh_scene.argtypes = [vp, vp, C.c_long, C.c_float, vp, C.c_uint]
+    L.ref_mesh_scene.restype = C.c_uint
     L.ref_mat4_inv.argtypes = [P(C.c_float), P(C.c_float)]
     L.ref_mat4_mul.argtypes = [P(C.c_float), P(C.c_float), P(C.c_float)]
     L.ref_mat4_mul.restype = None

@@ -249,3 +249,29 @@ def test_view_filter_and_update_view_bit_exact():
         assert np.array_equal(nrm_o.view(np.uint32), nrm_r.view(np.uint32))
         assert np.array_equal(sig_o.view(np.uint32), sig_r.view(np.uint32))
         assert (nrm_o[..., 3] == 1.0).sum() > 0.3 * w * h
+
+
+def test_mesh_oracle_equals_reference_cpu_engine():
+    """Meshing: oracle/mesh_oracle.c against the reference's OWN serial engine,
+    ITMMeshingEngine_CPU<ITMVoxel, ITMVoxelBlockHash>::MeshScene (Engine/DeviceSpecific/CPU/ITMMeshingEngine_CPU.cpp:19-80, live
+    code, compiled from its source into oracle/_ref/libitmref.so), on a map fused by the oracle: same triangle count, every
+    vertex and colour bit for bit, same order."""
+    from dynslam_b200 import abi, synth
+    from tests import parity as P
+    L, R = H.oracle(), H.ref()
+    cfg = P.Cfg(scale=0.25, frames=4, numBlocks=16384, numBuckets=0x100000, excessSize=0x80000)    # the reference's compile-time table size
+    w, h = int(round(synth.KITTI_W * cfg.scale)), int(round(synth.KITTI_H * cfg.scale))
+    vol = H.HostVolume(cfg.numBlocks, cfg.numBuckets, cfg.excessSize, w, h)
+    for depth, rgb, M, proj in P.frames_of(cfg):
+        hv = H.make_view(depth, rgb, M, proj)
+        assert L.oracle_allocate_from_depth(vol.engine, C.byref(vol.scene), C.byref(vol.rs), C.byref(hv), 0, 0) == 0
+        L.oracle_integrate(vol.engine, C.byref(vol.scene), C.byref(vol.rs), C.byref(hv), 0)
+    nmax = cfg.numBlocks * 512 // 16
+    a = np.zeros(nmax, dtype=abi.TRIANGLE_DTYPE)
+    b = np.zeros(nmax, dtype=abi.TRIANGLE_DTYPE)
+    na = L.oracle_mesh_scene(C.byref(vol.scene), H.vptr(a), nmax)
+    nb = R.ref_mesh_scene(H.vptr(vol.hash), H.vptr(vol.voxels), cfg.numBlocks, C.c_float(cfg.voxelSize), H.vptr(b), nmax)
+    assert na == nb and na > 20000
+    assert a[:na].tobytes() == b[:na].tobytes()
+    # colours are really interpolated from the volume, vertices lie inside the fused region
+    assert a["c0"][:na].max() > 0.2 and np.isfinite(a["p0"][:na]).all()
