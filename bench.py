@@ -994,7 +994,7 @@ def run_own(args, rank, local_rank, world):
                    l2=(f"explicit flush between timed steps (256 MB read-modify-write, timed with CUDA events and subtracted, "
                           f"{flush_ms / max(K, 1) * 1000:.0f} us each); per-step footprint ~{footprint_mb:.0f} MB") if args.flush_l2 else
                          f"no flush (--no-flush-l2): per-step footprint ~{footprint_mb:.0f} MB, consecutive frames reuse L2",
-                   integrate_impl=os.environ.get("B200_INTEGRATE_IMPL", "v3"),
+                   integrate_impl=os.environ.get("B200_INTEGRATE_IMPL", "v4"),
                    parallelism=(f"configs[2]: one volume per GPU — rank 0 the static map (cars cut out with b200_process_silhouettes), ranks 1..{world - 1} one "
                                 "car volume each (voxel 0.035, mu 1.0, 7142 blocks) fed by b200_process_silhouettes; every frame each rank's colour + "
                                 "depth render goes to rank 0 over NCCL (C++ exchange, own stream, two slots) and is composited there inside the "
@@ -1004,7 +1004,7 @@ def run_own(args, rank, local_rank, world):
         "wall_ms_per_step": wall_ms / K,
         "stage_ms": {"allocate": stage[0], "integrate": stage[1], "expected_depths": stage[2], "raycast_icp": stage[3],
                      "decay": stage[4], "total": stage[5]},
-        "roofline": {"kernel": "k_integrate_" + os.environ.get("B200_INTEGRATE_IMPL", "v3"), "bound": "hbm", "achieved": achieved,
+        "roofline": {"kernel": "k_integrate_" + os.environ.get("B200_INTEGRATE_IMPL", "v4"), "bound": "hbm", "achieved": achieved,
                      "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None, "traffic": ncu_traffic(),
                      "peak_source": peak_src, "launches_timed": int_n, "mean_launch_us": 1000.0 * int_ms / max(int_n, 1),
                      "alg_bytes_per_launch": alg_bytes / max(int_n, 1)},

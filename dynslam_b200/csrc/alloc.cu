@@ -222,7 +222,7 @@ k_mark_prepare(const float *__restrict__ depth, const b200_hash_entry *__restric
         if (lane == 31 - __clz(peers)) {
           atomicMax(&reqKey[hashIdx], make_key(frameTag, pixel, (unsigned)(i0 + j)));
           bitmap_set(reqBits, hashIdx);
-          if (isExcess) bitmap_set(req2Bits, hashIdx);
+          if (isExcess) { bitmap_set(req2Bits, hashIdx); ctr->anyExcessRequest = 1; }   // k_serve_list: tiles of the excess part must wait for the service
           else markBytes[hashIdx] = 1;          // a requested ordered entry is visible (type 1) whether or not it gets a block
         }
       }
@@ -239,18 +239,20 @@ k_mark_prepare(const float *__restrict__ depth, const b200_hash_entry *__restric
 // NDESC descriptor arrays are walked together (the request ranks need the prefix of all requests AND of the excess ones).
 // ------------------------------------------------------------------------------------------------
 #define LB_WIN 8   // descriptors per lane and step
+// publish this tile's aggregates (tile 0: they are its inclusive prefixes). Called by warp 0 of the CTA.
 template <int NDESC>
-DEV void lookback_wide(unsigned long long *const *desc, unsigned gen, int tile, const unsigned *agg, bool needPrefix, unsigned *ex) {
+DEV void lookback_publish(unsigned long long *const *desc, unsigned gen, int tile, const unsigned *agg) {
+  if ((threadIdx.x & 31) == 0)
+    for (int d = 0; d < NDESC; ++d) ((volatile unsigned long long *)desc[d])[tile] = scan_pack(gen, tile == 0 ? 2 : 1, agg[d]);
+}
+// exclusive prefixes of `tile` (its aggregates must have been published); publishes its inclusive prefixes. Warp 0 of the CTA.
+template <int NDESC>
+DEV void lookback_walk(unsigned long long *const *desc, unsigned gen, int tile, const unsigned *agg, unsigned *ex) {
   const int lane = threadIdx.x & 31;
   const unsigned g30 = gen & 0x3fffffffu;
 #pragma unroll
   for (int d = 0; d < NDESC; ++d) ex[d] = 0;
-  if (tile == 0) {
-    if (lane == 0) for (int d = 0; d < NDESC; ++d) ((volatile unsigned long long *)desc[d])[0] = scan_pack(gen, 2, agg[d]);
-    return;
-  }
-  if (lane == 0) for (int d = 0; d < NDESC; ++d) ((volatile unsigned long long *)desc[d])[tile] = scan_pack(gen, 1, agg[d]);
-  if (!needPrefix) return;
+  if (tile == 0) return;
   int look = tile - 1;          // nearest tile not yet accounted for
   for (;;) {
     // window: tiles look, look-1, ..., look-255; lane l holds look - (l + 32 j), j = 0..7
@@ -270,8 +272,8 @@ DEV void lookback_wide(unsigned long long *const *desc, unsigned gen, int tile, 
     for (int j = 0; j < LB_WIN; ++j) {
       const int t = look - (lane + 32 * j);
       unsigned st = 3;              // beyond tile 0: nothing to add, ends the walk
-      bool mixed = false;
       if (t >= 0) {
+        bool mixed = false;
         st = 2;
 #pragma unroll
         for (int d = 0; d < NDESC; ++d) {
@@ -342,6 +344,25 @@ DEV unsigned nz_bytes(unsigned w) { return ((__vcmpne4(w, 0u) & 0x80808080u) * 0
 // ------------------------------------------------------------------------------------------------
 #define AL_EPT 32
 #define AL_TILE (256 * AL_EPT)   // 8192 entries = 256 bitmap words per tile
+#define AL_BIG 64                // boxes of more than 512 live cells are rasterised by the whole CTA (at most AL_BIG per tile pass)
+
+// rasterises the part [ax..bx] x [ay..by] of a block's box into the expected-depth image, one warp, no integer divisions in the loop
+DEV void raster_box_warp(float2 *minmax, int rw, int ax, int ay, int bx, int by, float zn, float zx) {
+  const int lane = threadIdx.x & 31;
+  const int bw = bx - ax + 1;
+  if (bw <= 32) {
+    const int rpi = 32 / bw, inv = (65536 + bw - 1) / bw;          // warp-uniform; rows per iteration, magic number of lane / bw
+    const int r = (lane * inv) >> 16, c = lane - r * bw;
+    for (int y0 = ay; y0 <= by; y0 += rpi) {
+      const int yy = y0 + r;
+      if (r < rpi && yy <= by) { float2 *px = &minmax[(ax + c) + yy * rw]; atomic_min_posf(&px->x, zn); atomic_max_posf(&px->y, zx); }
+    }
+  } else {
+    for (int yy = ay; yy <= by; ++yy)
+      for (int xx = ax + lane; xx <= bx; xx += 32) { float2 *px = &minmax[xx + yy * rw]; atomic_min_posf(&px->x, zn); atomic_max_posf(&px->y, zx); }
+  }
+}
+
 __global__ void __launch_bounds__(256, 2)
 k_serve_list(const float *__restrict__ depth, b200_hash_entry *table, int numBuckets, int noTotal, uint8_t *visType,
              const unsigned long long *__restrict__ reqKey, unsigned *reqBits, unsigned *req2Bits, uint8_t *markBytes,
@@ -352,6 +373,8 @@ k_serve_list(const float *__restrict__ depth, b200_hash_entry *table, int numBuc
   __shared__ unsigned sm[33];
   __shared__ unsigned tileBase, tileBase2;
   __shared__ unsigned hits[AL_TILE];   // entry index | bit 31: observed this frame
+  __shared__ BlockRec bigRecs[AL_BIG];
+  __shared__ int bigCount;
   // measurement hook (b200_diag_read_debug): CTAs 0, 1/3, 2/3 and the last one stamp %globaltimer at their phase boundaries
   const int dbgSlot = !dbg ? -1 : (blockIdx.x == 0 ? 0 : (blockIdx.x == gridDim.x / 3 ? 1 : (blockIdx.x == 2 * gridDim.x / 3 ? 2 : (blockIdx.x == gridDim.x - 1 ? 3 : -1))));
 #define K2_STAMP(i) do { if (dbgSlot >= 0 && threadIdx.x == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); dbg[dbgSlot * 8 + (i)] = t_; } } while (0)
@@ -359,214 +382,254 @@ k_serve_list(const float *__restrict__ depth, b200_hash_entry *table, int numBuc
   const int noWords = noTotal >> 5;
   const int noTiles = (noTotal + AL_TILE - 1) / AL_TILE;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  // ---------------- phase A: requests ----------------
-  {
-    const int baseVba = ctr->lastFreeBlockId, baseExl = ctr->lastFreeExcessListId;   // only the last tile updates them, at its very end
-    const float invfx = 1.0f / g.proj_d[0], invfy = 1.0f / g.proj_d[1];
-    const float oneOverVoxelSize = 1.0f / (g.voxelSize * BS);
-    for (int tile = blockIdx.x; tile < noTiles; tile += gridDim.x) {
-      const int w = tile * 256 + threadIdx.x;
-      unsigned rq = 0, rq2 = 0;
-      if (w < noWords) {
-        rq = reqBits[w]; rq2 = req2Bits[w];
-        if (rq) reqBits[w] = 0u;                 // consumed: clean for the next frame
-        if (rq2) req2Bits[w] = 0u;
-      }
-      if (onlyVisible) { rq = 0u; rq2 = 0u; }     // onlyUpdateVisibleList: the marking ran, nothing is allocated (Reco_CUDA.cu:254-262)
-      unsigned totalPacked;
-      const unsigned localPacked = block_exclusive_scan(__popc(rq) | (__popc(rq2) << 16), sm, &totalPacked);   // <= 8192 each: no carry
-      const unsigned total = totalPacked & 0xffffu, total2 = totalPacked >> 16;
-      const bool last = (tile == noTiles - 1);
-      if (threadIdx.x < 32) {
-        unsigned long long *const d2[2] = {descA, descB};
-        const unsigned agg[2] = {total, total2};
-        unsigned ex[2];
-        lookback_wide<2>(d2, gen, tile, agg, total != 0 || last, ex);    // the last tile needs the grand totals for the counters
-        if (threadIdx.x == 0) { tileBase = ex[0]; tileBase2 = ex[1]; }
-      }
-      __syncthreads();
-      unsigned rank = tileBase + (localPacked & 0xffffu), rank2 = tileBase2 + (localPacked >> 16);
-      const unsigned grand = tileBase + total, grand2 = tileBase2 + total2;
-      while (rq) {
-        const int b = __ffs(rq) - 1;
-        rq &= rq - 1;
-        const int targetIdx = w * 32 + b;
-        const bool isExcess = (rq2 >> b) & 1u;
-        const int vbaIdx = baseVba - (int)rank;
-        const int exlIdx = baseExl - (int)rank2;
-        rank++;
-        if (isExcess) rank2++;
-        if (vbaIdx < 0 || (isExcess && exlIdx < 0)) continue;   // exhausted: the counters still go negative
-        const unsigned long long key = reqKey[targetIdx];
-        const unsigned step = (unsigned)(key & ((1u << KEY_STEP_BITS) - 1));
-        const unsigned pixel = (unsigned)((key >> KEY_STEP_BITS) & ((1u << KEY_PIXEL_BITS) - 1));
-        const int x = pixel % g.w, y = pixel / g.w;
-        Ray r;
-        make_ray(r, x, y, __ldg(depth + pixel), g, invfx, invfy, oneOverVoxelSize);
-        float px = r.px, py = r.py, pz = r.pz;
-        for (unsigned i = 0; i < step; ++i) { px += r.dx; py += r.dy; pz += r.dz; }
-        const int bx = (short)(int)floorf(px), by = (short)(int)floorf(py), bz = (short)(int)floorf(pz);
-        int *ew;
-        if (!isExcess) {
-          ew = reinterpret_cast<int *>(table) + (size_t)targetIdx * 5;
-        } else {
-          const int exlOffset = excessList[exlIdx];
-          reinterpret_cast<int *>(table)[(size_t)targetIdx * 5 + 2] = exlOffset + 1;   // connect to child
-          ew = reinterpret_cast<int *>(table) + (size_t)(numBuckets + exlOffset) * 5;
-          markBytes[numBuckets + exlOffset] = 1;                                       // child visible (:875)
-        }
-        ew[0] = (int)(((unsigned)bx & 0xffffu) | ((unsigned)by << 16));
-        ew[1] = (bz & 0xffff);
-        ew[2] = 0;
-        ew[3] = allocList[vbaIdx];
-        ew[4] = currentFrame;
-      }
-      __syncthreads();
-      if (threadIdx.x == 0) {
-        if (last) {
-          ctr->allocBaseVba = baseVba; ctr->allocBaseExl = baseExl;
-          ctr->noRequests = (int)grand; ctr->noRequestsExcess = (int)grand2;
-          ctr->lastFreeBlockId = baseVba - (int)grand;
-          ctr->lastFreeExcessListId = baseExl - (int)grand2;
-        }
-        __threadfence();                          // this tile's new entries and child marks are visible device-wide ...
-        atomicAdd(&ctr->tilesServed, 1u);         // ... before it counts as served
-      }
-    }
-  }
-  K2_STAMP(1);
-  // ---------------- phase B: visibility bytes and the ordered list ----------------
-  unsigned myTiles = 0;   // rendering tiles of the blocks this thread projected (fused frame only)
+  // One pass (every tile: requests, then its list) when each CTA owns a single tile — the usual case: 192 tiles for the
+  // default table — so that a tile's list count is published before anybody serves a request and nobody waits on a serving
+  // tile. Two passes (all requests first) when CTAs own several tiles: a tile of the excess part may have to wait for every
+  // tile's requests, including those this very CTA still has to serve.
+  const bool twoPass = noTiles > (int)gridDim.x;
+  // the marking kernel says whether ANY excess-list request was filed this frame: only then can a tile of the excess part
+  // receive an entry (and a visibility mark) from another tile's service, and has to wait for all of them
+  const bool anyExcess = !onlyVisible && *(volatile int *)&ctr->anyExcessRequest != 0;
+  const int baseVba = ctr->lastFreeBlockId, baseExl = ctr->lastFreeExcessListId;   // only the last tile updates them
+  const float invfx = 1.0f / g.proj_d[0], invfy = 1.0f / g.proj_d[1];
+  const float oneOverVoxelSize = 1.0f / (g.voxelSize * BS);
   const long long ringStart = ctr->ringHead;   // advanced by the last tile only, at its very end
   const int liveX = (rw - 1) / B200_MINMAX_SUBSAMPLE, liveY = (rh - 1) / B200_MINMAX_SUBSAMPLE;   // last live cell of the expected-depth image
-  for (int tile = blockIdx.x; tile < noTiles; tile += gridDim.x) {
-    const int first = tile * AL_TILE + threadIdx.x * AL_EPT;
-    const int w = tile * 256 + threadIdx.x;
-    if ((tile + 1) * AL_TILE > numBuckets) {
-      // the tile reaches into the excess part: entries created and child marks set by OTHER tiles' phase A must be in
-      if (threadIdx.x == 0) { while (*(volatile unsigned *)&ctr->tilesServed < (unsigned)noTiles) { } __threadfence(); }
-      __syncthreads();
-    }
-    K2_STAMP(2);
-    unsigned mask = 0;   // bit k: entry first+k goes to the list
-    unsigned mk = 0;     // bit k: entry first+k was observed this frame
-    if (w < noWords) {
-      uint4 raw[2], mb[2];
-      raw[0] = *reinterpret_cast<const uint4 *>(visType + first);          // noTotal is a multiple of 32
-      raw[1] = *reinterpret_cast<const uint4 *>(visType + first + 16);
-      mb[0] = __ldcg(reinterpret_cast<const uint4 *>(markBytes + first));  // written by the marking kernel and by other tiles' phase A: L2
-      mb[1] = __ldcg(reinterpret_cast<const uint4 *>(markBytes + first + 16));
+  unsigned long long *const dAB[2] = {descA, descB};
+  unsigned long long *const dC[1] = {descC};
+  unsigned myTiles = 0;   // rendering tiles of the blocks this thread projected (fused frame only)
+
+  for (int pass = 0; pass < (twoPass ? 2 : 1); ++pass) {
+    const bool doReq = !twoPass || pass == 0, doList = !twoPass || pass == 1;
+    for (int tile = blockIdx.x; tile < noTiles; tile += gridDim.x) {
+      const int first = tile * AL_TILE + threadIdx.x * AL_EPT;
+      const int w = tile * 256 + threadIdx.x;
+      const bool last = (tile == noTiles - 1);
+      const bool deferList = anyExcess && ((tile + 1) * AL_TILE > numBuckets);   // wait for the other tiles' service before listing
+      // ---- requests: rank (published at once), serve later ----
+      unsigned rq = 0, rq2 = 0, localPacked = 0, total = 0, total2 = 0;
+      if (doReq) {
+        if (w < noWords) {
+          rq = reqBits[w]; rq2 = req2Bits[w];
+          if (rq) reqBits[w] = 0u;                 // consumed: clean for the next frame
+          if (rq2) req2Bits[w] = 0u;
+        }
+        if (onlyVisible) { rq = 0u; rq2 = 0u; }     // onlyUpdateVisibleList: the marking ran, nothing is allocated (Reco_CUDA.cu:254-262)
+        unsigned totalPacked;
+        localPacked = block_exclusive_scan(__popc(rq) | (__popc(rq2) << 16), sm, &totalPacked);   // <= 8192 each: no carry
+        total = totalPacked & 0xffffu; total2 = totalPacked >> 16;
+        if (threadIdx.x < 32) { const unsigned agg[2] = {total, total2}; lookback_publish<2>(dAB, gen, tile, agg); }
+      }
+      // ---- list, first half: visibility bytes -> mask of listed entries, count published ----
+      unsigned mask = 0, mk = 0, local = 0, totalC = 0;
+      auto decode_and_count = [&]() {
+        if (w < noWords) {
+          uint4 raw[2], mb[2];
+          raw[0] = *reinterpret_cast<const uint4 *>(visType + first);          // noTotal is a multiple of 32
+          raw[1] = *reinterpret_cast<const uint4 *>(visType + first + 16);
+          mb[0] = __ldcg(reinterpret_cast<const uint4 *>(markBytes + first));  // written by the marking kernel and by other tiles' service: L2
+          mb[1] = __ldcg(reinterpret_cast<const uint4 *>(markBytes + first + 16));
 #pragma unroll
-      for (int q = 0; q < 2; ++q) {
-        const unsigned m16 = nz_bytes(mb[q].x) | (nz_bytes(mb[q].y) << 4) | (nz_bytes(mb[q].z) << 8) | (nz_bytes(mb[q].w) << 12);
-        if (m16) *reinterpret_cast<uint4 *>(markBytes + first + q * 16) = make_uint4(0u, 0u, 0u, 0u);   // consumed
-        mk |= m16 << (q * 16);
-        unsigned todo = m16 | nz_bytes(raw[q].x) | (nz_bytes(raw[q].y) << 4) | (nz_bytes(raw[q].z) << 8) | (nz_bytes(raw[q].w) << 12);
-        if (!todo) continue;
-        unsigned wv[4] = {raw[q].x, raw[q].y, raw[q].z, raw[q].w};
-        bool dirty = false;
-        while (todo) {            // the few interesting bytes of the group (a thread lists ~0.1 entries on average)
-          const int k = __ffs(todo) - 1;
-          todo &= todo - 1;
-          const unsigned sh = (k & 3) * 8;
-          unsigned word = (k < 4) ? wv[0] : (k < 8) ? wv[1] : (k < 12) ? wv[2] : wv[3];
-          const unsigned old = (word >> sh) & 0xffu;
-          unsigned v = old;
-          if ((m16 >> k) & 1u) v = 1;                 // observed this frame (2 = swapped out is patched below, where the entry is read)
-          else if (v == VT_PREV_VISIBLE) v = 3;
-          else if (v == VT_PREV_HIDDEN) v = 0;
-          else if (v == 3) { if (!stale_three_visible(table, first + q * 16 + k, &g)) v = 0; }
-          if (v != old) {
-            dirty = true;
-            word = (word & ~(0xffu << sh)) | (v << sh);
-            if (k < 4) wv[0] = word; else if (k < 8) wv[1] = word; else if (k < 12) wv[2] = word; else wv[3] = word;
-          }
-          if (v > 0) mask |= 1u << (q * 16 + k);
-        }
-        if (dirty) *reinterpret_cast<uint4 *>(visType + first + q * 16) = make_uint4(wv[0], wv[1], wv[2], wv[3]);
-      }
-    }
-    K2_STAMP(3);
-    unsigned total;
-    const unsigned local = block_exclusive_scan(__popc(mask), sm, &total);
-    if (threadIdx.x < 32) {
-      unsigned long long *const d1[1] = {descC};
-      const unsigned agg[1] = {total};
-      unsigned ex[1];
-      lookback_wide<1>(d1, gen, tile, agg, total != 0 || tile == noTiles - 1, ex);
-      if (threadIdx.x == 0) tileBase = ex[0];
-    }
-    unsigned o = local;
-    while (mask) {
-      const int k = __ffs(mask) - 1;
-      mask &= mask - 1;
-      hits[o++] = (unsigned)(first + k) | (((mk >> k) & 1u) << 31);
-    }
-    __syncthreads();
-    K2_STAMP(4);
-    const unsigned base = tileBase;
-    // listed entry t of the tile is handled by lane (t / 8) % 32 of warp t % 8: the ~25 entries of a KITTI tile become ~3 per warp
-    for (unsigned t0 = 0; t0 < total; t0 += blockDim.x) {
-      const unsigned t = t0 + (unsigned)(lane * 8 + warp);
-      BlockRec r; r.ulx = 1; r.uly = 1; r.lrx = 0; r.lry = 0; r.zmin = 0; r.zmax = 0;
-      bool draw = false;
-      if (t < total) {
-        const int idx = (int)(hits[t] & 0x7fffffffu);
-        const Entry en = load_entry(table, idx);
-        if (en.ptr == -1 && (hits[t] >> 31)) visType[idx] = 2;   // observed while swapped out (DA/ITMSceneReconstructionEngine.h:261, :281)
-        const long long out = (long long)base + t;
-        if (out < capacity) {
-          b200_vec3i p; p.x = en.x; p.y = en.y; p.z = en.z;
-          visiblePos[out] = p;
-          ring[(ringStart + out) % ringCap] = p;
-          int ptr = en.ptr;
-          if (ptr < 0) { if (find_block<false>(table, numBuckets, en.x, en.y, en.z, &ptr) < 0) ptr = -1; }   // stale entry: what findBlock(pos) would hit
-          visiblePtr[out] = ptr;
-          if (recs) {
-            // fused frame: the block's 1/8-resolution box (ProjectSingleBlock). All blocks are assumed drawn; if the tile total
-            // breaks MAX_RENDERING_BLOCKS (never at KITTI sizes) the last CTA re-applies the ordered rule and rebuilds the image.
-            int ulx, uly, lrx, lry; float zmin, zmax;
-            if (ptr >= 0 && project_single_block(en.x, en.y, en.z, g.M_d, g.proj_d, rw, rh, g.voxelSize, ulx, uly, lrx, lry, zmin, zmax)) {
-              r.ulx = (short)ulx; r.uly = (short)uly; r.lrx = (short)lrx; r.lry = (short)lry; r.zmin = zmin; r.zmax = zmax;
-              myTiles += rendering_tiles(ulx, uly, lrx, lry);
-              draw = true;
+          for (int q = 0; q < 2; ++q) {
+            const unsigned m16 = nz_bytes(mb[q].x) | (nz_bytes(mb[q].y) << 4) | (nz_bytes(mb[q].z) << 8) | (nz_bytes(mb[q].w) << 12);
+            if (m16) *reinterpret_cast<uint4 *>(markBytes + first + q * 16) = make_uint4(0u, 0u, 0u, 0u);   // consumed
+            mk |= m16 << (q * 16);
+            unsigned todo = m16 | nz_bytes(raw[q].x) | (nz_bytes(raw[q].y) << 4) | (nz_bytes(raw[q].z) << 8) | (nz_bytes(raw[q].w) << 12);
+            if (!todo) continue;
+            unsigned wv[4] = {raw[q].x, raw[q].y, raw[q].z, raw[q].w};
+            bool dirty = false;
+            while (todo) {            // the few interesting bytes of the group (a thread lists ~0.1 entries on average)
+              const int k = __ffs(todo) - 1;
+              todo &= todo - 1;
+              const unsigned sh = (k & 3) * 8;
+              unsigned word = (k < 4) ? wv[0] : (k < 8) ? wv[1] : (k < 12) ? wv[2] : wv[3];
+              const unsigned old = (word >> sh) & 0xffu;
+              unsigned v = old;
+              if ((m16 >> k) & 1u) v = 1;                 // observed this frame (2 = swapped out is patched below, where the entry is read)
+              else if (v == VT_PREV_VISIBLE) v = 3;
+              else if (v == VT_PREV_HIDDEN) v = 0;
+              else if (v == 3) { if (!stale_three_visible(table, first + q * 16 + k, &g)) v = 0; }
+              if (v != old) {
+                dirty = true;
+                word = (word & ~(0xffu << sh)) | (v << sh);
+                if (k < 4) wv[0] = word; else if (k < 8) wv[1] = word; else if (k < 12) wv[2] = word; else wv[3] = word;
+              }
+              if (v > 0) mask |= 1u << (q * 16 + k);
             }
-            recs[out] = r;
+            if (dirty) *reinterpret_cast<uint4 *>(visType + first + q * 16) = make_uint4(wv[0], wv[1], wv[2], wv[3]);
           }
         }
-      }
-      if (recs) {
-        // rasterise: warp-cooperative, one box at a time, the part of the box inside the live 1/8-resolution corner — the
-        // only cells the raycast reads. The reference clamps boxes to the FULL-resolution bounds
-        // (DA/ITMVisualisationEngine.h:57-60), so a block next to the camera can cover 10^5 cells outside the corner: those are
-        // rasterised from the records by k_project_blocks on the side stream, off the frame's critical path.
-        unsigned todo = __ballot_sync(0xffffffffu, draw && r.ulx <= liveX && r.uly <= liveY);
-        while (todo) {
-          const int src = __ffs(todo) - 1;
-          todo &= todo - 1;
-          const int ax = __shfl_sync(0xffffffffu, (int)r.ulx, src), ay = __shfl_sync(0xffffffffu, (int)r.uly, src);
-          const int bxx = min(__shfl_sync(0xffffffffu, (int)r.lrx, src), liveX), byy = min(__shfl_sync(0xffffffffu, (int)r.lry, src), liveY);
-          const float zn = __shfl_sync(0xffffffffu, r.zmin, src), zx = __shfl_sync(0xffffffffu, r.zmax, src);
-          const int bw = bxx - ax + 1, cnt = bw * (byy - ay + 1);
-          for (int k = lane; k < cnt; k += 32) {
-            float2 *px = &minmax[(ax + k % bw) + (ay + k / bw) * rw];
-            atomic_min_posf(&px->x, zn); atomic_max_posf(&px->y, zx);
+        local = block_exclusive_scan(__popc(mask), sm, &totalC);
+        if (threadIdx.x < 32) { const unsigned agg[1] = {totalC}; lookback_publish<1>(dC, gen, tile, agg); }
+      };
+      K2_STAMP(1);
+      if (doList && !deferList) decode_and_count();
+      K2_STAMP(2);
+      // ---- requests, second half: ranks of this tile's requests (and the grand totals on the last tile), service ----
+      if (doReq) {
+        const bool needRank = (total != 0) || last;
+        if (needRank && threadIdx.x < 32) {
+          const unsigned agg[2] = {total, total2};
+          unsigned ex[2];
+          lookback_walk<2>(dAB, gen, tile, agg, ex);
+          if (threadIdx.x == 0) { tileBase = ex[0]; tileBase2 = ex[1]; }
+        }
+        __syncthreads();
+        if (needRank) {
+          unsigned rank = tileBase + (localPacked & 0xffffu), rank2 = tileBase2 + (localPacked >> 16);
+          const unsigned grand = tileBase + total, grand2 = tileBase2 + total2;
+          while (rq) {
+            const int b = __ffs(rq) - 1;
+            rq &= rq - 1;
+            const int targetIdx = w * 32 + b;
+            const bool isExcess = (rq2 >> b) & 1u;
+            const int vbaIdx = baseVba - (int)rank;
+            const int exlIdx = baseExl - (int)rank2;
+            rank++;
+            if (isExcess) rank2++;
+            if (vbaIdx < 0 || (isExcess && exlIdx < 0)) continue;   // exhausted: the counters still go negative
+            const unsigned long long key = reqKey[targetIdx];
+            const unsigned step = (unsigned)(key & ((1u << KEY_STEP_BITS) - 1));
+            const unsigned pixel = (unsigned)((key >> KEY_STEP_BITS) & ((1u << KEY_PIXEL_BITS) - 1));
+            const int x = pixel % g.w, y = pixel / g.w;
+            Ray r;
+            make_ray(r, x, y, __ldg(depth + pixel), g, invfx, invfy, oneOverVoxelSize);
+            float px = r.px, py = r.py, pz = r.pz;
+            for (unsigned i = 0; i < step; ++i) { px += r.dx; py += r.dy; pz += r.dz; }
+            const int bx = (short)(int)floorf(px), by = (short)(int)floorf(py), bz = (short)(int)floorf(pz);
+            int *ew;
+            if (!isExcess) {
+              ew = reinterpret_cast<int *>(table) + (size_t)targetIdx * 5;
+            } else {
+              const int exlOffset = excessList[exlIdx];
+              reinterpret_cast<int *>(table)[(size_t)targetIdx * 5 + 2] = exlOffset + 1;   // connect to child
+              ew = reinterpret_cast<int *>(table) + (size_t)(numBuckets + exlOffset) * 5;
+              markBytes[numBuckets + exlOffset] = 1;                                       // child visible (:875)
+            }
+            ew[0] = (int)(((unsigned)bx & 0xffffu) | ((unsigned)by << 16));
+            ew[1] = (bz & 0xffff);
+            ew[2] = 0;
+            ew[3] = allocList[vbaIdx];
+            ew[4] = currentFrame;
+          }
+          if (last && threadIdx.x == 0) {
+            ctr->allocBaseVba = baseVba; ctr->allocBaseExl = baseExl;
+            ctr->noRequests = (int)grand; ctr->noRequestsExcess = (int)grand2;
+            ctr->lastFreeBlockId = baseVba - (int)grand;
+            ctr->lastFreeExcessListId = baseExl - (int)grand2;
           }
         }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+          __threadfence();                          // this tile's new entries and child marks are visible device-wide ...
+          atomicAdd(&ctr->tilesServed, 1u);         // ... before it counts as served
+        }
       }
-    }
-    __syncthreads();
-    K2_STAMP(5);
-    if (tile == noTiles - 1 && threadIdx.x == 0) {
-      const int n = (int)(base + total);
-      ctr->noVisibleBlocks = n;
-      ctr->noIntegrated = 0;            // IntegrateIntoScene of this frame counts from zero (no separate memset)
-      const int kept = n < capacity ? n : capacity;
-      // (a snapshot that wraps onto older live ones simply overwrites them: decay.cu recognises an overwritten snapshot by
-      // ringHead - snapStart > ringCap when its turn comes and sweeps nothing — the oldest snapshots are dropped, never an error)
-      snapStart[slot] = ringStart;
-      snapCount[slot] = kept;
-      ctr->ringHead = ringStart + kept;
+      K2_STAMP(3);
+      if (!doList) continue;
+      // ---- list, deferred first half: a tile of the excess part in a frame with excess requests ----
+      if (deferList) {
+        if (threadIdx.x == 0) { while (*(volatile unsigned *)&ctr->tilesServed < (unsigned)noTiles) { } __threadfence(); }
+        __syncthreads();
+        decode_and_count();
+      }
+      // ---- list, second half: global offset, then the listed entries ----
+      if (threadIdx.x < 32) {
+        unsigned ex[1] = {0};
+        if (totalC != 0 || last) { const unsigned agg[1] = {totalC}; lookback_walk<1>(dC, gen, tile, agg, ex); }
+        if (threadIdx.x == 0) { tileBase = ex[0]; bigCount = 0; }
+      }
+      unsigned o = local;
+      while (mask) {
+        const int k = __ffs(mask) - 1;
+        mask &= mask - 1;
+        hits[o++] = (unsigned)(first + k) | (((mk >> k) & 1u) << 31);
+      }
+      __syncthreads();
+      K2_STAMP(4);
+      const unsigned base = tileBase;
+      // listed entry t of the tile is handled by lane (t / 8) % 32 of warp t % 8: the ~25 entries of a KITTI tile become ~3 per warp
+      for (unsigned t0 = 0; t0 < totalC; t0 += blockDim.x) {
+        const unsigned t = t0 + (unsigned)(lane * 8 + warp);
+        BlockRec r; r.ulx = 1; r.uly = 1; r.lrx = 0; r.lry = 0; r.zmin = 0; r.zmax = 0;
+        bool draw = false;
+        if (t < totalC) {
+          const int idx = (int)(hits[t] & 0x7fffffffu);
+          const Entry en = load_entry(table, idx);
+          if (en.ptr == -1 && (hits[t] >> 31)) visType[idx] = 2;   // observed while swapped out (DA/ITMSceneReconstructionEngine.h:261, :281)
+          const long long out = (long long)base + t;
+          if (out < capacity) {
+            b200_vec3i p; p.x = en.x; p.y = en.y; p.z = en.z;
+            visiblePos[out] = p;
+            ring[(ringStart + out) % ringCap] = p;
+            int ptr = en.ptr;
+            if (ptr < 0) { if (find_block<false>(table, numBuckets, en.x, en.y, en.z, &ptr) < 0) ptr = -1; }   // stale entry: what findBlock(pos) would hit
+            visiblePtr[out] = ptr;
+            if (recs) {
+              // fused frame: the block's 1/8-resolution box (ProjectSingleBlock). All blocks are assumed drawn; if the tile total
+              // breaks MAX_RENDERING_BLOCKS (never at KITTI sizes) the last CTA re-applies the ordered rule and rebuilds the image.
+              int ulx, uly, lrx, lry; float zmin, zmax;
+              if (ptr >= 0 && project_single_block(en.x, en.y, en.z, g.M_d, g.proj_d, rw, rh, g.voxelSize, ulx, uly, lrx, lry, zmin, zmax)) {
+                r.ulx = (short)ulx; r.uly = (short)uly; r.lrx = (short)lrx; r.lry = (short)lry; r.zmin = zmin; r.zmax = zmax;
+                myTiles += rendering_tiles(ulx, uly, lrx, lry);
+                draw = true;
+              }
+              recs[out] = r;
+            }
+          }
+        }
+        if (recs) {
+          // rasterise the part of the box inside the live 1/8-resolution corner — the only cells the raycast reads. (The
+          // reference clamps boxes to the FULL-resolution bounds, DA/ITMVisualisationEngine.h:57-60: the cells outside the corner
+          // are brought up to date from the records when the host can next see the image, engine.cu.) One box at a time per
+          // warp; the rare box with hundreds of live cells — a block next to the camera — is left to the whole CTA.
+          unsigned todo = __ballot_sync(0xffffffffu, draw && r.ulx <= liveX && r.uly <= liveY);
+          while (todo) {
+            const int src = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const int ax = __shfl_sync(0xffffffffu, (int)r.ulx, src), ay = __shfl_sync(0xffffffffu, (int)r.uly, src);
+            const int bxx = min(__shfl_sync(0xffffffffu, (int)r.lrx, src), liveX), byy = min(__shfl_sync(0xffffffffu, (int)r.lry, src), liveY);
+            const float zn = __shfl_sync(0xffffffffu, r.zmin, src), zx = __shfl_sync(0xffffffffu, r.zmax, src);
+            if ((bxx - ax + 1) * (byy - ay + 1) > 512) {
+              int slotBig = -1;
+              if (lane == 0) slotBig = atomicAdd(&bigCount, 1);
+              slotBig = __shfl_sync(0xffffffffu, slotBig, 0);
+              if (slotBig < AL_BIG) {
+                if (lane == 0) { BlockRec b; b.ulx = (short)ax; b.uly = (short)ay; b.lrx = (short)bxx; b.lry = (short)byy; b.zmin = zn; b.zmax = zx; bigRecs[slotBig] = b; }
+                continue;
+              }
+            }
+            raster_box_warp(minmax, rw, ax, ay, bxx, byy, zn, zx);
+          }
+        }
+        __syncthreads();
+        if (recs) {     // the big boxes of this round: every thread of the CTA takes cells
+          const int nb = bigCount < AL_BIG ? bigCount : AL_BIG;
+          for (int b = 0; b < nb; ++b) {
+            const BlockRec br = bigRecs[b];
+            const int bw = br.lrx - br.ulx + 1, cnt = bw * (br.lry - br.uly + 1);
+            for (int k = threadIdx.x; k < cnt; k += blockDim.x) {
+              float2 *px = &minmax[(br.ulx + k % bw) + (br.uly + k / bw) * rw];
+              atomic_min_posf(&px->x, br.zmin); atomic_max_posf(&px->y, br.zmax);
+            }
+          }
+          __syncthreads();
+          if (threadIdx.x == 0) bigCount = 0;
+        }
+      }
+      __syncthreads();
+      K2_STAMP(5);
+      if (last && threadIdx.x == 0) {
+        const int n = (int)(base + totalC);
+        ctr->noVisibleBlocks = n;
+        ctr->noIntegrated = 0;            // IntegrateIntoScene of this frame counts from zero (no separate memset)
+        const int kept = n < capacity ? n : capacity;
+        // (a snapshot that wraps onto older live ones simply overwrites them: decay.cu recognises an overwritten snapshot by
+        // ringHead - snapStart > ringCap when its turn comes and sweeps nothing — the oldest snapshots are dropped, never an error)
+        snapStart[slot] = ringStart;
+        snapCount[slot] = kept;
+        ctr->ringHead = ringStart + kept;
+      }
     }
   }
   // ---------------- tail: the CTA that finishes last resets the per-launch counters and owns the cap rule ----------------
@@ -581,7 +644,7 @@ k_serve_list(const float *__restrict__ depth, b200_hash_entry *table, int numBuc
   if (threadIdx.x == 0) lastCta = (atomicAdd(&ctr->visCtasDone, 1u) == gridDim.x - 1);
   __syncthreads();
   if (!lastCta) return;
-  if (threadIdx.x == 0) { ctr->visCtasDone = 0; ctr->tilesServed = 0; }
+  if (threadIdx.x == 0) { ctr->visCtasDone = 0; ctr->tilesServed = 0; ctr->anyExcessRequest = 0; }
   __threadfence();
   if (!recs) return;
   // The last CTA knows the tile total. In the (pathological) case that it breaks MAX_RENDERING_BLOCKS it re-applies the
@@ -620,11 +683,7 @@ k_serve_list(const float *__restrict__ depth, b200_hash_entry *table, int numBuc
       const int ax = __shfl_sync(0xffffffffu, (int)r.ulx, src), ay = __shfl_sync(0xffffffffu, (int)r.uly, src);
       const int bxx = min(__shfl_sync(0xffffffffu, (int)r.lrx, src), liveX), byy = min(__shfl_sync(0xffffffffu, (int)r.lry, src), liveY);
       const float zn = __shfl_sync(0xffffffffu, r.zmin, src), zx = __shfl_sync(0xffffffffu, r.zmax, src);
-      const int bw = bxx - ax + 1, cnt = bw * (byy - ay + 1);
-      for (int k = lane; k < cnt; k += 32) {
-        float2 *px = &minmax[(ax + k % bw) + (ay + k / bw) * rw];
-        atomic_min_posf(&px->x, zn); atomic_max_posf(&px->y, zx);
-      }
+      raster_box_warp(minmax, rw, ax, ay, bxx, byy, zn, zx);
     }
   }
 }
