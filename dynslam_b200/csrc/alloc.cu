@@ -363,6 +363,13 @@ DEV void raster_box_warp(float2 *minmax, int rw, int ax, int ay, int bx, int by,
   }
 }
 
+// the same for a small box, by ONE lane (the lanes of a warp rasterise their own small boxes side by side)
+DEV void raster_box_lane(float2 *minmax, int rw, int ax, int ay, int bx, int by, float zn, float zx) {
+  for (int yy = ay; yy <= by; ++yy)
+    for (int xx = ax; xx <= bx; ++xx) { float2 *px = &minmax[xx + yy * rw]; atomic_min_posf(&px->x, zn); atomic_max_posf(&px->y, zx); }
+}
+#define AL_SMALL_BOX 24          // live cells up to which a lane rasterises its own box
+
 __global__ void __launch_bounds__(256, 2)
 k_serve_list(const float *__restrict__ depth, b200_hash_entry *table, int numBuckets, int noTotal, uint8_t *visType,
              const unsigned long long *__restrict__ reqKey, unsigned *reqBits, unsigned *req2Bits, uint8_t *markBytes,
@@ -377,6 +384,7 @@ k_serve_list(const float *__restrict__ depth, b200_hash_entry *table, int numBuc
   __shared__ int bigCount;
   // measurement hook (b200_diag_read_debug): CTAs 0, 1/3, 2/3 and the last one stamp %globaltimer at their phase boundaries
   const int dbgSlot = !dbg ? -1 : (blockIdx.x == 0 ? 0 : (blockIdx.x == gridDim.x / 3 ? 1 : (blockIdx.x == 2 * gridDim.x / 3 ? 2 : (blockIdx.x == gridDim.x - 1 ? 3 : -1))));
+#define K2_TILE_STAMP(k, tile) do { if (dbg && threadIdx.x == 0 && (tile) < 1024) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); dbg[64 + (k) * 1024 + (tile)] = t_; } } while (0)
 #define K2_STAMP(i) do { if (dbgSlot >= 0 && threadIdx.x == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); dbg[dbgSlot * 8 + (i)] = t_; } } while (0)
   K2_STAMP(0);
   const int noWords = noTotal >> 5;
@@ -406,6 +414,7 @@ k_serve_list(const float *__restrict__ depth, b200_hash_entry *table, int numBuc
       const int w = tile * 256 + threadIdx.x;
       const bool last = (tile == noTiles - 1);
       const bool deferList = anyExcess && ((tile + 1) * AL_TILE > numBuckets);   // wait for the other tiles' service before listing
+      K2_TILE_STAMP(0, tile);
       // ---- requests: rank (published at once), serve later ----
       unsigned rq = 0, rq2 = 0, localPacked = 0, total = 0, total2 = 0;
       if (doReq) {
@@ -419,14 +428,19 @@ k_serve_list(const float *__restrict__ depth, b200_hash_entry *table, int numBuc
         localPacked = block_exclusive_scan(__popc(rq) | (__popc(rq2) << 16), sm, &totalPacked);   // <= 8192 each: no carry
         total = totalPacked & 0xffffu; total2 = totalPacked >> 16;
         if (threadIdx.x < 32) { const unsigned agg[2] = {total, total2}; lookback_publish<2>(dAB, gen, tile, agg); }
+        if (threadIdx.x == 0) {
+          if (total2) atomicAdd(&ctr->tilesWithExcess, 1u);
+          __threadfence();
+          atomicAdd(&ctr->tilesRanked, 1u);         // after the count above: tilesRanked == noTiles makes tilesWithExcess final
+        }
       }
       // ---- list, first half: visibility bytes -> mask of listed entries, count published ----
       unsigned mask = 0, mk = 0, local = 0, totalC = 0;
-      auto decode_and_count = [&]() {
+      auto decode = [&](const bool marksOnly) {
         if (w < noWords) {
           uint4 raw[2], mb[2];
-          raw[0] = *reinterpret_cast<const uint4 *>(visType + first);          // noTotal is a multiple of 32
-          raw[1] = *reinterpret_cast<const uint4 *>(visType + first + 16);
+          raw[0] = __ldcg(reinterpret_cast<const uint4 *>(visType + first));          // noTotal is a multiple of 32
+          raw[1] = __ldcg(reinterpret_cast<const uint4 *>(visType + first + 16));
           mb[0] = __ldcg(reinterpret_cast<const uint4 *>(markBytes + first));  // written by the marking kernel and by other tiles' service: L2
           mb[1] = __ldcg(reinterpret_cast<const uint4 *>(markBytes + first + 16));
 #pragma unroll
@@ -434,7 +448,8 @@ k_serve_list(const float *__restrict__ depth, b200_hash_entry *table, int numBuc
             const unsigned m16 = nz_bytes(mb[q].x) | (nz_bytes(mb[q].y) << 4) | (nz_bytes(mb[q].z) << 8) | (nz_bytes(mb[q].w) << 12);
             if (m16) *reinterpret_cast<uint4 *>(markBytes + first + q * 16) = make_uint4(0u, 0u, 0u, 0u);   // consumed
             mk |= m16 << (q * 16);
-            unsigned todo = m16 | nz_bytes(raw[q].x) | (nz_bytes(raw[q].y) << 4) | (nz_bytes(raw[q].z) << 8) | (nz_bytes(raw[q].w) << 12);
+            unsigned todo = m16;
+            if (!marksOnly) todo |= nz_bytes(raw[q].x) | (nz_bytes(raw[q].y) << 4) | (nz_bytes(raw[q].z) << 8) | (nz_bytes(raw[q].w) << 12);
             if (!todo) continue;
             unsigned wv[4] = {raw[q].x, raw[q].y, raw[q].z, raw[q].w};
             bool dirty = false;
@@ -459,11 +474,16 @@ k_serve_list(const float *__restrict__ depth, b200_hash_entry *table, int numBuc
             if (dirty) *reinterpret_cast<uint4 *>(visType + first + q * 16) = make_uint4(wv[0], wv[1], wv[2], wv[3]);
           }
         }
+      };
+      auto count_and_publish = [&]() {
         local = block_exclusive_scan(__popc(mask), sm, &totalC);
         if (threadIdx.x < 32) { const unsigned agg[1] = {totalC}; lookback_publish<1>(dC, gen, tile, agg); }
+        K2_TILE_STAMP(1, tile);
       };
       K2_STAMP(1);
-      if (doList && !deferList) decode_and_count();
+      // A tile with excess-list requests of its own serves them first: the tiles of the excess part wait for exactly those.
+      const bool listFirst = doList && !(doReq && total2 != 0);
+      if (listFirst) { decode(false); if (!deferList) count_and_publish(); }
       K2_STAMP(2);
       // ---- requests, second half: ranks of this tile's requests (and the grand totals on the last tile), service ----
       if (doReq) {
@@ -519,25 +539,37 @@ k_serve_list(const float *__restrict__ depth, b200_hash_entry *table, int numBuc
             ctr->lastFreeExcessListId = baseExl - (int)grand2;
           }
         }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-          __threadfence();                          // this tile's new entries and child marks are visible device-wide ...
-          atomicAdd(&ctr->tilesServed, 1u);         // ... before it counts as served
+        if (total2 != 0) {
+          __syncthreads();
+          if (threadIdx.x == 0) {
+            __threadfence();                              // this tile's new child entries and their marks are visible device-wide ...
+            atomicAdd(&ctr->tilesExcessServed, 1u);       // ... before it counts as served
+          }
         }
       }
       K2_STAMP(3);
       if (!doList) continue;
+      if (!listFirst) { decode(false); if (!deferList) count_and_publish(); }
       // ---- list, deferred first half: a tile of the excess part in a frame with excess requests ----
       if (deferList) {
-        if (threadIdx.x == 0) { while (*(volatile unsigned *)&ctr->tilesServed < (unsigned)noTiles) { } __threadfence(); }
+        // everything but this frame's new children is decoded already; wait until every tile with excess requests has
+        // served them (their number is final once all tiles have published their counts), then pick up the new marks
+        if (threadIdx.x == 0) {
+          while (*(volatile unsigned *)&ctr->tilesRanked < (unsigned)noTiles) { }
+          const unsigned need = *(volatile unsigned *)&ctr->tilesWithExcess;
+          while (*(volatile unsigned *)&ctr->tilesExcessServed < need) { }
+          __threadfence();
+        }
         __syncthreads();
-        decode_and_count();
+        decode(true);
+        count_and_publish();
       }
       // ---- list, second half: global offset, then the listed entries ----
       if (threadIdx.x < 32) {
         unsigned ex[1] = {0};
         if (totalC != 0 || last) { const unsigned agg[1] = {totalC}; lookback_walk<1>(dC, gen, tile, agg, ex); }
         if (threadIdx.x == 0) { tileBase = ex[0]; bigCount = 0; }
+        K2_TILE_STAMP(2, tile);
       }
       unsigned o = local;
       while (mask) {
@@ -583,12 +615,16 @@ k_serve_list(const float *__restrict__ depth, b200_hash_entry *table, int numBuc
           // reference clamps boxes to the FULL-resolution bounds, DA/ITMVisualisationEngine.h:57-60: the cells outside the corner
           // are brought up to date from the records when the host can next see the image, engine.cu.) One box at a time per
           // warp; the rare box with hundreds of live cells — a block next to the camera — is left to the whole CTA.
-          unsigned todo = __ballot_sync(0xffffffffu, draw && r.ulx <= liveX && r.uly <= liveY);
+          const bool live = draw && r.ulx <= liveX && r.uly <= liveY;
+          const int myBx = min((int)r.lrx, liveX), myBy = min((int)r.lry, liveY);
+          const bool small = live && (myBx - r.ulx + 1) * (myBy - r.uly + 1) <= AL_SMALL_BOX;
+          if (small) raster_box_lane(minmax, rw, r.ulx, r.uly, myBx, myBy, r.zmin, r.zmax);
+          unsigned todo = __ballot_sync(0xffffffffu, live && !small);
           while (todo) {
             const int src = __ffs(todo) - 1;
             todo &= todo - 1;
             const int ax = __shfl_sync(0xffffffffu, (int)r.ulx, src), ay = __shfl_sync(0xffffffffu, (int)r.uly, src);
-            const int bxx = min(__shfl_sync(0xffffffffu, (int)r.lrx, src), liveX), byy = min(__shfl_sync(0xffffffffu, (int)r.lry, src), liveY);
+            const int bxx = __shfl_sync(0xffffffffu, myBx, src), byy = __shfl_sync(0xffffffffu, myBy, src);
             const float zn = __shfl_sync(0xffffffffu, r.zmin, src), zx = __shfl_sync(0xffffffffu, r.zmax, src);
             if ((bxx - ax + 1) * (byy - ay + 1) > 512) {
               int slotBig = -1;
@@ -644,7 +680,7 @@ k_serve_list(const float *__restrict__ depth, b200_hash_entry *table, int numBuc
   if (threadIdx.x == 0) lastCta = (atomicAdd(&ctr->visCtasDone, 1u) == gridDim.x - 1);
   __syncthreads();
   if (!lastCta) return;
-  if (threadIdx.x == 0) { ctr->visCtasDone = 0; ctr->tilesServed = 0; ctr->anyExcessRequest = 0; }
+  if (threadIdx.x == 0) { ctr->visCtasDone = 0; ctr->tilesRanked = 0; ctr->tilesWithExcess = 0; ctr->tilesExcessServed = 0; ctr->anyExcessRequest = 0; }
   __threadfence();
   if (!recs) return;
   // The last CTA knows the tile total. In the (pathological) case that it breaks MAX_RENDERING_BLOCKS it re-applies the

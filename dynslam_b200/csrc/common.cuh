@@ -98,7 +98,8 @@ struct DevCounters {
   int droppedSnapshots;    // decay: snapshots found overwritten in the ring when their turn came (swept as empty)
   unsigned noRenderingBlocks;
   unsigned visCtasDone;    // k_serve_list: CTAs that have finished (the last one applies the rendering-block cap if needed)
-  unsigned tilesServed;    // k_serve_list: tiles whose requests have been served (excess-part tiles list only after all have)
+  unsigned tilesRanked;    // k_serve_list: tiles that have published their request counts
+  unsigned tilesWithExcess, tilesExcessServed;   // ... of which have excess-list requests / have served them (excess-part tiles list only after all have)
   int anyExcessRequest;    // set by the marking kernel when it files an excess-list request; cleared by k_serve_list's last CTA
   int noNeededEntries;     // swapping
   unsigned noTotalPoints;

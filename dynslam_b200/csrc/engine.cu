@@ -146,8 +146,8 @@ static b200_status engine_create_body(const b200_engine_config *cfg, b200_engine
   CK(cudaMalloc(&e->d_reqBits, sizeof(unsigned) * (size_t)e->noWords * 2));
   e->d_req2Bits = e->d_reqBits + e->noWords;
   CK(cudaMemset(e->d_reqBits, 0, sizeof(unsigned) * (size_t)e->noWords * 2));   // kept clean by k_serve_list from here on
-  CK(cudaMalloc(&e->d_dbg, 64 * sizeof(unsigned long long)));
-  CK(cudaMemset(e->d_dbg, 0, 64 * sizeof(unsigned long long)));
+  CK(cudaMalloc(&e->d_dbg, B200_DBG_WORDS * sizeof(unsigned long long)));
+  CK(cudaMemset(e->d_dbg, 0, B200_DBG_WORDS * sizeof(unsigned long long)));
   CK(cudaMalloc(&e->d_markBytes, (size_t)e->noTotal));
   CK(cudaMemset(e->d_markBytes, 0, (size_t)e->noTotal));
   long long px = (long long)e->img_w * e->img_h;
@@ -258,7 +258,7 @@ void b200_diag_set_max_rendering_blocks(b200_engine *e, int n) { e->maxRendering
 
 int b200_diag_read_debug(b200_engine *e, unsigned long long *out, int n) {
   if (!e || !out || n <= 0) return 0;
-  if (n > 64) n = 64;
+  if (n > B200_DBG_WORDS) n = B200_DBG_WORDS;
   cudaSetDevice(e->device);
   cudaDeviceSynchronize();
   return cudaMemcpy(out, e->d_dbg, sizeof(unsigned long long) * (size_t)n, cudaMemcpyDeviceToHost) == cudaSuccess ? n : 0;

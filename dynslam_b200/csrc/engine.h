@@ -27,6 +27,7 @@ struct SceneRef {           // raw device views of the caller-owned scene / rend
 
 struct DecaySnap { long long start; int frameIdx; int hostCountKnown; };
 
+#define B200_DBG_WORDS (64 + 3 * 1024)   // 4 CTAs x 8 phase stamps, then per tile (first 1024): start, list count published, list offset known
 struct b200_engine {
   int device;
   cudaStream_t stream;
@@ -88,7 +89,7 @@ struct b200_engine {
   // expected-depth cells outside the live corner of the latest fused frame: rasterised lazily at b200_sync()
   bool deadPending; SceneRef deadScene; Mat4 deadM; float deadProj[4]; int deadW, deadH; float deadVoxelSize; b200_vec2f *deadMinmax;
   unsigned long long *d_meshDesc;     // meshing: chained-scan descriptors, one per VBA block (allocated on first use)
-  unsigned long long *d_dbg;          // 64 timestamps written by instrumented kernels while the launch trace is on (b200_diag_read_debug)
+  unsigned long long *d_dbg;          // timestamps written by instrumented kernels while the launch trace is on (b200_diag_read_debug)
   long long launches;
   int lastNoIntegrated;
   int integrateImpl;                  // 0 = LDG variant, 1 = TMA bulk-copy variant (env B200_INTEGRATE_IMPL=ldg|tma)

@@ -182,3 +182,150 @@ __host__ __device__ inline bool cast_ray(float4 &out, int x, int y, const b200_v
   return found;
 }
 
+// ------------------------------------------------------------------------------------------------
+// castRay with a neighbourhood cache (k_raycast). Same reads, same arithmetic, same results as cast_ray above; what changes
+// is how the blocks are resolved. Measured on B200 (profiles/r02_raycast.md): cast_ray spends 465 warp-instructions per
+// interpolated sample because a warp almost always holds lanes of all three tap paths (inside one block, across one face,
+// across an edge or corner) and executes all of them, the last one re-hashing for each of its eight taps; and the block that
+// hash_found asks for (the block of round(p)) is not the block the taps start in (the block of floor(p)), which thrashes a
+// one-entry cache near every block face. Here every step works on the 2x2x2 BLOCK neighbourhood of floor(p)'s block:
+//   * entry s (bit 0/1/2 = +1 block in x/y/z) is resolved at most once while floor(p) stays in the block (lazily, `valid` bits);
+//   * the block of round(p) is entry sR of it (round(p) is floor(p) or floor(p)+1 on every axis), so hash_found costs no walk
+//     of its own when the ray samples the block again;
+//   * the eight taps read entry (t & m), m = the axes on which floor(p) sits on the block's last voxel: one straight-line
+//     path for every lane.
+// The entries live in shared memory (one 8-int column per thread: bank = lane, conflict-free for any index); the host build
+// passes a local array.
+// ------------------------------------------------------------------------------------------------
+struct NbrCache { int kx, ky, kz; unsigned valid; };
+
+HD int lowest_bit_(unsigned v) {
+#ifdef __CUDA_ARCH__
+  return __ffs((int)v) - 1;
+#else
+  return __builtin_ffs((int)v) - 1;
+#endif
+}
+
+HD float s16_to_float_(int v) {   // exact: 1.5 * 2^23 + v stays in [2^23, 2^24) for |v| < 2^22 — two full-rate instructions instead of I2F
+#ifdef __CUDA_ARCH__
+  return __int_as_float(0x4B400000 + v) - 12582912.0f;
+#else
+  return (float)v;
+#endif
+}
+
+// chain walk with three loads per entry (position words and ptr; `offset` only when the entry is not the block): ptr*512 or -1
+HD int block_lookup3(const b200_hash_entry *__restrict__ table, int numBuckets, int bx, int by, int bz) {
+  int hashIdx = hash_index(bx, by, bz, numBuckets - 1);
+  // entry positions are shorts: a block outside their range matches nothing (the reference compares short with int)
+  const bool inRange = ((unsigned)(bx + 32768) | (unsigned)(by + 32768) | (unsigned)(bz + 32768)) < 65536u;
+  const int key0 = (bx & 0xffff) | (int)((unsigned)by << 16), key1 = bz & 0xffff;
+  for (;;) {
+    const int *p = reinterpret_cast<const int *>(table) + (size_t)hashIdx * 5;
+    const int w0 = RC_LDG(p), w1 = RC_LDG(p + 1), w3 = RC_LDG(p + 3);
+    if (w0 == key0 && (w1 & 0xffff) == key1 && w3 >= 0 && inRange) return w3 * BS3;
+    const int offset = RC_LDG(p + 2);
+    if (offset < 1) return -1;
+    hashIdx = numBuckets + offset - 1;
+  }
+}
+
+#define NBR(s) nbr[(s) * nbrStride]
+
+HD void nbr_rekey(NbrCache &c, int kx, int ky, int kz) {
+  if (kx != c.kx || ky != c.ky || kz != c.kz) { c.kx = kx; c.ky = ky; c.kz = kz; c.valid = 0u; }
+}
+
+HD void nbr_ensure(unsigned need, NbrCache &c, int *nbr, int nbrStride, const b200_hash_entry *__restrict__ table, int nb) {
+  unsigned todo = need & ~c.valid;
+  while (todo) {
+    const int s = lowest_bit_(todo);
+    todo &= todo - 1;
+    NBR(s) = block_lookup3(table, nb, c.kx + (s & 1), c.ky + ((s >> 1) & 1), c.kz + (s >> 2));
+  }
+  c.valid |= need;
+}
+
+// readFromSDF_float_interpolated (DA/ITMRepresentationAccess.h:252-278) on the neighbourhood cache
+HD float sdf_interp_nbr(const b200_voxel *__restrict__ voxels, const b200_hash_entry *__restrict__ table, int nb, float px, float py, float pz,
+                        NbrCache &c, int *nbr, int nbrStride) {
+  const float fx = floorf(px), fy = floorf(py), fz = floorf(pz);
+  const float cx = px - fx, cy = py - fy, cz = pz - fz;
+  const int x = (int)fx, y = (int)fy, z = (int)fz;
+  nbr_rekey(c, x >> 3, y >> 3, z >> 3);
+  const int lx = x & 7, ly = y & 7, lz = z & 7;
+  const int m = (lx == 7 ? 1 : 0) | (ly == 7 ? 2 : 0) | (lz == 7 ? 4 : 0);   // axes on which the +1 tap is in the next block
+  // the blocks the taps touch: entries s with s a subset of m — bit s of byte m of the constant
+  nbr_ensure((unsigned)((0xFF5533110F050301ull >> (8 * m)) & 0xffu), c, nbr, nbrStride, table, nb);
+  const int ox0 = lx, ox1 = (lx + 1) & 7, oy0 = ly << 3, oy1 = ((ly + 1) & 7) << 3, oz0 = lz << 6, oz1 = ((lz + 1) & 7) << 6;
+  const short *sv = reinterpret_cast<const short *>(voxels);
+#define TAP(t, off) [&]() { const int b_ = NBR((t) & m); return s16_to_float_(b_ >= 0 ? (int)RC_LDG(sv + (size_t)(b_ + (off)) * 4) : 32767); }()
+  const float v000 = TAP(0, ox0 + oy0 + oz0), v100 = TAP(1, ox1 + oy0 + oz0), v010 = TAP(2, ox0 + oy1 + oz0), v110 = TAP(3, ox1 + oy1 + oz0);
+  const float v001 = TAP(4, ox0 + oy0 + oz1), v101 = TAP(5, ox1 + oy0 + oz1), v011 = TAP(6, ox0 + oy1 + oz1), v111 = TAP(7, ox1 + oy1 + oz1);
+#undef TAP
+  float res1, res2;
+  res1 = (1.0f - cx) * v000 + cx * v100;
+  res1 = (1.0f - cy) * res1 + cy * ((1.0f - cx) * v010 + cx * v110);
+  res2 = (1.0f - cx) * v001 + cx * v101;
+  res2 = (1.0f - cy) * res2 + cy * ((1.0f - cx) * v011 + cx * v111);
+  return ((1.0f - cz) * res1 + cz * res2) / 32767.0f;
+}
+
+// castRay — DA/ITMVisualisationEngine.h:93-179 (see cast_ray for the notes on the loop)
+__host__ __device__ inline bool cast_ray_nbr(float4 &out, int x, int y, const b200_voxel *__restrict__ voxels, const b200_hash_entry *__restrict__ table,
+                                             int nb, const Mat4 &invM, float invfx, float invfy, float cxp, float cyp, float oneOverVoxelSize, float mu,
+                                             float2 minmax, int *nbr, int nbrStride) {
+  const float stepScale = mu * oneOverVoxelSize * 1.0f;
+  float cz = minmax.x;
+  float cx = cz * (((float)x - cxp) * invfx), cy = cz * (((float)y - cyp) * invfy);
+  float totalLength = sqrtf(cx * cx + cy * cy + cz * cz) * oneOverVoxelSize;
+  Vec4 r = m4v4(invM, cx, cy, cz, 1.0f);
+  const float sx = r.x * oneOverVoxelSize, sy = r.y * oneOverVoxelSize, sz = r.z * oneOverVoxelSize;
+  cz = minmax.y;
+  cx = cz * (((float)x - cxp) * invfx); cy = cz * (((float)y - cyp) * invfy);
+  const float totalLengthMax = sqrtf(cx * cx + cy * cy + cz * cz) * oneOverVoxelSize;
+  r = m4v4(invM, cx, cy, cz, 1.0f);
+  float dx = r.x * oneOverVoxelSize - sx, dy = r.y * oneOverVoxelSize - sy, dz = r.z * oneOverVoxelSize - sz;
+  const float direction_norm = 1.0f / sqrtf(dx * dx + dy * dy + dz * dz);
+  dx *= direction_norm; dy *= direction_norm; dz *= direction_norm;
+  float px = sx, py = sy, pz = sz;
+  NbrCache c; c.kx = c.ky = c.kz = 0x7fffffff; c.valid = 0u;
+  float sdfValue = 1.0f, stepLength;
+  while (totalLength < totalLengthMax) {
+    // hash_found of readFromSDF_float_uninterpolated(round(p)) (:133): entry sR of floor(p)'s neighbourhood
+    const int kx = ((int)floorf(px)) >> 3, ky = ((int)floorf(py)) >> 3, kz = ((int)floorf(pz)) >> 3;
+    nbr_rekey(c, kx, ky, kz);
+    const int sR = ((((int)round_(px)) >> 3) - kx) | (((((int)round_(py)) >> 3) - ky) << 1) | (((((int)round_(pz)) >> 3) - kz) << 2);
+    nbr_ensure(1u << sR, c, nbr, nbrStride, table, nb);
+    if (NBR(sR) < 0) {
+      sdfValue = 1.0f;   // TVoxel() = 32767 / 32767
+      stepLength = BS;
+#ifdef __CUDA_ARCH__
+      {  // the next position is known now: touch its bucket head so that the next lookup hits L1 (hint only)
+        const float qx = px + (float)BS * dx, qy = py + (float)BS * dy, qz = pz + (float)BS * dz;
+        const int hidx = hash_index(((int)round_(qx)) >> 3, ((int)round_(qy)) >> 3, ((int)round_(qz)) >> 3, nb - 1);
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(reinterpret_cast<const int *>(table) + (size_t)hidx * 5));
+      }
+#endif
+    } else {
+      sdfValue = sdf_interp_nbr(voxels, table, nb, px, py, pz, c, nbr, nbrStride);
+      if (sdfValue <= 0.0f) break;
+      stepLength = maxf_(sdfValue * stepScale, 1.0f);
+    }
+    px += stepLength * dx; py += stepLength * dy; pz += stepLength * dz;
+    totalLength += stepLength;
+  }
+  bool found;
+  if (sdfValue <= 0.0f) {
+    stepLength = sdfValue * stepScale;
+    px += stepLength * dx; py += stepLength * dy; pz += stepLength * dz;
+    sdfValue = sdf_interp_nbr(voxels, table, nb, px, py, pz, c, nbr, nbrStride);
+    stepLength = sdfValue * stepScale;
+    px += stepLength * dx; py += stepLength * dy; pz += stepLength * dz;
+    found = true;
+  } else found = false;
+  out = make_float4(px, py, pz, found ? 1.0f : 0.0f);
+  return found;
+}
+#undef NBR

@@ -195,6 +195,7 @@ void launch_expected_depths_dead(b200_engine *e, const SceneRef &s, const Mat4 &
 // the maximum number of independent rays in flight and shortens the chain per step instead (see cast_ray).
 // 64-thread CTAs: rays finish at very different times, small CTAs hand their SM slots back sooner.
 #define RC_THREADS 64
+template <bool useNbr>
 __global__ void __launch_bounds__(RC_THREADS)
 k_raycast(float4 *out, const b200_voxel *__restrict__ voxels, const b200_hash_entry *__restrict__ table, int nb, int w, int h, Mat4 invM,
           float fx, float fy, float cxp, float cyp, float voxelSize, float mu, const float2 *__restrict__ minmax, int twLog2, int centreRow) {
@@ -217,7 +218,12 @@ k_raycast(float4 *out, const b200_voxel *__restrict__ voxels, const b200_hash_en
   if (x >= w || y >= h) return;
   const int locId2 = (int)floorf((float)x / B200_MINMAX_SUBSAMPLE) + (int)floorf((float)y / B200_MINMAX_SUBSAMPLE) * w;
   float4 o;
-  cast_ray(o, x, y, voxels, table, nb, invM, 1.0f / fx, 1.0f / fy, cxp, cyp, 1.0f / voxelSize, mu, __ldg(minmax + locId2));
+  if (useNbr) {
+    __shared__ int nbr[8][RC_THREADS];     // per thread: the 2x2x2 block neighbourhood of the ray's current block (raycast_ray.cuh)
+    cast_ray_nbr(o, x, y, voxels, table, nb, invM, 1.0f / fx, 1.0f / fy, cxp, cyp, 1.0f / voxelSize, mu, __ldg(minmax + locId2), &nbr[0][threadIdx.x], RC_THREADS);
+  } else {
+    cast_ray(o, x, y, voxels, table, nb, invM, 1.0f / fx, 1.0f / fy, cxp, cyp, 1.0f / voxelSize, mu, __ldg(minmax + locId2));
+  }
   out[x + y * w] = o;
 }
 
@@ -237,10 +243,17 @@ void launch_raycast(b200_engine *e, const SceneRef &s, const Mat4 &invM, const f
     if (centreRow < 0) centreRow = 0;
     if (centreRow > tilesY - 1) centreRow = tilesY - 1;
   }
+  static int impl = -1;
+  if (impl < 0) { const char *v = getenv("B200_RC_IMPL"); impl = (v && v[0] == 'o') ? 0 : 1; }   // "old": per-lane one-entry cache (cross-check); default: neighbourhood cache
   trace_begin(e, e->stream, "k_raycast");
-  k_raycast<<<(tiles + warpsPerCta - 1) / warpsPerCta, RC_THREADS, 0, e->stream>>>((float4 *)out, s.voxels, s.hash, s.numBuckets, w, h, invM,
-                                                                                  proj[0], proj[1], proj[2], proj[3], voxelSize, mu,
-                                                                                  (const float2 *)minmax, twLog2, centreRow);
+  if (impl)
+    k_raycast<true><<<(tiles + warpsPerCta - 1) / warpsPerCta, RC_THREADS, 0, e->stream>>>((float4 *)out, s.voxels, s.hash, s.numBuckets, w, h, invM,
+                                                                                          proj[0], proj[1], proj[2], proj[3], voxelSize, mu,
+                                                                                          (const float2 *)minmax, twLog2, centreRow);
+  else
+    k_raycast<false><<<(tiles + warpsPerCta - 1) / warpsPerCta, RC_THREADS, 0, e->stream>>>((float4 *)out, s.voxels, s.hash, s.numBuckets, w, h, invM,
+                                                                                           proj[0], proj[1], proj[2], proj[3], voxelSize, mu,
+                                                                                           (const float2 *)minmax, twLog2, centreRow);
   trace_end(e, e->stream);
   e->launches++;
 }

@@ -31,15 +31,19 @@ for i, v in enumerate(views[N0:]):
     eng.sync(rs)
     tr = eng.trace()
     import ctypes as C
-    dbg = (C.c_uint64 * 32)()
-    eng.lib.b200_diag_read_debug(eng.h, dbg, 32)
+    dbg = (C.c_uint64 * (64 + 3072))()
+    eng.lib.b200_diag_read_debug(eng.h, dbg, 64 + 3072)
     eng.set_timing(0)
     if i >= 2:
         print("--- frame", i)
         t0 = min(dbg[s * 8] for s in range(4) if dbg[s * 8])
         for s in range(4):
             print("  k_serve_list CTA slot", s, "phase stamps (us):", ["%.1f" % ((dbg[s * 8 + k] - t0) / 1000.0) if dbg[s * 8 + k] else "-" for k in range(7)])
-        prev_end = 0.0
+        for k, what in enumerate(["tile start", "list count published", "list offset known"]):
+            v = np.array([dbg[64 + k * 1024 + t] for t in range(1024)], dtype=np.float64)
+            v = (v[v > 0] - t0) / 1000.0
+            if len(v):
+                print("  per tile, %-22s n %4d  min %5.1f  p50 %5.1f  p90 %5.1f  max %5.1f (tile %d)" % (what, len(v), v.min(), np.percentile(v, 50), np.percentile(v, 90), v.max(), int(v.argmax())))
         for name, a, b in tr:
             print("%-22s start %7.1f  end %7.1f  dur %6.1f" % (name, a, b, b - a))
 

@@ -20,7 +20,7 @@ def lib():
     subprocess.run(["make", "-C", HERE, "all"], check=True, stdout=subprocess.DEVNULL)
     L = C.CDLL(os.path.join(HERE, "libhostcheck.so"))
     vp = C.c_void_p
-    L.hostcheck_raycast.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_float, C.c_float, vp, vp]
+    L.hostcheck_raycast.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_float, C.c_float, vp, vp, C.c_int]
     L.hostcheck_raycast.restype = None
     return L
 
@@ -47,8 +47,9 @@ def test_cast_ray_equals_oracle(lib, voxel, mu, nbuckets, frames):
         L.oracle_find_visible_blocks(C.byref(vol.scene), C.byref(vol.rs), C.byref(cam))
         L.oracle_expected_depths(C.byref(vol.scene), C.byref(vol.rs), C.byref(cam))
         L.oracle_icp_maps(C.byref(vol.scene), C.byref(vol.rs), C.byref(hv), H.vptr(vol.points), H.vptr(vol.normals), 0)
-        out = np.zeros((h, w, 4), np.float32)
-        lib.hostcheck_raycast(H.vptr(vol.voxels), H.vptr(vol.hash), nbuckets, w, h, hv.invM_d, hv.proj_d, voxel, mu, H.vptr(vol.minmax), H.vptr(out))
-        hit = int((out[..., 3] > 0).sum())
-        assert hit > w * h // 4
-        assert out.tobytes() == vol.raycastResult.tobytes()
+        for variant in (0, 1):      # 0: cast_ray (one-entry cache), 1: cast_ray_nbr (neighbourhood cache, k_raycast's default)
+            out = np.zeros((h, w, 4), np.float32)
+            lib.hostcheck_raycast(H.vptr(vol.voxels), H.vptr(vol.hash), nbuckets, w, h, hv.invM_d, hv.proj_d, voxel, mu, H.vptr(vol.minmax), H.vptr(out), variant)
+            hit = int((out[..., 3] > 0).sum())
+            assert hit > w * h // 4
+            assert out.tobytes() == vol.raycastResult.tobytes(), variant
