@@ -19,7 +19,7 @@ SDF_BLOCK_SIZE3 = 512
 MAX_RENDERING_BLOCKS = 65536 * 4
 TRANSFER_BLOCK_NUM = 0x1000
 
-OK, ERR_CUDA, ERR_VBA_FULL, ERR_EXCESS_FULL, ERR_INVALID, ERR_DECAY_RING_FULL, ERR_UNSUPPORTED = range(7)
+OK, ERR_CUDA, ERR_VBA_FULL, ERR_EXCESS_FULL, ERR_INVALID, ERR_DECAY_RING_FULL, ERR_UNSUPPORTED, ERR_NEGATIVE_DISPARITY = range(8)
 
 RENDER_SHADED_GREYSCALE, RENDER_COLOUR_FROM_VOLUME, RENDER_COLOUR_FROM_NORMAL, \
     RENDER_COLOUR_FROM_DEPTH_WEIGHT, RENDER_DEPTH_MAP = range(5)
@@ -35,6 +35,37 @@ assert HASH_ENTRY_DTYPE.itemsize == 20 and VOXEL_DTYPE.itemsize == 8
 
 f16 = C.c_float * 16
 f4 = C.c_float * 4
+
+
+class EvalParams(C.Structure):          # b200_eval_params
+    _fields_ = [("velo_to_cam", C.c_double * 16), ("proj_left", C.c_double * 12), ("proj_right", C.c_double * 12),
+                ("baseline_m", C.c_float), ("left_focal_length_px", C.c_float), ("min_depth_m", C.c_float), ("max_depth_m", C.c_float),
+                ("frame_width", C.c_int32), ("frame_height", C.c_int32)]
+
+
+class EvalCallback(C.Structure):        # b200_eval_callback
+    _fields_ = [("delta_max", C.c_float), ("compare_on_intersection", C.c_int32), ("kitti_style", C.c_int32)]
+
+
+class EvalStats(C.Structure):
+    _fields_ = [("missing", C.c_int64), ("error", C.c_int64), ("correct", C.c_int64), ("missing_separate", C.c_int64)]
+
+
+class EvalResult(C.Structure):
+    _fields_ = [("measurement_count", C.c_int64), ("rendered", EvalStats), ("input", EvalStats)]
+
+    def as_dict(self):
+        f = lambda s: dict(missing=s.missing, error=s.error, correct=s.correct, missing_separate=s.missing_separate)
+        return dict(measurement_count=self.measurement_count, rendered=f(self.rendered), input=f(self.input))
+
+
+class EvalSummary(C.Structure):
+    _fields_ = [("valid_lidar_points", C.c_int64), ("epi_errors", C.c_int64), ("negative_disparities", C.c_int64),
+                ("skipped_lidar_points", C.c_int64)]
+
+
+EVAL_STATIC, EVAL_DYNAMIC, EVAL_NEITHER = 0, 1, 2
+EVAL_MAX_CALLBACKS = 16
 
 
 class Scene(C.Structure):
@@ -122,7 +153,7 @@ EXPORTS = [
     "b200_convert_disparity_to_depth", "b200_convert_depth_affine_to_float", "b200_depth_filtering",
     "b200_compute_normal_and_weights", "b200_update_view", "b200_update_view_async", "b200_host_frame_submit_raw",
     "b200_process_silhouettes", "b200_process_silhouettes_async", "b200_composite_depth", "b200_composite_color",
-    "b200_composite_instances",
+    "b200_composite_instances", "b200_evaluate_depth",
     "b200_mesh_scene", "b200_comm_unique_id", "b200_comm_create", "b200_comm_destroy", "b200_comm_last_error", "b200_gather_composite_submit",
     "b200_gather_composite_release", "b200_gather_composite_wait",
 ]
@@ -190,6 +221,7 @@ def load_library():
     lib.b200_composite_color.argtypes = [vp, vp, vp, vp, vp, C.c_int, P(C.c_int32), C.c_float]
     lib.b200_composite_instances.argtypes = [vp, vp, vp, C.c_int, P(InstanceLayer), C.c_int, C.c_float, C.c_float]
     lib.b200_mesh_scene.argtypes = [vp, P(Scene), vp, C.c_uint32, P(C.c_uint32)]
+    lib.b200_evaluate_depth.argtypes = [vp, P(EvalParams), vp, C.c_int, vp, vp, vp, P(EvalCallback), C.c_int, P(EvalResult), P(EvalResult), P(EvalSummary)]
     lib.b200_comm_unique_id.argtypes = [C.c_char_p]
     lib.b200_comm_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_int, C.c_int, P(vp)]
     lib.b200_comm_destroy.argtypes = [vp]

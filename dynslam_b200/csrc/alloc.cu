@@ -363,12 +363,7 @@ DEV void raster_box_warp(float2 *minmax, int rw, int ax, int ay, int bx, int by,
   }
 }
 
-// the same for a small box, by ONE lane (the lanes of a warp rasterise their own small boxes side by side)
-DEV void raster_box_lane(float2 *minmax, int rw, int ax, int ay, int bx, int by, float zn, float zx) {
-  for (int yy = ay; yy <= by; ++yy)
-    for (int xx = ax; xx <= bx; ++xx) { float2 *px = &minmax[xx + yy * rw]; atomic_min_posf(&px->x, zn); atomic_max_posf(&px->y, zx); }
-}
-#define AL_SMALL_BOX 24          // live cells up to which a lane rasterises its own box
+#define AL_GROUP_BOX 64          // live cells up to which the entry's 8-lane group rasterises the box
 
 __global__ void __launch_bounds__(256, 2)
 k_serve_list(const float *__restrict__ depth, b200_hash_entry *table, int numBuckets, int noTotal, uint8_t *visType,
@@ -385,6 +380,7 @@ k_serve_list(const float *__restrict__ depth, b200_hash_entry *table, int numBuc
   // measurement hook (b200_diag_read_debug): CTAs 0, 1/3, 2/3 and the last one stamp %globaltimer at their phase boundaries
   const int dbgSlot = !dbg ? -1 : (blockIdx.x == 0 ? 0 : (blockIdx.x == gridDim.x / 3 ? 1 : (blockIdx.x == 2 * gridDim.x / 3 ? 2 : (blockIdx.x == gridDim.x - 1 ? 3 : -1))));
 #define K2_TILE_STAMP(k, tile) do { if (dbg && threadIdx.x == 0 && (tile) < 1024) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); dbg[64 + (k) * 1024 + (tile)] = t_; } } while (0)
+#define K2_SUB(j, cond) do { if (dbgSlot >= 0 && threadIdx.x == 0 && (cond)) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); dbg[32 + dbgSlot * 8 + (j)] = t_; } } while (0)
 #define K2_STAMP(i) do { if (dbgSlot >= 0 && threadIdx.x == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); dbg[dbgSlot * 8 + (i)] = t_; } } while (0)
   K2_STAMP(0);
   const int noWords = noTotal >> 5;
@@ -407,23 +403,38 @@ k_serve_list(const float *__restrict__ depth, b200_hash_entry *table, int numBuc
   unsigned long long *const dC[1] = {descC};
   unsigned myTiles = 0;   // rendering tiles of the blocks this thread projected (fused frame only)
 
+  const long long ringBase = ringStart % ringCap;   // one 64-bit division per thread instead of one per listed entry
+  const int grp = warp * 4 + (lane >> 3), sub = lane & 7;   // hit phase: an 8-lane group per listed entry, one lane per block corner
   for (int pass = 0; pass < (twoPass ? 2 : 1); ++pass) {
     const bool doReq = !twoPass || pass == 0, doList = !twoPass || pass == 1;
     for (int tile = blockIdx.x; tile < noTiles; tile += gridDim.x) {
       const int first = tile * AL_TILE + threadIdx.x * AL_EPT;
       const int w = tile * 256 + threadIdx.x;
       const bool last = (tile == noTiles - 1);
-      const bool deferList = anyExcess && ((tile + 1) * AL_TILE > numBuckets);   // wait for the other tiles' service before listing
+      const bool deferList = anyExcess && ((tile + 1) * AL_TILE > numBuckets);   // its new children arrive from other tiles' service
       K2_TILE_STAMP(0, tile);
-      // ---- requests: rank (published at once), serve later ----
+      // ---- every load of the tile is issued up front: request words, the first request's key, visibility and mark bytes ----
       unsigned rq = 0, rq2 = 0, localPacked = 0, total = 0, total2 = 0;
+      unsigned long long key0 = 0ull;
+      uint4 raw[2], mb[2];
+      raw[0] = raw[1] = mb[0] = mb[1] = make_uint4(0u, 0u, 0u, 0u);
+      if (w < noWords) {
+        if (doReq) { rq = reqBits[w]; rq2 = req2Bits[w]; }
+        if (doList) {
+          raw[0] = __ldcg(reinterpret_cast<const uint4 *>(visType + first));          // noTotal is a multiple of 32
+          raw[1] = __ldcg(reinterpret_cast<const uint4 *>(visType + first + 16));
+          mb[0] = __ldcg(reinterpret_cast<const uint4 *>(markBytes + first));         // written by the marking kernel and by other tiles' service: L2
+          mb[1] = __ldcg(reinterpret_cast<const uint4 *>(markBytes + first + 16));
+        }
+      }
+      // ---- requests: rank (published at once), serve later ----
       if (doReq) {
         if (w < noWords) {
-          rq = reqBits[w]; rq2 = req2Bits[w];
           if (rq) reqBits[w] = 0u;                 // consumed: clean for the next frame
           if (rq2) req2Bits[w] = 0u;
         }
         if (onlyVisible) { rq = 0u; rq2 = 0u; }     // onlyUpdateVisibleList: the marking ran, nothing is allocated (Reco_CUDA.cu:254-262)
+        if (rq) key0 = reqKey[w * 32 + __ffs(rq) - 1];
         unsigned totalPacked;
         localPacked = block_exclusive_scan(__popc(rq) | (__popc(rq2) << 16), sm, &totalPacked);   // <= 8192 each: no carry
         total = totalPacked & 0xffffu; total2 = totalPacked >> 16;
@@ -436,17 +447,12 @@ k_serve_list(const float *__restrict__ depth, b200_hash_entry *table, int numBuc
       }
       // ---- list, first half: visibility bytes -> mask of listed entries, count published ----
       unsigned mask = 0, mk = 0, local = 0, totalC = 0;
-      auto decode = [&](const bool marksOnly) {
+      auto decode = [&](const bool marksOnly, const bool clearMarks) {
         if (w < noWords) {
-          uint4 raw[2], mb[2];
-          raw[0] = __ldcg(reinterpret_cast<const uint4 *>(visType + first));          // noTotal is a multiple of 32
-          raw[1] = __ldcg(reinterpret_cast<const uint4 *>(visType + first + 16));
-          mb[0] = __ldcg(reinterpret_cast<const uint4 *>(markBytes + first));  // written by the marking kernel and by other tiles' service: L2
-          mb[1] = __ldcg(reinterpret_cast<const uint4 *>(markBytes + first + 16));
 #pragma unroll
           for (int q = 0; q < 2; ++q) {
             const unsigned m16 = nz_bytes(mb[q].x) | (nz_bytes(mb[q].y) << 4) | (nz_bytes(mb[q].z) << 8) | (nz_bytes(mb[q].w) << 12);
-            if (m16) *reinterpret_cast<uint4 *>(markBytes + first + q * 16) = make_uint4(0u, 0u, 0u, 0u);   // consumed
+            if (m16 && clearMarks) *reinterpret_cast<uint4 *>(markBytes + first + q * 16) = make_uint4(0u, 0u, 0u, 0u);   // consumed
             mk |= m16 << (q * 16);
             unsigned todo = m16;
             if (!marksOnly) todo |= nz_bytes(raw[q].x) | (nz_bytes(raw[q].y) << 4) | (nz_bytes(raw[q].z) << 8) | (nz_bytes(raw[q].w) << 12);
@@ -471,7 +477,10 @@ k_serve_list(const float *__restrict__ depth, b200_hash_entry *table, int numBuc
               }
               if (v > 0) mask |= 1u << (q * 16 + k);
             }
-            if (dirty) *reinterpret_cast<uint4 *>(visType + first + q * 16) = make_uint4(wv[0], wv[1], wv[2], wv[3]);
+            if (dirty) {
+              raw[q] = make_uint4(wv[0], wv[1], wv[2], wv[3]);
+              *reinterpret_cast<uint4 *>(visType + first + q * 16) = raw[q];
+            }
           }
         }
       };
@@ -479,11 +488,14 @@ k_serve_list(const float *__restrict__ depth, b200_hash_entry *table, int numBuc
         local = block_exclusive_scan(__popc(mask), sm, &totalC);
         if (threadIdx.x < 32) { const unsigned agg[1] = {totalC}; lookback_publish<1>(dC, gen, tile, agg); }
         K2_TILE_STAMP(1, tile);
+        if (dbg && threadIdx.x == 0 && tile < 1024) dbg[64 + 3 * 1024 + tile] = totalC;
       };
       K2_STAMP(1);
-      // A tile with excess-list requests of its own serves them first: the tiles of the excess part wait for exactly those.
-      const bool listFirst = doList && !(doReq && total2 != 0);
-      if (listFirst) { decode(false); if (!deferList) count_and_publish(); }
+      // The list count of a tile never depends on the tile's OWN service (the marking kernel already marked the ordered entries
+      // it requested; children land in the excess part), so it is published before anybody serves anything: no tile of the
+      // ordered part ever waits for a serving tile. (A tile that still waits for other tiles' child marks leaves the mark bytes
+      // alone in this early pass: clearing a 16-byte group here could wipe a mark another tile is writing into it right now.)
+      if (doList) { decode(false, !deferList); if (!deferList) count_and_publish(); }
       K2_STAMP(2);
       // ---- requests, second half: ranks of this tile's requests (and the grand totals on the last tile), service ----
       if (doReq) {
@@ -498,6 +510,7 @@ k_serve_list(const float *__restrict__ depth, b200_hash_entry *table, int numBuc
         if (needRank) {
           unsigned rank = tileBase + (localPacked & 0xffffu), rank2 = tileBase2 + (localPacked >> 16);
           const unsigned grand = tileBase + total, grand2 = tileBase2 + total2;
+          bool firstReq = true;
           while (rq) {
             const int b = __ffs(rq) - 1;
             rq &= rq - 1;
@@ -507,8 +520,9 @@ k_serve_list(const float *__restrict__ depth, b200_hash_entry *table, int numBuc
             const int exlIdx = baseExl - (int)rank2;
             rank++;
             if (isExcess) rank2++;
+            const unsigned long long key = firstReq ? key0 : reqKey[targetIdx];
+            firstReq = false;
             if (vbaIdx < 0 || (isExcess && exlIdx < 0)) continue;   // exhausted: the counters still go negative
-            const unsigned long long key = reqKey[targetIdx];
             const unsigned step = (unsigned)(key & ((1u << KEY_STEP_BITS) - 1));
             const unsigned pixel = (unsigned)((key >> KEY_STEP_BITS) & ((1u << KEY_PIXEL_BITS) - 1));
             const int x = pixel % g.w, y = pixel / g.w;
@@ -539,18 +553,16 @@ k_serve_list(const float *__restrict__ depth, b200_hash_entry *table, int numBuc
             ctr->lastFreeExcessListId = baseExl - (int)grand2;
           }
         }
-        if (total2 != 0) {
-          __syncthreads();
-          if (threadIdx.x == 0) {
-            __threadfence();                              // this tile's new child entries and their marks are visible device-wide ...
-            atomicAdd(&ctr->tilesExcessServed, 1u);       // ... before it counts as served
-          }
+        __syncthreads();             // the hit phase below reads entries this tile's service wrote
+        if (total2 != 0 && threadIdx.x == 0) {
+          __threadfence();                              // this tile's new child entries and their marks are visible device-wide ...
+          atomicAdd(&ctr->tilesExcessServed, 1u);       // ... before it counts as served
         }
       }
       K2_STAMP(3);
+      K2_TILE_STAMP(4, tile);
       if (!doList) continue;
-      if (!listFirst) { decode(false); if (!deferList) count_and_publish(); }
-      // ---- list, deferred first half: a tile of the excess part in a frame with excess requests ----
+      // ---- list, late part of the first half: a tile of the excess part in a frame with excess requests ----
       if (deferList) {
         // everything but this frame's new children is decoded already; wait until every tile with excess requests has
         // served them (their number is final once all tiles have published their counts), then pick up the new marks
@@ -561,7 +573,11 @@ k_serve_list(const float *__restrict__ depth, b200_hash_entry *table, int numBuc
           __threadfence();
         }
         __syncthreads();
-        decode(true);
+        if (w < noWords) {
+          mb[0] = __ldcg(reinterpret_cast<const uint4 *>(markBytes + first));
+          mb[1] = __ldcg(reinterpret_cast<const uint4 *>(markBytes + first + 16));
+        }
+        decode(true, true);
         count_and_publish();
       }
       // ---- list, second half: global offset, then the listed entries ----
@@ -580,77 +596,132 @@ k_serve_list(const float *__restrict__ depth, b200_hash_entry *table, int numBuc
       __syncthreads();
       K2_STAMP(4);
       const unsigned base = tileBase;
-      // listed entry t of the tile is handled by lane (t / 8) % 32 of warp t % 8: the ~25 entries of a KITTI tile become ~3 per warp
-      for (unsigned t0 = 0; t0 < totalC; t0 += blockDim.x) {
-        const unsigned t = t0 + (unsigned)(lane * 8 + warp);
-        BlockRec r; r.ulx = 1; r.uly = 1; r.lrx = 0; r.lry = 0; r.zmin = 0; r.zmax = 0;
-        bool draw = false;
+      // Listed entry t of the tile is handled by the 8-lane group t % 32 of the CTA: lane 0 of the group writes the list items,
+      // each lane projects one corner of the block (ProjectSingleBlock's loop body; the min/max over the corners by shuffles —
+      // min and max do not depend on the order), the group rasterises the box. The ~25 entries of a KITTI tile take one
+      // round; what used to be a serial 8-corner loop and a serial cell loop per entry is spread over the idle lanes.
+      for (unsigned t0 = 0; t0 < totalC; t0 += 32) {
+        const unsigned t = t0 + (unsigned)grp;
+        K2_SUB(0, t0 == 0);
+        bool have = false;       // group-uniform: the entry is listed within capacity and its box is wanted
+        int ex = 0, ey = 0, ez = 0;
+        long long out = 0;
         if (t < totalC) {
           const int idx = (int)(hits[t] & 0x7fffffffu);
-          const Entry en = load_entry(table, idx);
-          if (en.ptr == -1 && (hits[t] >> 31)) visType[idx] = 2;   // observed while swapped out (DA/ITMSceneReconstructionEngine.h:261, :281)
-          const long long out = (long long)base + t;
+          const Entry en = load_entry(table, idx);          // the 8 lanes read the same words: one transaction
+          out = (long long)base + t;
           if (out < capacity) {
-            b200_vec3i p; p.x = en.x; p.y = en.y; p.z = en.z;
-            visiblePos[out] = p;
-            ring[(ringStart + out) % ringCap] = p;
             int ptr = en.ptr;
             if (ptr < 0) { if (find_block<false>(table, numBuckets, en.x, en.y, en.z, &ptr) < 0) ptr = -1; }   // stale entry: what findBlock(pos) would hit
-            visiblePtr[out] = ptr;
-            if (recs) {
-              // fused frame: the block's 1/8-resolution box (ProjectSingleBlock). All blocks are assumed drawn; if the tile total
-              // breaks MAX_RENDERING_BLOCKS (never at KITTI sizes) the last CTA re-applies the ordered rule and rebuilds the image.
-              int ulx, uly, lrx, lry; float zmin, zmax;
-              if (ptr >= 0 && project_single_block(en.x, en.y, en.z, g.M_d, g.proj_d, rw, rh, g.voxelSize, ulx, uly, lrx, lry, zmin, zmax)) {
-                r.ulx = (short)ulx; r.uly = (short)uly; r.lrx = (short)lrx; r.lry = (short)lry; r.zmin = zmin; r.zmax = zmax;
-                myTiles += rendering_tiles(ulx, uly, lrx, lry);
-                draw = true;
-              }
-              recs[out] = r;
+            if (sub == 0) {
+              if (en.ptr == -1 && (hits[t] >> 31)) visType[idx] = 2;   // observed while swapped out (DA/ITMSceneReconstructionEngine.h:261, :281)
+              b200_vec3i p; p.x = en.x; p.y = en.y; p.z = en.z;
+              visiblePos[out] = p;
+              long long rp = ringBase + out;                // out < capacity <= ringCap
+              if (rp >= ringCap) rp -= ringCap;
+              ring[rp] = p;
+              visiblePtr[out] = ptr;
             }
+            have = recs != nullptr;
+            ex = en.x; ey = en.y; ez = en.z;
+            if (recs && ptr < 0 && sub == 0) { BlockRec e0; e0.ulx = 1; e0.uly = 1; e0.lrx = 0; e0.lry = 0; e0.zmin = 0; e0.zmax = 0; recs[out] = e0; }
+            if (ptr < 0) have = false;
           }
         }
+        K2_SUB(1, t0 == 0);
         if (recs) {
+          // fused frame: the block's 1/8-resolution box (ProjectSingleBlock, DA/ITMVisualisationEngine.h:29-71). All blocks are
+          // assumed drawn; if the tile total breaks MAX_RENDERING_BLOCKS (never at KITTI sizes) the last CTA re-applies the
+          // ordered rule and rebuilds the image.
+          float fxl = 3.0e38f, fxh = -3.0e38f, fyl = 3.0e38f, fyh = -3.0e38f, zl = B200_FAR_AWAY, zh = B200_VERY_CLOSE;
+          if (have) {
+            const short tx = (short)(ex + (sub & 1)), ty = (short)(ey + ((sub >> 1) & 1)), tz = (short)(ez + (sub >> 2));
+            const Vec4 q = m4v4(g.M_d, (float)tx * (float)BS * g.voxelSize, (float)ty * (float)BS * g.voxelSize, (float)tz * (float)BS * g.voxelSize, 1.0f);
+            if (!(q.z < 1e-6)) {
+              const float px = (g.proj_d[0] * q.x / q.z + g.proj_d[2]) / B200_MINMAX_SUBSAMPLE;
+              const float py = (g.proj_d[1] * q.y / q.z + g.proj_d[3]) / B200_MINMAX_SUBSAMPLE;
+              fxl = floorf(px); fxh = ceilf(px); fyl = floorf(py); fyh = ceilf(py);
+              zl = fminf(zl, q.z); zh = fmaxf(zh, q.z);
+            }
+          }
+#pragma unroll
+          for (int d = 1; d < 8; d <<= 1) {
+            fxl = fminf(fxl, __shfl_xor_sync(0xffffffffu, fxl, d)); fxh = fmaxf(fxh, __shfl_xor_sync(0xffffffffu, fxh, d));
+            fyl = fminf(fyl, __shfl_xor_sync(0xffffffffu, fyl, d)); fyh = fmaxf(fyh, __shfl_xor_sync(0xffffffffu, fyh, d));
+            zl = fminf(zl, __shfl_xor_sync(0xffffffffu, zl, d)); zh = fmaxf(zh, __shfl_xor_sync(0xffffffffu, zh, d));
+          }
+          // the function's bookkeeping on the reduced values (ulx starts at w/8, lrx at -1; then the clamps and the early outs)
+          int ulx = rw / B200_MINMAX_SUBSAMPLE, uly = rh / B200_MINMAX_SUBSAMPLE, lrx = -1, lry = -1;
+          if ((float)ulx > fxl) ulx = (int)fxl;
+          if ((float)lrx < fxh) lrx = (int)fxh;
+          if ((float)uly > fyl) uly = (int)fyl;
+          if ((float)lry < fyh) lry = (int)fyh;
+          if (ulx < 0) ulx = 0;
+          if (uly < 0) uly = 0;
+          if (lrx >= rw) lrx = rw - 1;
+          if (lry >= rh) lry = rh - 1;
+          bool draw = have && !(ulx > lrx) && !(uly > lry);
+          if (zl < B200_VERY_CLOSE) zl = B200_VERY_CLOSE;
+          if (zh < B200_VERY_CLOSE) draw = false;
+          K2_SUB(2, t0 == 0);
+          if (have && sub == 0) {
+            BlockRec r; r.ulx = 1; r.uly = 1; r.lrx = 0; r.lry = 0; r.zmin = 0; r.zmax = 0;
+            if (draw) {
+              r.ulx = (short)ulx; r.uly = (short)uly; r.lrx = (short)lrx; r.lry = (short)lry; r.zmin = zl; r.zmax = zh;
+              myTiles += rendering_tiles(ulx, uly, lrx, lry);
+            }
+            recs[out] = r;
+          }
           // rasterise the part of the box inside the live 1/8-resolution corner — the only cells the raycast reads. (The
           // reference clamps boxes to the FULL-resolution bounds, DA/ITMVisualisationEngine.h:57-60: the cells outside the corner
-          // are brought up to date from the records when the host can next see the image, engine.cu.) One box at a time per
-          // warp; the rare box with hundreds of live cells — a block next to the camera — is left to the whole CTA.
-          const bool live = draw && r.ulx <= liveX && r.uly <= liveY;
-          const int myBx = min((int)r.lrx, liveX), myBy = min((int)r.lry, liveY);
-          const bool small = live && (myBx - r.ulx + 1) * (myBy - r.uly + 1) <= AL_SMALL_BOX;
-          if (small) raster_box_lane(minmax, rw, r.ulx, r.uly, myBx, myBy, r.zmin, r.zmax);
-          unsigned todo = __ballot_sync(0xffffffffu, live && !small);
+          // are brought up to date from the records when the host can next see the image, engine.cu.) Up to 64 cells: the
+          // group's 8 lanes; more: the whole warp, one box at a time; hundreds (a block next to the camera): the whole CTA.
+          const bool live = draw && ulx <= liveX && uly <= liveY;
+          const int bxx = min(lrx, liveX), byy = min(lry, liveY);
+          const int bw = bxx - ulx + 1, cells = live ? bw * (byy - uly + 1) : 0;
+          if (cells > 0 && cells <= AL_GROUP_BOX) {
+            int xx = ulx + sub, yy = uly;
+            while (xx > bxx) { xx -= bw; ++yy; }
+            while (yy <= byy) {
+              float2 *pxl = &minmax[xx + yy * rw];
+              atomic_min_posf(&pxl->x, zl); atomic_max_posf(&pxl->y, zh);
+              xx += 8;
+              while (xx > bxx) { xx -= bw; ++yy; }
+            }
+          }
+          K2_SUB(3, t0 == 0);
+          unsigned todo = __ballot_sync(0xffffffffu, sub == 0 && cells > AL_GROUP_BOX);
           while (todo) {
             const int src = __ffs(todo) - 1;
             todo &= todo - 1;
-            const int ax = __shfl_sync(0xffffffffu, (int)r.ulx, src), ay = __shfl_sync(0xffffffffu, (int)r.uly, src);
-            const int bxx = __shfl_sync(0xffffffffu, myBx, src), byy = __shfl_sync(0xffffffffu, myBy, src);
-            const float zn = __shfl_sync(0xffffffffu, r.zmin, src), zx = __shfl_sync(0xffffffffu, r.zmax, src);
-            if ((bxx - ax + 1) * (byy - ay + 1) > 512) {
+            const int ax = __shfl_sync(0xffffffffu, ulx, src), ay = __shfl_sync(0xffffffffu, uly, src);
+            const int cx = __shfl_sync(0xffffffffu, bxx, src), cy = __shfl_sync(0xffffffffu, byy, src);
+            const float zn = __shfl_sync(0xffffffffu, zl, src), zx = __shfl_sync(0xffffffffu, zh, src);
+            if ((cx - ax + 1) * (cy - ay + 1) > 512) {
               int slotBig = -1;
               if (lane == 0) slotBig = atomicAdd(&bigCount, 1);
               slotBig = __shfl_sync(0xffffffffu, slotBig, 0);
               if (slotBig < AL_BIG) {
-                if (lane == 0) { BlockRec b; b.ulx = (short)ax; b.uly = (short)ay; b.lrx = (short)bxx; b.lry = (short)byy; b.zmin = zn; b.zmax = zx; bigRecs[slotBig] = b; }
+                if (lane == 0) { BlockRec b; b.ulx = (short)ax; b.uly = (short)ay; b.lrx = (short)cx; b.lry = (short)cy; b.zmin = zn; b.zmax = zx; bigRecs[slotBig] = b; }
                 continue;
               }
             }
-            raster_box_warp(minmax, rw, ax, ay, bxx, byy, zn, zx);
+            raster_box_warp(minmax, rw, ax, ay, cx, cy, zn, zx);
           }
+          K2_SUB(4, t0 == 0);
         }
-        __syncthreads();
-        if (recs) {     // the big boxes of this round: every thread of the CTA takes cells
-          const int nb = bigCount < AL_BIG ? bigCount : AL_BIG;
-          for (int b = 0; b < nb; ++b) {
-            const BlockRec br = bigRecs[b];
-            const int bw = br.lrx - br.ulx + 1, cnt = bw * (br.lry - br.uly + 1);
-            for (int k = threadIdx.x; k < cnt; k += blockDim.x) {
-              float2 *px = &minmax[(br.ulx + k % bw) + (br.uly + k / bw) * rw];
-              atomic_min_posf(&px->x, br.zmin); atomic_max_posf(&px->y, br.zmax);
-            }
+      }
+      __syncthreads();
+      K2_SUB(5, true);
+      if (recs) {     // the big boxes of this tile: every thread of the CTA takes cells
+        const int nb = bigCount < AL_BIG ? bigCount : AL_BIG;
+        for (int b = 0; b < nb; ++b) {
+          const BlockRec br = bigRecs[b];
+          const int bw = br.lrx - br.ulx + 1, cnt = bw * (br.lry - br.uly + 1);
+          for (int k = threadIdx.x; k < cnt; k += blockDim.x) {
+            float2 *px = &minmax[(br.ulx + k % bw) + (br.uly + k / bw) * rw];
+            atomic_min_posf(&px->x, br.zmin); atomic_max_posf(&px->y, br.zmax);
           }
-          __syncthreads();
-          if (threadIdx.x == 0) bigCount = 0;
         }
       }
       __syncthreads();

@@ -156,6 +156,7 @@ static b200_status engine_create_body(const b200_engine_config *cfg, b200_engine
   CK(cudaMalloc(&e->d_scanDesc, sizeof(unsigned long long) * (size_t)e->scanDescCap));
   CK(cudaMemset(e->d_scanDesc, 0, sizeof(unsigned long long) * (size_t)e->scanDescCap));
   e->ringCap = cfg->decayRingItems > 0 ? cfg->decayRingItems : 24ll * e->numBlocks;
+  if (e->ringCap < e->numBlocks) e->ringCap = e->numBlocks;   // one frame's list (at most numBlocks items) always fits: k_serve_list wraps with one subtraction
   CK(cudaMalloc(&e->d_ring, sizeof(b200_vec3i) * (size_t)e->ringCap));
   CK(cudaMalloc(&e->d_snapCount, sizeof(int) * SNAP_SLOTS));
   CK(cudaMalloc(&e->d_snapStart, sizeof(long long) * SNAP_SLOTS));
@@ -192,7 +193,7 @@ void b200_engine_destroy(b200_engine *e) {
   if (!e) return;
   cudaSetDevice(e->device);
   if (e->stream) cudaStreamSynchronize(e->stream);
-  cudaFree(e->d_ctr); cudaFreeHost(e->h_ctr); cudaFree(e->d_reqKey); cudaFree(e->d_reqBits); cudaFree(e->d_markBytes); cudaFree(e->d_dbg); cudaFree(e->d_meshDesc); cudaFree(e->d_scanDesc);
+  cudaFree(e->d_ctr); cudaFreeHost(e->h_ctr); cudaFree(e->d_reqKey); cudaFree(e->d_reqBits); cudaFree(e->d_markBytes); cudaFree(e->d_dbg); cudaFree(e->d_meshDesc); cudaFree(e->d_evalCounters); cudaFreeHost(e->h_evalCounters); cudaFree(e->d_scanDesc);
   cudaFree(e->d_ring); cudaFree(e->d_snapCount); cudaFree(e->d_snapStart); cudaFree(e->d_delTag); cudaFree(e->d_itemPtr); cudaFree(e->d_visiblePtr);
   cudaFree(e->d_viewScratch); cudaFree(e->d_delList); cudaFree(e->d_candList); cudaFree(e->d_isLeader); cudaFree(e->d_allocatedPos); cudaFree(e->d_tileCounts); cudaFree(e->d_blockRecs);
   for (int i = 0; i < 8; ++i) if (e->ev[i]) cudaEventDestroy(e->ev[i]);
@@ -429,6 +430,47 @@ b200_status b200_mesh_scene(b200_engine *e, const b200_scene *s, b200_triangle *
   CK(cudaGetLastError());
   st = download_sync(e, nullptr, nullptr); if (st) return st;
   *noTotalTriangles = e->h_ctr->noTotalPoints;
+  return B200_OK;
+}
+
+// ---- evaluation consumer (Evaluation::EvaluateDepth) -----------------------------------------------
+
+b200_status b200_evaluate_depth(b200_engine *e, const b200_eval_params *params, const float *d_lidar, int n, const float *d_rendered_depth,
+                                const int16_t *d_input_depth_mm, const uint8_t *d_association, const b200_eval_callback *callbacks,
+                                int n_callbacks, b200_eval_result *out_static, b200_eval_result *out_dynamic, b200_eval_summary *summary) {
+  if (!e) return B200_ERR_INVALID;
+  if (!params || !d_rendered_depth || !d_input_depth_mm || !callbacks || !out_static || !summary || n < 0 || (n > 0 && !d_lidar) ||
+      n_callbacks < 1 || n_callbacks > B200_EVAL_MAX_CALLBACKS || params->frame_width <= 0 || params->frame_height <= 0) {
+    snprintf(e->err, sizeof(e->err), "evaluate_depth: bad arguments (1..%d callbacks)", B200_EVAL_MAX_CALLBACKS);
+    return B200_ERR_INVALID;
+  }
+  if (((uintptr_t)d_lidar & 15) != 0) { snprintf(e->err, sizeof(e->err), "evaluate_depth: the point array must be 16-byte aligned"); return B200_ERR_INVALID; }
+  CK(cudaSetDevice(e->device));
+  const int maxWords = eval_counter_words(B200_EVAL_MAX_CALLBACKS);
+  if (!e->d_evalCounters) {
+    CK(cudaMalloc(&e->d_evalCounters, sizeof(unsigned long long) * (size_t)maxWords));
+    CK(cudaMallocHost(&e->h_evalCounters, sizeof(unsigned long long) * (size_t)maxWords));
+  }
+  launch_evaluate_depth(e, params, callbacks, n_callbacks, out_dynamic ? 1 : 0, d_lidar, n, d_rendered_depth, d_input_depth_mm, d_association,
+                        e->d_evalCounters);
+  const int words = eval_counter_words(n_callbacks);
+  CK(cudaMemcpyAsync(e->h_evalCounters, e->d_evalCounters, sizeof(unsigned long long) * (size_t)words, cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaStreamSynchronize(e->stream)); CK(cudaGetLastError());
+  const unsigned long long *h = e->h_evalCounters;
+  for (int cls = 0; cls < 2; ++cls) {
+    b200_eval_result *out = cls ? out_dynamic : out_static;
+    if (!out) continue;
+    for (int c = 0; c < n_callbacks; ++c) {
+      const unsigned long long *q = h + (size_t)(cls * n_callbacks + c) * 9;
+      out[c].measurement_count = (int64_t)q[0];
+      out[c].rendered.missing = (int64_t)q[1]; out[c].rendered.error = (int64_t)q[2]; out[c].rendered.correct = (int64_t)q[3]; out[c].rendered.missing_separate = (int64_t)q[4];
+      out[c].input.missing = (int64_t)q[5]; out[c].input.error = (int64_t)q[6]; out[c].input.correct = (int64_t)q[7]; out[c].input.missing_separate = (int64_t)q[8];
+    }
+  }
+  const unsigned long long *sq = h + (size_t)2 * n_callbacks * 9;
+  summary->valid_lidar_points = (int64_t)sq[0]; summary->epi_errors = (int64_t)sq[1];
+  summary->negative_disparities = (int64_t)sq[2]; summary->skipped_lidar_points = (int64_t)sq[3];
+  if (sq[2]) { snprintf(e->err, sizeof(e->err), "Negative disparity in ground truth."); return B200_ERR_NEGATIVE_DISPARITY; }
   return B200_OK;
 }
 

@@ -27,7 +27,7 @@ struct SceneRef {           // raw device views of the caller-owned scene / rend
 
 struct DecaySnap { long long start; int frameIdx; int hostCountKnown; };
 
-#define B200_DBG_WORDS (64 + 3 * 1024)   // 4 CTAs x 8 phase stamps, then per tile (first 1024): start, list count published, list offset known
+#define B200_DBG_WORDS (64 + 5 * 1024)   // 4 CTAs x 8 phase stamps, then per tile (first 1024): start, list count published, list offset known
 struct b200_engine {
   int device;
   cudaStream_t stream;
@@ -88,6 +88,7 @@ struct b200_engine {
   bool traceOn; int traceCount, traceCap; cudaEvent_t *traceEv; const char **traceName;
   // expected-depth cells outside the live corner of the latest fused frame: rasterised lazily at b200_sync()
   bool deadPending; SceneRef deadScene; Mat4 deadM; float deadProj[4]; int deadW, deadH; float deadVoxelSize; b200_vec2f *deadMinmax;
+  unsigned long long *d_evalCounters, *h_evalCounters;   // evaluation consumer: counters (device) and their pinned mirror, allocated on first use
   unsigned long long *d_meshDesc;     // meshing: chained-scan descriptors, one per VBA block (allocated on first use)
   unsigned long long *d_dbg;          // timestamps written by instrumented kernels while the launch trace is on (b200_diag_read_debug)
   long long launches;
@@ -125,6 +126,10 @@ void launch_forward_render(b200_engine *e, const SceneRef &s, const FrameGeom &g
                            const b200_vec4f *rays, b200_vec4f *fwd, int *missing, b200_vec4u *outImg);
 void launch_point_cloud(b200_engine *e, const SceneRef &s, const Mat4 &invM, int w, int h, float voxelSize, int skipPoints,
                         const b200_vec4f *rays, b200_vec4u *outImg, b200_vec4f *locations, b200_vec4f *colours);
+int eval_counter_words(int nCallbacks);
+void launch_evaluate_depth(b200_engine *e, const b200_eval_params *p, const b200_eval_callback *cb, int nCallbacks, int hasDynamic,
+                           const float *lidar, int n, const float *rendered, const int16_t *inputMm, const uint8_t *association,
+                           unsigned long long *counters);
 void launch_mesh_scene(b200_engine *e, const SceneRef &s, float voxelSize, b200_triangle *triangles, unsigned noMaxTriangles);
 void launch_swap_list_in(b200_engine *e, const SceneRef &s, int *needed);
 void launch_swap_integrate_in(b200_engine *e, const SceneRef &s, const b200_voxel *synced, const int *needed, int n, int maxW);

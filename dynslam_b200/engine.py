@@ -517,6 +517,49 @@ class MeshingEngine:
         return n.value
 
 
+class Evaluation:
+    """dynslam::eval::Evaluation's depth evaluation (DS/Evaluation/Evaluation.h:52-190, Evaluation.cpp:150-304) on the B200
+    back-end: the rendered depth stays on the device, one launch evaluates every LIDAR return against every callback."""
+
+    def __init__(self, engine, velo_to_left_gray_cam, proj_left_color, proj_right_color, baseline_m, frame_width, frame_height,
+                 min_depth_m, max_depth_m):
+        self.e = engine
+        p = abi.EvalParams()
+        p.velo_to_cam[:] = list(np.asarray(velo_to_left_gray_cam, dtype=np.float64).reshape(4, 4).T.reshape(-1))   # column-major, like Eigen
+        p.proj_left[:] = list(np.asarray(proj_left_color, dtype=np.float64).reshape(3, 4).T.reshape(-1))
+        p.proj_right[:] = list(np.asarray(proj_right_color, dtype=np.float64).reshape(3, 4).T.reshape(-1))
+        p.baseline_m = float(baseline_m)
+        p.left_focal_length_px = float(np.float32(np.asarray(proj_left_color, dtype=np.float64).reshape(3, 4)[0, 0]))   # Evaluation.h:174
+        p.min_depth_m, p.max_depth_m = float(min_depth_m), float(max_depth_m)
+        p.frame_width, p.frame_height = int(frame_width), int(frame_height)
+        self.params = p
+
+    @staticmethod
+    def default_callbacks(compare_on_intersection=True):
+        """the callback list of Evaluation::EvaluateFrame (Evaluation.cpp:176-195): delta_max 0.5, 1..12, then the KITTI-style 3 px / 5 %"""
+        return [(0.5, compare_on_intersection, False)] + [(float(d), compare_on_intersection, False) for d in range(1, 13)] + \
+               [(3.0, compare_on_intersection, True)]
+
+    def EvaluateDepth(self, lidar_points, rendered_depth, input_depth_mm, callbacks=None, association=None, with_dynamic=False):
+        """lidar_points: cuda float32 [n, 4] (KITTI .bin records); rendered_depth: cuda float32 [h, w] metres; input_depth_mm: cuda
+        int16 [h, w]; association: cuda uint8 [h, w] or None. Returns (static results, dynamic results or None, summary)."""
+        cbs = callbacks if callbacks is not None else self.default_callbacks()
+        n = len(cbs)
+        arr = (abi.EvalCallback * n)(*[abi.EvalCallback(float(d), int(bool(c)), int(bool(k))) for d, c, k in cbs])
+        out_s = (abi.EvalResult * n)()
+        out_d = (abi.EvalResult * n)() if with_dynamic else None
+        summ = abi.EvalSummary()
+        self.e.after_torch()
+        rc = self.e.lib.b200_evaluate_depth(self.e.h, C.byref(self.params), _ptr(lidar_points), int(lidar_points.shape[0]), _ptr(rendered_depth),
+                                            _ptr(input_depth_mm), _ptr(association) if association is not None else None, arr, n, out_s,
+                                            out_d, C.byref(summ))
+        if rc == abi.ERR_NEGATIVE_DISPARITY:
+            raise RuntimeError(self.e.lib.b200_last_error(self.e.h).decode())      # the reference throws std::runtime_error
+        self.e.check(rc)
+        summary = dict(valid_lidar_points=summ.valid_lidar_points, epi_errors=summ.epi_errors, skipped_lidar_points=summ.skipped_lidar_points)
+        return [r.as_dict() for r in out_s], ([r.as_dict() for r in out_d] if with_dynamic else None), summary
+
+
 class GlobalCache:
     """Host half of ITMGlobalCache (Objects/ITMGlobalCache.h:17-129): stored blocks per entry."""
 

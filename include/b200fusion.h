@@ -45,7 +45,8 @@ typedef enum {
   B200_ERR_EXCESS_FULL = 3,   /* reference: throw runtime_error, Reco_CUDA.cu:353-357 */
   B200_ERR_INVALID = 4,
   B200_ERR_DECAY_RING_FULL = 5, /* no longer returned: a full decay queue drops its oldest snapshots (see b200_engine_config) */
-  B200_ERR_UNSUPPORTED = 6
+  B200_ERR_UNSUPPORTED = 6,
+  B200_ERR_NEGATIVE_DISPARITY = 7  /* reference: throw runtime_error("Negative disparity in ground truth."), Evaluation.cpp:273-275 */
 } b200_status;
 
 /* ---- byte-exact mirrors of the reference PODs ---------------------------------------- */
@@ -351,6 +352,45 @@ b200_status b200_composite_color(b200_engine *e, b200_vec4u *d_target_color, flo
 b200_status b200_composite_instances(b200_engine *e, b200_vec4u *d_out_color, float *d_out_depth, int n,
                                      const b200_instance_layer *layers, int n_layers, float dim_factor,
                                      float tint_strength);
+
+/* ---- evaluation consumer of the float raycast: Evaluation::EvaluateDepth ----------------------------
+   DS/Evaluation/Evaluation.cpp:241-304 with ProjectLidar (:214-238) and EvaluationCallback::ProcessLidarPoint /
+   ComputeAccuracy (DS/Evaluation/EvaluationCallback.cpp:15-103): every LIDAR return of a frame is projected into the left
+   and right colour cameras (double precision), the rendered depth (the float raycast / composite preview, metres) and the
+   input depth (int16 millimetres) under it become disparities, and each callback — one per delta_max, plus the KITTI-style
+   one — counts the point as missing, erroneous or correct for the fused and for the input depth. One launch for all points
+   and all callbacks; only the counters come back. */
+
+typedef struct b200_eval_params {
+  double velo_to_cam[16];      /* Evaluation::velo_to_left_gray_cam_ (Eigen::Matrix4d, column-major) */
+  double proj_left[12];        /* proj_left_color_  (Eigen::Matrix<double, 3, 4>, column-major) */
+  double proj_right[12];       /* proj_right_color_ */
+  float baseline_m, left_focal_length_px, min_depth_m, max_depth_m;
+  int32_t frame_width, frame_height;
+} b200_eval_params;
+
+typedef struct b200_eval_callback {   /* EvaluationCallback's constructor arguments (EvaluationCallback.h:14-24) */
+  float delta_max;
+  int32_t compare_on_intersection, kitti_style;
+} b200_eval_callback;
+
+typedef struct b200_eval_stats { int64_t missing, error, correct, missing_separate; } b200_eval_stats;   /* Evaluation.h:27-33 */
+typedef struct b200_eval_result { int64_t measurement_count; b200_eval_stats rendered, input; } b200_eval_result;
+typedef struct b200_eval_summary { int64_t valid_lidar_points, epi_errors, negative_disparities, skipped_lidar_points; } b200_eval_summary;
+
+/* SegmentedCallback::GetPointAssociation's verdict for the pixel a point falls on (SegmentedCallback.h), one byte per pixel */
+enum { B200_EVAL_STATIC = 0, B200_EVAL_DYNAMIC = 1, B200_EVAL_NEITHER = 2 };
+#define B200_EVAL_MAX_CALLBACKS 16
+
+/* d_lidar: n points of four floats (x, y, z, reflectance — the KITTI velodyne .bin record); d_rendered_depth, d_input_depth_mm:
+   frame_width x frame_height; d_association: one byte per pixel or NULL (every point static: Evaluation::EvaluateFrame);
+   callbacks / out_static / out_dynamic: host arrays of n_callbacks (out_dynamic may be NULL: dynamic points are skipped).
+   Synchronous, like the reference. A negative ground-truth disparity returns B200_ERR_NEGATIVE_DISPARITY (the reference
+   throws at the first one; the counts are then unspecified). */
+b200_status b200_evaluate_depth(b200_engine *e, const b200_eval_params *params, const float *d_lidar, int n,
+                                const float *d_rendered_depth, const int16_t *d_input_depth_mm, const uint8_t *d_association,
+                                const b200_eval_callback *callbacks, int n_callbacks, b200_eval_result *out_static,
+                                b200_eval_result *out_dynamic, b200_eval_summary *summary);
 
 /* ---- meshing: ITMMeshingEngine<TVoxel, ITMVoxelBlockHash>::MeshScene --------------------------------
    Engine/DeviceSpecific/CUDA/ITMMeshingEngine_CUDA.cu:37-81 with DeviceAgnostic/ITMMeshingEngine.h. d_triangles is

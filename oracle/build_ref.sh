@@ -36,6 +36,24 @@ if [ -f "$IRC" ]; then
   fi
 fi
 
+# ---- evaluation consumer: the reference's own ProjectLidar / EvaluateDepth / ComputeAccuracy (oracle/_ref/libevalref.so) ---------
+# Evaluation.cpp and EvaluationCallback.cpp need Eigen, OpenCV, Pangolin and the DynSlam class as translation units; the four
+# function bodies only need what oracle/ref_eval_driver.cpp declares around them. They are cut out of the reference files here,
+# at build time, into oracle/_ref/ (git-ignored) and compiled unmodified.
+EVC="$DS/Evaluation/Evaluation.cpp"; ECB="$DS/Evaluation/EvaluationCallback.cpp"
+if [ -f "$EVC" ] && [ -f "$ECB" ]; then
+  awk '/^bool Evaluation::ProjectLidar\(/ {on=1} /^\/\/ Track = ours, tracklet = ground truth/ {on=0} on' "$EVC" > "$HERE/_ref/eval_extract.inc"
+  awk '/^void EvaluationCallback::ProcessLidarPoint\(/ {on=1} /^DepthEvaluation EvaluationCallback::CreateDepthEvaluation\(/ {on=0} on' "$ECB" >> "$HERE/_ref/eval_extract.inc"
+  awk '/^void EvaluationCallback::ComputeAccuracy\(/ {on=1} on {print} on && /^}$/ {on=0}' "$ECB" >> "$HERE/_ref/eval_extract.inc"
+  if grep -q "Evaluation::EvaluateDepth" "$HERE/_ref/eval_extract.inc" && grep -q "EvaluationCallback::ComputeAccuracy" "$HERE/_ref/eval_extract.inc"; then
+    /usr/bin/g++ -std=c++14 -O2 -ffp-contract=off -fno-fast-math -shared -fPIC -w -I"$HERE/stubs" -I"$DS/Evaluation" -I"$HERE" \
+        -o "$HERE/_ref/libevalref.so" "$HERE/ref_eval_driver.cpp" && echo "built $HERE/_ref/libevalref.so"
+    rm -f "$HERE/_ref/eval_extract.inc"   # the cut-out text is a build intermediate only
+  else
+    echo "could not locate the evaluation functions in $EVC / $ECB" >&2; rm -f "$HERE/_ref/eval_extract.inc"
+  fi
+fi
+
 # ---- reference CUDA build + ITMLib harness (oracle/_ref/libitmharness.so) -------------------------
 # The reference's own CUDA engines, unmodified, compiled per-TU for sm_100a with the reference's
 # flags (--use_fast_math, ITMLib/CMakeLists.txt:226-230) directly from /root/reference, plus the few

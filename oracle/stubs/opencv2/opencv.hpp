@@ -25,3 +25,10 @@ class Mat1b : public Mat {
   explicit Mat1b(Size s) : Mat(s.height, s.width) {}
 };
 }   // namespace cv
+namespace cv {
+class Mat1s : public Mat {   // 16-bit signed single-channel matrix (the input depth map in millimetres, Evaluation.cpp:280)
+ public:
+  Mat1s() {}
+  Mat1s(int r, int c) { rows = r; cols = c; bytes.resize((size_t)r * c * 2); }
+};
+}   // namespace cv

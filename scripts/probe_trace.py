@@ -31,14 +31,24 @@ for i, v in enumerate(views[N0:]):
     eng.sync(rs)
     tr = eng.trace()
     import ctypes as C
-    dbg = (C.c_uint64 * (64 + 3072))()
-    eng.lib.b200_diag_read_debug(eng.h, dbg, 64 + 3072)
+    dbg = (C.c_uint64 * (64 + 5120))()
+    eng.lib.b200_diag_read_debug(eng.h, dbg, 64 + 5120)
     eng.set_timing(0)
     if i >= 2:
         print("--- frame", i)
         t0 = min(dbg[s * 8] for s in range(4) if dbg[s * 8])
         for s in range(4):
             print("  k_serve_list CTA slot", s, "phase stamps (us):", ["%.1f" % ((dbg[s * 8 + k] - t0) / 1000.0) if dbg[s * 8 + k] else "-" for k in range(7)])
+        for s_ in range(4):
+            print("  k_serve_list CTA slot", s_, "first hit round (us): loads-start, list-written, projected, small boxes, warp boxes, barrier:", ["%.1f" % ((dbg[32 + s_ * 8 + k] - t0) / 1000.0) if dbg[32 + s_ * 8 + k] else "-" for k in range(6)])
+        cnt = [int(dbg[64 + 3 * 1024 + t]) for t in range(192)]
+        pub = [(dbg[64 + 1024 + t] - t0) / 1000.0 for t in range(192)]
+        srv = [(dbg[64 + 4 * 1024 + t] - t0) / 1000.0 if dbg[64 + 4 * 1024 + t] else -1 for t in range(192)]
+        off = [(dbg[64 + 2 * 1024 + t] - t0) / 1000.0 for t in range(192)]
+        print("  listed entries per tile: ordered part mean %.1f max %d; excess part:" % (np.mean(cnt[:128]), max(cnt[:128])), cnt[128:])
+        print("  excess-part tiles, count published (us):", ["%.1f" % v for v in pub[128:]])
+        print("  tiles by service end (us), slowest 12:", sorted([("%.1f" % v, t) for t, v in enumerate(srv)], key=lambda a: -float(a[0]))[:12])
+        print("  ordered tiles, offset known (us), slowest 8:", sorted([("%.1f" % v, t) for t, v in enumerate(off[:128])], key=lambda a: -float(a[0]))[:8])
         for k, what in enumerate(["tile start", "list count published", "list offset known"]):
             v = np.array([dbg[64 + k * 1024 + t] for t in range(1024)], dtype=np.float64)
             v = (v[v > 0] - t0) / 1000.0

@@ -26,7 +26,7 @@ def oracle():
     global _oracle
     if _oracle is not None:
         return _oracle
-    srcs = [os.path.join(ROOT, "oracle", f) for f in ("tsdf_oracle.c", "view_oracle.c", "frames_oracle.c", "mesh_oracle.c")]
+    srcs = [os.path.join(ROOT, "oracle", f) for f in ("tsdf_oracle.c", "view_oracle.c", "frames_oracle.c", "mesh_oracle.c", "eval_oracle.c")]
     if not os.path.exists(ORACLE_SO) or os.path.getmtime(ORACLE_SO) < max(os.path.getmtime(s) for s in srcs):
         build_oracle()
     L = C.CDLL(ORACLE_SO)
@@ -42,6 +42,8 @@ def oracle():
     L.oracle_integrated_blocks.argtypes = [vp]
     L.oracle_mesh_scene.argtypes = [P(abi.Scene), vp, C.c_uint32]
     L.oracle_mesh_scene.restype = C.c_uint32
+    L.oracle_evaluate_depth.argtypes = [P(abi.EvalParams), vp, C.c_int, vp, vp, vp, P(abi.EvalCallback), C.c_int, P(abi.EvalResult), P(abi.EvalResult),
+                                        P(abi.EvalSummary)]
     L.oracle_mat4_inv.argtypes = [P(C.c_float), P(C.c_float)]
     L.oracle_mat4_mul.argtypes = [P(C.c_float), P(C.c_float), P(C.c_float)]
     L.oracle_mat4_mul.restype = None
