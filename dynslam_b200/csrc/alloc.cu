@@ -374,7 +374,6 @@ k_serve_list(const float *__restrict__ depth, b200_hash_entry *table, int numBuc
              int *snapCount, int slot, BlockRec *recs, float2 *minmax, int rw, int rh, unsigned maxRB, unsigned long long *dbg) {
   __shared__ unsigned sm[33];
   __shared__ unsigned tileBase, tileBase2;
-  __shared__ unsigned hits[AL_TILE];   // entry index | bit 31: observed this frame
   __shared__ BlockRec bigRecs[AL_BIG];
   __shared__ int bigCount;
   // measurement hook (b200_diag_read_debug): CTAs 0, 1/3, 2/3 and the last one stamp %globaltimer at their phase boundaries
@@ -448,37 +447,39 @@ k_serve_list(const float *__restrict__ depth, b200_hash_entry *table, int numBuc
       // ---- list, first half: visibility bytes -> mask of listed entries, count published ----
       unsigned mask = 0, mk = 0, local = 0, totalC = 0;
       auto decode = [&](const bool marksOnly, const bool clearMarks) {
+        // Byte-parallel (four entries per 32-bit operation, no loop over the interesting bytes): the excess part of the table
+        // is dense — every listed excess entry of a KITTI frame sits in the last tile, a dozen per thread — and a per-byte
+        // loop there was the longest chain of the launch.
         if (w < noWords) {
 #pragma unroll
           for (int q = 0; q < 2; ++q) {
-            const unsigned m16 = nz_bytes(mb[q].x) | (nz_bytes(mb[q].y) << 4) | (nz_bytes(mb[q].z) << 8) | (nz_bytes(mb[q].w) << 12);
-            if (m16 && clearMarks) *reinterpret_cast<uint4 *>(markBytes + first + q * 16) = make_uint4(0u, 0u, 0u, 0u);   // consumed
-            mk |= m16 << (q * 16);
-            unsigned todo = m16;
-            if (!marksOnly) todo |= nz_bytes(raw[q].x) | (nz_bytes(raw[q].y) << 4) | (nz_bytes(raw[q].z) << 8) | (nz_bytes(raw[q].w) << 12);
-            if (!todo) continue;
-            unsigned wv[4] = {raw[q].x, raw[q].y, raw[q].z, raw[q].w};
+            const unsigned mw[4] = {mb[q].x, mb[q].y, mb[q].z, mb[q].w};
+            unsigned xv[4] = {raw[q].x, raw[q].y, raw[q].z, raw[q].w};
+            if ((mw[0] | mw[1] | mw[2] | mw[3]) && clearMarks) *reinterpret_cast<uint4 *>(markBytes + first + q * 16) = make_uint4(0u, 0u, 0u, 0u);   // consumed
             bool dirty = false;
-            while (todo) {            // the few interesting bytes of the group (a thread lists ~0.1 entries on average)
-              const int k = __ffs(todo) - 1;
-              todo &= todo - 1;
-              const unsigned sh = (k & 3) * 8;
-              unsigned word = (k < 4) ? wv[0] : (k < 8) ? wv[1] : (k < 12) ? wv[2] : wv[3];
-              const unsigned old = (word >> sh) & 0xffu;
-              unsigned v = old;
-              if ((m16 >> k) & 1u) v = 1;                 // observed this frame (2 = swapped out is patched below, where the entry is read)
-              else if (v == VT_PREV_VISIBLE) v = 3;
-              else if (v == VT_PREV_HIDDEN) v = 0;
-              else if (v == 3) { if (!stale_three_visible(table, first + q * 16 + k, &g)) v = 0; }
-              if (v != old) {
-                dirty = true;
-                word = (word & ~(0xffu << sh)) | (v << sh);
-                if (k < 4) wv[0] = word; else if (k < 8) wv[1] = word; else if (k < 12) wv[2] = word; else wv[3] = word;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const unsigned markM = __vcmpne4(mw[j], 0u);      // 0xff where the entry was observed this frame
+              const unsigned x = xv[j];
+              unsigned nv;
+              if (marksOnly) nv = (x & ~markM) | (markM & 0x01010101u);
+              else {
+                const unsigned pvM = __vcmpeq4(x, VT_PREV_VISIBLE * 0x01010101u) & ~markM, phM = __vcmpeq4(x, VT_PREV_HIDDEN * 0x01010101u) & ~markM;
+                // observed -> 1 (2 = swapped out is patched where the entry is read); previous list: re-tested visible -> 3, hidden -> 0
+                nv = (x & ~(markM | pvM | phM)) | (markM & 0x01010101u) | (pvM & 0x03030303u);
+                unsigned st = __vcmpeq4(x, 0x03030303u) & ~markM & 0x80808080u;      // a 3 the prepare pass did not re-test (list overflow): rare
+                while (st) {
+                  const int byte = (__ffs(st) - 1) >> 3;
+                  st &= st - 1;
+                  if (!stale_three_visible(table, first + q * 16 + j * 4 + byte, &g)) nv &= ~(0xffu << (byte * 8));
+                }
               }
-              if (v > 0) mask |= 1u << (q * 16 + k);
+              if (nv != x) { dirty = true; xv[j] = nv; }
+              mask |= nz_bytes(nv) << (q * 16 + j * 4);
+              mk |= nz_bytes(mw[j]) << (q * 16 + j * 4);
             }
             if (dirty) {
-              raw[q] = make_uint4(wv[0], wv[1], wv[2], wv[3]);
+              raw[q] = make_uint4(xv[0], xv[1], xv[2], xv[3]);
               *reinterpret_cast<uint4 *>(visType + first + q * 16) = raw[q];
             }
           }
@@ -580,154 +581,28 @@ k_serve_list(const float *__restrict__ depth, b200_hash_entry *table, int numBuc
         decode(true, true);
         count_and_publish();
       }
-      // ---- list, second half: global offset, then the listed entries ----
+      // ---- list, second half: global offset; the listed entries go to their places in the list ----
       if (threadIdx.x < 32) {
         unsigned ex[1] = {0};
         if (totalC != 0 || last) { const unsigned agg[1] = {totalC}; lookback_walk<1>(dC, gen, tile, agg, ex); }
-        if (threadIdx.x == 0) { tileBase = ex[0]; bigCount = 0; }
+        if (threadIdx.x == 0) tileBase = ex[0];
         K2_TILE_STAMP(2, tile);
-      }
-      unsigned o = local;
-      while (mask) {
-        const int k = __ffs(mask) - 1;
-        mask &= mask - 1;
-        hits[o++] = (unsigned)(first + k) | (((mk >> k) & 1u) << 31);
       }
       __syncthreads();
       K2_STAMP(4);
-      const unsigned base = tileBase;
-      // Listed entry t of the tile is handled by the 8-lane group t % 32 of the CTA: lane 0 of the group writes the list items,
-      // each lane projects one corner of the block (ProjectSingleBlock's loop body; the min/max over the corners by shuffles —
-      // min and max do not depend on the order), the group rasterises the box. The ~25 entries of a KITTI tile take one
-      // round; what used to be a serial 8-corner loop and a serial cell loop per entry is spread over the idle lanes.
-      for (unsigned t0 = 0; t0 < totalC; t0 += 32) {
-        const unsigned t = t0 + (unsigned)grp;
-        K2_SUB(0, t0 == 0);
-        bool have = false;       // group-uniform: the entry is listed within capacity and its box is wanted
-        int ex = 0, ey = 0, ez = 0;
-        long long out = 0;
-        if (t < totalC) {
-          const int idx = (int)(hits[t] & 0x7fffffffu);
-          const Entry en = load_entry(table, idx);          // the 8 lanes read the same words: one transaction
-          out = (long long)base + t;
-          if (out < capacity) {
-            int ptr = en.ptr;
-            if (ptr < 0) { if (find_block<false>(table, numBuckets, en.x, en.y, en.z, &ptr) < 0) ptr = -1; }   // stale entry: what findBlock(pos) would hit
-            if (sub == 0) {
-              if (en.ptr == -1 && (hits[t] >> 31)) visType[idx] = 2;   // observed while swapped out (DA/ITMSceneReconstructionEngine.h:261, :281)
-              b200_vec3i p; p.x = en.x; p.y = en.y; p.z = en.z;
-              visiblePos[out] = p;
-              long long rp = ringBase + out;                // out < capacity <= ringCap
-              if (rp >= ringCap) rp -= ringCap;
-              ring[rp] = p;
-              visiblePtr[out] = ptr;
-            }
-            have = recs != nullptr;
-            ex = en.x; ey = en.y; ez = en.z;
-            if (recs && ptr < 0 && sub == 0) { BlockRec e0; e0.ulx = 1; e0.uly = 1; e0.lrx = 0; e0.lry = 0; e0.zmin = 0; e0.zmax = 0; recs[out] = e0; }
-            if (ptr < 0) have = false;
-          }
-        }
-        K2_SUB(1, t0 == 0);
-        if (recs) {
-          // fused frame: the block's 1/8-resolution box (ProjectSingleBlock, DA/ITMVisualisationEngine.h:29-71). All blocks are
-          // assumed drawn; if the tile total breaks MAX_RENDERING_BLOCKS (never at KITTI sizes) the last CTA re-applies the
-          // ordered rule and rebuilds the image.
-          float fxl = 3.0e38f, fxh = -3.0e38f, fyl = 3.0e38f, fyh = -3.0e38f, zl = B200_FAR_AWAY, zh = B200_VERY_CLOSE;
-          if (have) {
-            const short tx = (short)(ex + (sub & 1)), ty = (short)(ey + ((sub >> 1) & 1)), tz = (short)(ez + (sub >> 2));
-            const Vec4 q = m4v4(g.M_d, (float)tx * (float)BS * g.voxelSize, (float)ty * (float)BS * g.voxelSize, (float)tz * (float)BS * g.voxelSize, 1.0f);
-            if (!(q.z < 1e-6)) {
-              const float px = (g.proj_d[0] * q.x / q.z + g.proj_d[2]) / B200_MINMAX_SUBSAMPLE;
-              const float py = (g.proj_d[1] * q.y / q.z + g.proj_d[3]) / B200_MINMAX_SUBSAMPLE;
-              fxl = floorf(px); fxh = ceilf(px); fyl = floorf(py); fyh = ceilf(py);
-              zl = fminf(zl, q.z); zh = fmaxf(zh, q.z);
-            }
-          }
-#pragma unroll
-          for (int d = 1; d < 8; d <<= 1) {
-            fxl = fminf(fxl, __shfl_xor_sync(0xffffffffu, fxl, d)); fxh = fmaxf(fxh, __shfl_xor_sync(0xffffffffu, fxh, d));
-            fyl = fminf(fyl, __shfl_xor_sync(0xffffffffu, fyl, d)); fyh = fmaxf(fyh, __shfl_xor_sync(0xffffffffu, fyh, d));
-            zl = fminf(zl, __shfl_xor_sync(0xffffffffu, zl, d)); zh = fmaxf(zh, __shfl_xor_sync(0xffffffffu, zh, d));
-          }
-          // the function's bookkeeping on the reduced values (ulx starts at w/8, lrx at -1; then the clamps and the early outs)
-          int ulx = rw / B200_MINMAX_SUBSAMPLE, uly = rh / B200_MINMAX_SUBSAMPLE, lrx = -1, lry = -1;
-          if ((float)ulx > fxl) ulx = (int)fxl;
-          if ((float)lrx < fxh) lrx = (int)fxh;
-          if ((float)uly > fyl) uly = (int)fyl;
-          if ((float)lry < fyh) lry = (int)fyh;
-          if (ulx < 0) ulx = 0;
-          if (uly < 0) uly = 0;
-          if (lrx >= rw) lrx = rw - 1;
-          if (lry >= rh) lry = rh - 1;
-          bool draw = have && !(ulx > lrx) && !(uly > lry);
-          if (zl < B200_VERY_CLOSE) zl = B200_VERY_CLOSE;
-          if (zh < B200_VERY_CLOSE) draw = false;
-          K2_SUB(2, t0 == 0);
-          if (have && sub == 0) {
-            BlockRec r; r.ulx = 1; r.uly = 1; r.lrx = 0; r.lry = 0; r.zmin = 0; r.zmax = 0;
-            if (draw) {
-              r.ulx = (short)ulx; r.uly = (short)uly; r.lrx = (short)lrx; r.lry = (short)lry; r.zmin = zl; r.zmax = zh;
-              myTiles += rendering_tiles(ulx, uly, lrx, lry);
-            }
-            recs[out] = r;
-          }
-          // rasterise the part of the box inside the live 1/8-resolution corner — the only cells the raycast reads. (The
-          // reference clamps boxes to the FULL-resolution bounds, DA/ITMVisualisationEngine.h:57-60: the cells outside the corner
-          // are brought up to date from the records when the host can next see the image, engine.cu.) Up to 64 cells: the
-          // group's 8 lanes; more: the whole warp, one box at a time; hundreds (a block next to the camera): the whole CTA.
-          const bool live = draw && ulx <= liveX && uly <= liveY;
-          const int bxx = min(lrx, liveX), byy = min(lry, liveY);
-          const int bw = bxx - ulx + 1, cells = live ? bw * (byy - uly + 1) : 0;
-          if (cells > 0 && cells <= AL_GROUP_BOX) {
-            int xx = ulx + sub, yy = uly;
-            while (xx > bxx) { xx -= bw; ++yy; }
-            while (yy <= byy) {
-              float2 *pxl = &minmax[xx + yy * rw];
-              atomic_min_posf(&pxl->x, zl); atomic_max_posf(&pxl->y, zh);
-              xx += 8;
-              while (xx > bxx) { xx -= bw; ++yy; }
-            }
-          }
-          K2_SUB(3, t0 == 0);
-          unsigned todo = __ballot_sync(0xffffffffu, sub == 0 && cells > AL_GROUP_BOX);
-          while (todo) {
-            const int src = __ffs(todo) - 1;
-            todo &= todo - 1;
-            const int ax = __shfl_sync(0xffffffffu, ulx, src), ay = __shfl_sync(0xffffffffu, uly, src);
-            const int cx = __shfl_sync(0xffffffffu, bxx, src), cy = __shfl_sync(0xffffffffu, byy, src);
-            const float zn = __shfl_sync(0xffffffffu, zl, src), zx = __shfl_sync(0xffffffffu, zh, src);
-            if ((cx - ax + 1) * (cy - ay + 1) > 512) {
-              int slotBig = -1;
-              if (lane == 0) slotBig = atomicAdd(&bigCount, 1);
-              slotBig = __shfl_sync(0xffffffffu, slotBig, 0);
-              if (slotBig < AL_BIG) {
-                if (lane == 0) { BlockRec b; b.ulx = (short)ax; b.uly = (short)ay; b.lrx = (short)cx; b.lry = (short)cy; b.zmin = zn; b.zmax = zx; bigRecs[slotBig] = b; }
-                continue;
-              }
-            }
-            raster_box_warp(minmax, rw, ax, ay, cx, cy, zn, zx);
-          }
-          K2_SUB(4, t0 == 0);
+      {
+        // the ptr list doubles as the hand-over: entry index | bit 31 (observed this frame) now, the block's ptr after the
+        // entry has been read (below, by whichever CTA gets the item)
+        long long o = (long long)tileBase + local;
+        while (mask) {
+          const int k = __ffs(mask) - 1;
+          mask &= mask - 1;
+          if (o < capacity) reinterpret_cast<unsigned *>(visiblePtr)[o] = (unsigned)(first + k) | (((mk >> k) & 1u) << 31);
+          ++o;
         }
       }
-      __syncthreads();
-      K2_SUB(5, true);
-      if (recs) {     // the big boxes of this tile: every thread of the CTA takes cells
-        const int nb = bigCount < AL_BIG ? bigCount : AL_BIG;
-        for (int b = 0; b < nb; ++b) {
-          const BlockRec br = bigRecs[b];
-          const int bw = br.lrx - br.ulx + 1, cnt = bw * (br.lry - br.uly + 1);
-          for (int k = threadIdx.x; k < cnt; k += blockDim.x) {
-            float2 *px = &minmax[(br.ulx + k % bw) + (br.uly + k / bw) * rw];
-            atomic_min_posf(&px->x, br.zmin); atomic_max_posf(&px->y, br.zmax);
-          }
-        }
-      }
-      __syncthreads();
-      K2_STAMP(5);
       if (last && threadIdx.x == 0) {
-        const int n = (int)(base + totalC);
+        const int n = (int)(tileBase + totalC);
         ctr->noVisibleBlocks = n;
         ctr->noIntegrated = 0;            // IntegrateIntoScene of this frame counts from zero (no separate memset)
         const int kept = n < capacity ? n : capacity;
@@ -736,6 +611,149 @@ k_serve_list(const float *__restrict__ depth, b200_hash_entry *table, int numBuc
         snapStart[slot] = ringStart;
         snapCount[slot] = kept;
         ctr->ringHead = ringStart + kept;
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        __threadfence();                         // this tile's items (and, on the last tile, the total) are visible device-wide ...
+        atomicAdd(&ctr->tilesListed, 1u);        // ... before the tile counts as listed
+      }
+      K2_STAMP(5);
+    }
+  }
+  // ---------------- the listed entries, dealt evenly over the grid ----------------
+  // Entries are not spread evenly over the tiles (every excess-list entry lives in the last tile or two, which are also the
+  // last to know their offset), so the per-entry work — read the entry, write the list items, project the block, rasterise
+  // its box — is done on the finished list: item i goes to 8-lane group i % 32 of CTA (i / 32) % gridDim. Lane 0 of the group
+  // writes the list items, each lane projects one corner of the block (ProjectSingleBlock's loop body; the min/max over the
+  // corners by shuffles — min and max do not depend on the order), the group rasterises the box.
+  if (threadIdx.x == 0) {
+    bigCount = 0;
+    while (*(volatile unsigned *)&ctr->tilesListed < (unsigned)noTiles) { }
+    __threadfence();
+  }
+  __syncthreads();
+  K2_STAMP(6);
+  {
+    int nList = *(volatile int *)&ctr->noVisibleBlocks;
+    if (nList > capacity) nList = capacity;
+    for (int i0 = blockIdx.x * 32; i0 < nList; i0 += gridDim.x * 32) {
+      const int item = i0 + grp;
+      bool have = false;       // group-uniform: the entry is listed and its box is wanted
+      int ex = 0, ey = 0, ez = 0;
+      if (item < nList) {
+        const unsigned hv = __ldcg(reinterpret_cast<const unsigned *>(visiblePtr) + item);
+        const int idx = (int)(hv & 0x7fffffffu);
+        const Entry en = load_entry_cg(table, idx);       // the 8 lanes read the same words: one transaction (L2: another CTA may have written the entry)
+        int ptr = en.ptr;
+        if (ptr < 0) { if (find_block_cg(table, numBuckets, en.x, en.y, en.z, &ptr) < 0) ptr = -1; }   // stale entry: what findBlock(pos) would hit
+        __syncwarp(0xffu << (lane & 24));                 // every lane of the group has read the hand-over word before lane 0 replaces it
+        if (sub == 0) {
+          if (en.ptr == -1 && (hv >> 31)) visType[idx] = 2;   // observed while swapped out (DA/ITMSceneReconstructionEngine.h:261, :281)
+          b200_vec3i p; p.x = en.x; p.y = en.y; p.z = en.z;
+          visiblePos[item] = p;
+          long long rp = ringBase + item;                 // item < capacity <= ringCap
+          if (rp >= ringCap) rp -= ringCap;
+          ring[rp] = p;
+          visiblePtr[item] = ptr;
+          if (recs && ptr < 0) { BlockRec e0; e0.ulx = 1; e0.uly = 1; e0.lrx = 0; e0.lry = 0; e0.zmin = 0; e0.zmax = 0; recs[item] = e0; }
+        }
+        have = recs != nullptr && ptr >= 0;
+        ex = en.x; ey = en.y; ez = en.z;
+      }
+      K2_SUB(0, i0 == blockIdx.x * 32);
+      if (recs) {
+        // fused frame: the block's 1/8-resolution box (ProjectSingleBlock, DA/ITMVisualisationEngine.h:29-71). All blocks are
+        // assumed drawn; if the tile total breaks MAX_RENDERING_BLOCKS (never at KITTI sizes) the last CTA re-applies the
+        // ordered rule and rebuilds the image.
+        float fxl = 3.0e38f, fxh = -3.0e38f, fyl = 3.0e38f, fyh = -3.0e38f, zl = B200_FAR_AWAY, zh = B200_VERY_CLOSE;
+        if (have) {
+          const short tx = (short)(ex + (sub & 1)), ty = (short)(ey + ((sub >> 1) & 1)), tz = (short)(ez + (sub >> 2));
+          const Vec4 q = m4v4(g.M_d, (float)tx * (float)BS * g.voxelSize, (float)ty * (float)BS * g.voxelSize, (float)tz * (float)BS * g.voxelSize, 1.0f);
+          if (!(q.z < 1e-6)) {
+            const float px = (g.proj_d[0] * q.x / q.z + g.proj_d[2]) / B200_MINMAX_SUBSAMPLE;
+            const float py = (g.proj_d[1] * q.y / q.z + g.proj_d[3]) / B200_MINMAX_SUBSAMPLE;
+            fxl = floorf(px); fxh = ceilf(px); fyl = floorf(py); fyh = ceilf(py);
+            zl = fminf(zl, q.z); zh = fmaxf(zh, q.z);
+          }
+        }
+#pragma unroll
+        for (int d = 1; d < 8; d <<= 1) {
+          fxl = fminf(fxl, __shfl_xor_sync(0xffffffffu, fxl, d)); fxh = fmaxf(fxh, __shfl_xor_sync(0xffffffffu, fxh, d));
+          fyl = fminf(fyl, __shfl_xor_sync(0xffffffffu, fyl, d)); fyh = fmaxf(fyh, __shfl_xor_sync(0xffffffffu, fyh, d));
+          zl = fminf(zl, __shfl_xor_sync(0xffffffffu, zl, d)); zh = fmaxf(zh, __shfl_xor_sync(0xffffffffu, zh, d));
+        }
+        // the function's bookkeeping on the reduced values (ulx starts at w/8, lrx at -1; then the clamps and the early outs)
+        int ulx = rw / B200_MINMAX_SUBSAMPLE, uly = rh / B200_MINMAX_SUBSAMPLE, lrx = -1, lry = -1;
+        if ((float)ulx > fxl) ulx = (int)fxl;
+        if ((float)lrx < fxh) lrx = (int)fxh;
+        if ((float)uly > fyl) uly = (int)fyl;
+        if ((float)lry < fyh) lry = (int)fyh;
+        if (ulx < 0) ulx = 0;
+        if (uly < 0) uly = 0;
+        if (lrx >= rw) lrx = rw - 1;
+        if (lry >= rh) lry = rh - 1;
+        bool draw = have && !(ulx > lrx) && !(uly > lry);
+        if (zl < B200_VERY_CLOSE) zl = B200_VERY_CLOSE;
+        if (zh < B200_VERY_CLOSE) draw = false;
+        if (have && sub == 0) {
+          BlockRec r; r.ulx = 1; r.uly = 1; r.lrx = 0; r.lry = 0; r.zmin = 0; r.zmax = 0;
+          if (draw) {
+            r.ulx = (short)ulx; r.uly = (short)uly; r.lrx = (short)lrx; r.lry = (short)lry; r.zmin = zl; r.zmax = zh;
+            myTiles += rendering_tiles(ulx, uly, lrx, lry);
+          }
+          recs[item] = r;
+        }
+        K2_SUB(1, i0 == blockIdx.x * 32);
+        // rasterise the part of the box inside the live 1/8-resolution corner — the only cells the raycast reads. (The
+        // reference clamps boxes to the FULL-resolution bounds, DA/ITMVisualisationEngine.h:57-60: the cells outside the corner
+        // are brought up to date from the records when the host can next see the image, engine.cu.) Up to 64 cells: the
+        // group's 8 lanes; more: the whole warp, one box at a time; hundreds (a block next to the camera): the whole CTA.
+        const bool live = draw && ulx <= liveX && uly <= liveY;
+        const int bxx = min(lrx, liveX), byy = min(lry, liveY);
+        const int bw = bxx - ulx + 1, cells = live ? bw * (byy - uly + 1) : 0;
+        if (cells > 0 && cells <= AL_GROUP_BOX) {
+          int xx = ulx + sub, yy = uly;
+          while (xx > bxx) { xx -= bw; ++yy; }
+          while (yy <= byy) {
+            float2 *pxl = &minmax[xx + yy * rw];
+            atomic_min_posf(&pxl->x, zl); atomic_max_posf(&pxl->y, zh);
+            xx += 8;
+            while (xx > bxx) { xx -= bw; ++yy; }
+          }
+        }
+        K2_SUB(2, i0 == blockIdx.x * 32);
+        unsigned todo = __ballot_sync(0xffffffffu, sub == 0 && cells > AL_GROUP_BOX);
+        while (todo) {
+          const int src = __ffs(todo) - 1;
+          todo &= todo - 1;
+          const int ax = __shfl_sync(0xffffffffu, ulx, src), ay = __shfl_sync(0xffffffffu, uly, src);
+          const int cx = __shfl_sync(0xffffffffu, bxx, src), cy = __shfl_sync(0xffffffffu, byy, src);
+          const float zn = __shfl_sync(0xffffffffu, zl, src), zx = __shfl_sync(0xffffffffu, zh, src);
+          if ((cx - ax + 1) * (cy - ay + 1) > 512) {
+            int slotBig = -1;
+            if (lane == 0) slotBig = atomicAdd(&bigCount, 1);
+            slotBig = __shfl_sync(0xffffffffu, slotBig, 0);
+            if (slotBig < AL_BIG) {
+              if (lane == 0) { BlockRec b; b.ulx = (short)ax; b.uly = (short)ay; b.lrx = (short)cx; b.lry = (short)cy; b.zmin = zn; b.zmax = zx; bigRecs[slotBig] = b; }
+              continue;
+            }
+          }
+          raster_box_warp(minmax, rw, ax, ay, cx, cy, zn, zx);
+        }
+        K2_SUB(3, i0 == blockIdx.x * 32);
+      }
+    }
+    __syncthreads();
+    K2_SUB(4, true);
+    if (recs) {     // the big boxes this CTA met: every thread takes cells
+      const int nb = bigCount < AL_BIG ? bigCount : AL_BIG;
+      for (int b = 0; b < nb; ++b) {
+        const BlockRec br = bigRecs[b];
+        const int bw = br.lrx - br.ulx + 1, cnt = bw * (br.lry - br.uly + 1);
+        for (int k = threadIdx.x; k < cnt; k += blockDim.x) {
+          float2 *px = &minmax[(br.ulx + k % bw) + (br.uly + k / bw) * rw];
+          atomic_min_posf(&px->x, br.zmin); atomic_max_posf(&px->y, br.zmax);
+        }
       }
     }
   }
@@ -747,11 +765,11 @@ k_serve_list(const float *__restrict__ depth, b200_hash_entry *table, int numBuc
   __shared__ bool lastCta;
   __threadfence();
   __syncthreads();
-  K2_STAMP(6);
+  K2_STAMP(7);
   if (threadIdx.x == 0) lastCta = (atomicAdd(&ctr->visCtasDone, 1u) == gridDim.x - 1);
   __syncthreads();
   if (!lastCta) return;
-  if (threadIdx.x == 0) { ctr->visCtasDone = 0; ctr->tilesRanked = 0; ctr->tilesWithExcess = 0; ctr->tilesExcessServed = 0; ctr->anyExcessRequest = 0; }
+  if (threadIdx.x == 0) { ctr->visCtasDone = 0; ctr->tilesRanked = 0; ctr->tilesWithExcess = 0; ctr->tilesExcessServed = 0; ctr->tilesListed = 0; ctr->anyExcessRequest = 0; }
   __threadfence();
   if (!recs) return;
   // The last CTA knows the tile total. In the (pathological) case that it breaks MAX_RENDERING_BLOCKS it re-applies the

@@ -57,7 +57,7 @@ DEV Entry load_entry(const b200_hash_entry *table, int idx) {
   e.offset = __ldg(p + 2); e.ptr = __ldg(p + 3);
   return e;
 }
-// volatile-free but non-__ldg variant for kernels that also write the table
+// volatile-free but non-__ldg variant for kernels that also write the table (within one CTA: L1 is written through)
 DEV Entry load_entry_rw(const b200_hash_entry *table, int idx) {
   const int *p = reinterpret_cast<const int *>(table) + (size_t)idx * 5;
   int w0 = p[0], w1 = p[1];
@@ -65,6 +65,26 @@ DEV Entry load_entry_rw(const b200_hash_entry *table, int idx) {
   e.x = (short)(w0 & 0xffff); e.y = (short)(w0 >> 16); e.z = (short)(w1 & 0xffff);
   e.offset = p[2]; e.ptr = p[3];
   return e;
+}
+
+// L2 variant for entries OTHER CTAs of the same launch may have written (an L1 line fetched earlier in the launch would be stale)
+DEV Entry load_entry_cg(const b200_hash_entry *table, int idx) {
+  const int *p = reinterpret_cast<const int *>(table) + (size_t)idx * 5;
+  int w0 = __ldcg(p), w1 = __ldcg(p + 1);
+  Entry e;
+  e.x = (short)(w0 & 0xffff); e.y = (short)(w0 >> 16); e.z = (short)(w1 & 0xffff);
+  e.offset = __ldcg(p + 2); e.ptr = __ldcg(p + 3);
+  return e;
+}
+DEV int find_block_cg(const b200_hash_entry *table, int numBuckets, int x, int y, int z, int *ptrOut) {
+  int idx = hash_index(x, y, z, numBuckets - 1);
+  for (;;) {
+    const Entry e = load_entry_cg(table, idx);
+    if (e.x == x && e.y == y && e.z == z && e.ptr >= 0) { *ptrOut = e.ptr; return idx; }
+    if (e.offset < 1) break;
+    idx = numBuckets + e.offset - 1;
+  }
+  return -1;
 }
 
 // findBlock — DA/ITMRepresentationAccess.h:62-85; -1 when absent
@@ -99,6 +119,7 @@ struct DevCounters {
   unsigned noRenderingBlocks;
   unsigned visCtasDone;    // k_serve_list: CTAs that have finished (the last one applies the rendering-block cap if needed)
   unsigned tilesRanked;    // k_serve_list: tiles that have published their request counts
+  unsigned tilesListed;    // ... that have written their part of the visible list (the per-entry phase starts when all have)
   unsigned tilesWithExcess, tilesExcessServed;   // ... of which have excess-list requests / have served them (excess-part tiles list only after all have)
   int anyExcessRequest;    // set by the marking kernel when it files an excess-list request; cleared by k_serve_list's last CTA
   int noNeededEntries;     // swapping

@@ -5,5 +5,3 @@ timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_interfaces.
 tail -3 gpurun_out/pytest_parity5.log
 timeout 300 python scripts/probe_trace.py > gpurun_out/trace_5.txt 2>&1
 grep -A24 "frame 5" gpurun_out/trace_5.txt | cut -c1-900
-B200_INTEGRATE=f timeout 300 python scripts/probe_trace.py > gpurun_out/trace_5_fast.txt 2>&1
-grep -A24 "frame 5" gpurun_out/trace_5_fast.txt | grep integrate

@@ -38,9 +38,9 @@ for i, v in enumerate(views[N0:]):
         print("--- frame", i)
         t0 = min(dbg[s * 8] for s in range(4) if dbg[s * 8])
         for s in range(4):
-            print("  k_serve_list CTA slot", s, "phase stamps (us):", ["%.1f" % ((dbg[s * 8 + k] - t0) / 1000.0) if dbg[s * 8 + k] else "-" for k in range(7)])
+            print("  k_serve_list CTA slot", s, "phase stamps (us):", ["%.1f" % ((dbg[s * 8 + k] - t0) / 1000.0) if dbg[s * 8 + k] else "-" for k in range(8)])
         for s_ in range(4):
-            print("  k_serve_list CTA slot", s_, "first hit round (us): loads-start, list-written, projected, small boxes, warp boxes, barrier:", ["%.1f" % ((dbg[32 + s_ * 8 + k] - t0) / 1000.0) if dbg[32 + s_ * 8 + k] else "-" for k in range(6)])
+            print("  k_serve_list CTA slot", s_, "per-entry phase, first round (us): entry read, projected, group boxes, warp boxes, loop end:", ["%.1f" % ((dbg[32 + s_ * 8 + k] - t0) / 1000.0) if dbg[32 + s_ * 8 + k] else "-" for k in range(5)])
         cnt = [int(dbg[64 + 3 * 1024 + t]) for t in range(192)]
         pub = [(dbg[64 + 1024 + t] - t0) / 1000.0 for t in range(192)]
         srv = [(dbg[64 + 4 * 1024 + t] - t0) / 1000.0 if dbg[64 + 4 * 1024 + t] else -1 for t in range(192)]
