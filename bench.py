@@ -460,8 +460,42 @@ def run_frames_ops(local_rank, iters=30, ncars=7):
                        "k_composite_layers")
         # every layer's depth is read (4 B/px); its colour only where it wins; background read + written (16 B/px)
         bytes_cmp = W * H_ * 16 + ncars * W * H_ * 4
+        # evaluation consumer (Evaluation::EvaluateDepth): 120 k LIDAR returns x the reference's 14 callbacks on a frame-sized depth
+        evaluation = None
+        try:
+            fx, bl = 721.5377, 0.5371657
+            cxp, cyp = W / 2.0 + 3.2, H_ / 2.0 - 5.1
+            v2c = np.array([[7.5337e-03, -9.999714e-01, -6.16602e-04, -4.069766e-03], [1.480249e-02, 7.280733e-04, -9.998902e-01, -7.631618e-02],
+                            [9.998621e-01, 7.523790e-03, 1.480755e-02, -2.717806e-01], [0.0, 0.0, 0.0, 1.0]])
+            pl = np.array([[fx, 0, cxp, 44.85728], [0, fx, cyp, 0.2163791], [0, 0, 1, 2.745884e-03]])
+            pr = pl.copy(); pr[0, 3] -= fx * bl
+            npts = 120000
+            z = rng.uniform(0.6, 40.0, npts); u = rng.uniform(-30, W + 30, npts); r_ = rng.uniform(-20, H_ + 20, npts)
+            cam = np.stack([(u - cxp) * z / fx, (r_ - cyp) * z / fx, z, np.ones(npts)], 1)
+            velo = (np.linalg.inv(v2c) @ cam.T).T
+            pts = np.concatenate([velo[:, :3], rng.uniform(0, 1, (npts, 1))], 1).astype(np.float32)
+            d_pts = torch.from_numpy(pts).to(dev)
+            rendered = depth0.clone(); rendered[rendered > 18.0] = 0.0
+            inp = torch.clamp(torch.round(depth0 * 1000.0 + 50.0), 0, 32000).to(torch.int16)
+            ev = E.Evaluation(eng, v2c, pl, pr, bl, W, H_, 0.5, 30.0)
+            res = None
+            eng.set_timing(3)
+            t_wall = []
+            for it in range(iters + 3):
+                flush.add_(1); stream.synchronize()
+                t0 = time.perf_counter()
+                res = ev.EvaluateDepth(d_pts, rendered, inp)
+                t_wall.append((time.perf_counter() - t0) * 1e6)
+            d = [b - a for name, a, b in eng.trace() if name == "k_evaluate_depth"][3:]
+            eng.set_timing(0)
+            evaluation = {"kernel_us": sum(d) / len(d), "call_us": float(np.median(t_wall[3:])), "points": npts, "callbacks": 14,
+                          "measurements": res[0][0]["measurement_count"], "alg_bytes": npts * 16 + res[0][0]["measurement_count"] * 6,
+                          "what": "b200_evaluate_depth: every LIDAR return of a frame through the reference's 14 callbacks, one launch; call_us = the synchronous call incl. the counter read-back"}
+        except Exception as ex:
+            evaluation = {"error": str(ex)}
         eng.close()
-    return {"instance_split": {"us": us_split, "ops": ncars, "alg_bytes": bytes_split, "achieved": bytes_split / us_split / 1e3,
+    return {"evaluation": evaluation,
+            "instance_split": {"us": us_split, "ops": ncars, "alg_bytes": bytes_split, "achieved": bytes_split / us_split / 1e3,
                                "peak": peak, "unit": "GB/s", "frac": bytes_split / us_split / 1e3 / peak,
                                "what": "b200_process_silhouettes_async: 7 detections cut out of a 1242x375 frame into 7 instance frames, one launch"},
             "composite": {"us": us_cmp, "layers": ncars, "alg_bytes": bytes_cmp, "achieved": bytes_cmp / us_cmp / 1e3, "peak": peak,
@@ -888,6 +922,26 @@ def run_own(args, rank, local_rank, world):
             e2e_raw = {"frame_ms": frame_gaps(raw_marks[3:]), "value": (n_raw - 3) / t_raw, "unit": "frames/s", "h2d_bytes_per_step": W * H_ * 6, "d2h_bytes_per_step": W * H_ * 4,
                        "steps": n_raw - 3, "what": "raw int16 depth + RGB in -> UpdateView with bilateral filter -> fused frame -> image out"}
 
+        # ---- meshing of the map the run built (untimed region, 1 GPU only) ----
+        meshing = None
+        if world == 1 and args.harness_frames > 0:
+            try:
+                mesh = E.Mesh(scene)        # ITMMesh: noMaxTriangles = SDF_LOCAL_BLOCK_NUM * 32
+                me = E.MeshingEngine(eng)
+                ts = []
+                for _ in range(3):
+                    torch.cuda.synchronize(dev)
+                    t0 = time.perf_counter()
+                    ntri = me.MeshScene(mesh, scene)
+                    ts.append((time.perf_counter() - t0) * 1e3)
+                allocated = scene.numBlocks - 1 - scene.lastFreeBlockId
+                meshing = {"ms": sorted(ts)[1], "passes_ms": ts, "triangles": int(ntri), "allocated_blocks": int(allocated),
+                           "mblocks_per_s": allocated / (sorted(ts)[1] / 1e3) / 1e6,
+                           "what": "b200_mesh_scene (synchronous, incl. its counter round trip) over the map the timed run built; triangles in the CPU engine's order"}
+                del mesh
+            except Exception as ex:
+                meshing = {"error": str(ex)}
+
     sampler.stop()
     clk_all = len(sampler.rows)
     sampler.rows = sampler.rows[max(clk_first - 1, 0):clk_timed_end] or sampler.rows   # samples taken during the timed region
@@ -1015,6 +1069,7 @@ def run_own(args, rank, local_rank, world):
         "view_builder": vbuild,
         "frames_ops": frames_ops,
         "e2e_raw": e2e_raw,
+        "meshing": meshing,
         "e2e": {"value": world * e2e_frames / t_e2e, "unit": "frames/s", "h2d_bytes_per_step": W * H_ * 8,
                 "d2h_bytes_per_step": W * H_ * 4, "steps": e2e_frames, "frame_ms": frame_gaps(e2e_marks[e2e_warm:])},
         "gpu_launches": int(launches_all),

@@ -181,7 +181,6 @@ static b200_status engine_create_body(const b200_engine_config *cfg, b200_engine
   e->hostAuthoritative = true;
   integrate_init_device(e);     // per-device tables and function attributes of integrate.cu (one engine per GPU is the multi-GPU unit)
   CK(cudaGetLastError());
-  // default: V3 (warp-decoupled TMA ring, integrate.cu); B200_INTEGRATE_IMPL=tma|ldg select the earlier variants
   // default: V4 (packed-pair arithmetic, integrate.cu); B200_INTEGRATE_IMPL = v3 | tma | ldg select the earlier bit-exact variants,
   // fast = V4 in tolerance mode (TSDF within 1 LSB of the 16-bit code, everything else bit-exact)
   { const char *v = getenv("B200_INTEGRATE_IMPL");

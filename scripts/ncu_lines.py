@@ -1,10 +1,11 @@
 #!/usr/bin/env python
 """Warp-instructions executed / stall samples per SOURCE line of one kernel: joins the SASS page of an ncu report with the
 line table of the object file (nvdisasm -g), instruction by instruction. The object must be the build that was profiled.
-usage: python scripts/ncu_lines.py report.ncu-rep kernel_name object.o [top=40]"""
+usage: python scripts/ncu_lines.py report.ncu-rep kernel_name object.o [top=40] [symbol_substring_in_object=kernel_name]"""
 import csv, os, re, subprocess, sys, tempfile
 rep, kern, obj = sys.argv[1], sys.argv[2], sys.argv[3]
 top_n = int(sys.argv[4]) if len(sys.argv) > 4 else 40
+sym = sys.argv[5] if len(sys.argv) > 5 else kern
 raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", kern, "--print-source", "sass"], capture_output=True, text=True).stdout
 rows = list(csv.reader(raw.splitlines()))
 hi = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
@@ -21,7 +22,7 @@ dis = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(tmp, cubin)], capture
 lines, cur, on = [], ("?", 0), False
 for ln in dis:
     if ln.startswith("//---------------------"):
-        on = (".text." in ln) and (kern in ln)
+        on = (".text." in ln) and (sym in ln)
         continue
     if not on: continue
     m = re.search(r'//## File "([^"]+)", line (\d+)', ln)
