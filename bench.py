@@ -737,7 +737,7 @@ def run_own(args, rank, local_rank, world):
                         keep.append(t)
                         ops.append((E.REMOVE, None, E.make_mask(m[0], t), None, None))
                 v = E.View(d, c, M, proj)
-                v.ops, v.keep = ops, keep
+                v.ops, v.keep = (E.InstanceFrames.prepare_ops(ops) if ops else None), keep
                 return v
             m = masks[rank - 1]  # ProcessSilhouette: the car's pixels are copied into the instance frame (:91-127), fused with the object pose
             v = E.View(inst_depth, inst_rgb, car.object_pose(f, M), proj)
@@ -745,12 +745,13 @@ def run_own(args, rank, local_rank, world):
             if m is not None:
                 t = torch.from_numpy(m[1]).to(dev)
                 mk = E.make_mask(m[0], t)
-                v.ops, v.keep = [(E.EXTRACT, mk, mk, inst_rgb, inst_depth)], [t]
+                v.ops, v.keep = E.InstanceFrames.prepare_ops([(E.EXTRACT, mk, mk, inst_rgb, inst_depth)]), [t]
             else:
-                v.ops, v.keep = [], []
+                v.ops, v.keep = None, []
             return v
 
         step_no = [0]
+        diag = os.environ.get("B200_BENCH_DIAG", "")
 
         def step(view, host=None):
             """one frame of this rank's volume; at N > 1 preceded by the instance split and followed by the hand-over of the
@@ -760,22 +761,28 @@ def run_own(args, rank, local_rank, world):
                 return
             k = step_no[0]; step_no[0] += 1
             s = k & 1
-            xch.release(k)                                   # slot s was handed over with frame k - 2: its buffers are free again
+            # B200_BENCH_DIAG (measurement aid, not a bench mode): noxch = no hand-over / composite, nosplit = no silhouette pass,
+            # norender = no extra colour / depth renders — to attribute the per-step cost of configs[2] over configs[1]
+            do_xch, do_split, do_render = "noxch" not in diag, "nosplit" not in diag, "norender" not in diag
+            if do_xch and "norelease" not in diag:
+                xch.release(k)                               # slot s was handed over with frame k - 2: its buffers are free again
             if rank == 0:
-                if view.ops:
+                if view.ops and do_split:
                     frames_api.ProcessSilhouettes(view.rgb, view.depth, view.ops, sync=False, wait_inputs=False)
                 rs.c.d_raycastImage = lay_col[s].data_ptr()   # the static map's layer is its shaded raycast image (the ICP pass writes it)
-                eng.process_frame_async(rs, view, points, normals, decay=DECAY, depth_out=lay_dep[s])
-                xch.submit(k, lay_col[s], lay_dep[s], out_col[s], out_dep[s])
+                eng.process_frame_async(rs, view, points, normals, decay=DECAY, depth_out=lay_dep[s] if do_render else None)
+                if do_xch:
+                    xch.submit(k, lay_col[s], lay_dep[s], out_col[s], out_dep[s])
             else:
-                if view.ops:
+                if view.ops and do_split:
                     frames_api.ProcessSilhouettes(view.src[1], view.src[0], view.ops, sync=False, wait_inputs=False)
-                else:                                         # car not in view: the reference feeds nothing; an empty frame is the no-op
+                elif do_split:                                # car not in view: the reference feeds nothing; an empty frame is the no-op
                     inst_depth.zero_()
-                eng.process_frame_async(rs, view, points, normals, decay=DECAY, colour_out=lay_col[s], depth_out=lay_dep[s])
-                xch.submit(k, lay_col[s], lay_dep[s])
+                eng.process_frame_async(rs, view, points, normals, decay=DECAY, colour_out=lay_col[s] if do_render else None,
+                                        depth_out=lay_dep[s] if do_render else None)
+                if do_xch:
+                    xch.submit(k, lay_col[s], lay_dep[s])
 
-        diag = os.environ.get("B200_BENCH_DIAG", "")
         sampler = ClockSampler(local_rank)
         if "nosampler" not in diag:
             sampler.start()

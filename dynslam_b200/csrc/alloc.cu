@@ -140,7 +140,7 @@ __global__ void __launch_bounds__(256)
 k_mark_prepare(const float *__restrict__ depth, const b200_hash_entry *__restrict__ table, int numBuckets,
                const b200_vec3i *__restrict__ prevList, uint8_t *visType, DevCounters *ctr, unsigned long long *reqKey, unsigned *reqBits,
                unsigned *req2Bits, uint8_t *markBytes, const __grid_constant__ FrameGeom g, unsigned frameTag, int capacity, int prepCtas,
-               float2 *minmax, int mw, int mh) {
+               float2 *minmax, int mw, int mh, unsigned tilesXMagic) {
   if ((int)blockIdx.x < prepCtas) {
     // ---- prepare part ----
     const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = prepCtas * blockDim.x;
@@ -172,7 +172,8 @@ k_mark_prepare(const float *__restrict__ depth, const b200_hash_entry *__restric
   const int warpGlobal = (((int)blockIdx.x - prepCtas) * blockDim.x + threadIdx.x) >> 5;
   if (warpGlobal >= tilesX * tilesY) return;
   const int lane = threadIdx.x & 31;
-  const int x = (warpGlobal % tilesX) * 8 + (lane & 7), y = (warpGlobal / tilesX) * 4 + (lane >> 3);
+  const int tileY = (int)__umulhi((unsigned)warpGlobal, tilesXMagic);      // warpGlobal / tilesX (magic = ceil(2^32 / tilesX), exact for these sizes)
+  const int x = (warpGlobal - tileY * tilesX) * 8 + (lane & 7), y = tileY * 4 + (lane >> 3);
   if (x >= g.w || y >= g.h) return;
   const float invfx = 1.0f / g.proj_d[0], invfy = 1.0f / g.proj_d[1];
   const float oneOverVoxelSize = 1.0f / (g.voxelSize * BS);
@@ -187,15 +188,18 @@ k_mark_prepare(const float *__restrict__ depth, const b200_hash_entry *__restric
     Entry head[MARK_BATCH];
 #pragma unroll
     for (int j = 0; j < MARK_BATCH; ++j) {
-      bx[j] = (short)(int)floorf(px); by[j] = (short)(int)floorf(py); bz[j] = (short)(int)floorf(pz);
-      // A step is half a block long, so about every other step lands in the block of the step before: probing it again
-      // would find (or request) the same entry — same mark, same request up to the step number in its key, which only
-      // breaks ties between requests of the SAME pixel for the SAME block. Skipped.
-      fresh[j] = (i0 + j < r.noSteps) && !(bx[j] == lastX && by[j] == lastY && bz[j] == lastZ);
-      lastX = bx[j]; lastY = by[j]; lastZ = bz[j];
-      hidx[j] = hash_index(bx[j], by[j], bz[j], numBuckets - 1);
-      if (fresh[j]) head[j] = load_entry(table, hidx[j]);
-      px += r.dx; py += r.dy; pz += r.dz;     // the reference's own accumulation (DA/ITMSceneReconstructionEngine.h:311)
+      fresh[j] = false;
+      if (i0 + j < r.noSteps) {      // (a ray has two or three steps at the default band: the rest of the batch costs nothing)
+        // (short)(int)floorf(p): cvt.rmi is floor and conversion in one instruction, same value
+        bx[j] = (short)__float2int_rd(px); by[j] = (short)__float2int_rd(py); bz[j] = (short)__float2int_rd(pz);
+        // A step is half a block long, so about every other step lands in the block of the step before: probing it again
+        // would find (or request) the same entry — same mark, same request up to the step number in its key, which only
+        // breaks ties between requests of the SAME pixel for the SAME block. Skipped.
+        fresh[j] = !(bx[j] == lastX && by[j] == lastY && bz[j] == lastZ);
+        lastX = bx[j]; lastY = by[j]; lastZ = bz[j];
+        if (fresh[j]) { hidx[j] = hash_index(bx[j], by[j], bz[j], numBuckets - 1); head[j] = load_entry(table, hidx[j]); }
+        px += r.dx; py += r.dy; pz += r.dz;     // the reference's own accumulation (DA/ITMSceneReconstructionEngine.h:311)
+      }
     }
 #pragma unroll
     for (int j = 0; j < MARK_BATCH; ++j) {
@@ -345,23 +349,6 @@ DEV unsigned nz_bytes(unsigned w) { return ((__vcmpne4(w, 0u) & 0x80808080u) * 0
 #define AL_EPT 32
 #define AL_TILE (256 * AL_EPT)   // 8192 entries = 256 bitmap words per tile
 #define AL_BIG 64                // boxes of more than 512 live cells are rasterised by the whole CTA (at most AL_BIG per tile pass)
-
-// rasterises the part [ax..bx] x [ay..by] of a block's box into the expected-depth image, one warp, no integer divisions in the loop
-DEV void raster_box_warp(float2 *minmax, int rw, int ax, int ay, int bx, int by, float zn, float zx) {
-  const int lane = threadIdx.x & 31;
-  const int bw = bx - ax + 1;
-  if (bw <= 32) {
-    const int rpi = 32 / bw, inv = (65536 + bw - 1) / bw;          // warp-uniform; rows per iteration, magic number of lane / bw
-    const int r = (lane * inv) >> 16, c = lane - r * bw;
-    for (int y0 = ay; y0 <= by; y0 += rpi) {
-      const int yy = y0 + r;
-      if (r < rpi && yy <= by) { float2 *px = &minmax[(ax + c) + yy * rw]; atomic_min_posf(&px->x, zn); atomic_max_posf(&px->y, zx); }
-    }
-  } else {
-    for (int yy = ay; yy <= by; ++yy)
-      for (int xx = ax + lane; xx <= bx; xx += 32) { float2 *px = &minmax[xx + yy * rw]; atomic_min_posf(&px->x, zn); atomic_max_posf(&px->y, zx); }
-  }
-}
 
 #define AL_GROUP_BOX 64          // live cells up to which the entry's 8-lane group rasterises the box
 
@@ -665,36 +652,8 @@ k_serve_list(const float *__restrict__ depth, b200_hash_entry *table, int numBuc
         // fused frame: the block's 1/8-resolution box (ProjectSingleBlock, DA/ITMVisualisationEngine.h:29-71). All blocks are
         // assumed drawn; if the tile total breaks MAX_RENDERING_BLOCKS (never at KITTI sizes) the last CTA re-applies the
         // ordered rule and rebuilds the image.
-        float fxl = 3.0e38f, fxh = -3.0e38f, fyl = 3.0e38f, fyh = -3.0e38f, zl = B200_FAR_AWAY, zh = B200_VERY_CLOSE;
-        if (have) {
-          const short tx = (short)(ex + (sub & 1)), ty = (short)(ey + ((sub >> 1) & 1)), tz = (short)(ez + (sub >> 2));
-          const Vec4 q = m4v4(g.M_d, (float)tx * (float)BS * g.voxelSize, (float)ty * (float)BS * g.voxelSize, (float)tz * (float)BS * g.voxelSize, 1.0f);
-          if (!(q.z < 1e-6)) {
-            const float px = (g.proj_d[0] * q.x / q.z + g.proj_d[2]) / B200_MINMAX_SUBSAMPLE;
-            const float py = (g.proj_d[1] * q.y / q.z + g.proj_d[3]) / B200_MINMAX_SUBSAMPLE;
-            fxl = floorf(px); fxh = ceilf(px); fyl = floorf(py); fyh = ceilf(py);
-            zl = fminf(zl, q.z); zh = fmaxf(zh, q.z);
-          }
-        }
-#pragma unroll
-        for (int d = 1; d < 8; d <<= 1) {
-          fxl = fminf(fxl, __shfl_xor_sync(0xffffffffu, fxl, d)); fxh = fmaxf(fxh, __shfl_xor_sync(0xffffffffu, fxh, d));
-          fyl = fminf(fyl, __shfl_xor_sync(0xffffffffu, fyl, d)); fyh = fmaxf(fyh, __shfl_xor_sync(0xffffffffu, fyh, d));
-          zl = fminf(zl, __shfl_xor_sync(0xffffffffu, zl, d)); zh = fmaxf(zh, __shfl_xor_sync(0xffffffffu, zh, d));
-        }
-        // the function's bookkeeping on the reduced values (ulx starts at w/8, lrx at -1; then the clamps and the early outs)
-        int ulx = rw / B200_MINMAX_SUBSAMPLE, uly = rh / B200_MINMAX_SUBSAMPLE, lrx = -1, lry = -1;
-        if ((float)ulx > fxl) ulx = (int)fxl;
-        if ((float)lrx < fxh) lrx = (int)fxh;
-        if ((float)uly > fyl) uly = (int)fyl;
-        if ((float)lry < fyh) lry = (int)fyh;
-        if (ulx < 0) ulx = 0;
-        if (uly < 0) uly = 0;
-        if (lrx >= rw) lrx = rw - 1;
-        if (lry >= rh) lry = rh - 1;
-        bool draw = have && !(ulx > lrx) && !(uly > lry);
-        if (zl < B200_VERY_CLOSE) zl = B200_VERY_CLOSE;
-        if (zh < B200_VERY_CLOSE) draw = false;
+        int ulx, uly, lrx, lry; float zl, zh;
+        const bool draw = project_block_group(have, ex, ey, ez, g.M_d, g.proj_d, rw, rh, g.voxelSize, ulx, uly, lrx, lry, zl, zh);
         if (have && sub == 0) {
           BlockRec r; r.ulx = 1; r.uly = 1; r.lrx = 0; r.lry = 0; r.zmin = 0; r.zmax = 0;
           if (draw) {
@@ -711,16 +670,7 @@ k_serve_list(const float *__restrict__ depth, b200_hash_entry *table, int numBuc
         const bool live = draw && ulx <= liveX && uly <= liveY;
         const int bxx = min(lrx, liveX), byy = min(lry, liveY);
         const int bw = bxx - ulx + 1, cells = live ? bw * (byy - uly + 1) : 0;
-        if (cells > 0 && cells <= AL_GROUP_BOX) {
-          int xx = ulx + sub, yy = uly;
-          while (xx > bxx) { xx -= bw; ++yy; }
-          while (yy <= byy) {
-            float2 *pxl = &minmax[xx + yy * rw];
-            atomic_min_posf(&pxl->x, zl); atomic_max_posf(&pxl->y, zh);
-            xx += 8;
-            while (xx > bxx) { xx -= bw; ++yy; }
-          }
-        }
+        if (cells > 0 && cells <= AL_GROUP_BOX) raster_box_group(minmax, rw, ulx, uly, bxx, byy, zl, zh);
         K2_SUB(2, i0 == blockIdx.x * 32);
         unsigned todo = __ballot_sync(0xffffffffu, sub == 0 && cells > AL_GROUP_BOX);
         while (todo) {
@@ -870,7 +820,8 @@ void launch_allocate(b200_engine *e, const SceneRef &s, const FrameGeom &g, cons
   trace_begin(e, st, "k_mark_prepare");
   k_mark_prepare<<<prepCtas + (tiles + 7) / 8, 256, 0, st>>>(depth, s.hash, s.numBuckets, s.visiblePos, s.visType, e->d_ctr, e->d_reqKey,
                                                             e->d_reqBits, e->d_req2Bits, e->d_markBytes, g, frameTag, s.numBlocks, prepCtas,
-                                                            (float2 *)minmaxFused, mw, mh);
+                                                            (float2 *)minmaxFused, mw, mh,
+                                                            (unsigned)((0x100000000ull + (unsigned)((g.w + 7) / 8) - 1) / (unsigned)((g.w + 7) / 8)));
   trace_end(e, st);
   const int noTiles = (s.noTotal + AL_TILE - 1) / AL_TILE;
   const unsigned gen = ++e->scanGen;

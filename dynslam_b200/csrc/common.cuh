@@ -248,6 +248,76 @@ DEV bool project_single_block(int bx, int by, int bz, const Mat4 &pose, const fl
 }
 
 
+// ProjectSingleBlock for an 8-lane group: lane (lane & 7) projects corner (lane & 7) of block (ex, ey, ez), the min / max over the
+// corners are taken with shuffles (min and max do not depend on the order; NaNs are skipped by fminf / fmaxf exactly as the
+// serial comparisons skip them), then every lane applies the function's bookkeeping. All 32 lanes of the warp must call it;
+// `have` (group-uniform) says whether the group has a block at all. Returns whether the block is drawn (all 8 lanes agree).
+DEV bool project_block_group(bool have, int ex, int ey, int ez, const Mat4 &M, const float *proj, int rw, int rh, float voxelSize,
+                             int &ulx, int &uly, int &lrx, int &lry, float &zl, float &zh) {
+  const int sub = threadIdx.x & 7;
+  float fxl = 3.0e38f, fxh = -3.0e38f, fyl = 3.0e38f, fyh = -3.0e38f;
+  zl = B200_FAR_AWAY; zh = B200_VERY_CLOSE;
+  if (have) {
+    const short tx = (short)(ex + (sub & 1)), ty = (short)(ey + ((sub >> 1) & 1)), tz = (short)(ez + (sub >> 2));
+    const Vec4 q = m4v4(M, (float)tx * (float)BS * voxelSize, (float)ty * (float)BS * voxelSize, (float)tz * (float)BS * voxelSize, 1.0f);
+    if (!(q.z < 1e-6)) {
+      const float px = (proj[0] * q.x / q.z + proj[2]) / B200_MINMAX_SUBSAMPLE;
+      const float py = (proj[1] * q.y / q.z + proj[3]) / B200_MINMAX_SUBSAMPLE;
+      fxl = floorf(px); fxh = ceilf(px); fyl = floorf(py); fyh = ceilf(py);
+      zl = fminf(zl, q.z); zh = fmaxf(zh, q.z);
+    }
+  }
+#pragma unroll
+  for (int d = 1; d < 8; d <<= 1) {
+    fxl = fminf(fxl, __shfl_xor_sync(0xffffffffu, fxl, d)); fxh = fmaxf(fxh, __shfl_xor_sync(0xffffffffu, fxh, d));
+    fyl = fminf(fyl, __shfl_xor_sync(0xffffffffu, fyl, d)); fyh = fmaxf(fyh, __shfl_xor_sync(0xffffffffu, fyh, d));
+    zl = fminf(zl, __shfl_xor_sync(0xffffffffu, zl, d)); zh = fmaxf(zh, __shfl_xor_sync(0xffffffffu, zh, d));
+  }
+  // the function's bookkeeping on the reduced values (ulx starts at w/8, lrx at -1; then the clamps and the early outs)
+  ulx = rw / B200_MINMAX_SUBSAMPLE; uly = rh / B200_MINMAX_SUBSAMPLE; lrx = -1; lry = -1;
+  if ((float)ulx > fxl) ulx = (int)fxl;
+  if ((float)lrx < fxh) lrx = (int)fxh;
+  if ((float)uly > fyl) uly = (int)fyl;
+  if ((float)lry < fyh) lry = (int)fyh;
+  if (ulx < 0) ulx = 0;
+  if (uly < 0) uly = 0;
+  if (lrx >= rw) lrx = rw - 1;
+  if (lry >= rh) lry = rh - 1;
+  bool draw = have && !(ulx > lrx) && !(uly > lry);
+  if (zl < B200_VERY_CLOSE) zl = B200_VERY_CLOSE;
+  if (zh < B200_VERY_CLOSE) draw = false;
+  return draw;
+}
+
+// rasterises [ax..bx] x [ay..by] into the expected-depth image: by the 8 lanes of a group (no divisions) ...
+DEV void raster_box_group(float2 *minmax, int rw, int ax, int ay, int bx, int by, float zn, float zx) {
+  const int sub = threadIdx.x & 7, bw = bx - ax + 1;
+  int xx = ax + sub, yy = ay;
+  while (xx > bx) { xx -= bw; ++yy; }
+  while (yy <= by) {
+    float2 *pxl = &minmax[xx + yy * rw];
+    atomic_min_posf(&pxl->x, zn); atomic_max_posf(&pxl->y, zx);
+    xx += 8;
+    while (xx > bx) { xx -= bw; ++yy; }
+  }
+}
+// ... or by one warp
+DEV void raster_box_warp(float2 *minmax, int rw, int ax, int ay, int bx, int by, float zn, float zx) {
+  const int lane = threadIdx.x & 31;
+  const int bw = bx - ax + 1;
+  if (bw <= 32) {
+    const int rpi = 32 / bw, inv = (65536 + bw - 1) / bw;          // warp-uniform; rows per iteration, magic number of lane / bw
+    const int r = (lane * inv) >> 16, c = lane - r * bw;
+    for (int y0 = ay; y0 <= by; y0 += rpi) {
+      const int yy = y0 + r;
+      if (r < rpi && yy <= by) { float2 *px = &minmax[(ax + c) + yy * rw]; atomic_min_posf(&px->x, zn); atomic_max_posf(&px->y, zx); }
+    }
+  } else {
+    for (int yy = ay; yy <= by; ++yy)
+      for (int xx = ax + lane; xx <= bx; xx += 32) { float2 *px = &minmax[xx + yy * rw]; atomic_min_posf(&px->x, zn); atomic_max_posf(&px->y, zx); }
+  }
+}
+
 // one visible block's 1/8-resolution bounding box + depth range (an undrawn block has ulx > lrx)
 struct __align__(16) BlockRec { short ulx, uly, lrx, lry; float zmin, zmax; };
 

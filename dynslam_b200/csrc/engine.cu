@@ -354,6 +354,11 @@ b200_status b200_expected_depths(b200_engine *e, const b200_scene *s, b200_rende
   CK(cudaSetDevice(e->device));
   st = upload(e, s, rs); if (st) return st;
   e->deadPending = false;      // the whole image is rebuilt here
+  // one pass with atomics; it counts the rendering tiles, and only if they break MAX_RENDERING_BLOCKS (whose rule depends on the
+  // list order) the ordered two-kernel form rebuilds the image
+  launch_expected_depths_fast(e, scene_ref(s, rs), to_mat(cam->M), cam->proj, rs->img_w, rs->img_h, s->voxelSize, rs->d_minmax);
+  st = download_sync(e, nullptr, nullptr); if (st) return st;
+  if (e->h_ctr->noRenderingBlocks <= (unsigned)e->maxRenderingBlocks) return B200_OK;
   launch_expected_depths(e, scene_ref(s, rs), to_mat(cam->M), cam->proj, rs->img_w, rs->img_h, s->voxelSize, rs->d_minmax);
   return download_sync(e, nullptr, nullptr);
 }

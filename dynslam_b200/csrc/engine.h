@@ -114,6 +114,8 @@ void launch_decay_full(b200_engine *e, const SceneRef &s, int minAge, int maxWei
 void launch_find_visible(b200_engine *e, const SceneRef &s, const Mat4 &M, const float proj[4], int w, int h, float voxelSize);
 void launch_expected_depths(b200_engine *e, const SceneRef &s, const Mat4 &M, const float proj[4], int w, int h,
                             float voxelSize, b200_vec2f *minmax, bool deadInitDone = false, bool recsReady = false);
+void launch_expected_depths_fast(b200_engine *e, const SceneRef &s, const Mat4 &M, const float proj[4], int w, int h, float voxelSize,
+                                 b200_vec2f *minmax);
 void launch_expected_depths_dead(b200_engine *e, const SceneRef &s, const Mat4 &M, const float proj[4], int w, int h, float voxelSize,
                                  b200_vec2f *minmax);
 void launch_raycast(b200_engine *e, const SceneRef &s, const Mat4 &invM, const float proj[4], int w, int h, float voxelSize,
@@ -145,7 +147,7 @@ void launch_view_normals(b200_engine *e, const float *depth, b200_vec4f *normal,
 void launch_process_silhouettes(b200_engine *e, b200_vec4u *rgb, float *depth, int w, int h, const b200_silhouette_op *ops, int n);
 void launch_composite_depth(b200_engine *e, float *target, const float *source, int n);
 void launch_composite_layers(b200_engine *e, b200_vec4u *tcol, float *tdep, int n, const b200_instance_layer *layers, int nLayers,
-                             bool dim, float dimFactor, float tintStrength);
+                             bool dim, float dimFactor, float tintStrength, cudaStream_t other = nullptr);
 
 // Launch trace (timing mode 3): TRACED(e, stream, "kernel", launch-statement) brackets the launch with two events.
 static inline void trace_begin(b200_engine *e, cudaStream_t st, const char *name) {

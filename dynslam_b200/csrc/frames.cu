@@ -113,16 +113,17 @@ void launch_composite_depth(b200_engine *e, float *target, const float *source, 
 }
 
 void launch_composite_layers(b200_engine *e, b200_vec4u *tcol, float *tdep, int n, const b200_instance_layer *layers, int nLayers,
-                             bool dim, float dimFactor, float tintStrength) {
+                             bool dim, float dimFactor, float tintStrength, cudaStream_t other) {
+  // other != 0: launched on that stream by the exchange's own host thread (comm.cu) — the engine's state is not touched
+  const cudaStream_t st = other ? other : e->stream;
   int base = 0;
   do {
     Layers L;
     L.n = nLayers - base < CMP_MAX_LAYERS ? nLayers - base : CMP_MAX_LAYERS;
     for (int k = 0; k < L.n; ++k) L.l[k] = layers[base + k];
-    trace_begin(e, e->stream, "k_composite_layers");
-    k_composite_layers<<<(n + 255) / 256, 256, 0, e->stream>>>((uchar4 *)tcol, tdep, n, L, (dim && base == 0) ? 1 : 0, dimFactor, tintStrength);
-    trace_end(e, e->stream);
-    e->launches++;
+    if (!other) trace_begin(e, st, "k_composite_layers");
+    k_composite_layers<<<(n + 255) / 256, 256, 0, st>>>((uchar4 *)tcol, tdep, n, L, (dim && base == 0) ? 1 : 0, dimFactor, tintStrength);
+    if (!other) { trace_end(e, st); e->launches++; }
     base += CMP_MAX_LAYERS;
   } while (base < nLayers);
 }

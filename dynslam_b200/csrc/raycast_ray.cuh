@@ -256,8 +256,9 @@ HD float sdf_interp_nbr(const b200_voxel *__restrict__ voxels, const b200_hash_e
   nbr_rekey(c, x >> 3, y >> 3, z >> 3);
   const int lx = x & 7, ly = y & 7, lz = z & 7;
   const int m = (lx == 7 ? 1 : 0) | (ly == 7 ? 2 : 0) | (lz == 7 ? 4 : 0);   // axes on which the +1 tap is in the next block
-  // the blocks the taps touch: entries s with s a subset of m — bit s of byte m of the constant
-  nbr_ensure((unsigned)((0xFF5533110F050301ull >> (8 * m)) & 0xffu), c, nbr, nbrStride, table, nb);
+  // the blocks the taps touch: entries s with s a subset of m. As a bit set: (1 + 2a)(1 + 4b)(1 + 16c) for m = a + 2b + 4c —
+  // the product's bits sit at the sums of the chosen exponents {1}, {2}, {4}, which are exactly the subsets
+  nbr_ensure((1u + ((unsigned)m & 1u) * 2u) * (1u + ((unsigned)m & 2u) * 2u) * (1u + ((unsigned)m & 4u) * 4u), c, nbr, nbrStride, table, nb);
   const int ox0 = lx, ox1 = (lx + 1) & 7, oy0 = ly << 3, oy1 = ((ly + 1) & 7) << 3, oz0 = lz << 6, oz1 = ((lz + 1) & 7) << 6;
   const short *sv = reinterpret_cast<const short *>(voxels);
 #define TAP(t, off) [&]() { const int b_ = NBR((t) & m); return s16_to_float_(b_ >= 0 ? (int)RC_LDG(sv + (size_t)(b_ + (off)) * 4) : 32767); }()

@@ -176,6 +176,94 @@ void launch_expected_depths(b200_engine *e, const SceneRef &s, const Mat4 &M, co
   e->launches += 1;
 }
 
+// ---- stand-alone CreateExpectedDepths, fast form ------------------------------------------------------------------------
+// One pass over the visible list: every listed block goes to an 8-lane group (a corner per lane, project_block_group), its box
+// — clamped to the FULL-resolution bounds, as the reference does — is rasterised with atomic min / max into the image that
+// k_minmax_init_all reset: by the group up to 64 cells, by the warp up to 512, by the whole CTA beyond (the boxes of blocks
+// that leave the frustum on the right or at the bottom spill over up to 10^5 cells of the part of the image nothing reads).
+// The MAX_RENDERING_BLOCKS rule is order dependent; this pass only COUNTS the rendering tiles, and when the total breaks the cap
+// (never at KITTI sizes) the host runs the ordered two-kernel form above instead (engine.cu).
+#define XD_BIG 64
+__global__ void k_minmax_init_all(float2 *minmax, int n, DevCounters *ctr) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) ctr->noRenderingBlocks = 0;
+  const float2 v = make_float2(B200_FAR_AWAY, B200_VERY_CLOSE);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) minmax[i] = v;
+}
+
+__global__ void __launch_bounds__(256)
+k_expected_depths_fast(const b200_hash_entry *__restrict__ table, int numBuckets, const b200_vec3i *__restrict__ visiblePos,
+                       const int *__restrict__ visiblePtr, int capacity, DevCounters *ctr, Mat4 M, float p0, float p1, float p2, float p3, int w,
+                       int h, float voxelSize, float2 *minmax) {
+  __shared__ BlockRec bigRecs[XD_BIG];
+  __shared__ int bigCount;
+  const float intr[4] = {p0, p1, p2, p3};
+  const int lane = threadIdx.x & 31, grp = threadIdx.x >> 3, sub = threadIdx.x & 7;
+  if (threadIdx.x == 0) bigCount = 0;
+  __syncthreads();
+  int n = ctr->noVisibleBlocks;
+  if (n > capacity) n = capacity;
+  unsigned myTiles = 0;
+  for (int i0 = blockIdx.x * 32; i0 < n; i0 += gridDim.x * 32) {
+    const int item = i0 + grp;
+    bool have = false;
+    int ex = 0, ey = 0, ez = 0;
+    if (item < n) {
+      const b200_vec3i p = visiblePos[item];
+      ex = p.x; ey = p.y; ez = p.z;
+      have = visiblePtr ? (__ldg(visiblePtr + item) >= 0) : (find_block<false>(table, numBuckets, p.x, p.y, p.z) >= 0);
+    }
+    int ulx, uly, lrx, lry; float zl, zh;
+    const bool draw = project_block_group(have, ex, ey, ez, M, intr, w, h, voxelSize, ulx, uly, lrx, lry, zl, zh);
+    if (draw && sub == 0) myTiles += rendering_tiles(ulx, uly, lrx, lry);
+    const int cells = draw ? (lrx - ulx + 1) * (lry - uly + 1) : 0;
+    if (cells > 0 && cells <= 64) raster_box_group(minmax, w, ulx, uly, lrx, lry, zl, zh);
+    unsigned todo = __ballot_sync(0xffffffffu, sub == 0 && cells > 64);
+    while (todo) {
+      const int src = __ffs(todo) - 1;
+      todo &= todo - 1;
+      const int ax = __shfl_sync(0xffffffffu, ulx, src), ay = __shfl_sync(0xffffffffu, uly, src);
+      const int cx = __shfl_sync(0xffffffffu, lrx, src), cy = __shfl_sync(0xffffffffu, lry, src);
+      const float zn = __shfl_sync(0xffffffffu, zl, src), zx = __shfl_sync(0xffffffffu, zh, src);
+      if ((cx - ax + 1) * (cy - ay + 1) > 512) {
+        int slotBig = -1;
+        if (lane == 0) slotBig = atomicAdd(&bigCount, 1);
+        slotBig = __shfl_sync(0xffffffffu, slotBig, 0);
+        if (slotBig < XD_BIG) {
+          if (lane == 0) { BlockRec b; b.ulx = (short)ax; b.uly = (short)ay; b.lrx = (short)cx; b.lry = (short)cy; b.zmin = zn; b.zmax = zx; bigRecs[slotBig] = b; }
+          continue;
+        }
+      }
+      raster_box_warp(minmax, w, ax, ay, cx, cy, zn, zx);
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) myTiles += __shfl_xor_sync(0xffffffffu, myTiles, o);
+  if (lane == 0 && myTiles) atomicAdd(&ctr->noRenderingBlocks, myTiles);
+  __syncthreads();
+  const int nb = bigCount < XD_BIG ? bigCount : XD_BIG;
+  for (int b = 0; b < nb; ++b) {
+    const BlockRec br = bigRecs[b];
+    const int bw = br.lrx - br.ulx + 1, bh = br.lry - br.uly + 1;
+    // rows of the box over the warps, columns over the lanes: no division per cell
+    for (int yy = br.uly + (int)(threadIdx.x >> 5); yy < br.uly + bh; yy += (int)(blockDim.x >> 5))
+      for (int xx = br.ulx + lane; xx < br.ulx + bw; xx += 32) {
+        float2 *px = &minmax[xx + yy * w];
+        atomic_min_posf(&px->x, br.zmin); atomic_max_posf(&px->y, br.zmax);
+      }
+  }
+}
+
+void launch_expected_depths_fast(b200_engine *e, const SceneRef &s, const Mat4 &M, const float proj[4], int w, int h, float voxelSize,
+                                 b200_vec2f *minmax) {
+  k_minmax_init_all<<<e->smCount * 4, 256, 0, e->stream>>>((float2 *)minmax, w * h, e->d_ctr);
+  const int groupsOf32 = (s.numBlocks + 31) / 32;
+  trace_begin(e, e->stream, "k_expected_depths_fast");
+  k_expected_depths_fast<<<persistent_grid(e, 4, groupsOf32), 256, 0, e->stream>>>(s.hash, s.numBuckets, s.visiblePos, fresh_ptr_list(e, s), s.numBlocks,
+                                                                                  e->d_ctr, M, proj[0], proj[1], proj[2], proj[3], w, h, voxelSize,
+                                                                                  (float2 *)minmax);
+  trace_end(e, e->stream);
+  e->launches += 2;
+}
+
 // second half of the fused frame's expected-depth work: the dead cells (after launch_expected_depths(..., recsReady = true))
 void launch_expected_depths_dead(b200_engine *e, const SceneRef &s, const Mat4 &M, const float proj[4], int w, int h, float voxelSize,
                                  b200_vec2f *minmax) {
@@ -198,14 +286,15 @@ void launch_expected_depths_dead(b200_engine *e, const SceneRef &s, const Mat4 &
 template <bool useNbr>
 __global__ void __launch_bounds__(RC_THREADS)
 k_raycast(float4 *out, const b200_voxel *__restrict__ voxels, const b200_hash_entry *__restrict__ table, int nb, int w, int h, Mat4 invM,
-          float fx, float fy, float cxp, float cyp, float voxelSize, float mu, const float2 *__restrict__ minmax, int twLog2, int centreRow) {
+          float fx, float fy, float cxp, float cyp, float voxelSize, float mu, const float2 *__restrict__ minmax, int twLog2, int centreRow,
+          int tilesX, int tilesY, unsigned tilesXMagic) {
   // warp tile: (1 << twLog2) x (32 >> twLog2) pixels
   const int tw = 1 << twLog2, th = 32 >> twLog2;
-  const int tilesX = (w + tw - 1) >> twLog2, tilesY = (h + th - 1) / th;
   const int warpGlobal = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (warpGlobal >= tilesX * tilesY) return;
   const int lane = threadIdx.x & 31;
-  int tileRow = warpGlobal / tilesX;
+  const int rowLinear = (int)__umulhi((unsigned)warpGlobal, tilesXMagic);      // warpGlobal / tilesX (magic = ceil(2^32 / tilesX))
+  int tileRow = rowLinear;
   if (centreRow >= 0) {
     // dispatch order = tile rows sorted by distance from `centreRow` (c, c+1, c-1, c+2, ...): the rows around the horizon
     // hold the rays that skim the ground inside its truncation band for hundreds of steps; started first, they overlap
@@ -214,7 +303,7 @@ k_raycast(float4 *out, const b200_voxel *__restrict__ voxels, const b200_hash_en
     if (k <= 2 * m) { const int off = (k + 1) >> 1; tileRow = (k & 1) ? c + off : c - off; }
     else { const int rest = k - 2 * m; tileRow = (up > down) ? c + m + rest : c - m - rest; }
   }
-  const int x = (warpGlobal % tilesX) * tw + (lane & (tw - 1)), y = tileRow * th + (lane >> twLog2);
+  const int x = (warpGlobal - rowLinear * tilesX) * tw + (lane & (tw - 1)), y = tileRow * th + (lane >> twLog2);
   if (x >= w || y >= h) return;
   const int locId2 = (int)floorf((float)x / B200_MINMAX_SUBSAMPLE) + (int)floorf((float)y / B200_MINMAX_SUBSAMPLE) * w;
   float4 o;
@@ -243,17 +332,19 @@ void launch_raycast(b200_engine *e, const SceneRef &s, const Mat4 &invM, const f
     if (centreRow < 0) centreRow = 0;
     if (centreRow > tilesY - 1) centreRow = tilesY - 1;
   }
+  const int tilesXh = (w + tw - 1) / tw, tilesYh = (h + th - 1) / th;
+  const unsigned magic = (unsigned)((0x100000000ull + (unsigned)tilesXh - 1) / (unsigned)tilesXh);
   static int impl = -1;
   if (impl < 0) { const char *v = getenv("B200_RC_IMPL"); impl = (v && v[0] == 'o') ? 0 : 1; }   // "old": per-lane one-entry cache (cross-check); default: neighbourhood cache
   trace_begin(e, e->stream, "k_raycast");
   if (impl)
     k_raycast<true><<<(tiles + warpsPerCta - 1) / warpsPerCta, RC_THREADS, 0, e->stream>>>((float4 *)out, s.voxels, s.hash, s.numBuckets, w, h, invM,
                                                                                           proj[0], proj[1], proj[2], proj[3], voxelSize, mu,
-                                                                                          (const float2 *)minmax, twLog2, centreRow);
+                                                                                          (const float2 *)minmax, twLog2, centreRow, tilesXh, tilesYh, magic);
   else
     k_raycast<false><<<(tiles + warpsPerCta - 1) / warpsPerCta, RC_THREADS, 0, e->stream>>>((float4 *)out, s.voxels, s.hash, s.numBuckets, w, h, invM,
                                                                                            proj[0], proj[1], proj[2], proj[3], voxelSize, mu,
-                                                                                           (const float2 *)minmax, twLog2, centreRow);
+                                                                                           (const float2 *)minmax, twLog2, centreRow, tilesXh, tilesYh, magic);
   trace_end(e, e->stream);
   e->launches++;
 }

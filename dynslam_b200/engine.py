@@ -176,7 +176,9 @@ class Engine:
         """Order the engine's stream behind the work already enqueued on torch's current stream (tensor fills, uploads,
         torch kernels that produced depth / rgb): the engine runs on its own non-blocking stream and would otherwise race
         with them. One event record + one stream wait, no host synchronisation; a no-op when both are the same stream."""
-        self._ext.wait_stream(torch.cuda.current_stream(self.scene.device))
+        cur = torch.cuda.current_stream(self.scene.device)
+        if cur.cuda_stream != self._ext.cuda_stream:
+            self._ext.wait_stream(cur)
 
     def close(self):
         if getattr(self, "h", None):
@@ -367,6 +369,14 @@ class InstanceFrames:
         if wait_inputs:
             torch.cuda.current_stream().synchronize()
         h, w = depth.shape
+        arr, n = ops if isinstance(ops, tuple) else self.prepare_ops(ops)
+        f = self.e.lib.b200_process_silhouettes if sync else self.e.lib.b200_process_silhouettes_async
+        self.e.check(f(self.e.h, _ptr(rgb), _ptr(depth), w, h, arr, n))
+
+    @staticmethod
+    def prepare_ops(ops):
+        """the b200_silhouette_op array of a list of ops — build it once for a frame that is processed more than once (or ahead of
+        time: a Python host spends longer marshalling the array than the GPU spends on the launch)"""
         arr = (abi.SilhouetteOp * max(len(ops), 1))()
         for k, (action, cm, dm, drgb, ddepth) in enumerate(ops):
             arr[k].action = int(action)
@@ -375,8 +385,7 @@ class InstanceFrames:
             if dm is not None:
                 arr[k].delete_mask = dm
             arr[k].d_dest_rgb, arr[k].d_dest_depth = _ptr(drgb), _ptr(ddepth)
-        f = self.e.lib.b200_process_silhouettes if sync else self.e.lib.b200_process_silhouettes_async
-        self.e.check(f(self.e.h, _ptr(rgb), _ptr(depth), w, h, arr, len(ops)))
+        return arr, len(ops)
 
     def CompositeDepth(self, target, source):
         torch.cuda.current_stream().synchronize()

@@ -105,7 +105,9 @@ class NcclCxxTransport:
             raise RuntimeError(self.lib.b200_comm_last_error(self.h).decode())
 
     def submit(self, slot, color, depth, out_color, out_depth, tints, dim_factor, tint_strength):
-        t = (C.c_int32 * max(len(tints), 1))(*tints) if tints else None
+        if tints is not getattr(self, "_tints_src", None):        # marshalled once: the tints of a run do not change
+            self._tints_src, self._tints_c = tints, ((C.c_int32 * max(len(tints), 1))(*tints) if tints else None)
+        t = self._tints_c
         self._check(self.lib.b200_gather_composite_submit(self.h, self.e.h, color.data_ptr(), depth.data_ptr(),
                                                           out_color.data_ptr() if out_color is not None else None,
                                                           out_depth.data_ptr() if out_depth is not None else None, t,
