@@ -257,6 +257,14 @@ def host_library():
         h.b200h_mat4_inv.argtypes = [P(C.c_float), P(C.c_float)]
         h.b200h_mat4_mul.argtypes = [P(C.c_float), P(C.c_float), P(C.c_float)]
         h.b200h_mat4_mul.restype = None
+        vp = C.c_void_p
+        h.b200h_free.argtypes = [vp]; h.b200h_free.restype = None
+        h.b200h_read_pfm.argtypes = [C.c_char_p, P(C.c_int), P(C.c_int), P(C.c_int), P(P(C.c_float))]
+        h.b200h_read_depth_xml.argtypes = [C.c_char_p, P(C.c_int), P(C.c_int), P(P(C.c_int16))]
+        h.b200h_clamp_max_depth_s16.argtypes = [vp, C.c_size_t, C.c_float]; h.b200h_clamp_max_depth_s16.restype = None
+        h.b200h_clamp_max_depth_f32.argtypes = [vp, C.c_size_t, C.c_float]; h.b200h_clamp_max_depth_f32.restype = None
+        h.b200h_read_mask_txt.argtypes = [C.c_char_p, C.c_int, C.c_int, vp]
+        h.b200h_write_obj.argtypes = [C.c_char_p, vp, C.c_uint32, C.c_uint32]
         _host = h
     return _host
 

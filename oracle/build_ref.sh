@@ -54,6 +54,20 @@ if [ -f "$EVC" ] && [ -f "$ECB" ]; then
   fi
 fi
 
+# ---- on-disk formats: the reference's own ReadFilePFM, ReadMask and ITMMesh::WriteOBJ (oracle/_ref/libioref.so) -----------------
+PFM=${PFM:-/root/reference/src/pfmLib/ImageIOpfm.cpp}; PSP="$DS/InstRecLib/PrecomputedSegmentationProvider.cpp"
+if [ -f "$PFM" ] && [ -f "$PSP" ]; then
+  awk '/^int ReadFilePFM\(/ {inr=1} {print} inr && /^}$/ {exit}' "$PFM" > "$HERE/_ref/pfm_extract.inc"
+  awk '/^uint8_t \*ReadMask\(/ {on=1} on {print} on && /^}$/ {exit}' "$PSP" > "$HERE/_ref/mask_extract.inc"
+  if grep -q "int ReadFilePFM" "$HERE/_ref/pfm_extract.inc" && grep -q "ReadMask" "$HERE/_ref/mask_extract.inc"; then
+    /usr/bin/g++ -std=c++14 -O2 -shared -fPIC -w -DCOMPILE_WITHOUT_CUDA -I"$HERE/stubs" -I"$REF" -I"$(dirname "$PFM")" -I"$HERE" \
+        -o "$HERE/_ref/libioref.so" "$HERE/ref_io_driver.cpp" && echo "built $HERE/_ref/libioref.so"
+  else
+    echo "could not locate ReadFilePFM / ReadMask" >&2
+  fi
+  rm -f "$HERE/_ref/pfm_extract.inc" "$HERE/_ref/mask_extract.inc"   # the cut-out text is a build intermediate only
+fi
+
 # ---- reference CUDA build + ITMLib harness (oracle/_ref/libitmharness.so) -------------------------
 # The reference's own CUDA engines, unmodified, compiled per-TU for sm_100a with the reference's
 # flags (--use_fast_math, ITMLib/CMakeLists.txt:226-230) directly from /root/reference, plus the few

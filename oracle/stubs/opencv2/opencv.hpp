@@ -17,6 +17,7 @@ class Mat {
   template <typename T> T &at(int r, int c) { return reinterpret_cast<T *>(bytes.data())[(size_t)r * cols + c]; }
   template <typename T> const T &at(int r, int c) const { return reinterpret_cast<const T *>(bytes.data())[(size_t)r * cols + c]; }
   Size size() const { return Size(cols, rows); }
+  static Mat zeros(int r, int c, int type) { Mat m; m.rows = r; m.cols = c; m.bytes.assign((size_t)r * c * (type == 21 ? 12 : 4), 0); return m; }   // CV_32FC1 = 5, CV_32FC3 = 21
 };
 class Mat1b : public Mat {
  public:
@@ -32,3 +33,12 @@ class Mat1s : public Mat {   // 16-bit signed single-channel matrix (the input d
   Mat1s(int r, int c) { rows = r; cols = c; bytes.resize((size_t)r * c * 2); }
 };
 }   // namespace cv
+// what src/pfmLib/ImageIOpfm.cpp's ReadFilePFM needs on top (oracle/ref_io_driver.cpp): float matrices of 1 or 3 channels
+#ifndef B200_STUB_CV_FLOAT
+#define B200_STUB_CV_FLOAT
+#define CV_32FC1 5
+#define CV_32FC3 21
+namespace cv {
+struct Vec3f { float v[3]; float &operator[](int i) { return v[i]; } const float &operator[](int i) const { return v[i]; } };
+}   // namespace cv
+#endif
