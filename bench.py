@@ -980,11 +980,18 @@ def run_own(args, rank, local_rank, world):
     # ---- reduce over ranks (max time) ----
     ms = max(gpu_ms, 0.0)
     if world > 1:
-        t = torch.tensor([ms, wall_ms, t_e2e, float(blocks), float(launches)], dtype=torch.float64, device=dev)
+        # The ranks run in lock step (a volume may be at most two frames ahead of the compositor), so every rank's timed region
+        # lasts as long as the slowest rank's INCLUDING that rank's L2 flushes, and the flushes take different times on different
+        # ranks (84 us on a GPU that then waits, 128 us on the one that is busy). Subtracting each rank's OWN flush time before the
+        # max would book the waiting for the slowest rank's longer flushes as work of the faster one (measured: 222 us "for" the
+        # instance volume against 180 us for the static map that actually paces the job). So: max over ranks of the whole region,
+        # minus the max over ranks of the flush time — the flushes on the critical path.
+        log(f"[rank {rank}] own timed region: {gpu_ms / K * 1000.0:.1f} us/step on the device after {flush_ms / K * 1000.0:.1f} us/step of L2 flush")
+        t = torch.tensor([gpu_ms + flush_ms, flush_ms, wall_ms + flush_ms, t_e2e, float(blocks), float(launches)], dtype=torch.float64, device=dev)
         tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
-        ms, wall_ms, t_e2e = float(tmax[0]), float(tmax[1]), float(tmax[2])
-        blocks_all, launches_all = float(tsum[3]), float(tsum[4])
+        ms, wall_ms, t_e2e = float(tmax[0] - tmax[1]), float(tmax[2] - tmax[1]), float(tmax[3])
+        blocks_all, launches_all = float(tsum[4]), float(tsum[5])
     else:
         blocks_all, launches_all = float(blocks), float(launches)
     if rank != 0:
@@ -1053,13 +1060,15 @@ def run_own(args, rank, local_rank, world):
         "data": "synthetic",
         "config": dict(base_config(args.preroll),
                    l2=(f"explicit flush between timed steps (256 MB read-modify-write, timed with CUDA events and subtracted, "
-                          f"{flush_ms / max(K, 1) * 1000:.0f} us each); per-step footprint ~{footprint_mb:.0f} MB") if args.flush_l2 else
+                          f"{flush_ms / max(K, 1) * 1000:.0f} us each" + ("; N > 1: the ranks run in lock step, so the whole region is max-reduced and the "
+                          "slowest rank's flushes are subtracted" if world > 1 else "") + f"); per-step footprint ~{footprint_mb:.0f} MB") if args.flush_l2 else
                          f"no flush (--no-flush-l2): per-step footprint ~{footprint_mb:.0f} MB, consecutive frames reuse L2",
                    integrate_impl=os.environ.get("B200_INTEGRATE_IMPL", "v4"),
                    parallelism=(f"configs[2]: one volume per GPU — rank 0 the static map (cars cut out with b200_process_silhouettes), ranks 1..{world - 1} one "
                                 "car volume each (voxel 0.035, mu 1.0, 7142 blocks) fed by b200_process_silhouettes; every frame each rank's colour + "
-                                "depth render goes to rank 0 over NCCL (C++ exchange, own stream, two slots) and is composited there inside the "
-                                "timed loop; value = volume-frames/s") if world > 1 else "1 volume"),
+                                "depth render goes to rank 0 (C++ exchange: copy-engine push over NVLink into rank 0's IPC-exported buffers, stream "
+                                "memory operations for the flags, own stream + own host thread, two slots; NCCL for the bootstrap) and is composited "
+                                "there inside the timed loop; value = volume-frames/s") if world > 1 else "1 volume"),
         "parity_checked": bool(parity.get("parity_checked")), "parity": parity,
         "mvoxels_per_s": mvox, "rays_hit": rays_hit, "visible_blocks": n_vis, "allocated_blocks": used_blocks, "decayed_blocks": int(decayed),
         "wall_ms_per_step": wall_ms / K,
