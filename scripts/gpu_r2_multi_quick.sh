@@ -3,9 +3,9 @@
 set -u
 N=${1:-2}
 mkdir -p gpurun_out
-COMMON="--gpus $N --steps 200 --warmup 5 --harness-frames 0 --hires-frames 0 --decay-blocks 0 --no-parity-check --cpu-steps 0 --e2e-steps 8"
-for v in push nowait; do
-  B200_COMM_DIAG=$([ $v = nowait ] && echo 4 || echo 0) timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29533 bench.py $COMMON \
+COMMON="--gpus $N --steps 200 --warmup 5 --harness-frames 0 --hires-frames 0 --decay-blocks 0 --no-parity-check --cpu-steps 0 --e2e-steps 60"
+for v in push; do
+  timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29533 bench.py $COMMON \
      > gpurun_out/xch_n${N}_$v.json 2> gpurun_out/xch_n${N}_$v.err
   echo "rc=$?"; grep -i "error\|composite\|own timed" gpurun_out/xch_n${N}_$v.err | head -8
   python - <<PY

@@ -29,6 +29,22 @@ def test_hash_collisions_excess_list():
     assert used_excess > 1000
 
 
+def test_large_table_list_kernel_in_two_passes():
+    """3.1 M hash entries = 384 tiles of the list kernel, more than the 2 x 148 CTAs it launches: CTAs own several tiles, so the
+    kernel runs its requests pass before its list pass (alloc.cu: twoPass) — and, in the same test, the excess list is used."""
+    cfg = P.Cfg(frames=4, scale=0.25, numBlocks=16384, numBuckets=0x200000, excessSize=0x100000, decay=(3, 2))
+    pair, _ = P.run_sequence(cfg)
+    assert pair.rs.noVisibleBlocks > 500
+
+
+def test_large_table_small_buckets_two_passes_with_excess_requests():
+    """the same with a bucket part of one tile and an excess part of 300: nearly every allocation is an excess request, and the
+    tiles that wait for them are spread over both passes"""
+    cfg = P.Cfg(frames=4, scale=0.25, numBlocks=16384, numBuckets=0x400, excessSize=0x258000)
+    pair, _ = P.run_sequence(cfg)
+    assert cfg.excessSize - 1 - pair.scene.lastFreeExcessListId > 500
+
+
 def test_decay_partial_with_chains():
     """minAge 2 / maxWeight 3: blocks are reset and deleted every frame, chains get unlinked."""
     cfg = P.Cfg(frames=10, frame_step=3, numBuckets=0x400, excessSize=0x4000, decay=(3, 2))
