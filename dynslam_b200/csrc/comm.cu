@@ -98,7 +98,7 @@ struct b200_comm {
   float *d_layerDepth[2];
   // push transport
   bool push;
-  int diag;                        // B200_COMM_DIAG (measurement aid): 1 = skip the composite launch, 2 = skip the composite and rank 0's own copies
+  int diag;                        // B200_COMM_DIAG (measurement aid): 1 = skip the composite launch, 4 = release does not wait
   unsigned seq[2];                 // hand-overs submitted per slot
   char *d_block;                   // rank 0: layers + ready flags in one exported allocation; other ranks: their two "slot free" flags
   size_t blockBytes;
@@ -307,10 +307,6 @@ static b200_status enqueue_exchange(b200_comm *c, const b200_comm::Work &w) {
   if (c->rank == 0) {
     // CompositeInstances (InstanceReconstructor.cpp:932-987): the background render dimmed, every instance layer z-composited
     // on top in rank order — on the communicator's stream, behind the layers' arrival
-    if (c->diag < 2) {
-      CCK(cudaMemcpyAsync(d_out_color, d_color, n * sizeof(b200_vec4u), cudaMemcpyDeviceToDevice, c->stream));
-      CCK(cudaMemcpyAsync(d_out_depth, d_depth, n * sizeof(float), cudaMemcpyDeviceToDevice, c->stream));
-    }
     b200_instance_layer layersArr[64];
     const int nl = c->nranks - 1 < 64 ? c->nranks - 1 : 64;
     for (int r = 0; r < nl; ++r) {
@@ -318,7 +314,9 @@ static b200_status enqueue_exchange(b200_comm *c, const b200_comm::Work &w) {
       layersArr[r].d_depth = c->d_layerDepth[slot] + (size_t)r * n;
       for (int k = 0; k < 4; ++k) layersArr[r].tint[k] = tints ? tints[4 * r + k] : 0;
     }
-    if (c->diag < 1) launch_composite_layers(w.e, d_out_color, d_out_depth, (int)n, layersArr, nl, dim_factor >= 0.0f, dim_factor, tint_strength, c->stream);
+    // rank 0's own render is the background: read in place by the composite kernel, never copied
+    if (c->diag < 1) launch_composite_layers(w.e, d_out_color, d_out_depth, (int)n, layersArr, nl, dim_factor >= 0.0f, dim_factor, tint_strength, c->stream,
+                                             d_color, d_depth);
     CCK(cudaGetLastError());
     if (c->push) {
       FlagList f; f.n = nl;

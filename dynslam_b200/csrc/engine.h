@@ -147,7 +147,8 @@ void launch_view_normals(b200_engine *e, const float *depth, b200_vec4f *normal,
 void launch_process_silhouettes(b200_engine *e, b200_vec4u *rgb, float *depth, int w, int h, const b200_silhouette_op *ops, int n);
 void launch_composite_depth(b200_engine *e, float *target, const float *source, int n);
 void launch_composite_layers(b200_engine *e, b200_vec4u *tcol, float *tdep, int n, const b200_instance_layer *layers, int nLayers,
-                             bool dim, float dimFactor, float tintStrength, cudaStream_t other = nullptr);
+                             bool dim, float dimFactor, float tintStrength, cudaStream_t other = nullptr, const b200_vec4u *bgcol = nullptr,
+                             const float *bgdep = nullptr);
 
 // Launch trace (timing mode 3): TRACED(e, stream, "kernel", launch-statement) brackets the launch with two events.
 static inline void trace_begin(b200_engine *e, cudaStream_t st, const char *name) {

@@ -66,12 +66,13 @@ constexpr int CMP_MAX_LAYERS = 16;
 struct Layers { b200_instance_layer l[CMP_MAX_LAYERS]; int n; };
 
 // dim (optional) + CompositeColor for every layer in order (InstanceReconstructor.cpp:873-905, :944-985)
-__global__ void k_composite_layers(uchar4 *__restrict__ tcol, float *__restrict__ tdep, int n, const __grid_constant__ Layers layers, int dim,
-                                   float dim_factor, float tint_strength) {
+// (bgcol / bgdep: where the background is read from — the target itself, or the render it would otherwise be copied from first)
+__global__ void k_composite_layers(uchar4 *tcol, float *tdep, const uchar4 *bgcol, const float *bgdep, int n, const __grid_constant__ Layers layers,
+                                   int dim, float dim_factor, float tint_strength) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  uchar4 c = tcol[i];
-  float d = tdep[i];
+  uchar4 c = bgcol[i];
+  float d = bgdep[i];
   if (dim) {
     const double f = 1.0 - (double)dim_factor;
     c.x = (unsigned char)((double)c.x * f); c.y = (unsigned char)((double)c.y * f); c.z = (unsigned char)((double)c.z * f);
@@ -113,7 +114,7 @@ void launch_composite_depth(b200_engine *e, float *target, const float *source, 
 }
 
 void launch_composite_layers(b200_engine *e, b200_vec4u *tcol, float *tdep, int n, const b200_instance_layer *layers, int nLayers,
-                             bool dim, float dimFactor, float tintStrength, cudaStream_t other) {
+                             bool dim, float dimFactor, float tintStrength, cudaStream_t other, const b200_vec4u *bgcol, const float *bgdep) {
   // other != 0: launched on that stream by the exchange's own host thread (comm.cu) — the engine's state is not touched
   const cudaStream_t st = other ? other : e->stream;
   int base = 0;
@@ -122,7 +123,11 @@ void launch_composite_layers(b200_engine *e, b200_vec4u *tcol, float *tdep, int 
     L.n = nLayers - base < CMP_MAX_LAYERS ? nLayers - base : CMP_MAX_LAYERS;
     for (int k = 0; k < L.n; ++k) L.l[k] = layers[base + k];
     if (!other) trace_begin(e, st, "k_composite_layers");
-    k_composite_layers<<<(n + 255) / 256, 256, 0, st>>>((uchar4 *)tcol, tdep, n, L, (dim && base == 0) ? 1 : 0, dimFactor, tintStrength);
+    // the first chunk reads the background from bgcol / bgdep when given (the exchange composites rank 0's render without
+    // copying it into the destination first); later chunks continue in place
+    const uchar4 *bc = (base == 0 && bgcol) ? (const uchar4 *)bgcol : (const uchar4 *)tcol;
+    const float *bd = (base == 0 && bgdep) ? bgdep : tdep;
+    k_composite_layers<<<(n + 255) / 256, 256, 0, st>>>((uchar4 *)tcol, tdep, bc, bd, n, L, (dim && base == 0) ? 1 : 0, dimFactor, tintStrength);
     if (!other) { trace_end(e, st); e->launches++; }
     base += CMP_MAX_LAYERS;
   } while (base < nLayers);
