@@ -786,9 +786,9 @@ def run_own(args, rank, local_rank, world):
         sampler = ClockSampler(local_rank)
         if "nosampler" not in diag:
             sampler.start()
-        if "nogc" in diag:
-            import gc
-            gc.disable()
+        import gc
+        gc.collect()
+        gc.disable()        # no collector pauses inside the timed loops (they show up as millisecond gaps between two frame submissions)
         # ---- pre-roll: build the map to steady state (untimed set-up) ----
         idx = 0
         for _ in range(args.preroll):
@@ -949,6 +949,7 @@ def run_own(args, rank, local_rank, world):
             except Exception as ex:
                 meshing = {"error": str(ex)}
 
+    gc.enable()
     sampler.stop()
     clk_all = len(sampler.rows)
     sampler.rows = sampler.rows[max(clk_first - 1, 0):clk_timed_end] or sampler.rows   # samples taken during the timed region

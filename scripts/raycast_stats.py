@@ -41,3 +41,12 @@ rows = tt.max(-1).sum(1)
 print("  heaviest tile rows:", np.argsort(-rows)[:8], rows[np.argsort(-rows)[:8]])
 hist = np.bincount(np.minimum(ne.ravel(), 200) // 10)
 print("  empty steps per ray histogram (bins of 10, last = 200+):", hist.tolist())
+
+# chain walks of the neighbourhood-cache march (cast_ray_nbr), per interpolated sample
+out = np.zeros((h, w, 4), np.float32)
+lib.hostcheck_raycast.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_float, C.c_float, vp, vp, C.c_int]
+lib.hostcheck_raycast_walks.restype = C.c_long
+lib.hostcheck_raycast_walks(1)
+lib.hostcheck_raycast(H.vptr(vol.voxels), H.vptr(vol.hash), 0x100000, w, h, hv.invM_d, hv.proj_d, p.voxelSize, p.mu, H.vptr(vol.minmax), H.vptr(out), 1)
+walks = lib.hostcheck_raycast_walks(1)
+print("cast_ray_nbr: %d chain walks = %.2f per step, %.2f per interpolated sample (per ray, not per warp)" % (walks, walks / max((ne + nf).sum(), 1), walks / max(nf.sum(), 1)))

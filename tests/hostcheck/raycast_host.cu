@@ -1,7 +1,11 @@
 // Test infrastructure (CPU): the raycast kernel's own castRay chain (dynslam_b200/csrc/raycast_ray.cuh, __host__ __device__)
 // compiled for the HOST and run over a whole image on host arrays, with k_raycast's pixel -> min/max-cell mapping
 // (vis.cu, GenericRaycast, Vis_CUDA.cu:672-684). tests/test_raycast_host.py compares every ray with the CPU oracle's.
+#define RC_COUNT_WALKS
+static long rc_walks = 0;      // chain walks of cast_ray_nbr (design statistics only)
 #include "../../dynslam_b200/csrc/raycast_ray.cuh"
+
+extern "C" long hostcheck_raycast_walks(int reset) { const long v = rc_walks; if (reset) rc_walks = 0; return v; }
 
 extern "C" void hostcheck_raycast(const b200_voxel *voxels, const b200_hash_entry *table, int nb, int w, int h, const float *invM16,
                                   const float *proj, float voxelSize, float mu, const b200_vec2f *minmax, b200_vec4f *out, int variant) {
