@@ -11,9 +11,9 @@
 //     a rank copies its two renders straight into rank 0's buffers with the COPY ENGINES over NVLink (cudaMemcpyAsync on
 //     peer-mapped memory) and then raises a sequence flag in rank 0's memory; rank 0's stream waits on the flags with
 //     cuStreamWaitValue32 (no SM), composites, and lowers the senders' "slot free" flags the same way. No rendez-vous kernel
-//     ever sits on an SM. Measured on 2 B200s (profiles/r02_multi.md): with ncclSend/ncclRecv the step took 221 us against
-//     179 us with the exchange switched off — the NCCL kernels compete for SM slots with the frame's persistent kernels
-//     (IntegrateIntoScene and the list kernel fill the register file) — with the push transport the exchange is free.
+//     ever sits on an SM and nothing competes with the frame's persistent kernels (IntegrateIntoScene and the list kernel fill
+//     the register file). Measured on 2 and 4 B200s (profiles/r02_multi.md): the compositor rank's step is 179.7 us with the
+//     exchange and 178.6 - 178.9 us without.
 //   * "nccl" transport (B200_COMM_IMPL=nccl, and the fallback where stream memory operations are unavailable): grouped
 //     ncclSend / ncclRecv (NCCL has no gather) on the communicator's stream.
 //
@@ -106,8 +106,7 @@ struct b200_comm {
   unsigned *d_free;                // ranks > 0: [slot], raised by rank 0 (== d_block)
   char *peerBlock[64];             // rank 0: rank r's flag block; rank r: rank 0's block (index 0)
   // The hand-over is a dozen stream operations per frame. They are issued by the communicator's OWN host thread, so the thread
-  // that drives the engine pays one event record and a queue push per frame (measured: with the calls inline a 2-GPU step was
-  // host-bound at 221 us against 179 us of GPU work).
+  // that drives the engine pays one event record and a queue push per frame.
   struct Work {
     int slot; unsigned seq;
     const b200_vec4u *d_color; const float *d_depth; b200_vec4u *d_out_color; float *d_out_depth;
