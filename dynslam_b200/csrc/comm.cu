@@ -98,7 +98,7 @@ struct b200_comm {
   float *d_layerDepth[2];
   // push transport
   bool push;
-  int diag;                        // B200_COMM_DIAG (measurement aid): 1 = skip the composite launch, 4 = release does not wait
+  int diag;                        // B200_COMM_DIAG (measurement / test aid): 1 = skip the composite launch, 4 = release does not wait, 8 = simulate a failed IPC open
   unsigned seq[2];                 // hand-overs submitted per slot
   char *d_block;                   // rank 0: layers + ready flags in one exported allocation; other ranks: their two "slot free" flags
   size_t blockBytes;
@@ -195,23 +195,20 @@ static b200_status comm_create_body(b200_comm *c, const char *id) {
   NCK(g_nccl.CommInitRank(&c->comm, c->nranks, u, c->rank));
   if (!c->push) return B200_OK;
   // ---- push transport: one exported allocation per rank, handles exchanged over the communicator ----
+  // Every CUDA step that can fail on a machine without peer access between the GPUs (export, open) only lowers `ok`; the ranks
+  // then agree on the verdict over the communicator and, if any of them failed, ALL fall back to the nccl transport.
   const size_t n = c->pixels, layers = (size_t)(c->nranks - 1);
   const size_t colBytes = sizeof(b200_vec4u) * n * layers, depBytes = sizeof(float) * n * layers;
   const size_t flagBytes = 256;      // rank 0: ready[rank-1][slot] (at most 63 x 2 words); others: free[slot]
   c->blockBytes = c->rank == 0 ? 2 * (colBytes + depBytes) + 4 * flagBytes : flagBytes;
-  CCK(cudaMalloc(&c->d_block, c->blockBytes));
-  CCK(cudaMemset(c->d_block, 0, c->blockBytes));
-  if (c->rank == 0) {
-    char *q = c->d_block;
-    for (int s = 0; s < 2; ++s) { c->d_layerColor[s] = reinterpret_cast<b200_vec4u *>(q); q += colBytes; }
-    for (int s = 0; s < 2; ++s) { c->d_layerDepth[s] = reinterpret_cast<float *>(q); q += depBytes; }
-    c->d_ready = reinterpret_cast<unsigned *>(q);
-  } else {
-    c->d_free = reinterpret_cast<unsigned *>(c->d_block);
-  }
-  cudaIpcMemHandle_t mine;
-  CCK(cudaIpcGetMemHandle(&mine, c->d_block));
-  const size_t hb = sizeof(cudaIpcMemHandle_t);
+  int ok = 1;
+  struct BootRec { cudaIpcMemHandle_t handle; int ok; int pad[3]; };
+  BootRec mine;
+  memset(&mine, 0, sizeof(mine));
+  if (cudaMalloc(&c->d_block, c->blockBytes) != cudaSuccess || cudaMemset(c->d_block, 0, c->blockBytes) != cudaSuccess ||
+      cudaIpcGetMemHandle(&mine.handle, c->d_block) != cudaSuccess) { ok = 0; cudaGetLastError(); }
+  mine.ok = ok;
+  const size_t hb = sizeof(BootRec);
   char *d_boot = nullptr;
   CCK(cudaMalloc(&d_boot, hb * (size_t)c->nranks));
   CCK(cudaMemcpy(d_boot + hb * (size_t)c->rank, &mine, hb, cudaMemcpyHostToDevice));
@@ -227,14 +224,60 @@ static b200_status comm_create_body(b200_comm *c, const char *id) {
   }
   NCK(g_nccl.GroupEnd());
   CCK(cudaStreamSynchronize(c->stream));
-  cudaIpcMemHandle_t all[64];
+  BootRec all[64];
   CCK(cudaMemcpy(all, d_boot, hb * (size_t)c->nranks, cudaMemcpyDeviceToHost));
-  cudaFree(d_boot);
   if (c->rank == 0) {
-    for (int r = 1; r < c->nranks; ++r) CCK(cudaIpcOpenMemHandle((void **)&c->peerBlock[r], all[r], cudaIpcMemLazyEnablePeerAccess));
-  } else {
-    CCK(cudaIpcOpenMemHandle((void **)&c->peerBlock[0], all[0], cudaIpcMemLazyEnablePeerAccess));
+    for (int r = 1; r < c->nranks && ok; ++r)
+      if (!all[r].ok || cudaIpcOpenMemHandle((void **)&c->peerBlock[r], all[r].handle, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = 0; cudaGetLastError(); }
+  } else if (ok) {
+    if (!all[0].ok || cudaIpcOpenMemHandle((void **)&c->peerBlock[0], all[0].handle, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = 0; cudaGetLastError(); }
   }
+  if (c->diag == 8 && c->rank == c->nranks - 1) ok = 0;      // B200_COMM_DIAG=8: the last rank pretends its open failed (test of the fallback)
+  // verdict = AND over the ranks: gathered by rank 0, sent back
+  int *d_ok = reinterpret_cast<int *>(d_boot);
+  CCK(cudaMemcpy(d_ok + c->rank, &ok, sizeof(int), cudaMemcpyHostToDevice));
+  if (c->rank == 0) {
+    NCK(g_nccl.GroupStart());
+    for (int r = 1; r < c->nranks; ++r) NCK(g_nccl.Recv(d_ok + r, sizeof(int), 0, r, c->comm, c->stream));
+    NCK(g_nccl.GroupEnd());
+    CCK(cudaStreamSynchronize(c->stream));
+    int oks[64];
+    CCK(cudaMemcpy(oks, d_ok, sizeof(int) * (size_t)c->nranks, cudaMemcpyDeviceToHost));
+    for (int r = 0; r < c->nranks; ++r) ok &= (oks[r] != 0);
+    CCK(cudaMemcpy(d_ok, &ok, sizeof(int), cudaMemcpyHostToDevice));
+    NCK(g_nccl.GroupStart());
+    for (int r = 1; r < c->nranks; ++r) NCK(g_nccl.Send(d_ok, sizeof(int), 0, r, c->comm, c->stream));
+    NCK(g_nccl.GroupEnd());
+    CCK(cudaStreamSynchronize(c->stream));
+  } else {
+    NCK(g_nccl.Send(d_ok + c->rank, sizeof(int), 0, 0, c->comm, c->stream));
+    CCK(cudaStreamSynchronize(c->stream));
+    NCK(g_nccl.Recv(d_ok, sizeof(int), 0, 0, c->comm, c->stream));
+    CCK(cudaStreamSynchronize(c->stream));
+    CCK(cudaMemcpy(&ok, d_ok, sizeof(int), cudaMemcpyDeviceToHost));
+  }
+  cudaFree(d_boot);
+  if (ok) {
+    if (c->rank == 0) {
+      char *q = c->d_block;
+      for (int s = 0; s < 2; ++s) { c->d_layerColor[s] = reinterpret_cast<b200_vec4u *>(q); q += colBytes; }
+      for (int s = 0; s < 2; ++s) { c->d_layerDepth[s] = reinterpret_cast<float *>(q); q += depBytes; }
+      c->d_ready = reinterpret_cast<unsigned *>(q);
+    } else {
+      c->d_free = reinterpret_cast<unsigned *>(c->d_block);
+    }
+    return B200_OK;
+  }
+  // fallback: the nccl transport on every rank
+  for (int r = 0; r < 64; ++r) if (c->peerBlock[r]) { cudaIpcCloseMemHandle(c->peerBlock[r]); c->peerBlock[r] = nullptr; }
+  cudaFree(c->d_block); c->d_block = nullptr;
+  cudaGetLastError();
+  c->push = false;
+  if (c->rank == 0)
+    for (int s = 0; s < 2; ++s) {
+      CCK(cudaMalloc(&c->d_layerColor[s], sizeof(b200_vec4u) * c->pixels * (size_t)(c->nranks - 1)));
+      CCK(cudaMalloc(&c->d_layerDepth[s], sizeof(float) * c->pixels * (size_t)(c->nranks - 1)));
+    }
   return B200_OK;
 }
 
@@ -314,7 +357,7 @@ static b200_status enqueue_exchange(b200_comm *c, const b200_comm::Work &w) {
       for (int k = 0; k < 4; ++k) layersArr[r].tint[k] = tints ? tints[4 * r + k] : 0;
     }
     // rank 0's own render is the background: read in place by the composite kernel, never copied
-    if (c->diag < 1) launch_composite_layers(w.e, d_out_color, d_out_depth, (int)n, layersArr, nl, dim_factor >= 0.0f, dim_factor, tint_strength, c->stream,
+    if (c->diag != 1) launch_composite_layers(w.e, d_out_color, d_out_depth, (int)n, layersArr, nl, dim_factor >= 0.0f, dim_factor, tint_strength, c->stream,
                                              d_color, d_depth);
     CCK(cudaGetLastError());
     if (c->push) {
