@@ -3,6 +3,7 @@ declares (no CUDA call is made), and the host helpers agree with the oracle."""
 import ctypes as C
 import os
 import re
+import subprocess
 
 import numpy as np
 
@@ -33,6 +34,36 @@ def test_pod_layouts_match_header():
     assert abi.HASH_ENTRY_DTYPE.itemsize == 20 and abi.VOXEL_DTYPE.itemsize == 8
     assert abi.HASH_ENTRY_DTYPE.fields["offset"][1] == 8 and abi.HASH_ENTRY_DTYPE.fields["ptr"][1] == 12
     assert abi.VOXEL_DTYPE.fields["w_depth"][1] == 2 and abi.VOXEL_DTYPE.fields["w_color"][1] == 6
+
+
+def test_ctypes_mirror_has_the_headers_layout(tmp_path):
+    """every POD of include/b200fusion.h (+ the diag header's stats), compiled by gcc: size and every field offset must equal the
+    ctypes.Structure the Python mirror passes across the boundary"""
+    pairs = [("b200_scene", abi.Scene), ("b200_render_state", abi.RenderState), ("b200_view", abi.View), ("b200_camera", abi.Camera),
+             ("b200_engine_config", abi.EngineConfig), ("b200_transfer_buffers", abi.TransferBuffers), ("b200_frame_opts", abi.FrameOpts),
+             ("b200_view_calib", abi.ViewCalib), ("b200_mask", abi.Mask), ("b200_silhouette_op", abi.SilhouetteOp),
+             ("b200_instance_layer", abi.InstanceLayer), ("b200_eval_params", abi.EvalParams), ("b200_eval_callback", abi.EvalCallback),
+             ("b200_eval_stats", abi.EvalStats), ("b200_eval_result", abi.EvalResult), ("b200_eval_summary", abi.EvalSummary),
+             ("b200_frame_stats", abi.FrameStats)]
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "b200fusion.h"', '#include "b200fusion_diag.h"', 'int main(void) {']
+    for cname, cls in pairs:
+        lines.append(f'  printf("{cname} size %zu\\n", sizeof({cname}));')
+        for fname, _ in cls._fields_:
+            lines.append(f'  printf("{cname} {fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines += ['  printf("b200_triangle size %zu\\n", sizeof(b200_triangle));', '  return 0;', '}']
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run(["/usr/bin/gcc", "-I", os.path.join(H.ROOT, "include"), "-o", str(exe), str(src)], check=True)
+    got = {}
+    for ln in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.splitlines():
+        a, b, c = ln.split()
+        got[(a, b)] = int(c)
+    for cname, cls in pairs:
+        assert got[(cname, "size")] == C.sizeof(cls), cname
+        for fname, _ in cls._fields_:
+            assert got[(cname, fname)] == getattr(cls, fname).offset, (cname, fname)
+    assert got[("b200_triangle", "size")] == abi.TRIANGLE_DTYPE.itemsize == 72
 
 
 def test_host_matrix_helpers_equal_oracle():
