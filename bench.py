@@ -1017,7 +1017,7 @@ def run_own(args, rank, local_rank, world):
         snap = None
 
     cpu = None
-    if args.cpu_steps > 0:
+    if args.cpu_steps > 0 and world == 1:      # the CPU baseline is timed at N = 1 only
         try:
             c = cpu_run(6, args.preroll, 1, args.cpu_steps, passes=1)
             cpu = {"value": c["fps"], "unit": "frames/s", "cores": c["cores"], "kind": "port",
